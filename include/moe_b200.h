@@ -1,0 +1,131 @@
+/*
+ * moe_b200.h — C ABI of libmoe_b200.so, the sm_100a implementation of the Switch-style MoE layer
+ * that d0-rb/slim-switch-moe-vit obtains from FastMoE (`fmoe.FMoETransformerMLP`, imported at
+ * /root/reference/models/resMoE.py:6, wrapped at models/resMoE.py:15-29, invoked at
+ * models/vision_transformer.py:321 and models/resMoE.py:121,143).
+ *
+ * The reference has no FFI of its own for this path: its native half is FastMoE's `fmoe_cuda`
+ * torch extension (un-vendored).  Each entry point below names the fmoe_cuda op / Python step it
+ * replaces; INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is DEVICE memory unless stated; caller allocates all
+ *     outputs and workspaces; `stream` is a cudaStream_t passed as void*; all work is enqueued
+ *     asynchronously, nothing synchronises the host.
+ *   - return value: 0 = OK, non-zero = error; moe_last_error() (thread-local) describes it.
+ *   - dtype codes: MOE_DTYPE_F32 = 0, MOE_DTYPE_BF16 = 1.
+ *   - packed row buffers ("xbuf", "U", "H", "Y", ...) are [rows_cap, cols] bf16 row-major;
+ *     expert e owns rows [seg_start[e], seg_start[e+1]), each segment start is a multiple of 128,
+ *     rows [seg_start[e] + kept[e], seg_start[e+1]) are padding.
+ *     rows_cap >= moe_rows_cap(T, k, E, capacity).
+ *   - constraints: d % 64 == 0, h % 64 == 0, 1 <= k <= 8, k <= E, E <= 1024.
+ */
+#ifndef MOE_B200_H
+#define MOE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOE_DTYPE_F32 0
+#define MOE_DTYPE_BF16 1
+
+#define MOE_SCORE_TOPK_SOFTMAX 0 /* NaiveGate / GShardGate: softmax over the k selected logits      */
+#define MOE_SCORE_FULL_SOFTMAX 1 /* SwitchGate: softmax over all experts, score = prob of selection */
+
+#define MOE_TOKEN_TILE 256 /* tokens per routing tile; ntiles = ceil(T / 256) */
+#define MOE_ROW_ALIGN 128  /* segment alignment of the packed buffers          */
+
+/* grouped GEMM ops (moe_grouped_gemm) */
+#define MOE_GEMM_FC1 0   /* out0 = U = A W^T + b, out1 = gelu_erf(U)    A[rows,K] B[E,N,K]            */
+#define MOE_GEMM_FC2 1   /* out0 = A W^T + b                            A[rows,K] B[E,N,K]            */
+#define MOE_GEMM_DGELU 2 /* out0 = (A W) * gelu'(aux)                   A[rows,K] B[E,K,N] aux[rows,N] */
+#define MOE_GEMM_DGRAD 3 /* out0 = A W                                  A[rows,K] B[E,K,N]            */
+#define MOE_GEMM_WGRAD 4 /* out0[e] (fp32 [E,M,N]) = A_e^T B_e          A[rows,M] B[rows,N]           */
+
+const char *moe_last_error(void);
+int moe_version(void);
+
+/* rows the packed buffers must hold: min(T*k, E*capacity) + 128*E */
+int64_t moe_rows_cap(int64_t T, int k, int E, int64_t capacity);
+
+/* ---- gate: replaces NaiveGate's nn.Linear + torch.topk + F.softmax and fmoe_cuda.expert_count.
+ * logits[T,E] fp32 (LOGIT ORDER v1, bit-identical to oracle/gate_ref.c), idx[T,k] i32,
+ * score[T,k] fp32, tile_hist[ntiles,E] i32, tile_psum[ntiles,E] fp32 (only if want_psum). */
+int moe_gate_fwd(const void *x, int x_dtype, const float *Wg, const float *bg /* nullable */,
+                 const float *noise /* nullable [T,E], added to the logits (SwitchGate jitter) */, int64_t T, int d, int E,
+                 int k, int score_mode, int want_psum, float *logits, int32_t *idx, float *score, int32_t *tile_hist,
+                 float *tile_psum, void *stream);
+
+/* ---- scan: replaces torch.cumsum + .item() + limit_by_capacity (no host sync).
+ * tile_base[ntiles,E], count[E], kept[E] = min(count, capacity), seg_start[E+1],
+ * tile_expert[max_mtiles] (expert of each 128-row tile, -1 past the end), num_mtiles[1],
+ * psum[E] = sum over tiles of tile_psum (nullable together with tile_psum). */
+int moe_route_scan(const int32_t *tile_hist, const float *tile_psum, int ntiles, int E, int64_t capacity,
+                   int32_t *tile_base, int32_t *count, int32_t *kept, int32_t *seg_start, int32_t *tile_expert,
+                   int32_t *num_mtiles, int max_mtiles, float *psum, void *stream);
+
+/* ---- dispatch: replaces fmoe_cuda.assign_pos + MOEScatter (deterministic, token order).
+ * pos[T,k] row of each (token,slot) or -1 if dropped; row_src[rows_cap] flattened pair index of
+ * each row (-1 on padding); xbuf[rows_cap,d] bf16 with padding rows zeroed. */
+int moe_dispatch_fwd(const void *x, int x_dtype, const int32_t *idx, const int32_t *tile_base, const int32_t *seg_start,
+                     const int32_t *kept, int64_t T, int d, int E, int k, int64_t capacity, int32_t *pos,
+                     int32_t *row_src, void *xbuf, void *stream);
+
+/* ---- expert FFN forward: replaces _Expert.forward = fmoe_cuda.linear_forward x2 + GELU.
+ * W1b[E,h,d], W2b[E,d,h] bf16 copies of the fp32 parameters; b1[E,h], b2[E,d] fp32.
+ * Writes U (pre-activation), H = gelu_erf(U), Y, all bf16 [rows_cap, .]. */
+int moe_expert_ffn_fwd(const void *xbuf, const void *W1b, const float *b1, const void *W2b, const float *b2,
+                       const int32_t *tile_expert, const int32_t *num_mtiles, int64_t rows_cap, int d, int h, int E,
+                       void *U, void *H, void *Y, void *stream);
+
+/* ---- combine: replaces MOEGather + torch.bmm(gate_score, expert_out). out[T,d] in out_dtype. */
+int moe_combine_fwd(const void *ybuf, const int32_t *pos, const float *score, int64_t T, int d, int k, void *out,
+                    int out_dtype, void *stream);
+
+/* ---- backward of combine: dybuf[rows_cap,d] bf16 (padding zeroed), dscore[T,k] fp32. */
+int moe_combine_bwd(const void *dy, int dy_dtype, const void *ybuf, const int32_t *pos, const float *score,
+                    const int32_t *seg_start, const int32_t *kept, int64_t T, int d, int k, int E, void *dybuf,
+                    float *dscore, void *stream);
+
+/* ---- expert FFN backward: replaces fmoe_cuda.linear_backward x2 + GELU' + column_reduce.
+ * dU[rows_cap,h] and dxbuf[rows_cap,d] are bf16 outputs (dU doubles as workspace);
+ * dW1[E,h,d], db1[E,h], dW2[E,d,h], db2[E,d] are fp32 and are overwritten. */
+int moe_expert_ffn_bwd(const void *dybuf, const void *xbuf, const void *U, const void *H, const void *W1b,
+                       const void *W2b, const int32_t *tile_expert, const int32_t *num_mtiles,
+                       const int32_t *seg_start, int64_t rows_cap, int d, int h, int E, void *dU, void *dxbuf,
+                       float *dW1, float *db1, float *dW2, float *db2, void *stream);
+
+/* ---- gate backward: dlogits[T,E] from dscore[T,k] and (nullable) dpsum[E]. */
+int moe_gate_bwd(const float *logits, const int32_t *idx, const float *score, const float *dscore, const float *dpsum,
+                 int64_t T, int E, int k, int score_mode, float *dlogits, void *stream);
+
+/* ---- dispatch backward (+ gate input gradient): dx[t] = sum_j dxbuf[pos[t,j]] + dlogits[t] Wg.
+ * dxbuf or dlogits may be NULL (term skipped).  dense_dlogits = 0 means only the k selected
+ * entries of each dlogits row are non-zero (NaiveGate without aux loss). */
+int moe_dispatch_bwd(const void *dxbuf, const int32_t *pos, const float *dlogits, const int32_t *idx, const float *Wg,
+                     int64_t T, int d, int E, int k, int dense_dlogits, void *dx, int dx_dtype, void *stream);
+
+/* ---- gate weight gradient: dWg[E,d] = dlogits^T x, dbg[E] (nullable) = colsum(dlogits).
+ * workspace: moe_gate_wgrad_workspace_bytes(T, d, E) bytes. */
+size_t moe_gate_wgrad_workspace_bytes(int64_t T, int d, int E);
+int moe_gate_wgrad(const float *dlogits, const void *x, int x_dtype, int64_t T, int d, int E, void *workspace,
+                   float *dWg, float *dbg, void *stream);
+
+/* ---- utilities */
+int moe_cast_bf16(const float *src, void *dst, int64_t n /* % 8 == 0 */, void *stream);
+int moe_segment_colsum(const void *buf, const int32_t *seg_start, int E, int cols, float *out, void *stream);
+
+/* ---- the grouped tcgen05 GEMM itself (building block of the two FFN entry points; exported so
+ * each contraction can be tested and timed on its own).  See MOE_GEMM_* for operand shapes. */
+int moe_grouped_gemm(int op, const void *A, const void *B, void *out0, void *out1, const float *bias, const void *aux,
+                     const int32_t *tile_expert, const int32_t *num_mtiles, const int32_t *seg_start, int64_t rows_cap,
+                     int E, int M, int N, int K, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOE_B200_H */

@@ -33,9 +33,9 @@
 #include <string.h>
 
 /* logits[T,E] from x[T,d] (fp32 values; bf16 inputs are widened exactly by the caller),
- * Wg[E,d], bg[E] (may be NULL). */
+ * Wg[E,d], bg[E] (may be NULL), optional additive noise[T,E] (SwitchGate jitter). */
 void moe_oracle_gate_logits(const float *x, int64_t T, int d, const float *Wg, const float *bg,
-                            int E, float *logits)
+                            const float *noise, int E, float *logits)
 {
     for (int64_t t = 0; t < T; ++t) {
         const float *xr = x + t * (int64_t)d;
@@ -52,7 +52,9 @@ void moe_oracle_gate_logits(const float *x, int64_t T, int d, const float *Wg, c
                 for (int l = 0; l < 32; ++l) nxt[l] = part[l] + part[l ^ off];
                 memcpy(part, nxt, sizeof(part));
             }
-            logits[t * E + e] = part[0] + (bg ? bg[e] : 0.0f);
+            float v = part[0] + (bg ? bg[e] : 0.0f);
+            if (noise) v += noise[t * E + e];
+            logits[t * E + e] = v;
         }
     }
 }

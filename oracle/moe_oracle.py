@@ -55,7 +55,8 @@ def capacity_from_factor(cf: float, T: int, k: int, E: int) -> int:
 # --------------------------------------------------------------------------------------
 # gate + routing (bit-exact restatement; C)
 # --------------------------------------------------------------------------------------
-def gate_logits(x: torch.Tensor, Wg: torch.Tensor, bg: torch.Tensor | None) -> torch.Tensor:
+def gate_logits(x: torch.Tensor, Wg: torch.Tensor, bg: torch.Tensor | None,
+                noise: torch.Tensor | None = None) -> torch.Tensor:
     """logits[T,E] in LOGIT ORDER v1 (oracle/gate_ref.c).  x may be fp32 or bf16."""
     lib = _build.load()
     xf = np.ascontiguousarray(x.detach().to(torch.float32).cpu().numpy())
@@ -63,8 +64,10 @@ def gate_logits(x: torch.Tensor, Wg: torch.Tensor, bg: torch.Tensor | None) -> t
     T, d = xf.shape
     E = w.shape[0]
     b = None if bg is None else np.ascontiguousarray(bg.detach().to(torch.float32).cpu().numpy())
+    nz = None if noise is None else np.ascontiguousarray(noise.detach().to(torch.float32).cpu().numpy())
     out = np.empty((T, E), dtype=np.float32)
-    lib.moe_oracle_gate_logits(_ptr(xf), T, d, _ptr(w), None if b is None else _ptr(b), E, _ptr(out))
+    lib.moe_oracle_gate_logits(_ptr(xf), T, d, _ptr(w), None if b is None else _ptr(b),
+                               None if nz is None else _ptr(nz), E, _ptr(out))
     return torch.from_numpy(out)
 
 

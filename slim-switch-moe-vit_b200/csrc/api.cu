@@ -1,0 +1,187 @@
+// api.cu — the extern "C" surface declared in include/moe_b200.h.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace moe {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+static int check(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 1;
+}
+
+static bool dims_ok(const char* fn, int64_t T, int d, int E, int k) {
+    if (T <= 0 || d <= 0 || d % 64 != 0 || E <= 0 || E > 1024 || k < 1 || k > 8 || k > E) {
+        set_error("%s: unsupported shape T=%lld d=%d E=%d k=%d (need d %% 64 == 0, 1 <= k <= min(8,E), E <= 1024)", fn,
+                  (long long)T, d, E, k);
+        return false;
+    }
+    return true;
+}
+static bool dtype_ok(const char* fn, int dt) {
+    if (dt != MOE_DTYPE_F32 && dt != MOE_DTYPE_BF16) { set_error("%s: unsupported dtype code %d", fn, dt); return false; }
+    return true;
+}
+
+}  // namespace moe
+
+using namespace moe;
+
+extern "C" {
+
+const char* moe_last_error(void) { return g_err; }
+int moe_version(void) { return 100; }
+
+int64_t moe_rows_cap(int64_t T, int k, int E, int64_t capacity) {
+    int64_t pairs = T * k;
+    if (capacity > 0 && capacity < pairs && capacity * E < pairs) pairs = capacity * E;
+    return (pairs + 127) / 128 * 128 + 128LL * E;
+}
+
+int moe_gate_fwd(const void* x, int x_dtype, const float* Wg, const float* bg, const float* noise, int64_t T, int d, int E, int k,
+                 int score_mode, int want_psum, float* logits, int32_t* idx, float* score, int32_t* tile_hist,
+                 float* tile_psum, void* stream) {
+    if (!dims_ok("moe_gate_fwd", T, d, E, k) || !dtype_ok("moe_gate_fwd", x_dtype)) return 1;
+    if (score_mode != MOE_SCORE_TOPK_SOFTMAX && score_mode != MOE_SCORE_FULL_SOFTMAX) { set_error("moe_gate_fwd: bad score_mode %d", score_mode); return 1; }
+    if (want_psum && tile_psum == nullptr) { set_error("moe_gate_fwd: want_psum needs tile_psum"); return 1; }
+    return check(launch_gate_fwd(x, x_dtype, Wg, bg, noise, T, d, E, k, score_mode, want_psum, logits, idx, score, tile_hist,
+                                 tile_psum, static_cast<cudaStream_t>(stream)),
+                 "moe_gate_fwd");
+}
+
+int moe_route_scan(const int32_t* tile_hist, const float* tile_psum, int ntiles, int E, int64_t capacity,
+                   int32_t* tile_base, int32_t* count, int32_t* kept, int32_t* seg_start, int32_t* tile_expert,
+                   int32_t* num_mtiles, int max_mtiles, float* psum, void* stream) {
+    if (ntiles <= 0 || E <= 0 || E > 1024 || capacity <= 0) { set_error("moe_route_scan: bad arguments ntiles=%d E=%d capacity=%lld", ntiles, E, (long long)capacity); return 1; }
+    return check(launch_route_scan(tile_hist, tile_psum, ntiles, E, capacity, tile_base, count, kept, seg_start,
+                                   tile_expert, num_mtiles, max_mtiles, psum, static_cast<cudaStream_t>(stream)),
+                 "moe_route_scan");
+}
+
+int moe_dispatch_fwd(const void* x, int x_dtype, const int32_t* idx, const int32_t* tile_base, const int32_t* seg_start,
+                     const int32_t* kept, int64_t T, int d, int E, int k, int64_t capacity, int32_t* pos,
+                     int32_t* row_src, void* xbuf, void* stream) {
+    if (!dims_ok("moe_dispatch_fwd", T, d, E, k) || !dtype_ok("moe_dispatch_fwd", x_dtype)) return 1;
+    return check(launch_dispatch_fwd(x, x_dtype, idx, tile_base, seg_start, kept, T, d, E, k, capacity, pos, row_src,
+                                     xbuf, static_cast<cudaStream_t>(stream)),
+                 "moe_dispatch_fwd");
+}
+
+int moe_combine_fwd(const void* ybuf, const int32_t* pos, const float* score, int64_t T, int d, int k, void* out,
+                    int out_dtype, void* stream) {
+    if (!dims_ok("moe_combine_fwd", T, d, 8, k) || !dtype_ok("moe_combine_fwd", out_dtype)) return 1;
+    return check(launch_combine_fwd(ybuf, pos, score, T, d, k, out, out_dtype, sm_count(), static_cast<cudaStream_t>(stream)),
+                 "moe_combine_fwd");
+}
+
+int moe_combine_bwd(const void* dy, int dy_dtype, const void* ybuf, const int32_t* pos, const float* score,
+                    const int32_t* seg_start, const int32_t* kept, int64_t T, int d, int k, int E, void* dybuf,
+                    float* dscore, void* stream) {
+    if (!dims_ok("moe_combine_bwd", T, d, E, k) || !dtype_ok("moe_combine_bwd", dy_dtype)) return 1;
+    return check(launch_combine_bwd(dy, dy_dtype, ybuf, pos, score, seg_start, kept, T, d, k, E, dybuf, dscore,
+                                    static_cast<cudaStream_t>(stream)),
+                 "moe_combine_bwd");
+}
+
+int moe_gate_bwd(const float* logits, const int32_t* idx, const float* score, const float* dscore, const float* dpsum,
+                 int64_t T, int E, int k, int score_mode, float* dlogits, void* stream) {
+    if (T <= 0 || E <= 0 || k < 1 || k > 8) { set_error("moe_gate_bwd: bad shape"); return 1; }
+    return check(launch_gate_bwd(logits, idx, score, dscore, dpsum, T, E, k, score_mode, dlogits, static_cast<cudaStream_t>(stream)),
+                 "moe_gate_bwd");
+}
+
+int moe_dispatch_bwd(const void* dxbuf, const int32_t* pos, const float* dlogits, const int32_t* idx, const float* Wg,
+                     int64_t T, int d, int E, int k, int dense_dlogits, void* dx, int dx_dtype, void* stream) {
+    if (!dims_ok("moe_dispatch_bwd", T, d, E, k) || !dtype_ok("moe_dispatch_bwd", dx_dtype)) return 1;
+    return check(launch_dispatch_bwd(dxbuf, pos, dlogits, idx, Wg, T, d, E, k, dense_dlogits, dx, dx_dtype, sm_count(),
+                                     static_cast<cudaStream_t>(stream)),
+                 "moe_dispatch_bwd");
+}
+
+size_t moe_gate_wgrad_workspace_bytes(int64_t T, int d, int E) { return gate_wgrad_workspace_bytes(T, d, E); }
+
+int moe_gate_wgrad(const float* dlogits, const void* x, int x_dtype, int64_t T, int d, int E, void* workspace,
+                   float* dWg, float* dbg, void* stream) {
+    if (!dims_ok("moe_gate_wgrad", T, d, E, 1) || !dtype_ok("moe_gate_wgrad", x_dtype)) return 1;
+    return check(launch_gate_wgrad(dlogits, x, x_dtype, T, d, E, workspace, dWg, dbg, static_cast<cudaStream_t>(stream)),
+                 "moe_gate_wgrad");
+}
+
+int moe_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
+    if (n <= 0 || n % 8 != 0) { set_error("moe_cast_bf16: n=%lld must be a positive multiple of 8", (long long)n); return 1; }
+    return check(launch_cast_bf16(src, dst, n, sm_count(), static_cast<cudaStream_t>(stream)), "moe_cast_bf16");
+}
+
+int moe_segment_colsum(const void* buf, const int32_t* seg_start, int E, int cols, float* out, void* stream) {
+    if (E <= 0 || cols <= 0 || cols % 2 != 0) { set_error("moe_segment_colsum: bad shape"); return 1; }
+    return check(launch_segment_colsum(buf, seg_start, E, cols, out, static_cast<cudaStream_t>(stream)), "moe_segment_colsum");
+}
+
+int moe_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out1, const float* bias, const void* aux,
+                     const int32_t* tile_expert, const int32_t* num_mtiles, const int32_t* seg_start, int64_t rows_cap,
+                     int E, int M, int N, int K, void* stream) {
+    return launch_grouped_gemm(op, A, B, out0, out1, bias, aux, tile_expert, num_mtiles, seg_start, rows_cap, E, M, N, K,
+                               sm_count(), static_cast<cudaStream_t>(stream));
+}
+
+int moe_expert_ffn_fwd(const void* xbuf, const void* W1b, const float* b1, const void* W2b, const float* b2,
+                       const int32_t* tile_expert, const int32_t* num_mtiles, int64_t rows_cap, int d, int h, int E,
+                       void* U, void* H, void* Y, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = launch_grouped_gemm(MOE_GEMM_FC1, xbuf, W1b, U, H, b1, nullptr, tile_expert, num_mtiles, nullptr, rows_cap,
+                                 E, 0, h, d, sm_count(), st);
+    if (rc) return rc;
+    return launch_grouped_gemm(MOE_GEMM_FC2, H, W2b, Y, nullptr, b2, nullptr, tile_expert, num_mtiles, nullptr, rows_cap,
+                               E, 0, d, h, sm_count(), st);
+}
+
+int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* U, const void* H, const void* W1b,
+                       const void* W2b, const int32_t* tile_expert, const int32_t* num_mtiles,
+                       const int32_t* seg_start, int64_t rows_cap, int d, int h, int E, void* dU, void* dxbuf,
+                       float* dW1, float* db1, float* dW2, float* db2, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int sms = sm_count();
+    int rc;
+    // dU = (dY W2) * gelu'(U)                     [rows, h]   K = d, B = W2b [E, d, h] read MN-major
+    rc = launch_grouped_gemm(MOE_GEMM_DGELU, dybuf, W2b, dU, nullptr, nullptr, U, tile_expert, num_mtiles, nullptr,
+                             rows_cap, E, 0, h, d, sms, st);
+    if (rc) return rc;
+    // dW2[e] = dY_e^T H_e                          [d, h]
+    rc = launch_grouped_gemm(MOE_GEMM_WGRAD, dybuf, H, dW2, nullptr, nullptr, nullptr, nullptr, nullptr, seg_start,
+                             rows_cap, E, d, h, 0, sms, st);
+    if (rc) return rc;
+    // dW1[e] = dU_e^T X_e                          [h, d]
+    rc = launch_grouped_gemm(MOE_GEMM_WGRAD, dU, xbuf, dW1, nullptr, nullptr, nullptr, nullptr, nullptr, seg_start,
+                             rows_cap, E, h, d, 0, sms, st);
+    if (rc) return rc;
+    // dX = dU W1                                   [rows, d]   K = h, B = W1b [E, h, d] read MN-major
+    rc = launch_grouped_gemm(MOE_GEMM_DGRAD, dU, W1b, dxbuf, nullptr, nullptr, nullptr, tile_expert, num_mtiles, nullptr,
+                             rows_cap, E, 0, d, h, sms, st);
+    if (rc) return rc;
+    if (check(launch_segment_colsum(dybuf, seg_start, E, d, db2, st), "db2 colsum")) return 1;
+    return check(launch_segment_colsum(dU, seg_start, E, h, db1, st), "db1 colsum");
+}
+
+}  // extern "C"

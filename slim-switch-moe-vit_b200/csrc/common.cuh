@@ -1,0 +1,47 @@
+// common.cuh — declarations shared by the translation units of libmoe_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/moe_b200.h"
+
+namespace moe {
+
+// routing.cu
+cudaError_t launch_gate_fwd(const void* x, int x_dtype, const float* Wg, const float* bg, const float* noise, int64_t T, int d, int E, int k,
+                            int score_mode, int want_psum, float* logits, int* idx, float* score, int* tile_hist,
+                            float* tile_psum, cudaStream_t st);
+cudaError_t launch_route_scan(const int* tile_hist, const float* tile_psum, int ntiles, int E, long long capacity,
+                              int* tile_base, int* count, int* kept, int* seg_start, int* tile_expert, int* num_mtiles,
+                              int max_mtiles, float* psum, cudaStream_t st);
+cudaError_t launch_dispatch_fwd(const void* x, int x_dtype, const int* idx, const int* tile_base, const int* seg_start,
+                                const int* kept, int64_t T, int d, int E, int k, long long capacity, int* pos,
+                                int* row_src, void* xbuf, cudaStream_t st);
+cudaError_t launch_combine_fwd(const void* ybuf, const int* pos, const float* score, int64_t T, int d, int k, void* out,
+                               int out_dtype, int sm_count, cudaStream_t st);
+cudaError_t launch_combine_bwd(const void* dy, int dy_dtype, const void* ybuf, const int* pos, const float* score,
+                               const int* seg_start, const int* kept, int64_t T, int d, int k, int E, void* dybuf,
+                               float* dscore, cudaStream_t st);
+cudaError_t launch_gate_bwd(const float* logits, const int* idx, const float* score, const float* dscore,
+                            const float* dpsum, int64_t T, int E, int k, int score_mode, float* dlogits,
+                            cudaStream_t st);
+cudaError_t launch_dispatch_bwd(const void* dxbuf, const int* pos, const float* dlogits, const int* idx, const float* Wg,
+                                int64_t T, int d, int E, int k, int dense_dlogits, void* dx, int dx_dtype, int sm_count,
+                                cudaStream_t st);
+size_t gate_wgrad_workspace_bytes(int64_t T, int d, int E);
+cudaError_t launch_gate_wgrad(const float* dlogits, const void* x, int x_dtype, int64_t T, int d, int E, void* workspace,
+                              float* dWg, float* dbg, cudaStream_t st);
+cudaError_t launch_cast_bf16(const float* src, void* dst, int64_t n, int sm_count, cudaStream_t st);
+cudaError_t launch_segment_colsum(const void* buf, const int* seg_start, int E, int cols, float* out, cudaStream_t st);
+
+// gemm_launch.cu — returns 0 on success, otherwise sets the error string via set_error()
+int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out1, const float* bias, const void* aux,
+                        const int* tile_expert, const int* num_mtiles, const int* seg_start, int64_t rows_cap, int E,
+                        int M, int N, int K, int sm_count, cudaStream_t st);
+
+// api.cu
+void set_error(const char* fmt, ...);
+int sm_count();
+
+}  // namespace moe

@@ -1,0 +1,151 @@
+// gemm_launch.cu — host side of the grouped tcgen05 GEMM: TMA tensor-map encoding and launch.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace moe {
+
+namespace {
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// 2-D row-major tensor [outer, inner] of `esz`-byte elements, 128-byte swizzle
+bool encode_2d(CUtensorMap* m, CUtensorMapDataType dt, int esz, const void* base, uint64_t inner, uint64_t outer,
+               uint32_t box_inner, uint32_t box_outer) {
+    auto fn = get_encode_fn();
+    if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {inner * static_cast<uint64_t>(esz)};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(2d) failed: CUresult %d (inner=%llu outer=%llu box=%u x %u)", (int)r,
+                  (unsigned long long)inner, (unsigned long long)outer, box_inner, box_outer);
+        return false;
+    }
+    return true;
+}
+
+// 3-D tensor [d2, d1, d0] (d0 innermost), fp32, 128-byte swizzle
+bool encode_3d_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+    auto fn = get_encode_fn();
+    if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3d) failed: CUresult %d", (int)r); return false; }
+    return true;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, bool WGRAD>
+int launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tO0, const CUtensorMap& tO1,
+               const GemmParams& p, int grid, cudaStream_t st) {
+    using Cfg = GemmCfg<BN, EPI>;
+    auto kfn = grouped_gemm_kernel<BN, A_MN, B_MN, EPI, WGRAD>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(tA, tB, tO0, tO1, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("grouped_gemm launch: %s", cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
+int pick_bn(int N) {
+    if (N % 256 == 0) return 256;
+    if (N % 192 == 0) return 192;
+    if (N % 128 == 0) return 128;
+    if (N % 64 == 0) return 64;
+    return 0;
+}
+
+}  // namespace
+
+int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out1, const float* bias, const void* aux,
+                        const int* tile_expert, const int* num_mtiles, const int* seg_start, int64_t rows_cap, int E,
+                        int M, int N, int K, int sm_count, cudaStream_t st) {
+    const int bn = pick_bn(N);
+    if (bn == 0) { set_error("grouped gemm: N=%d must be a multiple of 64", N); return 1; }
+    if (op != MOE_GEMM_WGRAD && (K % 64 != 0 || K <= 0)) { set_error("grouped gemm: K=%d must be a positive multiple of 64", K); return 1; }
+    if (op == MOE_GEMM_WGRAD && (M % 64 != 0 || M <= 0)) { set_error("grouped gemm: M=%d must be a positive multiple of 64", M); return 1; }
+    if (rows_cap % 128 != 0) { set_error("grouped gemm: rows_cap=%lld must be a multiple of 128", (long long)rows_cap); return 1; }
+
+    GemmParams p{};
+    p.tile_expert = tile_expert;
+    p.num_mtiles = num_mtiles;
+    p.seg_start = seg_start;
+    p.bias = bias;
+    p.aux = static_cast<const __nv_bfloat16*>(aux);
+    p.E = E; p.M = M; p.N = N; p.K = K;
+
+    CUtensorMap tA, tB, tO0, tO1;
+    const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const uint64_t R = static_cast<uint64_t>(rows_cap);
+    bool ok = true;
+    switch (op) {
+        case MOE_GEMM_FC1:
+        case MOE_GEMM_FC2:
+            ok = ok && encode_2d(&tA, BF, 2, A, K, R, 64, 128);
+            ok = ok && encode_2d(&tB, BF, 2, B, K, static_cast<uint64_t>(E) * N, 64, bn);
+            ok = ok && encode_2d(&tO0, BF, 2, out0, N, R, 64, 128);
+            ok = ok && encode_2d(&tO1, BF, 2, op == MOE_GEMM_FC1 ? out1 : out0, N, R, 64, 128);
+            break;
+        case MOE_GEMM_DGELU:
+        case MOE_GEMM_DGRAD:
+            ok = ok && encode_2d(&tA, BF, 2, A, K, R, 64, 128);
+            ok = ok && encode_2d(&tB, BF, 2, B, N, static_cast<uint64_t>(E) * K, 64, 64);
+            ok = ok && encode_2d(&tO0, BF, 2, out0, N, R, 64, 128);
+            tO1 = tO0;
+            break;
+        case MOE_GEMM_WGRAD:
+            ok = ok && encode_2d(&tA, BF, 2, A, M, R, 64, 64);
+            ok = ok && encode_2d(&tB, BF, 2, B, N, R, 64, 64);
+            ok = ok && encode_3d_f32(&tO0, out0, N, M, E, 32, 128);
+            tO1 = tO0;
+            break;
+        default:
+            set_error("grouped gemm: unknown op %d", op);
+            return 1;
+    }
+    if (!ok) return 1;
+
+#define MOE_BN_SWITCH(A_MN, B_MN, EPI, WG)                                                            \
+    switch (bn) {                                                                                     \
+        case 256: return launch_one<256, A_MN, B_MN, EPI, WG>(tA, tB, tO0, tO1, p, sm_count, st);     \
+        case 192: return launch_one<192, A_MN, B_MN, EPI, WG>(tA, tB, tO0, tO1, p, sm_count, st);     \
+        case 128: return launch_one<128, A_MN, B_MN, EPI, WG>(tA, tB, tO0, tO1, p, sm_count, st);     \
+        default: return launch_one<64, A_MN, B_MN, EPI, WG>(tA, tB, tO0, tO1, p, sm_count, st);       \
+    }
+    switch (op) {
+        case MOE_GEMM_FC1: MOE_BN_SWITCH(false, false, EPI_BIAS_GELU_DUAL, false)
+        case MOE_GEMM_FC2: MOE_BN_SWITCH(false, false, EPI_BIAS, false)
+        case MOE_GEMM_DGELU: MOE_BN_SWITCH(false, true, EPI_DGELU, false)
+        case MOE_GEMM_DGRAD: MOE_BN_SWITCH(false, true, EPI_PLAIN, false)
+        default: MOE_BN_SWITCH(true, true, EPI_F32, true)
+    }
+#undef MOE_BN_SWITCH
+}
+
+}  // namespace moe

@@ -1,0 +1,95 @@
+"""ctypes binding of libmoe_b200.so (C ABI: include/moe_b200.h).
+
+There is no fallback: if the library is missing the import fails, and every compute entry point
+raises when handed a non-CUDA tensor.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmoe_b200.so")
+
+DTYPE_F32, DTYPE_BF16 = 0, 1
+SCORE_TOPK_SOFTMAX, SCORE_FULL_SOFTMAX = 0, 1
+TOKEN_TILE, ROW_ALIGN = 256, 128
+GEMM_FC1, GEMM_FC2, GEMM_DGELU, GEMM_DGRAD, GEMM_WGRAD = range(5)
+
+_p, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/moe_b200.h one to one
+SIGNATURES = {
+    "moe_last_error": (ctypes.c_char_p, []),
+    "moe_version": (_i, []),
+    "moe_rows_cap": (_i64, [_i64, _i, _i, _i64]),
+    "moe_gate_fwd": (_i, [_p, _i, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "moe_route_scan": (_i, [_p, _p, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
+    "moe_dispatch_fwd": (_i, [_p, _i, _p, _p, _p, _p, _i64, _i, _i, _i, _i64, _p, _p, _p, _p]),
+    "moe_expert_ffn_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p, _p]),
+    "moe_combine_fwd": (_i, [_p, _p, _p, _i64, _i, _i, _p, _i, _p]),
+    "moe_combine_bwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p]),
+    "moe_expert_ffn_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "moe_gate_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p]),
+    "moe_dispatch_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _i, _p]),
+    "moe_gate_wgrad_workspace_bytes": (_sz, [_i64, _i, _i]),
+    "moe_gate_wgrad": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p, _p]),
+    "moe_cast_bf16": (_i, [_p, _p, _i64, _p]),
+    "moe_segment_colsum": (_i, [_p, _p, _i, _i, _p, _p]),
+    "moe_grouped_gemm": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
+}
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C slim-switch-moe-vit_b200/csrc`). There is no CPU / PyTorch fallback for this layer.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+class MoeB200Error(RuntimeError):
+    pass
+
+
+def call(name: str, *args) -> None:
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise MoeB200Error(f"{name} failed: {lib.moe_last_error().decode(errors='replace')}")
+
+
+def ptr(t: torch.Tensor | None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise MoeB200Error("fmoe (B200) has no CPU path: expected a CUDA tensor, got device=" + str(t.device))
+    if not t.is_contiguous():
+        raise MoeB200Error("internal error: non-contiguous tensor handed to the C ABI")
+    return t.data_ptr()
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return DTYPE_BF16
+    raise MoeB200Error(f"unsupported dtype {t.dtype} (fp32 or bf16 expected)")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rows_cap(T: int, k: int, E: int, capacity: int) -> int:
+    return int(lib.moe_rows_cap(T, k, E, capacity))

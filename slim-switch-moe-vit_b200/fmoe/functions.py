@@ -1,0 +1,239 @@
+"""Autograd functions of the B200 MoE layer.
+
+Mirrors the role of FastMoE's `fmoe/functions.py` (prepare_forward / MOEScatter / MOELinear /
+MOEGather — upstream, un-vendored; reached from /root/reference/models/resMoE.py:27-29), but the
+whole layer is ONE autograd node whose forward and backward are sequences of C-ABI kernel calls on
+the current CUDA stream, with no host synchronisation anywhere (upstream syncs twice per layer).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _cabi as C
+
+
+@dataclass(frozen=True)
+class RouteSpec:
+    """What the gate asks of the fused path."""
+    top_k: int
+    score_mode: int          # C.SCORE_TOPK_SOFTMAX | C.SCORE_FULL_SOFTMAX
+    capacity: int            # rows per expert (>= T*k means unlimited)
+    want_psum: bool          # also return sum_t softmax(logits)[e] (for load-balancing losses)
+
+
+class Bf16WeightCache:
+    """bf16 operand copies of the fp32 expert weights, refreshed only when a parameter changed
+    (optimizer step, load_state_dict, .to()).  Keyed on (data_ptr, _version)."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, W1: torch.Tensor, W2: torch.Tensor):
+        key = (W1.data_ptr(), W1._version, W2.data_ptr(), W2._version, W1.device)
+        if key != self._key:
+            W1b = torch.empty(W1.shape, dtype=torch.bfloat16, device=W1.device)
+            W2b = torch.empty(W2.shape, dtype=torch.bfloat16, device=W2.device)
+            st = C.stream_ptr()
+            C.call("moe_cast_bf16", C.ptr(W1.detach()), C.ptr(W1b), W1.numel(), st)
+            C.call("moe_cast_bf16", C.ptr(W2.detach()), C.ptr(W2b), W2.numel(), st)
+            self._key, self._val = key, (W1b, W2b)
+        return self._val
+
+    def __deepcopy__(self, memo):  # ModelEma deep-copies the model (reference main.py:602-607)
+        return Bf16WeightCache()
+
+
+def _as_kernel_input(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise C.MoeB200Error("fmoe (B200) has no CPU path: input must be a CUDA tensor")
+    if t.dtype not in (torch.float32, torch.bfloat16):
+        t = t.float()  # fp16 activations (reference engine.py:52 autocast) are widened, never narrowed
+    return t.contiguous()
+
+
+def _i32(n, dev):
+    return torch.empty(n, dtype=torch.int32, device=dev)
+
+
+def _f32(n, dev):
+    return torch.empty(n, dtype=torch.float32, device=dev)
+
+
+def route(x, Wg, bg, spec: RouteSpec, noise=None):
+    """gate + scan + dispatch.  Returns a dict of device tensors (no host sync)."""
+    T, d = x.shape
+    E = Wg.shape[0]
+    k = spec.top_k
+    dev = x.device
+    st = C.stream_ptr()
+    ntiles = (T + C.TOKEN_TILE - 1) // C.TOKEN_TILE
+    rows_cap = C.rows_cap(T, k, E, spec.capacity)
+    max_mtiles = rows_cap // C.ROW_ALIGN
+    r = dict(
+        logits=_f32((T, E), dev), idx=_i32((T, k), dev), score=_f32((T, k), dev),
+        tile_hist=_i32((ntiles, E), dev), tile_base=_i32((ntiles, E), dev),
+        count=_i32(E, dev), kept=_i32(E, dev), seg_start=_i32(E + 1, dev),
+        tile_expert=_i32(max_mtiles, dev), num_mtiles=_i32(1, dev),
+        pos=_i32((T, k), dev), row_src=_i32(rows_cap, dev),
+        xbuf=torch.empty((rows_cap, d), dtype=torch.bfloat16, device=dev),
+        rows_cap=rows_cap,
+    )
+    tile_psum = _f32((ntiles, E), dev) if spec.want_psum else None
+    r["psum"] = _f32(E, dev) if spec.want_psum else None
+    C.call("moe_gate_fwd", C.ptr(x), C.dtype_code(x), C.ptr(Wg), C.ptr(bg), C.ptr(noise), T, d, E, k,
+           spec.score_mode, int(spec.want_psum), C.ptr(r["logits"]), C.ptr(r["idx"]), C.ptr(r["score"]),
+           C.ptr(r["tile_hist"]), C.ptr(tile_psum), st)
+    C.call("moe_route_scan", C.ptr(r["tile_hist"]), C.ptr(tile_psum), ntiles, E, spec.capacity,
+           C.ptr(r["tile_base"]), C.ptr(r["count"]), C.ptr(r["kept"]), C.ptr(r["seg_start"]),
+           C.ptr(r["tile_expert"]), C.ptr(r["num_mtiles"]), max_mtiles, C.ptr(r["psum"]), st)
+    C.call("moe_dispatch_fwd", C.ptr(x), C.dtype_code(x), C.ptr(r["idx"]), C.ptr(r["tile_base"]),
+           C.ptr(r["seg_start"]), C.ptr(r["kept"]), T, d, E, k, spec.capacity, C.ptr(r["pos"]),
+           C.ptr(r["row_src"]), C.ptr(r["xbuf"]), st)
+    return r
+
+
+class MoEFunction(torch.autograd.Function):
+    """y, psum, count, kept = MoE(x; Wg, bg, W1, b1, W2, b2).
+
+    x [T,d] fp32|bf16; Wg [E,d], bg [E]|None, W1 [E,h,d], b1 [E,h], W2 [E,d,h], b2 [E,d] fp32.
+    y has x's dtype.  psum [E] (fp32, differentiable) is None unless spec.want_psum.
+    count/kept [E] int32 are the per-expert routed / kept pair counts (not differentiable).
+    """
+
+    @staticmethod
+    def forward(ctx, x, Wg, bg, W1, b1, W2, b2, spec: RouteSpec, cache: Bf16WeightCache, noise):
+        x = _as_kernel_input(x)
+        T, d = x.shape
+        E, h = W1.shape[0], W1.shape[1]
+        k = spec.top_k
+        dev = x.device
+        st = C.stream_ptr()
+        Wg_c, W1_c, W2_c = Wg.detach().contiguous(), W1.detach().contiguous(), W2.detach().contiguous()
+        for w in (Wg_c, W1_c, W2_c, b1, b2):
+            if w.dtype != torch.float32:
+                raise C.MoeB200Error("expert / gate parameters must be fp32 (master weights)")
+        bg_c = None if bg is None else bg.detach().contiguous()
+        r = route(x, Wg_c, bg_c, spec, noise)
+        rows_cap = r["rows_cap"]
+        W1b, W2b = cache.get(W1_c, W2_c)
+        U = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
+        H = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
+        Y = torch.empty((rows_cap, d), dtype=torch.bfloat16, device=dev)
+        C.call("moe_expert_ffn_fwd", C.ptr(r["xbuf"]), C.ptr(W1b), C.ptr(b1.detach().contiguous()), C.ptr(W2b),
+               C.ptr(b2.detach().contiguous()), C.ptr(r["tile_expert"]), C.ptr(r["num_mtiles"]), rows_cap, d, h, E,
+               C.ptr(U), C.ptr(H), C.ptr(Y), st)
+        y = torch.empty_like(x)
+        C.call("moe_combine_fwd", C.ptr(Y), C.ptr(r["pos"]), C.ptr(r["score"]), T, d, k, C.ptr(y),
+               C.dtype_code(y), st)
+
+        ctx.spec = spec
+        ctx.has_bg = bg is not None
+        ctx.rows_cap = rows_cap
+        ctx.save_for_backward(x, Wg_c, r["logits"], r["idx"], r["score"], r["pos"], r["seg_start"], r["kept"],
+                              r["tile_expert"], r["num_mtiles"], r["xbuf"], U, H, Y, W1b, W2b)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(r["count"], r["kept"])
+        psum = r["psum"]
+        if psum is None:
+            psum = torch.empty(0, dtype=torch.float32, device=dev)
+            ctx.mark_non_differentiable(psum)
+        return y, psum, r["count"], r["kept"]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy, dpsum, _dcount, _dkept):
+        (x, Wg, logits, idx, score, pos, seg_start, kept, tile_expert, num_mtiles, xbuf, U, H, Y, W1b,
+         W2b) = ctx.saved_tensors
+        spec: RouteSpec = ctx.spec
+        T, d = x.shape
+        E, h = W1b.shape[0], W1b.shape[1]
+        k = spec.top_k
+        dev = x.device
+        st = C.stream_ptr()
+        rows_cap = ctx.rows_cap
+        if dy is None:
+            dy = torch.zeros_like(x)
+        dy = _as_kernel_input(dy)
+        if not spec.want_psum:
+            dpsum = None
+        elif dpsum is not None:
+            dpsum = dpsum.float().contiguous()
+
+        dybuf = torch.empty((rows_cap, d), dtype=torch.bfloat16, device=dev)
+        dscore = _f32((T, k), dev)
+        C.call("moe_combine_bwd", C.ptr(dy), C.dtype_code(dy), C.ptr(Y), C.ptr(pos), C.ptr(score),
+               C.ptr(seg_start), C.ptr(kept), T, d, k, E, C.ptr(dybuf), C.ptr(dscore), st)
+
+        dU = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
+        dxbuf = torch.empty((rows_cap, d), dtype=torch.bfloat16, device=dev)
+        dW1, db1 = _f32((E, h, d), dev), _f32((E, h), dev)
+        dW2, db2 = _f32((E, d, h), dev), _f32((E, d), dev)
+        C.call("moe_expert_ffn_bwd", C.ptr(dybuf), C.ptr(xbuf), C.ptr(U), C.ptr(H), C.ptr(W1b), C.ptr(W2b),
+               C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_start), rows_cap, d, h, E, C.ptr(dU),
+               C.ptr(dxbuf), C.ptr(dW1), C.ptr(db1), C.ptr(dW2), C.ptr(db2), st)
+
+        dlogits = _f32((T, E), dev)
+        C.call("moe_gate_bwd", C.ptr(logits), C.ptr(idx), C.ptr(score), C.ptr(dscore), C.ptr(dpsum), T, E, k,
+               spec.score_mode, C.ptr(dlogits), st)
+        dense = int(spec.score_mode == C.SCORE_FULL_SOFTMAX or dpsum is not None)
+        dx = torch.empty_like(x)
+        C.call("moe_dispatch_bwd", C.ptr(dxbuf), C.ptr(pos), C.ptr(dlogits), C.ptr(idx), C.ptr(Wg), T, d, E, k,
+               dense, C.ptr(dx), C.dtype_code(dx), st)
+        ws = torch.empty(C.lib.moe_gate_wgrad_workspace_bytes(T, d, E), dtype=torch.uint8, device=dev)
+        dWg = _f32((E, d), dev)
+        dbg = _f32(E, dev) if ctx.has_bg else None
+        C.call("moe_gate_wgrad", C.ptr(dlogits), C.ptr(x), C.dtype_code(x), T, d, E, C.ptr(ws), C.ptr(dWg),
+               C.ptr(dbg), st)
+        return dx, dWg, dbg, dW1, db1, dW2, db2, None, None, None
+
+
+class GateFunction(torch.autograd.Function):
+    """Stand-alone gate (what `gate.forward(x)` returns in FastMoE): idx [T,k] int64, score [T,k]."""
+
+    @staticmethod
+    def forward(ctx, x, Wg, bg, spec: RouteSpec, noise):
+        x = _as_kernel_input(x)
+        T, d = x.shape
+        E = Wg.shape[0]
+        dev = x.device
+        st = C.stream_ptr()
+        ntiles = (T + C.TOKEN_TILE - 1) // C.TOKEN_TILE
+        logits, idx, score = _f32((T, E), dev), _i32((T, spec.top_k), dev), _f32((T, spec.top_k), dev)
+        tile_hist = _i32((ntiles, E), dev)
+        tile_psum = _f32((ntiles, E), dev) if spec.want_psum else None
+        Wg_c = Wg.detach().contiguous()
+        bg_c = None if bg is None else bg.detach().contiguous()
+        C.call("moe_gate_fwd", C.ptr(x), C.dtype_code(x), C.ptr(Wg_c), C.ptr(bg_c), C.ptr(noise), T, d, E,
+               spec.top_k, spec.score_mode, int(spec.want_psum), C.ptr(logits), C.ptr(idx), C.ptr(score),
+               C.ptr(tile_hist), C.ptr(tile_psum), st)
+        ctx.spec, ctx.has_bg = spec, bg is not None
+        ctx.save_for_backward(x, Wg_c, logits, idx, score)
+        idx64 = idx.long()
+        ctx.mark_non_differentiable(idx64, logits)
+        return idx64, score, logits
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, _didx, dscore, _dlogits):
+        x, Wg, logits, idx, score = ctx.saved_tensors
+        spec: RouteSpec = ctx.spec
+        T, d = x.shape
+        E = Wg.shape[0]
+        dev = x.device
+        st = C.stream_ptr()
+        dscore = torch.zeros_like(score) if dscore is None else dscore.float().contiguous()
+        dlogits = _f32((T, E), dev)
+        C.call("moe_gate_bwd", C.ptr(logits), C.ptr(idx), C.ptr(score), C.ptr(dscore), None, T, E, spec.top_k,
+               spec.score_mode, C.ptr(dlogits), st)
+        dx = torch.empty_like(x)
+        C.call("moe_dispatch_bwd", None, None, C.ptr(dlogits), C.ptr(idx), C.ptr(Wg), T, d, E, spec.top_k,
+               int(spec.score_mode == C.SCORE_FULL_SOFTMAX), C.ptr(dx), C.dtype_code(dx), st)
+        ws = torch.empty(C.lib.moe_gate_wgrad_workspace_bytes(T, d, E), dtype=torch.uint8, device=dev)
+        dWg = _f32((E, d), dev)
+        dbg = _f32(E, dev) if ctx.has_bg else None
+        C.call("moe_gate_wgrad", C.ptr(dlogits), C.ptr(x), C.dtype_code(x), T, d, E, C.ptr(ws), C.ptr(dWg),
+               C.ptr(dbg), st)
+        return dx, dWg, dbg, None, None

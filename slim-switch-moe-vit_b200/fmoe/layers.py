@@ -1,0 +1,76 @@
+"""`FMoE` — the sparse-MoE module, with FastMoE's constructor signature (`fmoe/layers.py` upstream,
+un-vendored; the reference reaches it through `FMoETransformerMLP`, /root/reference/models/resMoE.py:27-29).
+
+Differences from upstream that a user can observe:
+  * no CPU / eager fallback: inputs must be CUDA tensors on an sm_100a device;
+  * routing is deterministic (token-order positions, lowest-index tie-break) where upstream's
+    atomics make the intra-expert order and the capacity victims run-dependent;
+  * options whose semantics need a Python-level expert or hook (`expert=`, `gate_hook=`, `mask=`,
+    `mask_dict=`, `mp_group=` / `slice_group=`) raise NotImplementedError at construction.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .functions import Bf16WeightCache, MoEFunction
+from .gates import BaseGate, NaiveGate
+
+
+def mark_module_parallel_comm(module, comm):
+    """Tag every parameter with the data-parallel group it is synchronised in (FastMoE convention,
+    consumed by `fmoe.distributed.DistributedGroupedDataParallel`)."""
+    for p in module.parameters():
+        setattr(p, "dp_comm", comm)
+
+
+class FMoE(nn.Module):
+    def __init__(self, num_expert=32, d_model=1024, world_size=1, mp_group=None, slice_group=None, moe_group=None,
+                 top_k=2, gate=NaiveGate, expert=None, gate_hook=None, mask=None, mask_dict=None):
+        super().__init__()
+        for name, val in (("mp_group", mp_group), ("slice_group", slice_group), ("expert", expert),
+                          ("gate_hook", gate_hook), ("mask", mask), ("mask_dict", mask_dict)):
+            if val is not None:
+                raise NotImplementedError(f"FMoE({name}=...) is not supported by the B200 fused layer")
+        self.num_expert = num_expert
+        self.d_model = d_model
+        self.world_size = world_size
+        self.slice_group = None
+        self.slice_size = 1
+        self.slice_rank = 0
+        self.top_k = top_k
+        self.moe_group = moe_group
+        if isinstance(gate, type) and issubclass(gate, BaseGate):
+            self.gate = gate(d_model, num_expert, world_size, top_k)
+        else:
+            raise NotImplementedError("gate must be one of the fmoe.gates classes (NaiveGate, SwitchGate, GShardGate)")
+        if self.gate.top_k != top_k:
+            raise ValueError(f"gate {type(self.gate).__name__} fixes top_k={self.gate.top_k}, layer was given top_k={top_k}")
+        self.experts = None            # set by the subclass (FMoETransformerMLP)
+        self.experts_fused = True
+        self._bf16_cache = Bf16WeightCache()
+
+    def mark_parallel_comm(self, expert_dp_comm="none"):
+        if self.experts is not None:
+            mark_module_parallel_comm(self.experts, expert_dp_comm)
+        mark_module_parallel_comm(self.gate, "gate")
+
+    def _expert_params(self):
+        raise NotImplementedError
+
+    def forward(self, moe_inp: torch.Tensor) -> torch.Tensor:
+        """moe_inp [T, d_model] -> [T, d_model]; sets `self.gate`'s aux loss as a side effect."""
+        if moe_inp.dim() != 2 or moe_inp.shape[1] != self.d_model:
+            raise ValueError(f"expected [tokens, {self.d_model}] input, got {tuple(moe_inp.shape)}")
+        if self.world_size > 1:
+            from .distributed import ep_forward
+            return ep_forward(self, moe_inp)
+        T = moe_inp.shape[0]
+        W1, b1, W2, b2 = self._expert_params()
+        gate = self.gate
+        spec = gate.route_spec(T)
+        y, psum, count, kept = MoEFunction.apply(moe_inp, gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec,
+                                                 self._bf16_cache, gate.make_noise(moe_inp))
+        gate.finish(T, count, kept, psum)
+        self.last_count, self.last_kept = count, kept   # load-balance statistics (device tensors, no sync)
+        return y
