@@ -136,7 +136,8 @@ def test_ffn_intermediates_vs_model():
     rows_cap = r["rows_cap"]
     U = torch.zeros(rows_cap, h, dtype=torch.bfloat16, device="cuda")
     H, Y = torch.zeros_like(U), torch.zeros(rows_cap, d, dtype=torch.bfloat16, device="cuda")
-    C.call("moe_expert_ffn_fwd", C.ptr(r["xbuf"]), C.ptr(W1b), C.ptr(b1.cuda()), C.ptr(W2b), C.ptr(b2.cuda()),
+    b1d, b2d = b1.cuda(), b2.cuda()   # keep alive: the C ABI call is asynchronous
+    C.call("moe_expert_ffn_fwd", C.ptr(r["xbuf"]), C.ptr(W1b), C.ptr(b1d), C.ptr(W2b), C.ptr(b2d),
            C.ptr(r["tile_expert"]), C.ptr(r["num_mtiles"]), rows_cap, d, h, E, C.ptr(U), C.ptr(H), C.ptr(Y),
            C.stream_ptr())
     torch.cuda.synchronize()

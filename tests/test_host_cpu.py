@@ -1,0 +1,139 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header declares,
+and the `fmoe` drop-in mirrors the interface the reference relies on.  No compute
+calls are made here — there is no GPU and, by design, no CPU fallback."""
+import copy
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "moe_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(moe_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fmoe import _cabi as C
+    names = header_functions()
+    assert len(names) >= 17
+    assert set(names) == set(C.SIGNATURES), "ctypes table and header must list the same entry points"
+    out = subprocess.run(["nm", "-D", "--defined-only", C.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (moe_[a-z0-9_]+)", out))
+    assert set(names) <= exported
+    assert C.lib.moe_version() >= 100
+    assert C.lib.moe_rows_cap(1000, 2, 8, 2000) == 2048 + 128 * 8
+    assert C.lib.moe_rows_cap(1000, 1, 8, 100) == 896 + 1024     # min(T*k, E*C) rounded up, + 128 per expert
+
+
+def test_library_is_sm100a_tcgen05_code():
+    """The shipped kernels are Blackwell-native: tcgen05.mma (UTCHMMA), TMA (UTMALDG/UTMASTG), TMEM loads (LDTM)."""
+    from fmoe import _cabi as C
+    sass = subprocess.run(["cuobjdump", "-sass", C.LIB_PATH], capture_output=True, text=True)
+    if sass.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in sass.stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"):
+        assert mnemonic in sass.stdout, mnemonic
+
+
+def test_argument_validation_without_gpu():
+    from fmoe import _cabi as C
+    with pytest.raises(C.MoeB200Error, match="multiple of 8"):
+        C.call("moe_cast_bf16", None, None, 12, None)
+    with pytest.raises(C.MoeB200Error, match="unsupported shape"):
+        C.call("moe_gate_fwd", None, 0, None, None, None, 10, 100, 4, 1, 0, 0, None, None, None, None, None, None)
+    with pytest.raises(C.MoeB200Error, match="multiple of 64"):
+        C.call("moe_grouped_gemm", C.GEMM_FC2, None, None, None, None, None, None, None, None, None, 256, 2, 0, 100, 64, None)
+
+
+def _layer(**kw):
+    import fmoe
+    act = torch.nn.Sequential(torch.nn.GELU(), torch.nn.Dropout(p=0.0))
+    return fmoe.FMoETransformerMLP(8, 192, 768, act, **kw)
+
+
+def test_module_contract():
+    import fmoe
+    layer = _layer(top_k=2)
+    sd = layer.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {
+        "gate.gate.weight": (8, 192), "gate.gate.bias": (8,),
+        "experts.htoh4.weight": (8, 768, 192), "experts.htoh4.bias": (8, 768),
+        "experts.h4toh.weight": (8, 192, 768), "experts.h4toh.bias": (8, 192)}
+    assert sum(p.numel() for p in layer.parameters()) == 2_368_520
+    assert isinstance(layer.gate.gate, torch.nn.Linear)                   # resmoe_flop_hook.py:7
+    assert (layer.gate.gate.in_features, layer.gate.gate.out_features) == (192, 8)
+    assert (layer.top_k, layer.num_expert, layer.d_model, layer.world_size) == (2, 8, 192, 1)
+    assert all("moe_gate" not in n and "dense_gate" not in n for n, _ in layer.named_parameters())  # main.py:619-631
+    assert float(layer.experts.htoh4.bias.abs().sum()) == 0.0            # upstream init: zero expert bias
+    clone = copy.deepcopy(layer)                                          # ModelEma, main.py:602-607
+    clone.load_state_dict(sd)
+    assert not layer.gate.has_loss and layer.gate.get_loss() is None
+    layer.train(); layer.eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        layer(torch.randn(2, 5, 192))
+    with pytest.raises(ValueError):
+        layer.forward(torch.randn(2, 5, 100).cuda() if False else torch.randn(10, 100))
+
+
+def test_unsupported_configs_raise_at_construction():
+    import fmoe
+    with pytest.raises(NotImplementedError):
+        fmoe.FMoETransformerMLP(4, 64, 256, torch.nn.ReLU())
+    with pytest.raises(NotImplementedError):
+        fmoe.FMoETransformerMLP(4, 64, 256, torch.nn.Sequential(torch.nn.GELU(), torch.nn.Dropout(p=0.1)))
+    with pytest.raises(NotImplementedError):
+        fmoe.FMoETransformerMLP(4, 64, 256, torch.nn.GELU(approximate="tanh"))
+    with pytest.raises(ValueError):
+        fmoe.FMoETransformerMLP(4, 100, 256, torch.nn.GELU())
+    with pytest.raises(NotImplementedError):
+        fmoe.FMoETransformerMLP(4, 64, 256, torch.nn.GELU(), gate_hook=lambda *a: None)
+    with pytest.raises(ValueError):
+        fmoe.FMoETransformerMLP(4, 64, 256, torch.nn.GELU(), top_k=2, gate=fmoe.SwitchGate)
+    sw = fmoe.FMoETransformerMLP(16, 384, 1536, torch.nn.GELU(), top_k=1, gate=fmoe.SwitchGate)
+    spec = sw.gate.route_spec(50432)
+    assert (spec.top_k, spec.score_mode, spec.want_psum) == (1, 1, True)
+    assert spec.capacity == 3783      # ceil(1.2 * 50432 / 16) in training mode
+    sw.eval()
+    assert sw.gate.route_spec(50432).capacity == 7565
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not mounted (GPU box)")
+def test_unmodified_reference_models_build_on_the_drop_in():
+    """`import models` from /root/reference (through tiny timm stubs) must pick up OUR fmoe."""
+    code = r"""
+import sys
+sys.path[:0] = [%r, %r, '/root/reference']
+import torch, fmoe, models
+from timm.models import create_model
+kw = dict(num_classes=10, drop_rate=0., drop_path_rate=0., drop_block_rate=None, img_size=224)
+m = create_model('moe_tiny_patch16_224_expert8', **kw)
+assert sum(p.numel() for p in m.parameters()) == 30398122
+blocks = [b for b in m.modules() if type(b).__name__ == 'Block']
+assert len(blocks) == 12 and all(isinstance(b.mlp, fmoe.FMoETransformerMLP) for b in blocks)
+assert blocks[0].mlp.gate.gate.out_features == 8 and blocks[0].mlp.top_k == 2
+m2 = create_model('resmoe_tiny_patch16_224_expert8', starting_threshold=1., target_threshold=.9, **kw)
+assert sum(p.numel() for p in m2.parameters()) == 30402754
+import copy; copy.deepcopy(m)
+print('OK')
+""" % (os.path.join(ROOT, "oracle", "stubs"), os.path.join(ROOT, "slim-switch-moe-vit_b200"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "slim-switch-moe-vit_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "moe_oracle" not in text, f

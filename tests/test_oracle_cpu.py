@@ -1,0 +1,130 @@
+"""CPU tests (no GPU): the oracle against the committed golden vectors and against itself.
+
+The golden fixtures were produced by the reference's own `CustomizedMoEMLP`
+(/root/reference/models/resMoE.py:15-29) on top of oracle/fmoe_cpu.py — see tests/golden/make_golden.py.
+"""
+import glob
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from _util import make_problem, rel_err
+from oracle import moe_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+sys.path.insert(0, GOLDEN)
+from make_golden_params import build_params, weights_digest  # noqa: E402
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d, hid, E, k, B, N = [int(v) for v in z["meta"]]
+    if "param.gate.gate.weight" in z.files:
+        sd = {n[6:]: torch.from_numpy(z[n]) for n in z.files if n.startswith("param.")}
+    else:
+        sd = build_params(d, hid, E)
+    assert weights_digest(sd) == str(z["weights_sha256"]), "torch CPU RNG drifted: regenerate the fixtures"
+    return z, sd, (d, hid, E, k, B, N)
+
+
+GOLDEN_NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_oracle_matches_golden(name):
+    z, sd, (d, hid, E, k, B, N) = load_golden(name)
+    T = B * N
+    x = torch.from_numpy(z["x"]).reshape(T, d)
+    logits = O.gate_logits(x, sd["gate.gate.weight"], sd["gate.gate.bias"])
+    assert np.array_equal(logits.numpy(), z["logits"])            # bit-exact
+    r = O.route(logits, k, O.SCORE_TOPK_SOFTMAX, T * k)
+    for f in ("idx", "pos", "count"):
+        assert np.array_equal(getattr(r, f).numpy(), z[f]), f      # bit-exact integers
+    assert np.abs(r.score.numpy() - z["score"]).max() <= 1e-6
+    args = (x, sd["gate.gate.weight"], sd["gate.gate.bias"], sd["experts.htoh4.weight"], sd["experts.htoh4.bias"],
+            sd["experts.h4toh.weight"], sd["experts.h4toh.bias"])
+    # fp64 ideal vs the fp32 golden: tight
+    xs = [t.clone().double().requires_grad_() for t in args]
+    yi, _ = O.ideal_forward(*xs, r, O.SCORE_TOPK_SOFTMAX)
+    (yi * torch.from_numpy(z["dy"]).reshape(T, d).double()).sum().backward()
+    assert rel_err(yi, torch.from_numpy(z["y"]).reshape(T, d)) <= 1e-5
+    assert rel_err(xs[0].grad, torch.from_numpy(z["dx"]).reshape(T, d)) <= 1e-4
+    assert rel_err(xs[1].grad, torch.from_numpy(z["grad.gate.gate.weight"])) <= 1e-4
+    assert rel_err(xs[4].grad, torch.from_numpy(z["grad.experts.htoh4.bias"])) <= 1e-4
+    # bf16 arithmetic model vs the fp32 golden: bf16-level tolerance (2e-2, as for the CUDA path)
+    ym, sv = O.forward_model(*args, k, O.SCORE_TOPK_SOFTMAX, T * k)
+    assert rel_err(ym, torch.from_numpy(z["y"]).reshape(T, d)) <= 2e-2
+    gm = O.backward_model(sv, torch.from_numpy(z["dy"]).reshape(T, d), sd["gate.gate.weight"])
+    assert rel_err(gm["dx"], torch.from_numpy(z["dx"]).reshape(T, d)) <= 2e-2
+    if "gradnorm.experts.htoh4.weight" in z.files:
+        got = torch.stack([gm["dW1"][e].norm() for e in range(E)]).double()
+        assert rel_err(got, torch.from_numpy(z["gradnorm.experts.htoh4.weight"])) <= 2e-2
+    else:
+        assert rel_err(gm["dW1"], torch.from_numpy(z["grad.experts.htoh4.weight"])) <= 2e-2
+        assert rel_err(gm["dW2"], torch.from_numpy(z["grad.experts.h4toh.weight"])) <= 2e-2
+
+
+@pytest.mark.parametrize("k,mode,cf", [(1, 0, 0.0), (2, 0, 0.0), (1, 1, 1.25), (2, 0, 1.0), (2, 1, 0.5)])
+def test_c_routing_matches_python_restatement(k, mode, cf):
+    T, d, E = 333, 64, 8
+    x, Wg, bg, *_ = make_problem(T, d, 128, E, seed=11, skew=1.0)
+    logits = O.gate_logits(x, Wg, bg)
+    cap = O.capacity_from_factor(cf, T, k, E)
+    a, b = O.route(logits, k, mode, cap), O.route_python(logits, k, mode, cap)
+    for f in ("idx", "count", "kept", "seg_start", "pos"):
+        assert torch.equal(getattr(a, f), getattr(b, f)), f
+    assert (a.score - b.score).abs().max() <= 1e-6
+    assert (a.psum - b.psum).abs().max() <= 1e-4
+    if cf:
+        assert int(a.kept.max()) <= cap and (a.pos < 0).any()
+
+
+def test_ties_resolve_to_lowest_index_and_edge_cases():
+    logits = torch.tensor([[1.0, 3.0, 3.0, 3.0], [0.0, 0.0, 0.0, 0.0], [-1.0, -1.0, 5.0, 5.0]])
+    r = O.route(logits, 2, 0, 6)
+    assert r.idx.tolist() == [[1, 2], [0, 1], [2, 3]]
+    assert torch.allclose(r.score, torch.full((3, 2), 0.5))
+    # capacity 1: only the first pair of each expert (token order) survives
+    r = O.route(logits, 2, 0, 1)
+    assert r.pos.tolist() == [[128, 256], [0, -1], [-1, 384]]
+    assert r.kept.tolist() == [1, 1, 1, 1] and r.seg_start.tolist() == [0, 128, 256, 384, 512]
+    # one token, one expert
+    r = O.route(torch.zeros(1, 1), 1, 1, 1)
+    assert r.idx.tolist() == [[0]] and r.score.tolist() == [[1.0]] and r.rows == 128
+
+
+def test_logit_order_is_what_the_header_says():
+    """LOGIT ORDER v1 restated a third time in numpy (float32 ops; exact because x,w are bf16-valued)."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(37, 192, generator=g).bfloat16().float()
+    w = torch.randn(5, 192, generator=g).bfloat16().float()
+    b = torch.randn(5, generator=g)
+    got = O.gate_logits(x, w, b).numpy()
+    xn, wn = x.numpy(), w.numpy()
+    want = np.zeros((37, 5), np.float32)
+    for t in range(37):
+        for e in range(5):
+            part = np.zeros(32, np.float32)
+            for i in range(192):
+                l = (i // 4) % 32
+                part[l] = np.float32(part[l] + np.float32(xn[t, i] * wn[e, i]))   # product of bf16 values is exact
+            for off in (16, 8, 4, 2, 1):
+                part = (part + part[np.arange(32) ^ off]).astype(np.float32)
+            want[t, e] = np.float32(part[0] + b[e].item())
+    assert np.array_equal(got, want)
+
+
+def test_model_ideal_and_bruteforce_agree():
+    for (k, mode, cf) in [(2, 0, 0.0), (1, 1, 1.25), (2, 0, 0.75)]:
+        T, d, h, E = 150, 64, 128, 4
+        prob = make_problem(T, d, h, E, seed=21, skew=0.5)
+        cap = O.capacity_from_factor(cf, T, k, E)
+        ym, sv = O.forward_model(*prob, k, mode, cap)
+        yi, _ = O.ideal_forward(*prob, sv.r, mode)
+        yb = O.bruteforce_forward(*prob, k, mode, cap)
+        assert rel_err(yi, yb) <= 1e-5          # two independent fp64 restatements
+        assert rel_err(ym, yi) <= 1e-2          # bf16 arithmetic model vs ideal
