@@ -81,7 +81,7 @@ def test_module_contract():
     with pytest.raises(RuntimeError, match="no CPU path"):
         layer(torch.randn(2, 5, 192))
     with pytest.raises(ValueError):
-        layer.forward(torch.randn(2, 5, 100).cuda() if False else torch.randn(10, 100))
+        fmoe.FMoE.forward(layer, torch.randn(10, 100))     # wrong feature size
 
 
 def test_unsupported_configs_raise_at_construction():
