@@ -96,7 +96,7 @@ def test_unsupported_configs_raise_at_construction():
         fmoe.FMoETransformerMLP(4, 100, 256, torch.nn.GELU())
     with pytest.raises(NotImplementedError):
         fmoe.FMoETransformerMLP(4, 64, 256, torch.nn.GELU(), gate_hook=lambda *a: None)
-    with pytest.raises(ValueError):
+    with pytest.raises(AssertionError):   # same assertion as upstream SwitchGate
         fmoe.FMoETransformerMLP(4, 64, 256, torch.nn.GELU(), top_k=2, gate=fmoe.SwitchGate)
     sw = fmoe.FMoETransformerMLP(16, 384, 1536, torch.nn.GELU(), top_k=1, gate=fmoe.SwitchGate)
     spec = sw.gate.route_spec(50432)
