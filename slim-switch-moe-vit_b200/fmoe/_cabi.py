@@ -62,8 +62,45 @@ class MoeB200Error(RuntimeError):
     pass
 
 
-def call(name: str, *args) -> None:
-    rc = getattr(lib, name)(*args)
+# kernels launched by each entry point (for the launch count the bench reports)
+KERNELS_PER_CALL = {
+    "moe_gate_fwd": 1, "moe_route_scan": 1, "moe_dispatch_fwd": 1, "moe_expert_ffn_fwd": 2, "moe_combine_fwd": 1,
+    "moe_combine_bwd": 1, "moe_expert_ffn_bwd": 6, "moe_gate_bwd": 1, "moe_dispatch_bwd": 1, "moe_gate_wgrad": 2,
+    "moe_cast_bf16": 1, "moe_segment_colsum": 1, "moe_grouped_gemm": 1,
+}
+
+
+class Profiler:
+    """Optional per-call CUDA-event timing on the launching stream + kernel launch counter.
+    Off by default (zero overhead beyond one attribute test); bench.py switches it on."""
+
+    def __init__(self):
+        self.enabled = False
+        self.launches = 0
+        self.events = {}   # tag -> list of (start, stop) torch.cuda.Event
+
+    def reset(self):
+        self.launches = 0
+        self.events = {}
+
+    def summary_ms(self):
+        """tag -> (count, mean ms); call after torch.cuda.synchronize()."""
+        return {t: (len(ev), sum(a.elapsed_time(b) for a, b in ev) / len(ev)) for t, ev in self.events.items()}
+
+
+PROF = Profiler()
+
+
+def call(name: str, *args, tag: str | None = None) -> None:
+    if PROF.enabled:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(lib, name)(*args)
+        b.record()
+        PROF.events.setdefault(tag or name, []).append((a, b))
+        PROF.launches += KERNELS_PER_CALL.get(name, 0)
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise MoeB200Error(f"{name} failed: {lib.moe_last_error().decode(errors='replace')}")
 

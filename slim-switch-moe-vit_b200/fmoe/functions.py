@@ -122,9 +122,13 @@ class MoEFunction(torch.autograd.Function):
         U = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
         H = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
         Y = torch.empty((rows_cap, d), dtype=torch.bfloat16, device=dev)
-        C.call("moe_expert_ffn_fwd", C.ptr(r["xbuf"]), C.ptr(W1b), C.ptr(b1.detach().contiguous()), C.ptr(W2b),
-               C.ptr(b2.detach().contiguous()), C.ptr(r["tile_expert"]), C.ptr(r["num_mtiles"]), rows_cap, d, h, E,
-               C.ptr(U), C.ptr(H), C.ptr(Y), st)
+        # the two forward GEMMs (same kernels as the bundled moe_expert_ffn_fwd entry point)
+        b1_c, b2_c = b1.detach().contiguous(), b2.detach().contiguous()
+        te, nm = C.ptr(r["tile_expert"]), C.ptr(r["num_mtiles"])
+        C.call("moe_grouped_gemm", C.GEMM_FC1, C.ptr(r["xbuf"]), C.ptr(W1b), C.ptr(U), C.ptr(H), C.ptr(b1_c), None,
+               te, nm, None, rows_cap, E, 0, h, d, st, tag="gemm_fc1")
+        C.call("moe_grouped_gemm", C.GEMM_FC2, C.ptr(H), C.ptr(W2b), C.ptr(Y), None, C.ptr(b2_c), None,
+               te, nm, None, rows_cap, E, 0, d, h, st, tag="gemm_fc2")
         y = torch.empty_like(x)
         C.call("moe_combine_fwd", C.ptr(Y), C.ptr(r["pos"]), C.ptr(r["score"]), T, d, k, C.ptr(y),
                C.dtype_code(y), st)
@@ -171,10 +175,18 @@ class MoEFunction(torch.autograd.Function):
         dxbuf = torch.empty((rows_cap, d), dtype=torch.bfloat16, device=dev)
         dW1, db1 = _f32((E, h, d), dev), _f32((E, h), dev)
         dW2, db2 = _f32((E, d, h), dev), _f32((E, d), dev)
-        C.call("moe_expert_ffn_bwd", C.ptr(dybuf), C.ptr(xbuf), C.ptr(U), C.ptr(H), C.ptr(W1b), C.ptr(W2b),
-               C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_start), rows_cap, d, h, E, C.ptr(dU),
-               C.ptr(dxbuf), C.ptr(dW1), C.ptr(db1), C.ptr(dW2), C.ptr(db2), st)
-
+        # same kernel sequence as the bundled moe_expert_ffn_bwd entry point
+        te, nm, sg = C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_start)
+        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2b), C.ptr(dU), None, None, C.ptr(U),
+               te, nm, None, rows_cap, E, 0, h, d, st, tag="gemm_dgelu")
+        C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dybuf), C.ptr(H), C.ptr(dW2), None, None, None,
+               None, None, sg, rows_cap, E, d, h, 0, st, tag="gemm_wgrad2")
+        C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dU), C.ptr(xbuf), C.ptr(dW1), None, None, None,
+               None, None, sg, rows_cap, E, h, d, 0, st, tag="gemm_wgrad1")
+        C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1b), C.ptr(dxbuf), None, None, None,
+               te, nm, None, rows_cap, E, 0, d, h, st, tag="gemm_dgrad")
+        C.call("moe_segment_colsum", C.ptr(dybuf), sg, E, d, C.ptr(db2), st, tag="colsum_db2")
+        C.call("moe_segment_colsum", C.ptr(dU), sg, E, h, C.ptr(db1), st, tag="colsum_db1")
         dlogits = _f32((T, E), dev)
         C.call("moe_gate_bwd", C.ptr(logits), C.ptr(idx), C.ptr(score), C.ptr(dscore), C.ptr(dpsum), T, E, k,
                spec.score_mode, C.ptr(dlogits), st)
