@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the B200 Switch-MoE layer and the MoE-ViT built on it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  A *step* is one full training step (forward, loss + Switch aux
+loss, backward, fused AdamW) of BASELINE.json configs[1] — ViT-Small/16 Switch-MoE, 16 experts, top-1,
+capacity 1.25, MoE every other block, bf16 autocast, synthetic 224x224 batch 256 PER GPU — so every
+step makes 6 forward+backward passes through the hot path at T = 50 432 tokens.  With N > 1 the
+experts are sharded N ways (expert parallel, all-to-all dispatch/combine) and the dense blocks are
+data parallel: weak scaling.
+
+  value   images/s, inputs resident in HBM (CUDA events, max over ranks)
+  e2e     images/s through the public module API with HOST inputs: per step a pinned-host -> device
+          copy of the batch and a device -> host read of the loss are inside the timed region
+  roofline   the grouped tcgen05 expert GEMM (the dominant kernel of the hot path): algorithmic flops
+             12*R*d*h per layer fwd+bwd over the CUDA-event time of its launches inside the timed region
+  moe_layer  the isolated layer at the same shape: tokens/s fwd+bwd and per-kernel times / HBM fractions
+  cpu_baseline / --impl reference   the CPU restatement of the reference's layer (oracle/fmoe_cpu.py —
+             FastMoE has no CPU kernels and is not installable here) inside the same host model, fp32,
+             on the box's host cores, on a bounded sample (batch 8) of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "slim-switch-moe-vit_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+METRIC = "MoE-ViT training throughput (ViT-S/16 Switch-MoE E16 top-1 cf1.25, bf16, 224px, batch 256/GPU)"
+UNIT = "images/s"
+PER_GPU_BATCH = 256
+CPU_SAMPLE_BATCH = 8
+AUX_COEF = 0.01
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out = self.proc.communicate()[0]
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in out.splitlines():
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(self.NAMES, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the workload
+# ------------------------------------------------------------------------------------------------
+def make_cfg(world_size: int):
+    from moe_vit import MoEViTConfig
+    return MoEViTConfig(size="small", num_experts=16, top_k=1, capacity_factor=1.25, moe_stride=2, gate="switch",
+                        num_classes=1000, world_size=world_size)
+
+
+def synthetic_batch(batch: int, seed: int, pin: bool):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(batch, 3, 224, 224, generator=g)
+    lab = torch.randint(0, 1000, (batch,), generator=g)
+    if pin:
+        img, lab = img.pin_memory(), lab.pin_memory()
+    return img, lab
+
+
+def train_step(model, opt, img, lab, autocast_dtype):
+    if autocast_dtype is not None:
+        with torch.autocast("cuda", dtype=autocast_dtype):
+            logits = model(img)
+            loss = F.cross_entropy(logits.float(), lab)
+    else:
+        logits = model(img)
+        loss = F.cross_entropy(logits, lab)
+    inner = model.module if hasattr(model, "module") else model
+    aux = inner.aux_loss()
+    total = loss if aux is None else loss + AUX_COEF * aux
+    total.backward()
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    return loss
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (reported baseline): same host model around the CPU restatement of the reference's layer
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, budget_s: float | None):
+    """Times `steps` training steps (after `warmup`) of the config on the host cores at batch
+    CPU_SAMPLE_BATCH, fp32.  With `budget_s` the step count is cut so the leg stays inside the budget."""
+    from moe_vit import MoEViT
+    from oracle import fmoe_cpu, moe_oracle as O
+
+    cfg = make_cfg(1)
+    act = torch.nn.Sequential(torch.nn.GELU(), torch.nn.Dropout(p=0.0))
+
+    def moe_mlp(dim, hidden):
+        return fmoe_cpu.FMoETransformerMLP(cfg.num_experts, dim, hidden, act, top_k=cfg.top_k,
+                                           score_mode=O.SCORE_FULL_SOFTMAX, capacity_factor=cfg.capacity_factor)
+
+    torch.manual_seed(0)
+    model = MoEViT(cfg, moe_mlp=moe_mlp)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    img, lab = synthetic_batch(CPU_SAMPLE_BATCH, 0, pin=False)
+    t0 = time.perf_counter()
+    for _ in range(max(1, warmup)):
+        train_step(model, opt, img, lab, None)
+    per = (time.perf_counter() - t0) / max(1, warmup)
+    if budget_s is not None:
+        steps = max(2, min(steps, int(budget_s / max(per, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        train_step(model, opt, img, lab, None)
+    dt = time.perf_counter() - t0
+    T = CPU_SAMPLE_BATCH * 197
+    n_moe = len(model.moe_layers)
+    return dict(images_per_s=CPU_SAMPLE_BATCH * steps / dt, ms_per_step=1e3 * dt / steps, steps=steps,
+                cores=torch.get_num_threads(),
+                sample=f"{steps} training steps at batch {CPU_SAMPLE_BATCH} ({T} tokens x {n_moe} MoE layers per step), fp32, "
+                       f"{cfg.describe()}; oracle/fmoe_cpu.py (CPU restatement of FastMoE; FastMoE has no CPU kernels)")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup, budget_s=150.0)
+    cfg = make_cfg(1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["images_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": max(1, args.warmup), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg.describe() + f", training step at batch {CPU_SAMPLE_BATCH} (bounded sample) on host cores",
+                   "global_batch": CPU_SAMPLE_BATCH, "parallelism": "cpu"},
+        "cpu_baseline": {"value": r["images_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["images_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# isolated layer (configs[1] layer shape): tokens/s and per-kernel breakdown
+# ------------------------------------------------------------------------------------------------
+PHASE_BYTES = {
+    # algorithmic HBM bytes, x and y in bf16 under autocast (s = 2), R = kept pairs
+    "moe_gate_fwd": lambda T, d, h, E, k, R: T * d * 2 + E * d * 4 + T * k * 8 + T * E * 4,
+    "moe_dispatch_fwd": lambda T, d, h, E, k, R: T * d * 2 + R * d * 2 + T * k * 4,
+    "moe_combine_fwd": lambda T, d, h, E, k, R: R * d * 2 + R * 4 + T * d * 2,
+    "moe_combine_bwd": lambda T, d, h, E, k, R: T * d * 2 + 2 * R * d * 2 + 2 * R * 4,
+    "moe_dispatch_bwd": lambda T, d, h, E, k, R: R * d * 2 + T * d * 2 + T * E * 4,
+}
+GEMM_FLOPS = {
+    "gemm_fc1": lambda R, d, h: 2 * R * d * h, "gemm_fc2": lambda R, d, h: 2 * R * d * h,
+    "gemm_dgelu": lambda R, d, h: 2 * R * d * h, "gemm_dgrad": lambda R, d, h: 2 * R * d * h,
+    "gemm_wgrad1": lambda R, d, h: 2 * R * d * h, "gemm_wgrad2": lambda R, d, h: 2 * R * d * h,
+}
+
+
+def layer_bench(peaks, iters=20, warmup=5, T=PER_GPU_BATCH * 197, d=384, E=16, k=1, cf=1.25):
+    import fmoe
+    from fmoe import _cabi as C
+
+    class Gate(fmoe.SwitchGate):
+        def __init__(self, d_model, num_expert, world_size, top_k):
+            super().__init__(d_model, num_expert, world_size, topk=top_k, switch_eps=0.0, capacity=(cf, cf))
+
+    torch.manual_seed(0)
+    h = 4 * d
+    layer = fmoe.FMoETransformerMLP(E, d, h, torch.nn.Sequential(torch.nn.GELU(), torch.nn.Dropout(p=0.0)), top_k=k,
+                                    gate=Gate).cuda()
+    x = torch.randn(T, d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    dy = torch.randn(T, d, device="cuda", dtype=torch.bfloat16)
+
+    def it():
+        y = layer(x)
+        aux = layer.gate.get_loss()
+        torch.autograd.backward([y, aux], [dy, torch.ones_like(aux) * AUX_COEF])
+        x.grad = None
+        for p in layer.parameters():
+            p.grad = None
+
+    for _ in range(warmup):
+        it()
+    torch.cuda.synchronize()
+    C.PROF.reset()
+    C.PROF.enabled = True
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        it()
+    b.record()
+    torch.cuda.synchronize()
+    C.PROF.enabled = False
+    ms = a.elapsed_time(b) / iters
+    R = int(layer.last_kept.sum())
+    phases = {}
+    for tag, (n, mean_ms) in sorted(C.PROF.summary_ms().items()):
+        ent = {"ms": round(mean_ms, 4), "calls_per_iter": n // iters}
+        if tag in PHASE_BYTES:
+            gbs = PHASE_BYTES[tag](T, d, h, E, k, R) / (mean_ms * 1e-3) / 1e9
+            ent.update(gbs=round(gbs, 1), frac_hbm=round(gbs / peaks["hbm"], 3))
+        if tag in GEMM_FLOPS:
+            tf = GEMM_FLOPS[tag](R, d, h) / (mean_ms * 1e-3) / 1e12
+            ent.update(tflops=round(tf, 1), frac_tensor=round(tf / peaks["tf_burst"], 3))
+        phases[tag] = ent
+    gemm_ms = sum(v["ms"] for t, v in phases.items() if t in GEMM_FLOPS)
+    flops = 12.0 * R * d * h
+    return {
+        "shape": {"T": T, "d": d, "h": h, "E": E, "k": k, "capacity_factor": cf, "kept_pairs": R},
+        "tokens_per_s_fwd_bwd": T / (ms * 1e-3), "ms_fwd_bwd": round(ms, 4),
+        "ffn_tflops_fwd_bwd": round(flops / (gemm_ms * 1e-3) / 1e12, 1),
+        "ffn_frac_of_burst_peak": round(flops / (gemm_ms * 1e-3) / 1e12 / peaks["tf_burst"], 3),
+        "layer_tflops": round(flops / (ms * 1e-3) / 1e12, 1),
+        "kernels": phases,
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# main arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-layer", action="store_true", help="skip the isolated-layer breakdown (profiling runs)")
+    ap.add_argument("--profile-window", action="store_true",
+                    help="cudaProfilerStart/Stop around the device-resident timed region (ncu --profile-from-start off)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from fmoe import _cabi as C
+    from moe_vit import MoEViT
+
+    peaks = load_peaks()
+    cfg = make_cfg(world)
+    torch.manual_seed(0)           # same dense/gate init on every rank; experts differ per rank below
+    model = MoEViT(cfg).cuda()
+    if world > 1:
+        from fmoe.distributed import wrap_ddp
+        model = wrap_ddp(model, local_rank)
+    inner = model.module if hasattr(model, "module") else model
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.05, fused=True)
+
+    B = PER_GPU_BATCH
+    img_h, lab_h = synthetic_batch(B, 1000 + rank, pin=True)
+    img_d, lab_d = img_h.cuda(), lab_h.cuda()
+    bf16 = torch.bfloat16
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        train_step(model, opt, img_d, lab_d, bf16)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    C.PROF.reset()
+    C.PROF.enabled = True
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if args.profile_window:
+        torch.cuda.cudart().cudaProfilerStart()
+    ev0.record()
+    for _ in range(args.steps):
+        train_step(model, opt, img_d, lab_d, bf16)
+    ev1.record()
+    barrier()
+    if args.profile_window:
+        torch.cuda.cudart().cudaProfilerStop()
+    C.PROF.enabled = False
+    launches = C.PROF.launches
+    ms_total = ev0.elapsed_time(ev1)
+    kern = C.PROF.summary_ms()
+    kept = [int(m.last_kept.sum()) for m in inner.moe_layers]
+
+    # ---- timed region 2: end to end from host buffers
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        img_d.copy_(img_h, non_blocking=True)
+        lab_d.copy_(lab_h, non_blocking=True)
+        loss = train_step(model, opt, img_d, lab_d, bf16)
+        loss_host = loss.item()      # device -> host read of the step's result
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler is not None else None
+    if not (loss_host == loss_host):
+        raise SystemExit("non-finite loss in the timed region")
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    global_batch = B * world
+    value = global_batch * args.steps / (ms_total * 1e-3)
+    e2e_value = global_batch * args.steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        d, depth, _ = cfg.dims
+        h = 4 * d
+        n_moe = len(inner.moe_layers)
+        # roofline of the dominant hot-path kernel family: the grouped tcgen05 GEMM (6 launches per layer fwd+bwd)
+        gemm_tags = [t_ for t_ in kern if t_.startswith("gemm_")]
+        gemm_calls = sum(kern[t_][0] for t_ in gemm_tags)
+        gemm_ms = sum(kern[t_][0] * kern[t_][1] for t_ in gemm_tags)         # total over the timed region
+        flops_per_launch = 2.0 * (sum(kept) / max(1, n_moe)) * d * h           # every launch is one R x d x h contraction
+        achieved = flops_per_launch * gemm_calls / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "moe::grouped_gemm_kernel (fc1+gelu, fc2, dgelu, dgrad, wgrad x2)",
+                    "achieved": round(achieved, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": round(achieved / peaks["tf_sustained"], 4), "traffic": None,
+                    "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                    "launches_timed": gemm_calls, "avg_launch_ms": round(gemm_ms / max(1, gemm_calls), 4),
+                    "flops_per_launch": flops_per_launch,
+                    "share_of_step": round(gemm_ms / ms_total, 4),
+                    "per_op_ms": {t_: round(kern[t_][1], 4) for t_ in sorted(gemm_tags)}}
+        moe_ms = sum(n * m for n, m in kern.values())
+        flops_img = inner.train_flops_per_image(kept_fraction=sum(kept) / max(1, n_moe) / (B * 197 * cfg.top_k))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": cfg.describe() + ", full training step (fwd + CE + aux loss + bwd + fused AdamW)",
+                       "global_batch": global_batch, "per_gpu_batch": B, "tokens_per_moe_layer_per_gpu": B * 197,
+                       "parallelism": "1 GPU" if world == 1 else f"dp{world} dense blocks + ep{world} experts (all-to-all)",
+                       "cache": "inputs and activations larger than L2 (154 MB fp32 image batch, >1 GB activations per step)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": (img_h.numel() * img_h.element_size() + lab_h.numel() * lab_h.element_size()) * world,
+                    "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "model_roofline": {"train_flops_per_image": flops_img, "achieved_tflops": round(flops_img * value / 1e12, 1),
+                               "frac_of_sustained_bf16": round(flops_img * value / 1e12 / (peaks["tf_sustained"] * world), 4),
+                               "moe_kernels_share_of_step": round(moe_ms / ms_total, 4)},
+        }
+        if not args.no_layer:
+            line["moe_layer"] = layer_bench(peaks)
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(steps=1000, warmup=1, budget_s=20.0)
+            line["cpu_baseline"] = {"value": r["images_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

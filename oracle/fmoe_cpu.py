@@ -88,7 +88,6 @@ class FMoETransformerMLP(nn.Module):
             score = torch.softmax(picked, dim=-1)
         else:
             score = torch.softmax(logits, dim=-1).gather(1, order)
-        self.gate.set_loss(torch.zeros(1, requires_grad=True))
         flat_e = order.reshape(-1)
         perm = torch.sort(flat_e, stable=True).indices            # token-order inside each expert
         counts = torch.bincount(flat_e, minlength=E)
@@ -97,6 +96,13 @@ class FMoETransformerMLP(nn.Module):
         rank = torch.empty_like(perm)
         rank[perm] = torch.arange(perm.numel()) - starts[flat_e[perm]]
         keep = rank < cap
+        if self.score_mode == O.SCORE_FULL_SOFTMAX:
+            # Switch load-balancing loss E * sum_e f_e P_e: f_e = share of kept pairs, P_e = mean prob
+            kept_e = torch.bincount(flat_e[keep], minlength=E).to(logits.dtype)
+            f = kept_e / kept_e.sum().clamp(min=1)
+            self.gate.set_loss(E * (f * torch.softmax(logits, dim=-1).mean(0)).sum())
+        else:
+            self.gate.set_loss(torch.zeros(1, requires_grad=True))   # NaiveGate: dummy zero loss
         y = x.new_zeros(T, self.d_model)
         W1, b1, W2, b2 = self.experts.htoh4.weight, self.experts.htoh4.bias, self.experts.h4toh.weight, self.experts.h4toh.bias
         flat_s = score.reshape(-1)

@@ -71,8 +71,8 @@ KERNELS_PER_CALL = {
 
 
 class Profiler:
-    """Optional per-call CUDA-event timing on the launching stream + kernel launch counter.
-    Off by default (zero overhead beyond one attribute test); bench.py switches it on."""
+    """Kernel launch counter (always on) + optional per-call CUDA-event timing on the launching
+    stream (off by default; bench.py switches it on for the timed region)."""
 
     def __init__(self):
         self.enabled = False
@@ -92,13 +92,13 @@ PROF = Profiler()
 
 
 def call(name: str, *args, tag: str | None = None) -> None:
+    PROF.launches += KERNELS_PER_CALL.get(name, 0)
     if PROF.enabled:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         rc = getattr(lib, name)(*args)
         b.record()
         PROF.events.setdefault(tag or name, []).append((a, b))
-        PROF.launches += KERNELS_PER_CALL.get(name, 0)
     else:
         rc = getattr(lib, name)(*args)
     if rc != 0:

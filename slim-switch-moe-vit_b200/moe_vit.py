@@ -1,0 +1,173 @@
+"""Host model for the MoE layer: a DeiT-style ViT whose MLPs are (some of them) Switch-MoE layers.
+
+This is the *caller* of the hot path, not the hot path.  It restates, in stock PyTorch, what the
+reference builds around the layer so that BASELINE.json's named configs can be run where
+/root/reference and timm do not exist (the GPU box):
+
+  * block structure      /root/reference/models/vision_transformer.py:283-322  (pre-norm attention +
+                          pre-norm MLP, both residual; `self.mlp` is the attribute the factories swap)
+  * model skeleton       /root/reference/models/vision_transformer.py:642-848  (conv patch embed, cls
+                          token, learned pos-embed, blocks, final norm, linear head on the cls token)
+  * the swap             /root/reference/models/resMoE.py:190-209  (`module.mlp = CustomizedMoEMLP(d, 4d,
+                          moe_num_experts=E, moe_top_k=k, drop=0.0)` for every Block)
+  * model sizes          /root/reference/models/vision_transformer.py:1084-1090 (Ti), :1124-1132 (S),
+                          :1170-1178 (B), :1216-1224 (L)
+
+The reference hard-codes E=8, k=2, every block (resMoE.py:194-207); `moe_stride`, `num_experts`,
+`top_k`, `gate` and `capacity_factor` are the north-star extensions.  The MoE module
+is injected through `moe_mlp` (default: the B200 `fmoe.FMoETransformerMLP`) so bench.py's CPU
+baseline can build the same model around the CPU restatement; nothing here imports `oracle/`.
+The dense parts (attention, LayerNorm, dense MLP) stay stock PyTorch and data-parallel.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from functools import partial
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+SIZES = {  # name -> (embed dim, depth, heads)
+    "tiny": (192, 12, 3),
+    "small": (384, 12, 6),
+    "base": (768, 12, 12),
+    "large": (1024, 24, 16),
+}
+
+
+@dataclass(frozen=True)
+class MoEViTConfig:
+    size: str = "small"
+    num_experts: int = 16          # GLOBAL number of experts
+    top_k: int = 1
+    capacity_factor: float = 1.25  # <= 0: no capacity limit (what the reference's NaiveGate does)
+    moe_stride: int = 2            # every `moe_stride`-th block is MoE (1 = every block, as in the reference)
+    gate: str = "switch"           # "switch" (top-1, full softmax, capacity, aux loss) | "naive" | "gshard"
+    num_classes: int = 1000
+    img_size: int = 224
+    patch: int = 16
+    world_size: int = 1            # expert-parallel group size (experts sharded contiguously)
+
+    @property
+    def dims(self):
+        return SIZES[self.size]
+
+    def is_moe_block(self, i: int) -> bool:
+        return self.moe_stride > 0 and i % self.moe_stride == self.moe_stride - 1
+
+    def describe(self) -> str:
+        d, depth, _ = self.dims
+        n_moe = sum(self.is_moe_block(i) for i in range(depth))
+        return (f"ViT-{self.size.capitalize()}/{self.patch} Switch-MoE E{self.num_experts} top-{self.top_k} "
+                f"cf{self.capacity_factor:g} gate={self.gate} moe_blocks={n_moe}/{depth}")
+
+
+class Attention(nn.Module):
+    """Dense multi-head self-attention (reference models/vision_transformer.py:260-280); stock SDPA."""
+
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.heads = heads
+        self.qkv = nn.Linear(dim, dim * 3)
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        qkv = self.qkv(x).reshape(B, N, 3, self.heads, C // self.heads).permute(2, 0, 3, 1, 4)
+        out = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])
+        return self.proj(out.transpose(1, 2).reshape(B, N, C))
+
+
+class Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden, dim)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.fc1(x)))
+
+
+class Block(nn.Module):
+    def __init__(self, dim, heads, mlp: nn.Module):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = Attention(dim, heads)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = mlp
+
+    def forward(self, x):
+        x = x + self.attn(self.norm1(x))
+        return x + self.mlp(self.norm2(x))
+
+
+def _b200_moe_mlp(cfg: MoEViTConfig, dim: int, hidden: int) -> nn.Module:
+    import fmoe  # the B200 drop-in (fails loudly without libmoe_b200.so)
+
+    cf = cfg.capacity_factor
+
+    class _Switch(fmoe.SwitchGate):
+        def __init__(self, d_model, num_expert, world_size, top_k):
+            super().__init__(d_model, num_expert, world_size, topk=top_k, switch_eps=0.0, capacity=(cf, cf))
+
+    class _GShard(fmoe.GShardGate):
+        def __init__(self, d_model, num_expert, world_size, top_k):
+            super().__init__(d_model, num_expert, world_size, topk=top_k, capacity=(cf, cf))
+
+    gate = {"switch": _Switch, "naive": fmoe.NaiveGate, "gshard": _GShard}[cfg.gate]
+    act = nn.Sequential(nn.GELU(), nn.Dropout(p=0.0))      # reference models/resMoE.py:25
+    if cfg.num_experts % cfg.world_size:
+        raise ValueError("num_experts must be divisible by the expert-parallel world size")
+    return fmoe.FMoETransformerMLP(cfg.num_experts // cfg.world_size, dim, hidden, act, top_k=cfg.top_k, gate=gate,
+                                   world_size=cfg.world_size)
+
+
+class MoEViT(nn.Module):
+    def __init__(self, cfg: MoEViTConfig, moe_mlp=None):
+        super().__init__()
+        self.cfg = cfg
+        dim, depth, heads = cfg.dims
+        moe_mlp = moe_mlp or partial(_b200_moe_mlp, cfg)
+        n_patches = (cfg.img_size // cfg.patch) ** 2
+        self.patch_embed = nn.Conv2d(3, dim, kernel_size=cfg.patch, stride=cfg.patch)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, n_patches + 1, dim))
+        self.blocks = nn.ModuleList(
+            Block(dim, heads, moe_mlp(dim, 4 * dim) if cfg.is_moe_block(i) else Mlp(dim, 4 * dim)) for i in range(depth))
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        self.head = nn.Linear(dim, cfg.num_classes)
+        nn.init.trunc_normal_(self.pos_embed, std=0.02)
+        nn.init.trunc_normal_(self.cls_token, std=0.02)
+
+    @property
+    def moe_layers(self):
+        return [b.mlp for i, b in enumerate(self.blocks) if self.cfg.is_moe_block(i)]
+
+    def aux_loss(self):
+        """Sum of the gates' load-balancing losses set during the last forward."""
+        losses = [m.gate.get_loss() for m in self.moe_layers if m.gate.has_loss]
+        return sum(l.sum() for l in losses) if losses else None
+
+    def forward(self, img):
+        x = self.patch_embed(img).flatten(2).transpose(1, 2)
+        x = torch.cat((self.cls_token.expand(x.shape[0], -1, -1), x), dim=1) + self.pos_embed
+        for blk in self.blocks:
+            x = blk(x)
+        return self.head(self.norm(x)[:, 0])
+
+    def train_flops_per_image(self, kept_fraction: float = 1.0) -> float:
+        """fwd+bwd (3x forward) matmul flops per image, SURVEY.md §8d formula."""
+        cfg = self.cfg
+        d, depth, _ = cfg.dims
+        n = (cfg.img_size // cfg.patch) ** 2 + 1
+        per_tok = 0.0
+        for i in range(depth):
+            per_tok += 8 * d * d + 4 * n * d
+            if cfg.is_moe_block(i):
+                per_tok += 16 * d * d * cfg.top_k * kept_fraction + 2 * d * cfg.num_experts
+            else:
+                per_tok += 16 * d * d
+        once = 2 * (3 * cfg.patch ** 2) * d * (n - 1) + 2 * d * cfg.num_classes
+        return 3.0 * (n * per_tok + once)
