@@ -15,7 +15,8 @@
  *   - return value: 0 = OK, non-zero = error; moe_last_error() (thread-local) describes it.
  *   - dtype codes: MOE_DTYPE_F32 = 0, MOE_DTYPE_BF16 = 1.
  *   - packed row buffers ("xbuf", "U", "H", "Y", ...) are [rows_cap, cols] bf16 row-major;
- *     expert e owns rows [seg_start[e], seg_start[e+1]), each segment start is a multiple of 128,
+ *     expert e owns rows [seg_start[e], seg_start[e+1]), each segment start is a multiple of 256
+ *     (one CTA-pair MMA tile; MOE_ROW_ALIGN),
  *     rows [seg_start[e] + kept[e], seg_start[e+1]) are padding.
  *     rows_cap >= moe_rows_cap(T, k, E, capacity).
  *   - constraints: d % 64 == 0, h % 64 == 0, 1 <= k <= 8, k <= E, E <= 1024.
@@ -37,19 +38,19 @@ extern "C" {
 #define MOE_SCORE_FULL_SOFTMAX 1 /* SwitchGate: softmax over all experts, score = prob of selection */
 
 #define MOE_TOKEN_TILE 256 /* tokens per routing tile; ntiles = ceil(T / 256) */
-#define MOE_ROW_ALIGN 128  /* segment alignment of the packed buffers          */
+#define MOE_ROW_ALIGN 256  /* segment alignment of the packed buffers = rows of one CTA-pair MMA tile */
 
 /* grouped GEMM ops (moe_grouped_gemm) */
 #define MOE_GEMM_FC1 0   /* out0 = U = A W^T + b, out1 = gelu_erf(U)    A[rows,K] B[E,N,K]            */
 #define MOE_GEMM_FC2 1   /* out0 = A W^T + b                            A[rows,K] B[E,N,K]            */
-#define MOE_GEMM_DGELU 2 /* out0 = (A W) * gelu'(aux)                   A[rows,K] B[E,K,N] aux[rows,N] */
-#define MOE_GEMM_DGRAD 3 /* out0 = A W                                  A[rows,K] B[E,K,N]            */
+#define MOE_GEMM_DGELU 2 /* out0 = (A Wt^T) * gelu'(aux)                A[rows,K] B[E,N,K] aux[rows,N] */
+#define MOE_GEMM_DGRAD 3 /* out0 = A Wt^T                               A[rows,K] B[E,N,K]            */
 #define MOE_GEMM_WGRAD 4 /* out0[e] (fp32 [E,M,N]) = A_e^T B_e          A[rows,M] B[rows,N]           */
 
 const char *moe_last_error(void);
 int moe_version(void);
 
-/* rows the packed buffers must hold: min(T*k, E*capacity) + 128*E */
+/* rows the packed buffers must hold: min(T*k, E*capacity) rounded up to 256, + 256*E */
 int64_t moe_rows_cap(int64_t T, int k, int E, int64_t capacity);
 
 /* ---- gate: replaces NaiveGate's nn.Linear + torch.topk + F.softmax and fmoe_cuda.expert_count.
@@ -62,7 +63,7 @@ int moe_gate_fwd(const void *x, int x_dtype, const float *Wg, const float *bg /*
 
 /* ---- scan: replaces torch.cumsum + .item() + limit_by_capacity (no host sync).
  * tile_base[ntiles,E], count[E], kept[E] = min(count, capacity), seg_start[E+1],
- * tile_expert[max_mtiles] (expert of each 128-row tile, -1 past the end), num_mtiles[1],
+ * tile_expert[max_mtiles] (expert of each 256-row tile, -1 past the end), num_mtiles[1],
  * psum[E] = sum over tiles of tile_psum (nullable together with tile_psum). */
 int moe_route_scan(const int32_t *tile_hist, const float *tile_psum, int ntiles, int E, int64_t capacity,
                    int32_t *tile_base, int32_t *count, int32_t *kept, int32_t *seg_start, int32_t *tile_expert,
@@ -92,10 +93,12 @@ int moe_combine_bwd(const void *dy, int dy_dtype, const void *ybuf, const int32_
                     float *dscore, void *stream);
 
 /* ---- expert FFN backward: replaces fmoe_cuda.linear_backward x2 + GELU' + column_reduce.
+ * W1tb[E,d,h] = W1^T and W2tb[E,h,d] = W2^T are the TRANSPOSED bf16 weight copies
+ * (moe_cast_bf16_transposed), so that every row-mode contraction reads K-major operands.
  * dU[rows_cap,h] and dxbuf[rows_cap,d] are bf16 outputs (dU doubles as workspace);
  * dW1[E,h,d], db1[E,h], dW2[E,d,h], db2[E,d] are fp32 and are overwritten. */
-int moe_expert_ffn_bwd(const void *dybuf, const void *xbuf, const void *U, const void *H, const void *W1b,
-                       const void *W2b, const int32_t *tile_expert, const int32_t *num_mtiles,
+int moe_expert_ffn_bwd(const void *dybuf, const void *xbuf, const void *U, const void *H, const void *W1tb,
+                       const void *W2tb, const int32_t *tile_expert, const int32_t *num_mtiles,
                        const int32_t *seg_start, int64_t rows_cap, int d, int h, int E, void *dU, void *dxbuf,
                        float *dW1, float *db1, float *dW2, float *db2, void *stream);
 
@@ -117,6 +120,8 @@ int moe_gate_wgrad(const float *dlogits, const void *x, int x_dtype, int64_t T, 
 
 /* ---- utilities */
 int moe_cast_bf16(const float *src, void *dst, int64_t n /* % 8 == 0 */, void *stream);
+/* src[E,R,C] fp32 -> dst[E,R,C] bf16 (nullable) and dst_t[E,C,R] bf16 (transposed per expert); R, C % 32 == 0 */
+int moe_cast_bf16_transposed(const float *src, void *dst, void *dst_t, int E, int R, int C, void *stream);
 int moe_segment_colsum(const void *buf, const int32_t *seg_start, int E, int cols, float *out, void *stream);
 
 /* ---- the grouped tcgen05 GEMM itself (building block of the two FFN entry points; exported so

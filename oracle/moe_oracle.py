@@ -30,7 +30,7 @@ import torch.nn.functional as F
 
 from . import build as _build
 
-ALIGN = 128  # rows; every expert segment of the packed buffers starts on a multiple of this
+ALIGN = 256  # rows; every expert segment of the packed buffers starts on a multiple of this (one CTA-pair tile)
 
 SCORE_TOPK_SOFTMAX = 0  # NaiveGate / GShardGate: softmax over the k selected logits
 SCORE_FULL_SOFTMAX = 1  # SwitchGate: probability of the selected expert under softmax over all E

@@ -57,7 +57,7 @@ int moe_version(void) { return 100; }
 int64_t moe_rows_cap(int64_t T, int k, int E, int64_t capacity) {
     int64_t pairs = T * k;
     if (capacity > 0 && capacity < pairs && capacity * E < pairs) pairs = capacity * E;
-    return (pairs + 127) / 128 * 128 + 128LL * E;
+    return (pairs + MOE_ROW_ALIGN - 1) / MOE_ROW_ALIGN * MOE_ROW_ALIGN + static_cast<int64_t>(MOE_ROW_ALIGN) * E;
 }
 
 int moe_gate_fwd(const void* x, int x_dtype, const float* Wg, const float* bg, const float* noise, int64_t T, int d, int E, int k,
@@ -134,6 +134,11 @@ int moe_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
     return check(launch_cast_bf16(src, dst, n, sm_count(), static_cast<cudaStream_t>(stream)), "moe_cast_bf16");
 }
 
+int moe_cast_bf16_transposed(const float* src, void* dst, void* dst_t, int E, int R, int C, void* stream) {
+    if (E <= 0 || R <= 0 || C <= 0 || R % 32 != 0 || C % 32 != 0 || dst_t == nullptr) { set_error("moe_cast_bf16_transposed: need E > 0, R, C positive multiples of 32 (E=%d R=%d C=%d)", E, R, C); return 1; }
+    return check(launch_cast_bf16_transposed(src, dst, dst_t, E, R, C, static_cast<cudaStream_t>(stream)), "moe_cast_bf16_transposed");
+}
+
 int moe_segment_colsum(const void* buf, const int32_t* seg_start, int E, int cols, float* out, void* stream) {
     if (E <= 0 || cols <= 0 || cols % 2 != 0) { set_error("moe_segment_colsum: bad shape"); return 1; }
     return check(launch_segment_colsum(buf, seg_start, E, cols, out, static_cast<cudaStream_t>(stream)), "moe_segment_colsum");
@@ -157,15 +162,15 @@ int moe_expert_ffn_fwd(const void* xbuf, const void* W1b, const float* b1, const
                                E, 0, d, h, sm_count(), st);
 }
 
-int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* U, const void* H, const void* W1b,
-                       const void* W2b, const int32_t* tile_expert, const int32_t* num_mtiles,
+int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* U, const void* H, const void* W1tb,
+                       const void* W2tb, const int32_t* tile_expert, const int32_t* num_mtiles,
                        const int32_t* seg_start, int64_t rows_cap, int d, int h, int E, void* dU, void* dxbuf,
                        float* dW1, float* db1, float* dW2, float* db2, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int sms = sm_count();
     int rc;
-    // dU = (dY W2) * gelu'(U)                     [rows, h]   K = d, B = W2b [E, d, h] read MN-major
-    rc = launch_grouped_gemm(MOE_GEMM_DGELU, dybuf, W2b, dU, nullptr, nullptr, U, tile_expert, num_mtiles, nullptr,
+    // dU = (dY W2) * gelu'(U)                     [rows, h]   K = d, B = W2^T [E, h, d] K-major
+    rc = launch_grouped_gemm(MOE_GEMM_DGELU, dybuf, W2tb, dU, nullptr, nullptr, U, tile_expert, num_mtiles, nullptr,
                              rows_cap, E, 0, h, d, sms, st);
     if (rc) return rc;
     // dW2[e] = dY_e^T H_e                          [d, h]
@@ -176,8 +181,8 @@ int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* U, const
     rc = launch_grouped_gemm(MOE_GEMM_WGRAD, dU, xbuf, dW1, nullptr, nullptr, nullptr, nullptr, nullptr, seg_start,
                              rows_cap, E, h, d, 0, sms, st);
     if (rc) return rc;
-    // dX = dU W1                                   [rows, d]   K = h, B = W1b [E, h, d] read MN-major
-    rc = launch_grouped_gemm(MOE_GEMM_DGRAD, dU, W1b, dxbuf, nullptr, nullptr, nullptr, tile_expert, num_mtiles, nullptr,
+    // dX = dU W1                                   [rows, d]   K = h, B = W1^T [E, d, h] K-major
+    rc = launch_grouped_gemm(MOE_GEMM_DGRAD, dU, W1tb, dxbuf, nullptr, nullptr, nullptr, tile_expert, num_mtiles, nullptr,
                              rows_cap, E, 0, d, h, sms, st);
     if (rc) return rc;
     if (check(launch_segment_colsum(dybuf, seg_start, E, d, db2, st), "db2 colsum")) return 1;

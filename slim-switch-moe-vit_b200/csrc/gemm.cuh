@@ -1,25 +1,33 @@
-// gemm.cuh — grouped expert GEMM on tcgen05 / TMEM, fed by TMA (sm_100a only).
+// gemm.cuh — grouped expert GEMM on tcgen05 / TMEM, fed by TMA, on CTA PAIRS (sm_100a only).
 //
 // One persistent, warp-specialised kernel template covers every dense contraction of the
 // expert FFN (replaces FastMoE's per-expert cuBLAS loop
 // `fmoe_cuda.linear_forward/backward`, reached from /root/reference/models/resMoE.py:27-29):
 //
-//   ROWS mode  (M = packed token rows, one weight matrix per 128-row tile):
-//     fc1   : U = X  W1^T + b1, H = gelu_erf(U)     A K-major, B K-major, EPI_BIAS_GELU_DUAL
-//     fc2   : Y = H  W2^T + b2                      A K-major, B K-major, EPI_BIAS
-//     dgelu : dU = (dY W2) * gelu'(U)               A K-major, B MN-major, EPI_DGELU
-//     dgrad : dX = dU W1                            A K-major, B MN-major, EPI_PLAIN
-//   WGRAD mode (K = the rows of one expert's segment, fp32 output per expert):
-//     dW2[e] = dY_e^T H_e , dW1[e] = dU_e^T X_e     A MN-major, B MN-major, EPI_F32
+//   ROWS mode  (M = packed token rows, one weight matrix per 256-row pair tile; A and B K-major):
+//     fc1   : U = X  W1^T + b1, H = gelu_erf(U)     B = W1   [E, h, d]      EPI_BIAS_GELU_DUAL
+//     fc2   : Y = H  W2^T + b2                      B = W2   [E, d, h]      EPI_BIAS
+//     dgelu : dU = (dY W2) * gelu'(U)               B = W2^T [E, h, d]      EPI_DGELU
+//     dgrad : dX = dU W1                            B = W1^T [E, d, h]      EPI_PLAIN
+//   WGRAD mode (K = the rows of one expert's segment, fp32 output per expert; A and B MN-major):
+//     dW2[e] = dY_e^T H_e , dW1[e] = dU_e^T X_e                             EPI_F32
 //
 // Layout contract: the packed row buffers are [rows_cap, cols] bf16, every expert's segment
-// starts at a multiple of 128 rows (so a 128-row tile never straddles two experts) and pad
+// starts at a multiple of 256 rows (so a 256-row pair tile never straddles two experts) and pad
 // rows are zero in X and dY (so they contribute nothing to WGRAD).
 //
-// CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..5 = epilogue (one TMEM lane quarter each).  Pipelines: smem ring full/empty
-// (TMA <-> MMA), two TMEM accumulator stages full/empty (MMA <-> epilogue), epilogue staging
-// ring drained by TMA stores.  Tile = 128 x BN x 64, UMMA 128 x BN x 16, cta_group::1.
+// Why pairs: with one CTA per 128 x BN tile every SM pulls (128 + BN) x 64 x 2 bytes from L2 per
+// 2 x 128 x BN x 64 flop — 0.012-0.013 B/flop, which at the ~6.3 KB/clk L2->SM ceiling caps the
+// chip at ~0.9 PFLOP/s (measured round 1a: tensor pipe 53 % active, fc2 at 800 TFLOP/s).  A CTA
+// pair (`tcgen05.mma.cta_group::2`, UMMA 256 x BN x 16) shares B: each CTA loads its own 128 A
+// rows and HALF of the B tile, 0.0078 B/flop at BN = 256.
+//
+// CTA = 320 threads: warp 0 = TMA producer, warp 1 = TMEM owner (+ single-thread MMA issuer in
+// the leader CTA), warps 2..9 = epilogue: two groups of four warps (one TMEM lane quarter each),
+// the groups take alternate column chunks of the accumulator.  Pipelines: smem ring full/empty
+// (TMA <-> MMA; `full` lives in the leader and is credited by both CTAs' TMA loads, `empty` is
+// multicast to both CTAs by tcgen05.commit), two TMEM accumulator stages full/empty
+// (MMA <-> epilogue of both CTAs), one store-staging buffer per group and output drained by TMA.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -30,8 +38,8 @@ namespace moe {
 enum : int { EPI_BIAS_GELU_DUAL = 0, EPI_BIAS = 1, EPI_DGELU = 2, EPI_PLAIN = 3, EPI_F32 = 4 };
 
 struct GemmParams {
-    const int* tile_expert;  // ROWS: expert of each 128-row tile            [max_mtiles]
-    const int* num_mtiles;   // ROWS: number of live 128-row tiles (device scalar)
+    const int* tile_expert;  // ROWS: expert of each 256-row pair tile       [max_mtiles]
+    const int* num_mtiles;   // ROWS: number of live 256-row tiles (device scalar)
     const int* seg_start;    // WGRAD: first row of each expert segment      [E+1]
     const float* bias;       // [E, N] fp32 or nullptr
     const __nv_bfloat16* aux;  // EPI_DGELU: pre-activation U [rows_cap, N]
@@ -41,65 +49,102 @@ struct GemmParams {
     int K;  // ROWS: reduction length
 };
 
-constexpr int kBM = 128;
+constexpr int kBM = 128;     // accumulator rows per CTA
+constexpr int kPairM = 256;  // rows per pair tile (UMMA M with cta_group::2)
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kStagingBytes = 16384;  // 128 rows x 128 B
 constexpr int kSmemLimit = 232448;    // 227 KB
 
 template <int BN, int EPI>
 struct GemmCfg {
     static constexpr int A_BYTES = kBM * kBK * 2;
-    static constexpr int B_BYTES = BN * kBK * 2;
+    static constexpr int B_BYTES = (BN / 2) * kBK * 2;  // this CTA's half of the B tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int NOUT = (EPI == EPI_BIAS_GELU_DUAL) ? 2 : 1;
-    static constexpr int NBUF = 2 * NOUT;
+    static constexpr int NBUF = 2 * NOUT;  // one staging buffer per epilogue group and output
     static constexpr int CHUNK_COLS = (EPI == EPI_F32) ? 32 : 64;
     static constexpr int NCHUNK = BN / CHUNK_COLS;
     static constexpr int BAR_BYTES = 256;
     static constexpr int STAGES_RAW = (kSmemLimit - 1024 - BAR_BYTES - NBUF * kStagingBytes) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + NBUF * kStagingBytes + BAR_BYTES;
-    static_assert(STAGES >= 2, "not enough shared memory for a pipelined tile");
+    static_assert(STAGES >= 3, "not enough shared memory for a pipelined tile");
     static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64, at most 256");
 };
 
-__device__ __forceinline__ float gelu_erf_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_erf_grad_f(float u) {
-    float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
-    float pdf = __expf(-0.5f * u * u) * 0.39894228040143268f;
-    return cdf + u * pdf;
+// ------------------------------------------------------------------------------------------------
+// exact-erf GELU and its derivative for the epilogues (coefficients: tools/fit_gelu.py)
+//   gelu(u)  = relu(u) - |u| Q(|u|),       Q(a) = Phi(-a) = g(a) W(a),  g(a) = exp(-a^2/2)
+//   gelu'(u) = 1/2 + copysign(1/2 - m(|u|), u),   m(a) = Phi(-a) - a phi(a) = g(a) w(a)
+// W, w: degree-10 polynomials on [0, 6.5] (|u| is clamped; beyond it both corrections are < 1e-9).
+// Max abs error vs float64 erfc: 1.2e-7 (gelu), 1.3e-7 (gelu') — the level of CUDA's erff — with one
+// MUFU (ex2) per element and packed fp32 FMAs (FFMA2) for the Horner chains: the epilogue of a
+// K = 384 tile has ~12 issue slots per element, erff + expf needs ~3x that.
+// ------------------------------------------------------------------------------------------------
+constexpr float kGeluAMax = 6.5f;
+constexpr float kNegHalfLog2e = -0.72134752044448170f;
+__device__ constexpr float kGeluNegW[11] = {  // -W(a)
+    -4.999984264e-01f, 3.988943415e-01f, -2.496126727e-01f, 1.315388586e-01f, -5.946753551e-02f, 2.258705447e-02f,
+    -6.850097529e-03f, 1.548216262e-03f, -2.391936664e-04f, 2.217437910e-05f, -9.204634787e-07f};
+__device__ constexpr float kGeluGradW[11] = {  // w(a)
+    4.999999215e-01f, -7.978779301e-01f, 2.499070795e-01f, -1.324720956e-01f, 6.106562675e-02f, -2.420641669e-02f,
+    7.862224466e-03f, -1.941088571e-03f, 3.311199745e-04f, -3.400798613e-05f, 1.562210311e-06f};
+
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+// g(a) * poly(a) for two elements; a = min(|u|, kGeluAMax)
+template <bool GRAD>
+__device__ __forceinline__ float2 gelu_core2(float2 a) {
+    float2 t = __fmul2_rn(__fmul2_rn(a, splat2(kNegHalfLog2e)), a);
+    const float2 g = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+    float2 p = splat2(GRAD ? kGeluGradW[10] : kGeluNegW[10]);
+#pragma unroll
+    for (int i = 9; i >= 0; --i) p = __ffma2_rn(p, a, splat2(GRAD ? kGeluGradW[i] : kGeluNegW[i]));
+    return __fmul2_rn(g, p);
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
+__device__ __forceinline__ float2 gelu_erf2(float2 u) {
+    const float2 a = make_float2(fminf(fabsf(u.x), kGeluAMax), fminf(fabsf(u.y), kGeluAMax));
+    const float2 nq = gelu_core2<false>(a);                                  // -Q(a)
+    return __ffma2_rn(a, nq, make_float2(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f)));  // relu(u) - a Q(a)
+}
+__device__ __forceinline__ float2 gelu_erf_grad2(float2 u) {
+    const float2 a = make_float2(fminf(fabsf(u.x), kGeluAMax), fminf(fabsf(u.y), kGeluAMax));
+    const float2 m = gelu_core2<true>(a);
+    const float2 hm = __ffma2_rn(m, splat2(-1.0f), splat2(0.5f));            // 1/2 - m
+    return __fadd2_rn(make_float2(copysignf(hm.x, u.x), copysignf(hm.y, u.y)), splat2(0.5f));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float2 v) {
+    __nv_bfloat162 b = __float22bfloat162_rn(v);
+    return *reinterpret_cast<uint32_t*>(&b);
 }
 
 struct TileCoord {
     int e;      // expert (weight index)
-    int m0;     // ROWS: first packed row of the tile.  WGRAD: first output row inside the expert
-    int n0;     // first output column
+    int m0;     // ROWS: first packed row of THIS CTA's half.  WGRAD: first output row of this CTA's half
+    int n0;     // first output column of the pair tile
     int row0;   // WGRAD: first packed row of the expert segment
     int kb;     // number of 64-deep k-blocks
 };
 
 template <int BN, bool WGRAD>
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, int n_ntiles) {
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, int n_ntiles, int rank) {
     TileCoord c;
     if constexpr (!WGRAD) {
         int m = tile / n_ntiles;
         c.e = __ldg(p.tile_expert + m);
-        c.m0 = m * kBM;
+        c.m0 = m * kPairM + rank * kBM;
         c.n0 = (tile - m * n_ntiles) * BN;
         c.row0 = 0;
         c.kb = p.K / kBK;
     } else {
-        int m_tiles = (p.M + kBM - 1) / kBM;
+        int m_tiles = (p.M + kPairM - 1) / kPairM;
         int per_e = m_tiles * n_ntiles;
         c.e = tile / per_e;
         int rem = tile - c.e * per_e;
         int mt = rem / n_ntiles;
-        c.m0 = mt * kBM;
+        c.m0 = mt * kPairM + rank * kBM;
         c.n0 = (rem - mt * n_ntiles) * BN;
         c.row0 = __ldg(p.seg_start + c.e);
         c.kb = (__ldg(p.seg_start + c.e + 1) - c.row0) / kBK;
@@ -107,15 +152,15 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
     return c;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool WGRAD>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, int EPI, bool WGRAD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                     const GemmParams p) {
     using Cfg = GemmCfg<BN, EPI>;
     constexpr int STAGES = Cfg::STAGES;
-    static_assert(!WGRAD || (A_MN && B_MN && EPI == EPI_F32), "WGRAD = MN-major operands, fp32 output");
-    static_assert(WGRAD || !A_MN, "ROWS mode reads the packed rows K-major");
+    static_assert(WGRAD == (EPI == EPI_F32), "WGRAD <=> fp32 output");
+    static_assert(!WGRAD || BN % 128 == 0, "MN-major B: each CTA's half must be whole 64-column swizzle atoms");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -128,6 +173,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int rank = static_cast<int>(cluster_ctarank());  // 0 = leader (issues the MMAs)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -135,12 +181,12 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmO0);
         if constexpr (Cfg::NOUT == 2) tma_prefetch_desc(&tmO1);
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar + s, 1);
-            mbar_init(empty_bar + s, 1);
+            mbar_init(full_bar + s, 1);   // leader's producer arrive.expect_tx; bytes from both CTAs
+            mbar_init(empty_bar + s, 1);  // one multicast tcgen05.commit
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(tfull_bar + s, 1);
-            mbar_init(tempty_bar + s, 4);
+            mbar_init(tfull_bar + s, 1);                // one multicast tcgen05.commit
+            mbar_init(tempty_bar + s, 2 * kEpiWarps);   // every epilogue warp of both CTAs (leader's copy is used)
         }
         fence_mbar_init();
     }
@@ -149,41 +195,39 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tmem_relinquish();
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();  // barrier inits + TMEM allocation visible in both CTAs before any cross-CTA signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int n_ntiles = p.N / BN;
+    const int n_ntiles = (p.N + BN - 1) / BN;
     int total_tiles;
-    if constexpr (WGRAD) total_tiles = p.E * ((p.M + kBM - 1) / kBM) * n_ntiles;
+    if constexpr (WGRAD) total_tiles = p.E * ((p.M + kPairM - 1) / kPairM) * n_ntiles;
     else total_tiles = __ldg(p.num_mtiles) * n_ntiles;
+    const int first_tile = blockIdx.x >> 1;
+    const int tile_stride = gridDim.x >> 1;
 
     if (warp == 0) {
-        // ================================ TMA producer (one thread) ================================
+        // ================================ TMA producer (one thread per CTA) =========================
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles);
+            for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+                const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
                 for (int kb = 0; kb < c.kb; ++kb) {
                     mbar_wait(empty_bar + s, ph ^ 1);
                     uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
-                    mbar_arrive_expect_tx(full_bar + s, Cfg::STAGE_BYTES);
-                    if constexpr (!A_MN) {
-                        tma_load_2d(sa, &tmA, full_bar + s, kb * kBK, c.m0);
+                    if (rank == 0) mbar_arrive_expect_tx(full_bar + s, 2 * Cfg::STAGE_BYTES);
+                    if constexpr (!WGRAD) {
+                        tma_load_2d_pair(sa, &tmA, full_bar + s, kb * kBK, c.m0);
+                        tma_load_2d_pair(sb, &tmB, full_bar + s, kb * kBK, c.e * p.N + c.n0 + rank * (BN / 2));
                     } else {
                         const int krow = c.row0 + kb * kBK;
-                        tma_load_2d(sa, &tmA, full_bar + s, c.m0, krow);
-                        tma_load_2d(sa + 8192, &tmA, full_bar + s, c.m0 + 64, krow);
-                    }
-                    if constexpr (!B_MN) {
-                        tma_load_2d(sb, &tmB, full_bar + s, kb * kBK, c.e * p.N + c.n0);
-                    } else {
-                        const int krow = WGRAD ? (c.row0 + kb * kBK) : (c.e * p.K + kb * kBK);
+                        tma_load_2d_pair(sa, &tmA, full_bar + s, c.m0, krow);
+                        tma_load_2d_pair(sa + 8192, &tmA, full_bar + s, c.m0 + 64, krow);
 #pragma unroll
-                        for (int i = 0; i < BN / 64; ++i)
-                            tma_load_2d(sb + i * 8192, &tmB, full_bar + s, c.n0 + i * 64, krow);
+                        for (int i = 0; i < BN / 128; ++i)
+                            tma_load_2d_pair(sb + i * 8192, &tmB, full_bar + s, c.n0 + rank * (BN / 2) + i * 64, krow);
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -191,13 +235,13 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ================================ MMA issuer (one thread) ==================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN, B_MN);
+        // ================================ MMA issuer (one thread of the leader CTA) =================
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kPairM, BN, WGRAD, WGRAD);
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles);
+            for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+                const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
                 if (c.kb == 0) continue;
                 mbar_wait(tempty_bar + as, aph ^ 1);
                 tc_fence_after();
@@ -209,140 +253,168 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
                     for (int k4 = 0; k4 < kBK / 16; ++k4) {
-                        const uint64_t ad = A_MN ? umma_smem_desc(a_addr + k4 * 2048, 8192, 1024)
-                                                 : umma_smem_desc(a_addr + k4 * 32, 16, 1024);
-                        const uint64_t bd = B_MN ? umma_smem_desc(b_addr + k4 * 2048, 8192, 1024)
-                                                 : umma_smem_desc(b_addr + k4 * 32, 16, 1024);
+                        const uint64_t ad = WGRAD ? umma_smem_desc(a_addr + k4 * 2048, 8192, 1024)
+                                                  : umma_smem_desc(a_addr + k4 * 32, 16, 1024);
+                        const uint64_t bd = WGRAD ? umma_smem_desc(b_addr + k4 * 2048, 8192, 1024)
+                                                  : umma_smem_desc(b_addr + k4 * 32, 16, 1024);
                         umma_bf16(tmem_d, ad, bd, idesc, (kb | k4) != 0);
                     }
-                    umma_commit(empty_bar + s);  // frees the smem slot once these MMAs retire
+                    umma_commit_pair(empty_bar + s);  // frees the smem slot in both CTAs once these MMAs retire
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                umma_commit(tfull_bar + as);  // accumulator complete -> epilogue
+                umma_commit_pair(tfull_bar + as);  // accumulator complete -> epilogues of both CTAs
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
         }
         __syncwarp();
     } else {
-        // ================================ epilogue (4 warps, 128 threads) ==========================
-        const int q = warp & 3;            // TMEM lane quarter this warp may touch
-        const int r = q * 32 + lane;       // row inside the 128-row tile
-        const int ep_tid = threadIdx.x - 64;
-        uint8_t* my_row = staging + r * 128;
+        // ================================ epilogue (2 groups x 4 warps) ============================
+        const int q = warp & 3;                  // TMEM lane quarter this warp may touch
+        const int grp = (warp - 2) >> 2;         // column-chunk parity this group owns
+        const int r = q * 32 + lane;             // row inside this CTA's 128-row half
+        const bool issuer = (warp - 2 == grp * 4) && lane == 0;  // first thread of the group issues its TMA stores
+        uint8_t* const gstage = staging + grp * Cfg::NOUT * kStagingBytes;
+        uint8_t* const my_row = gstage + r * 128;
         const int sw = r & 7;
+        const uint32_t bar_id = 1 + grp;
         int as = 0;
         uint32_t aph = 0;
-        uint32_t step = 0;  // staging ring position (monotonic over the CTA's lifetime)
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles);
+        for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+            const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
             const bool live = c.kb != 0;
+            const float* bias = (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS) && p.bias != nullptr
+                                    ? p.bias + static_cast<size_t>(c.e) * p.N + c.n0
+                                    : nullptr;
+            [[maybe_unused]] uint4 aux_cur[8];
+            [[maybe_unused]] const __nv_bfloat16* aux_row = nullptr;
+            if constexpr (EPI == EPI_DGELU) {
+                aux_row = p.aux + static_cast<size_t>(c.m0 + r) * p.N + c.n0;
+                if (grp < Cfg::NCHUNK) {
+                    const uint4* ap = reinterpret_cast<const uint4*>(aux_row + grp * 64);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) aux_cur[i] = __ldg(ap + i);
+                }
+            }
             if (live) {
                 mbar_wait(tfull_bar + as, aph);
                 tc_fence_after();
             }
             const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
-            const float* bias = (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS) && p.bias != nullptr
-                                    ? p.bias + static_cast<size_t>(c.e) * p.N + c.n0
-                                    : nullptr;
-#pragma unroll 1
-            for (int ch = 0; ch < Cfg::NCHUNK; ++ch, ++step) {
-                uint8_t* buf0 = my_row + ((step & 1) * Cfg::NOUT) * kStagingBytes;
-                // staging buffers of ring slot (step & 1) were last used two steps ago
-                if (ep_tid == 0) tma_store_wait_read<1>();
-                named_bar_sync(1, 128);
-
-                uint4 auxv[8];
-                if constexpr (EPI == EPI_DGELU) {
-                    const uint4* ap = reinterpret_cast<const uint4*>(
-                        p.aux + static_cast<size_t>(c.m0 + r) * p.N + c.n0 + ch * 64);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) auxv[i] = __ldg(ap + i);
-                }
-#pragma unroll
-                for (int half = 0; half < Cfg::CHUNK_COLS / 32; ++half) {
+            for (int ch = 0; ch < Cfg::NCHUNK; ++ch) {
+                if ((ch & 1) != grp) continue;
+                constexpr int last_of_group0 = (Cfg::NCHUNK - 1) & ~1;
+                const bool last_chunk = (ch + 2 >= Cfg::NCHUNK);
+                (void)last_of_group0;
+                if constexpr (EPI == EPI_F32) {
                     uint32_t acc[32];
                     if (live) {
-                        tmem_ld32(tmem_row + ch * Cfg::CHUNK_COLS + half * 32, acc);
+                        tmem_ld32(tmem_row + ch * 32, acc);
                         tmem_ld_wait();
+                        if (last_chunk) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(tempty_bar + as, 0);
+                        }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) acc[i] = 0u;
                     }
-                    if constexpr (EPI == EPI_F32) {
+                    if (issuer) tma_store_wait_read<0>();
+                    named_bar_sync(bar_id, 128);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            uint4 v = make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-                            *reinterpret_cast<uint4*>(buf0 + ((j ^ sw) << 4)) = v;
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) =
+                            make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                    fence_proxy_async_smem();
+                    named_bar_sync(bar_id, 128);
+                    if (issuer && c.m0 < p.M && c.n0 + ch * 32 < p.N) {
+                        tma_store_3d(&tmO0, gstage, c.n0 + ch * 32, c.m0, c.e);
+                        tma_store_commit();
+                    }
+                } else {
+                    [[maybe_unused]] uint4 aux_nxt[8];
+                    if constexpr (EPI == EPI_DGELU) {
+                        if (ch + 2 < Cfg::NCHUNK) {
+                            const uint4* ap = reinterpret_cast<const uint4*>(aux_row + (ch + 2) * 64);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) aux_nxt[i] = __ldg(ap + i);
                         }
-                    } else {
-                        float v[32];
+                    }
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-                        if (bias != nullptr) {
-                            const float4* bp = reinterpret_cast<const float4*>(bias + ch * 64 + half * 32);
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t acc[32];
+                        tmem_ld32(tmem_row + ch * 64 + half * 32, acc);
+                        tmem_ld_wait();
+                        if (last_chunk && half == 1) {
+                            // every TMEM read of this accumulator stage by this warp is done -> hand it back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(tempty_bar + as, 0);
+                        }
+                        uint32_t o0[16];                       // 32 columns of output 0, packed bf16x2
+                        [[maybe_unused]] uint32_t o1[16];      // 32 columns of output 1 (fc1: gelu)
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                float4 b = __ldg(bp + i);
-                                v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                        for (int i = 0; i < 16; ++i) {
+                            float2 v = make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+                            if constexpr (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS) {
+                                if (bias != nullptr) {
+                                    const float2 b = __ldg(reinterpret_cast<const float2*>(bias + ch * 64 + half * 32) + i);
+                                    v = __fadd2_rn(v, b);
+                                }
                             }
-                        }
-                        if constexpr (EPI == EPI_DGELU) {
-                            const uint32_t* aw = reinterpret_cast<const uint32_t*>(auxv) + half * 16;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                __nv_bfloat162 u2 = *reinterpret_cast<const __nv_bfloat162*>(aw + i);
-                                v[2 * i] *= gelu_erf_grad_f(__low2float(u2));
-                                v[2 * i + 1] *= gelu_erf_grad_f(__high2float(u2));
+                            if constexpr (EPI == EPI_DGELU) {
+                                const uint32_t uw = reinterpret_cast<const uint32_t*>(aux_cur)[half * 16 + i];
+                                const float2 u = make_float2(__uint_as_float(uw << 16), __uint_as_float(uw & 0xffff0000u));
+                                v = __fmul2_rn(v, gelu_erf_grad2(u));
                             }
+                            o0[i] = pack_bf16x2(v);
+                            if constexpr (EPI == EPI_BIAS_GELU_DUAL) o1[i] = pack_bf16x2(gelu_erf2(v));
                         }
-                        // first (or only) output: the linear result itself
+                        if (half == 0) {
+                            // the group's previous TMA store must have finished reading the staging buffer
+                            if (issuer) tma_store_wait_read<0>();
+                            named_bar_sync(bar_id, 128);
+                        }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            uint4 o = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-                            *reinterpret_cast<uint4*>(buf0 + (((half * 4 + j) ^ sw) << 4)) = o;
-                        }
-                        if constexpr (EPI == EPI_BIAS_GELU_DUAL) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = gelu_erf_f(v[i]);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint4 o = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                                     pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-                                *reinterpret_cast<uint4*>(buf0 + kStagingBytes + (((half * 4 + j) ^ sw) << 4)) = o;
-                            }
+                            const int slot = ((half * 4 + j) ^ sw) << 4;
+                            *reinterpret_cast<uint4*>(my_row + slot) = make_uint4(o0[4 * j], o0[4 * j + 1], o0[4 * j + 2], o0[4 * j + 3]);
+                            if constexpr (EPI == EPI_BIAS_GELU_DUAL)
+                                *reinterpret_cast<uint4*>(my_row + kStagingBytes + slot) =
+                                    make_uint4(o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
                         }
                     }
-                }
-                if (live && ch == Cfg::NCHUNK - 1) {
-                    // every TMEM read of this accumulator stage has completed -> hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar + as);
-                }
-                fence_proxy_async_smem();
-                named_bar_sync(1, 128);
-                if (ep_tid == 0) {
-                    const uint8_t* sbuf = staging + ((step & 1) * Cfg::NOUT) * kStagingBytes;
-                    if constexpr (WGRAD) {
-                        tma_store_3d(&tmO0, sbuf, c.n0 + ch * Cfg::CHUNK_COLS, c.m0, c.e);
-                    } else {
-                        tma_store_2d(&tmO0, sbuf, c.n0 + ch * Cfg::CHUNK_COLS, c.m0);
-                        if constexpr (Cfg::NOUT == 2)
-                            tma_store_2d(&tmO1, sbuf + kStagingBytes, c.n0 + ch * Cfg::CHUNK_COLS, c.m0);
+                    fence_proxy_async_smem();
+                    named_bar_sync(bar_id, 128);
+                    if (issuer) {
+                        tma_store_2d(&tmO0, gstage, c.n0 + ch * 64, c.m0);
+                        if constexpr (Cfg::NOUT == 2) tma_store_2d(&tmO1, gstage + kStagingBytes, c.n0 + ch * 64, c.m0);
+                        tma_store_commit();
                     }
-                    tma_store_commit();
+                    if constexpr (EPI == EPI_DGELU) {
+                        if (ch + 2 < Cfg::NCHUNK) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) aux_cur[i] = aux_nxt[i];
+                        }
+                    }
                 }
             }
             if (live) {
+                if (grp >= Cfg::NCHUNK) {  // a group without chunks (BN = 64) still has to release the stage
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tempty_bar + as, 0);
+                }
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
         }
-        if (ep_tid == 0) tma_store_wait_all<0>();
+        if (issuer) tma_store_wait_all<0>();
     }
 
+    // teardown: neither CTA may exit (or free TMEM) while its peer can still signal or read it
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);

@@ -56,29 +56,37 @@ bool encode_3d_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, u
     return true;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool WGRAD>
+template <int BN, int EPI, bool WGRAD>
 int launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tO0, const CUtensorMap& tO1,
                const GemmParams& p, int grid, cudaStream_t st) {
     using Cfg = GemmCfg<BN, EPI>;
-    auto kfn = grouped_gemm_kernel<BN, A_MN, B_MN, EPI, WGRAD>;
+    auto kfn = grouped_gemm_kernel<BN, EPI, WGRAD>;
     static bool configured = false;  // per instantiation
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return 1; }
         configured = true;
     }
+    // the kernel carries __cluster_dims__(2,1,1): the grid is a whole number of CTA pairs
     kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(tA, tB, tO0, tO1, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("grouped_gemm launch: %s", cudaGetErrorString(e)); return 1; }
     return 0;
 }
 
-int pick_bn(int N) {
+// ROWS mode: N must be tiled exactly (the outputs are dense row buffers)
+int pick_bn_rows(int N) {
     if (N % 256 == 0) return 256;
     if (N % 192 == 0) return 192;
     if (N % 128 == 0) return 128;
     if (N % 64 == 0) return 64;
     return 0;
+}
+// WGRAD mode: BN in {128, 256} (whole swizzle atoms per CTA half); ragged N is handled by TMA
+// zero-fill / clipping, so pick the width that wastes fewer MMA columns
+int pick_bn_wgrad(int N) {
+    const int w256 = (N + 255) / 256 * 256 - N, w128 = (N + 127) / 128 * 128 - N;
+    return w256 <= w128 ? 256 : 128;
 }
 
 }  // namespace
@@ -86,11 +94,13 @@ int pick_bn(int N) {
 int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out1, const float* bias, const void* aux,
                         const int* tile_expert, const int* num_mtiles, const int* seg_start, int64_t rows_cap, int E,
                         int M, int N, int K, int sm_count, cudaStream_t st) {
-    const int bn = pick_bn(N);
-    if (bn == 0) { set_error("grouped gemm: N=%d must be a multiple of 64", N); return 1; }
-    if (op != MOE_GEMM_WGRAD && (K % 64 != 0 || K <= 0)) { set_error("grouped gemm: K=%d must be a positive multiple of 64", K); return 1; }
-    if (op == MOE_GEMM_WGRAD && (M % 64 != 0 || M <= 0)) { set_error("grouped gemm: M=%d must be a positive multiple of 64", M); return 1; }
-    if (rows_cap % 128 != 0) { set_error("grouped gemm: rows_cap=%lld must be a multiple of 128", (long long)rows_cap); return 1; }
+    const bool wgrad = op == MOE_GEMM_WGRAD;
+    if (op < MOE_GEMM_FC1 || op > MOE_GEMM_WGRAD) { set_error("grouped gemm: unknown op %d", op); return 1; }
+    if (N <= 0 || N % 64 != 0) { set_error("grouped gemm: N=%d must be a positive multiple of 64", N); return 1; }
+    if (!wgrad && (K % 64 != 0 || K <= 0)) { set_error("grouped gemm: K=%d must be a positive multiple of 64", K); return 1; }
+    if (wgrad && (M % 64 != 0 || M <= 0)) { set_error("grouped gemm: M=%d must be a positive multiple of 64", M); return 1; }
+    if (rows_cap % MOE_ROW_ALIGN != 0) { set_error("grouped gemm: rows_cap=%lld must be a multiple of %d", (long long)rows_cap, MOE_ROW_ALIGN); return 1; }
+    const int bn = wgrad ? pick_bn_wgrad(N) : pick_bn_rows(N);
 
     GemmParams p{};
     p.tile_expert = tile_expert;
@@ -104,48 +114,39 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
     const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const uint64_t R = static_cast<uint64_t>(rows_cap);
     bool ok = true;
-    switch (op) {
-        case MOE_GEMM_FC1:
-        case MOE_GEMM_FC2:
-            ok = ok && encode_2d(&tA, BF, 2, A, K, R, 64, 128);
-            ok = ok && encode_2d(&tB, BF, 2, B, K, static_cast<uint64_t>(E) * N, 64, bn);
-            ok = ok && encode_2d(&tO0, BF, 2, out0, N, R, 64, 128);
-            ok = ok && encode_2d(&tO1, BF, 2, op == MOE_GEMM_FC1 ? out1 : out0, N, R, 64, 128);
-            break;
-        case MOE_GEMM_DGELU:
-        case MOE_GEMM_DGRAD:
-            ok = ok && encode_2d(&tA, BF, 2, A, K, R, 64, 128);
-            ok = ok && encode_2d(&tB, BF, 2, B, N, static_cast<uint64_t>(E) * K, 64, 64);
-            ok = ok && encode_2d(&tO0, BF, 2, out0, N, R, 64, 128);
-            tO1 = tO0;
-            break;
-        case MOE_GEMM_WGRAD:
-            ok = ok && encode_2d(&tA, BF, 2, A, M, R, 64, 64);
-            ok = ok && encode_2d(&tB, BF, 2, B, N, R, 64, 64);
-            ok = ok && encode_3d_f32(&tO0, out0, N, M, E, 32, 128);
-            tO1 = tO0;
-            break;
-        default:
-            set_error("grouped gemm: unknown op %d", op);
-            return 1;
+    if (!wgrad) {
+        // A [rows, K] and B [E*N, K] K-major; each CTA of a pair loads 128 A rows and bn/2 B rows per k-block
+        ok = ok && encode_2d(&tA, BF, 2, A, K, R, 64, 128);
+        ok = ok && encode_2d(&tB, BF, 2, B, K, static_cast<uint64_t>(E) * N, 64, bn / 2);
+        ok = ok && encode_2d(&tO0, BF, 2, out0, N, R, 64, 128);
+        ok = ok && encode_2d(&tO1, BF, 2, op == MOE_GEMM_FC1 ? out1 : out0, N, R, 64, 128);
+    } else {
+        // A [rows, M], B [rows, N] read MN-major in 64 x 64 boxes; out [E, M, N] fp32 in 32-column chunks
+        ok = ok && encode_2d(&tA, BF, 2, A, M, R, 64, 64);
+        ok = ok && encode_2d(&tB, BF, 2, B, N, R, 64, 64);
+        ok = ok && encode_3d_f32(&tO0, out0, N, M, E, 32, 128);
+        tO1 = tO0;
     }
     if (!ok) return 1;
+    const int grid = (sm_count / 2) * 2;
 
-#define MOE_BN_SWITCH(A_MN, B_MN, EPI, WG)                                                            \
-    switch (bn) {                                                                                     \
-        case 256: return launch_one<256, A_MN, B_MN, EPI, WG>(tA, tB, tO0, tO1, p, sm_count, st);     \
-        case 192: return launch_one<192, A_MN, B_MN, EPI, WG>(tA, tB, tO0, tO1, p, sm_count, st);     \
-        case 128: return launch_one<128, A_MN, B_MN, EPI, WG>(tA, tB, tO0, tO1, p, sm_count, st);     \
-        default: return launch_one<64, A_MN, B_MN, EPI, WG>(tA, tB, tO0, tO1, p, sm_count, st);       \
+#define MOE_BN_ROWS(EPI)                                                                  \
+    switch (bn) {                                                                         \
+        case 256: return launch_one<256, EPI, false>(tA, tB, tO0, tO1, p, grid, st);      \
+        case 192: return launch_one<192, EPI, false>(tA, tB, tO0, tO1, p, grid, st);      \
+        case 128: return launch_one<128, EPI, false>(tA, tB, tO0, tO1, p, grid, st);      \
+        default: return launch_one<64, EPI, false>(tA, tB, tO0, tO1, p, grid, st);        \
     }
     switch (op) {
-        case MOE_GEMM_FC1: MOE_BN_SWITCH(false, false, EPI_BIAS_GELU_DUAL, false)
-        case MOE_GEMM_FC2: MOE_BN_SWITCH(false, false, EPI_BIAS, false)
-        case MOE_GEMM_DGELU: MOE_BN_SWITCH(false, true, EPI_DGELU, false)
-        case MOE_GEMM_DGRAD: MOE_BN_SWITCH(false, true, EPI_PLAIN, false)
-        default: MOE_BN_SWITCH(true, true, EPI_F32, true)
+        case MOE_GEMM_FC1: MOE_BN_ROWS(EPI_BIAS_GELU_DUAL)
+        case MOE_GEMM_FC2: MOE_BN_ROWS(EPI_BIAS)
+        case MOE_GEMM_DGELU: MOE_BN_ROWS(EPI_DGELU)
+        case MOE_GEMM_DGRAD: MOE_BN_ROWS(EPI_PLAIN)
+        default:
+            if (bn == 256) return launch_one<256, EPI_F32, true>(tA, tB, tO0, tO1, p, grid, st);
+            return launch_one<128, EPI_F32, true>(tA, tB, tO0, tO1, p, grid, st);
     }
-#undef MOE_BN_SWITCH
+#undef MOE_BN_ROWS
 }
 
 }  // namespace moe

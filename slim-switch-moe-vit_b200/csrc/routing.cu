@@ -261,18 +261,18 @@ route_scan_kernel(const int* __restrict__ tile_hist, const float* __restrict__ t
             kept[e] = kp;
             seg_s[e] = start;
             seg_start[e] = start;
-            start += (kp + 127) / 128 * 128;
+            start += (kp + MOE_ROW_ALIGN - 1) / MOE_ROW_ALIGN * MOE_ROW_ALIGN;
         }
         seg_s[E] = start;
         seg_start[E] = start;
-        *num_mtiles = start / 128;
+        *num_mtiles = start / MOE_ROW_ALIGN;
     }
     __syncthreads();
-    const int nm = seg_s[E] / 128;
+    const int nm = seg_s[E] / MOE_ROW_ALIGN;
     for (int m = tid; m < max_mtiles; m += 1024) {
         int e = -1;
         if (m < nm) {
-            const int row = m * 128;
+            const int row = m * MOE_ROW_ALIGN;
             e = 0;
             while (e + 1 < E && seg_s[e + 1] <= row) ++e;
         }
@@ -592,6 +592,29 @@ cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
     }
 }
 
+// src[E,R,C] fp32 -> dst[E,R,C] bf16 (optional) + dst_t[E,C,R] bf16; 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256)
+cast_bf16_transposed_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                            __nv_bfloat16* __restrict__ dst_t, int R, int C) {
+    __shared__ float tile[32][33];
+    const int e = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const size_t base = static_cast<size_t>(e) * R * C;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + i * 8;
+        const float v = src[base + static_cast<size_t>(r) * C + c0 + tx];
+        tile[ty + i * 8][tx] = v;
+        if (dst != nullptr) dst[base + static_cast<size_t>(r) * C + c0 + tx] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + i * 8;
+        dst_t[base + static_cast<size_t>(c) * R + r0 + tx] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
+    }
+}
+
 // out[e, c] = sum over rows r in [seg_start[e], seg_start[e+1]) of buf[r, c]; block = 32 x 8 threads,
 // each lane owns 2 adjacent columns, the 8 row-lanes stride the segment; fixed-order smem reduction.
 __global__ void __launch_bounds__(256)
@@ -789,6 +812,13 @@ cudaError_t launch_gate_wgrad(const float* dlogits, const void* x, int x_dtype, 
 cudaError_t launch_cast_bf16(const float* src, void* dst, int64_t n, int sm_count, cudaStream_t st) {
     const int64_t n8 = n / 8;
     cast_bf16_kernel<<<grid_for(n8, sm_count), 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), n8);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cast_bf16_transposed(const float* src, void* dst, void* dst_t, int E, int R, int C, cudaStream_t st) {
+    dim3 grid(C / 32, R / 32, E);
+    cast_bf16_transposed_kernel<<<grid, 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst),
+                                                      static_cast<__nv_bfloat16*>(dst_t), R, C);
     return cudaGetLastError();
 }
 

@@ -24,8 +24,9 @@ class RouteSpec:
 
 
 class Bf16WeightCache:
-    """bf16 operand copies of the fp32 expert weights, refreshed only when a parameter changed
-    (optimizer step, load_state_dict, .to()).  Keyed on (data_ptr, _version)."""
+    """bf16 operand copies of the fp32 expert weights — W1b [E,h,d], W2b [E,d,h] and their per-expert
+    transposes W1tb [E,d,h], W2tb [E,h,d] (so that dgrad / dgelu read K-major operands too) — refreshed
+    only when a parameter changed (optimizer step, load_state_dict, .to()).  Keyed on (data_ptr, _version)."""
 
     def __init__(self):
         self._key = None
@@ -34,12 +35,14 @@ class Bf16WeightCache:
     def get(self, W1: torch.Tensor, W2: torch.Tensor):
         key = (W1.data_ptr(), W1._version, W2.data_ptr(), W2._version, W1.device)
         if key != self._key:
-            W1b = torch.empty(W1.shape, dtype=torch.bfloat16, device=W1.device)
-            W2b = torch.empty(W2.shape, dtype=torch.bfloat16, device=W2.device)
+            bf = torch.bfloat16
+            E, h, d = W1.shape
+            W1b, W2b = torch.empty((E, h, d), dtype=bf, device=W1.device), torch.empty((E, d, h), dtype=bf, device=W1.device)
+            W1tb, W2tb = torch.empty((E, d, h), dtype=bf, device=W1.device), torch.empty((E, h, d), dtype=bf, device=W1.device)
             st = C.stream_ptr()
-            C.call("moe_cast_bf16", C.ptr(W1.detach()), C.ptr(W1b), W1.numel(), st)
-            C.call("moe_cast_bf16", C.ptr(W2.detach()), C.ptr(W2b), W2.numel(), st)
-            self._key, self._val = key, (W1b, W2b)
+            C.call("moe_cast_bf16_transposed", C.ptr(W1.detach()), C.ptr(W1b), C.ptr(W1tb), E, h, d, st)
+            C.call("moe_cast_bf16_transposed", C.ptr(W2.detach()), C.ptr(W2b), C.ptr(W2tb), E, d, h, st)
+            self._key, self._val = key, (W1b, W2b, W1tb, W2tb)
         return self._val
 
     def __deepcopy__(self, memo):  # ModelEma deep-copies the model (reference main.py:602-607)
@@ -118,7 +121,7 @@ class MoEFunction(torch.autograd.Function):
         bg_c = None if bg is None else bg.detach().contiguous()
         r = route(x, Wg_c, bg_c, spec, noise)
         rows_cap = r["rows_cap"]
-        W1b, W2b = cache.get(W1_c, W2_c)
+        W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c)
         U = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
         H = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
         Y = torch.empty((rows_cap, d), dtype=torch.bfloat16, device=dev)
@@ -137,7 +140,7 @@ class MoEFunction(torch.autograd.Function):
         ctx.has_bg = bg is not None
         ctx.rows_cap = rows_cap
         ctx.save_for_backward(x, Wg_c, r["logits"], r["idx"], r["score"], r["pos"], r["seg_start"], r["kept"],
-                              r["tile_expert"], r["num_mtiles"], r["xbuf"], U, H, Y, W1b, W2b)
+                              r["tile_expert"], r["num_mtiles"], r["xbuf"], U, H, Y, W1tb, W2tb)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(r["count"], r["kept"])
         psum = r["psum"]
@@ -149,11 +152,11 @@ class MoEFunction(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy, dpsum, _dcount, _dkept):
-        (x, Wg, logits, idx, score, pos, seg_start, kept, tile_expert, num_mtiles, xbuf, U, H, Y, W1b,
-         W2b) = ctx.saved_tensors
+        (x, Wg, logits, idx, score, pos, seg_start, kept, tile_expert, num_mtiles, xbuf, U, H, Y, W1tb,
+         W2tb) = ctx.saved_tensors
         spec: RouteSpec = ctx.spec
         T, d = x.shape
-        E, h = W1b.shape[0], W1b.shape[1]
+        E, h = W1tb.shape[0], W1tb.shape[2]
         k = spec.top_k
         dev = x.device
         st = C.stream_ptr()
@@ -177,13 +180,13 @@ class MoEFunction(torch.autograd.Function):
         dW2, db2 = _f32((E, d, h), dev), _f32((E, d), dev)
         # same kernel sequence as the bundled moe_expert_ffn_bwd entry point
         te, nm, sg = C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_start)
-        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2b), C.ptr(dU), None, None, C.ptr(U),
+        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), None, None, C.ptr(U),
                te, nm, None, rows_cap, E, 0, h, d, st, tag="gemm_dgelu")
         C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dybuf), C.ptr(H), C.ptr(dW2), None, None, None,
                None, None, sg, rows_cap, E, d, h, 0, st, tag="gemm_wgrad2")
         C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dU), C.ptr(xbuf), C.ptr(dW1), None, None, None,
                None, None, sg, rows_cap, E, h, d, 0, st, tag="gemm_wgrad1")
-        C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1b), C.ptr(dxbuf), None, None, None,
+        C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1tb), C.ptr(dxbuf), None, None, None,
                te, nm, None, rows_cap, E, 0, d, h, st, tag="gemm_dgrad")
         C.call("moe_segment_colsum", C.ptr(dybuf), sg, E, d, C.ptr(db2), st, tag="colsum_db2")
         C.call("moe_segment_colsum", C.ptr(dU), sg, E, h, C.ptr(db1), st, tag="colsum_db1")

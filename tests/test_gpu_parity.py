@@ -65,15 +65,15 @@ def test_routing_and_dispatch_bit_exact(case):
     assert torch.equal(r["kept"].cpu(), ref.kept)
     assert torch.equal(r["seg_start"].cpu(), ref.seg_start)
     assert torch.equal(r["pos"].cpu(), ref.pos)
-    assert int(r["num_mtiles"].item()) == ref.rows // 128
+    assert int(r["num_mtiles"].item()) == ref.rows // C.ROW_ALIGN
     assert max_abs(r["score"], ref.score) <= 2e-6
     assert max_abs(r["psum"], ref.psum) <= 2e-6 * T
     # tile -> expert table
     te = r["tile_expert"].cpu()
     for e in range(E):
-        s, t = int(ref.seg_start[e]) // 128, int(ref.seg_start[e + 1]) // 128
+        s, t = int(ref.seg_start[e]) // C.ROW_ALIGN, int(ref.seg_start[e + 1]) // C.ROW_ALIGN
         assert (te[s:t] == e).all()
-    assert (te[ref.rows // 128:] == -1).all()
+    assert (te[ref.rows // C.ROW_ALIGN:] == -1).all()
     # packed buffer: live rows are bf16(x[token]), pad rows are zero, row_src inverts pos
     row_src, _ = O._row_tables(ref, E)
     rows = ref.rows
@@ -132,7 +132,7 @@ def test_ffn_intermediates_vs_model():
     x, Wg, bg, W1, b1, W2, b2 = make_problem(T, d, h, E, seed=5)
     spec = Fn.RouteSpec(k, mode, T * k, False)
     r = Fn.route(x.cuda(), Wg.cuda(), bg.cuda(), spec)
-    W1b, W2b = Fn.Bf16WeightCache().get(W1.cuda(), W2.cuda())
+    W1b, W2b, W1tb, W2tb = Fn.Bf16WeightCache().get(W1.cuda(), W2.cuda())
     rows_cap = r["rows_cap"]
     U = torch.zeros(rows_cap, h, dtype=torch.bfloat16, device="cuda")
     H, Y = torch.zeros_like(U), torch.zeros(rows_cap, d, dtype=torch.bfloat16, device="cuda")
@@ -144,6 +144,7 @@ def test_ffn_intermediates_vs_model():
     _, sv = O.forward_model(x, Wg, bg, W1, b1, W2, b2, k, mode, T * k)
     rows = sv.r.rows
     assert torch.equal(W1b.cpu().float(), sv.W1b) and torch.equal(W2b.cpu().float(), sv.W2b)
+    assert torch.equal(W1tb.cpu().float(), sv.W1b.transpose(1, 2)) and torch.equal(W2tb.cpu().float(), sv.W2b.transpose(1, 2))
     for name, got, want in (("U", U, sv.Ub), ("H", H, sv.Hb), ("Y", Y, sv.Yb)):
         assert rel_err(got[:rows], want) <= MODEL_REL, name
         assert max_abs(got[:rows], want) <= float(want.abs().max()) / 64, name

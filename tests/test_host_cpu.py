@@ -29,8 +29,9 @@ def test_library_exports_every_declared_symbol():
     exported = set(re.findall(r"\bT (moe_[a-z0-9_]+)", out))
     assert set(names) <= exported
     assert C.lib.moe_version() >= 100
-    assert C.lib.moe_rows_cap(1000, 2, 8, 2000) == 2048 + 128 * 8
-    assert C.lib.moe_rows_cap(1000, 1, 8, 100) == 896 + 1024     # min(T*k, E*C) rounded up, + 128 per expert
+    assert C.ROW_ALIGN == 256
+    assert C.lib.moe_rows_cap(1000, 2, 8, 2000) == 2048 + 256 * 8
+    assert C.lib.moe_rows_cap(1000, 1, 8, 100) == 1024 + 2048    # min(T*k, E*C) rounded up to 256, + 256 per expert
 
 
 def test_library_is_sm100a_tcgen05_code():

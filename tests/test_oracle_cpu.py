@@ -90,11 +90,12 @@ def test_ties_resolve_to_lowest_index_and_edge_cases():
     assert torch.allclose(r.score, torch.full((3, 2), 0.5))
     # capacity 1: only the first pair of each expert (token order) survives
     r = O.route(logits, 2, 0, 1)
-    assert r.pos.tolist() == [[128, 256], [0, -1], [-1, 384]]
-    assert r.kept.tolist() == [1, 1, 1, 1] and r.seg_start.tolist() == [0, 128, 256, 384, 512]
+    A = O.ALIGN
+    assert r.pos.tolist() == [[A, 2 * A], [0, -1], [-1, 3 * A]]
+    assert r.kept.tolist() == [1, 1, 1, 1] and r.seg_start.tolist() == [0, A, 2 * A, 3 * A, 4 * A]
     # one token, one expert
     r = O.route(torch.zeros(1, 1), 1, 1, 1)
-    assert r.idx.tolist() == [[0]] and r.score.tolist() == [[1.0]] and r.rows == 128
+    assert r.idx.tolist() == [[0]] and r.score.tolist() == [[1.0]] and r.rows == O.ALIGN
 
 
 def test_logit_order_is_what_the_header_says():

@@ -14,7 +14,7 @@ from fmoe import _cabi as C  # noqa: E402
 def segs(counts):
     seg = [0]
     for c in counts:
-        seg.append(seg[-1] + (c + 127) // 128 * 128)
+        seg.append(seg[-1] + (c + 255) // 256 * 256)
     return seg
 
 
@@ -28,13 +28,13 @@ def main():
     torch.manual_seed(0)
     seg = segs(counts)
     rows = seg[-1]
-    rows_cap = rows + 128
+    rows_cap = rows + 256
     seg_t = torch.tensor(seg, dtype=torch.int32, device=dev)
-    tile_e = torch.full((rows_cap // 128,), -1, dtype=torch.int32)
+    tile_e = torch.full((rows_cap // 256,), -1, dtype=torch.int32)
     for e in range(E):
-        tile_e[seg[e] // 128: seg[e + 1] // 128] = e
+        tile_e[seg[e] // 256: seg[e + 1] // 256] = e
     tile_e = tile_e.to(dev)
-    nm = torch.tensor([rows // 128], dtype=torch.int32, device=dev)
+    nm = torch.tensor([rows // 256], dtype=torch.int32, device=dev)
     st = C.stream_ptr()
     bf = torch.bfloat16
 
@@ -68,14 +68,14 @@ def main():
         print(f"      rows beyond live range untouched: {tail == 0.0}")
         ok = ok and tail == 0.0
     elif op in (C.GEMM_DGELU, C.GEMM_DGRAD):
-        A = rnd(rows_cap, K); B = rnd(E, K, N); aux = rnd(rows_cap, N)
+        A = rnd(rows_cap, K); B = rnd(E, N, K); aux = rnd(rows_cap, N)   # B = W^T, K-major like fc1/fc2
         o0 = torch.zeros(rows_cap, N, dtype=bf, device=dev)
         C.call("moe_grouped_gemm", op, C.ptr(A), C.ptr(B), C.ptr(o0), None, None,
                C.ptr(aux) if op == C.GEMM_DGELU else None, C.ptr(tile_e), C.ptr(nm), None, rows_cap, E, 0, N, K, st)
         torch.cuda.synchronize()
         ref = torch.zeros(rows_cap, N, device=dev)
         for e in range(E):
-            ref[seg[e]:seg[e + 1]] = A[seg[e]:seg[e + 1]].float() @ B[e].float()
+            ref[seg[e]:seg[e + 1]] = A[seg[e]:seg[e + 1]].float() @ B[e].float().t()
         if op == C.GEMM_DGELU:
             u = aux.float()
             gp = 0.5 * (1 + torch.erf(u / 2 ** 0.5)) + u * torch.exp(-0.5 * u * u) / (2 * 3.141592653589793) ** 0.5
