@@ -24,7 +24,8 @@
 //
 // CTA = 320 threads: warp 0 = TMA producer, warp 1 = TMEM owner (+ single-thread MMA issuer in
 // the leader CTA), warps 2..9 = epilogue: two groups of four warps (one TMEM lane quarter each),
-// the groups take alternate column chunks of the accumulator.  Pipelines: smem ring full/empty
+// the groups take alternate column chunks of the accumulator; every warp stages and TMA-stores its own
+// 32-row slab, so the epilogue has no CTA-level barrier.  Pipelines: smem ring full/empty
 // (TMA <-> MMA; `full` lives in the leader and is credited by both CTAs' TMA loads, `empty` is
 // multicast to both CTAs by tcgen05.commit), two TMEM accumulator stages full/empty
 // (MMA <-> epilogue of both CTAs), one store-staging buffer per group and output drained by TMA.
@@ -66,7 +67,7 @@ struct GemmCfg {
     static constexpr int NBUF = 2 * NOUT;  // one staging buffer per epilogue group and output
     static constexpr int CHUNK_COLS = (EPI == EPI_F32) ? 32 : 64;
     static constexpr int NCHUNK = BN / CHUNK_COLS;
-    static constexpr int BAR_BYTES = 256;
+    static constexpr int BAR_BYTES = 256 + kEpiWarps * 128 * 4;  // mbarriers + TMEM slot, then the per-warp bias copies
     static constexpr int STAGES_RAW = (kSmemLimit - 1024 - BAR_BYTES - NBUF * kStagingBytes) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + NBUF * kStagingBytes + BAR_BYTES;
@@ -94,30 +95,88 @@ __device__ constexpr float kGeluGradW[11] = {  // w(a)
 
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
-// g(a) * poly(a) for two elements; a = min(|u|, kGeluAMax)
-template <bool GRAD>
-__device__ __forceinline__ float2 gelu_core2(float2 a) {
-    float2 t = __fmul2_rn(__fmul2_rn(a, splat2(kNegHalfLog2e)), a);
-    const float2 g = make_float2(ex2_approx(t.x), ex2_approx(t.y));
-    float2 p = splat2(GRAD ? kGeluGradW[10] : kGeluNegW[10]);
-#pragma unroll
-    for (int i = 9; i >= 0; --i) p = __ffma2_rn(p, a, splat2(GRAD ? kGeluGradW[i] : kGeluNegW[i]));
-    return __fmul2_rn(g, p);
-}
-__device__ __forceinline__ float2 gelu_erf2(float2 u) {
-    const float2 a = make_float2(fminf(fabsf(u.x), kGeluAMax), fminf(fabsf(u.y), kGeluAMax));
-    const float2 nq = gelu_core2<false>(a);                                  // -Q(a)
-    return __ffma2_rn(a, nq, make_float2(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f)));  // relu(u) - a Q(a)
-}
-__device__ __forceinline__ float2 gelu_erf_grad2(float2 u) {
-    const float2 a = make_float2(fminf(fabsf(u.x), kGeluAMax), fminf(fabsf(u.y), kGeluAMax));
-    const float2 m = gelu_core2<true>(a);
-    const float2 hm = __ffma2_rn(m, splat2(-1.0f), splat2(0.5f));            // 1/2 - m
-    return __fadd2_rn(make_float2(copysignf(hm.x, u.x), copysignf(hm.y, u.y)), splat2(0.5f));
-}
 __device__ __forceinline__ uint32_t pack_bf16x2(float2 v) {
     __nv_bfloat162 b = __float22bfloat162_rn(v);
     return *reinterpret_cast<uint32_t*>(&b);
+}
+
+// g(a) * poly(a) for 8 element pairs at once.  The eight Horner chains are written step-major so
+// that consecutive FFMA2s are independent (a dependent FFMA2 chain is latency-bound: measured
+// round 1b, 0.25 IPC per scheduler with the pair-at-a-time form).
+template <bool GRAD>
+__device__ __forceinline__ void gelu_core8(const float2 (&a)[8], float2 (&out)[8]) {
+    float2 g[8], p[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = __fmul2_rn(__fmul2_rn(a[i], splat2(kNegHalfLog2e)), a[i]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = make_float2(ex2_approx(g[i].x), ex2_approx(g[i].y));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = splat2(GRAD ? kGeluGradW[10] : kGeluNegW[10]);
+#pragma unroll
+    for (int k = 9; k >= 0; --k) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] = __ffma2_rn(p[i], a[i], splat2(GRAD ? kGeluGradW[k] : kGeluNegW[k]));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = __fmul2_rn(g[i], p[i]);
+}
+
+// One block of 16 accumulator columns (8 pairs) of one row through the epilogue.
+//   acc: 16 fp32 accumulators; bias_saddr: shared-memory address of 16 fp32 (BIAS epilogues); aux: 8 packed bf16x2 of U (DGELU)
+//   o0 / o1: 8 packed bf16x2 outputs each (o1 = gelu, fc1 only)
+template <int EPI>
+__device__ __forceinline__ void epilogue_block16(const uint32_t* acc, uint32_t bias_saddr, const uint32_t* aux,
+                                                 uint32_t* o0, uint32_t* o1) {
+    float2 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+    if constexpr (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS) {
+        float2 b[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 b4;   // shared memory, warp-uniform address (broadcast)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bias_saddr + i * 16));
+            b[2 * i] = make_float2(b4.x, b4.y);
+            b[2 * i + 1] = make_float2(b4.z, b4.w);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __fadd2_rn(v[i], b[i]);
+    }
+    if constexpr (EPI == EPI_DGELU) {
+        float2 u[8], a[8], m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            u[i] = make_float2(__uint_as_float(aux[i] << 16), __uint_as_float(aux[i] & 0xffff0000u));
+            a[i] = make_float2(fminf(fabsf(u[i].x), kGeluAMax), fminf(fabsf(u[i].y), kGeluAMax));
+        }
+        gelu_core8<true>(a, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 hm = __ffma2_rn(m[i], splat2(-1.0f), splat2(0.5f));  // 1/2 - m
+            const float2 gp = __fadd2_rn(make_float2(copysignf(hm.x, u[i].x), copysignf(hm.y, u[i].y)), splat2(0.5f));
+            o0[i] = pack_bf16x2(__fmul2_rn(v[i], gp));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o0[i] = pack_bf16x2(v[i]);
+    }
+#ifdef MOE_DBG_NO_GELU
+    if constexpr (EPI == EPI_BIAS_GELU_DUAL) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o1[i] = pack_bf16x2(v[i]);
+    }
+    return;
+#endif
+    if constexpr (EPI == EPI_BIAS_GELU_DUAL) {
+        float2 a[8], nq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = make_float2(fminf(fabsf(v[i].x), kGeluAMax), fminf(fabsf(v[i].y), kGeluAMax));
+        gelu_core8<false>(a, nq);  // -Q(a)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)  // relu(v) - a Q(a)
+            o1[i] = pack_bf16x2(__ffma2_rn(a[i], nq[i], make_float2(fmaxf(v[i].x, 0.0f), fmaxf(v[i].y, 0.0f))));
+    }
 }
 
 struct TileCoord {
@@ -170,6 +229,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    [[maybe_unused]] float* bias_s = reinterpret_cast<float*>(staging + Cfg::NBUF * kStagingBytes + 256);  // [8 warps][128]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -269,30 +329,41 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
     } else {
         // ================================ epilogue (2 groups x 4 warps) ============================
+        // Every warp is independent: it owns 32 accumulator rows (its TMEM lane quarter), stages them in
+        // its own 32-row slab of the group's staging buffer and issues its own TMA stores, so there is
+        // no CTA-level barrier anywhere in the epilogue.
         const int q = warp & 3;                  // TMEM lane quarter this warp may touch
         const int grp = (warp - 2) >> 2;         // column-chunk parity this group owns
         const int r = q * 32 + lane;             // row inside this CTA's 128-row half
-        const bool issuer = (warp - 2 == grp * 4) && lane == 0;  // first thread of the group issues its TMA stores
         uint8_t* const gstage = staging + grp * Cfg::NOUT * kStagingBytes;
+        uint8_t* const slab = gstage + q * 4096;           // this warp's 32 rows x 128 B
         uint8_t* const my_row = gstage + r * 128;
         const int sw = r & 7;
-        const uint32_t bar_id = 1 + grp;
+        float* const wbias = bias_s + (warp - 2) * 128;     // this warp's copy of the bias values of its chunks
         int as = 0;
         uint32_t aph = 0;
         for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
             const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
             const bool live = c.kb != 0;
-            const float* bias = (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS) && p.bias != nullptr
-                                    ? p.bias + static_cast<size_t>(c.e) * p.N + c.n0
-                                    : nullptr;
-            [[maybe_unused]] uint4 aux_cur[8];
+            if constexpr (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS) {
+                // lane l fetches 4 consecutive bias values of the group's (at most two) chunks
+                const int lc = grp + 2 * (lane >> 4);       // chunk the lane's values belong to
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lc < Cfg::NCHUNK)
+                    bv = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(c.e) * p.N + c.n0 + lc * 64) + (lane & 15));
+                __syncwarp();                                // previous tile's reads of wbias are done
+                *reinterpret_cast<float4*>(wbias + lane * 4) = bv;
+                __syncwarp();
+            }
+            // DGELU: this row's pre-activations, 64 columns ahead of their use (rotating register window)
+            [[maybe_unused]] uint4 aux[8];
             [[maybe_unused]] const __nv_bfloat16* aux_row = nullptr;
             if constexpr (EPI == EPI_DGELU) {
                 aux_row = p.aux + static_cast<size_t>(c.m0 + r) * p.N + c.n0;
                 if (grp < Cfg::NCHUNK) {
                     const uint4* ap = reinterpret_cast<const uint4*>(aux_row + grp * 64);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) aux_cur[i] = __ldg(ap + i);
+                    for (int i = 0; i < 8; ++i) aux[i] = __ldg(ap + i);
                 }
             }
             if (live) {
@@ -300,12 +371,9 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tc_fence_after();
             }
             const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
-#pragma unroll
-            for (int ch = 0; ch < Cfg::NCHUNK; ++ch) {
-                if ((ch & 1) != grp) continue;
-                constexpr int last_of_group0 = (Cfg::NCHUNK - 1) & ~1;
+#pragma unroll 1
+            for (int ch = grp; ch < Cfg::NCHUNK; ch += 2) {
                 const bool last_chunk = (ch + 2 >= Cfg::NCHUNK);
-                (void)last_of_group0;
                 if constexpr (EPI == EPI_F32) {
                     uint32_t acc[32];
                     if (live) {
@@ -320,65 +388,63 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 32; ++i) acc[i] = 0u;
                     }
-                    if (issuer) tma_store_wait_read<0>();
-                    named_bar_sync(bar_id, 128);
+                    if (lane == 0) tma_store_wait_read<0>();   // this warp's previous store has left its slab
+                    __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) =
                             make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
                     fence_proxy_async_smem();
-                    named_bar_sync(bar_id, 128);
-                    if (issuer && c.m0 < p.M && c.n0 + ch * 32 < p.N) {
-                        tma_store_3d(&tmO0, gstage, c.n0 + ch * 32, c.m0, c.e);
+                    __syncwarp();
+                    if (lane == 0 && c.m0 + q * 32 < p.M && c.n0 + ch * 32 < p.N) {
+                        tma_store_3d(&tmO0, slab, c.n0 + ch * 32, c.m0 + q * 32, c.e);
                         tma_store_commit();
                     }
                 } else {
-                    [[maybe_unused]] uint4 aux_nxt[8];
-                    if constexpr (EPI == EPI_DGELU) {
-                        if (ch + 2 < Cfg::NCHUNK) {
-                            const uint4* ap = reinterpret_cast<const uint4*>(aux_row + (ch + 2) * 64);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) aux_nxt[i] = __ldg(ap + i);
-                        }
+#ifdef MOE_DBG_NO_EPI
+                    if (last_chunk) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(tempty_bar + as, 0);
                     }
+                    continue;
+#endif
+                    const uint32_t cbias = smem_u32(wbias) + ((ch - grp) >> 1) * 256;
+                    uint32_t acc[2][16];
+                    tmem_ld16(tmem_row + ch * 64, acc[0]);
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t acc[32];
-                        tmem_ld32(tmem_row + ch * 64 + half * 32, acc);
+                    for (int blk = 0; blk < 4; ++blk) {   // 16 accumulator columns at a time
                         tmem_ld_wait();
-                        if (last_chunk && half == 1) {
+                        if (blk < 3) {
+                            tmem_ld16(tmem_row + ch * 64 + (blk + 1) * 16, acc[(blk + 1) & 1]);
+                        } else if (last_chunk) {
                             // every TMEM read of this accumulator stage by this warp is done -> hand it back
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive_cluster(tempty_bar + as, 0);
                         }
-                        uint32_t o0[16];                       // 32 columns of output 0, packed bf16x2
-                        [[maybe_unused]] uint32_t o1[16];      // 32 columns of output 1 (fc1: gelu)
+                        // keep the block just loaded in its own registers: its consumers may not move above
+                        // the next tcgen05.ld (which would make ptxas reuse one register set and serialise)
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float2 v = make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-                            if constexpr (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS) {
-                                if (bias != nullptr) {
-                                    const float2 b = __ldg(reinterpret_cast<const float2*>(bias + ch * 64 + half * 32) + i);
-                                    v = __fadd2_rn(v, b);
-                                }
+                        for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(acc[blk & 1][i]));
+                        uint32_t o0[8];                       // 16 columns of output 0, packed bf16x2
+                        [[maybe_unused]] uint32_t o1[8];      // 16 columns of output 1 (fc1: gelu)
+                        epilogue_block16<EPI>(acc[blk & 1], cbias + blk * 64,
+                                              reinterpret_cast<const uint32_t*>(aux) + blk * 8, o0, o1);
+                        if constexpr (EPI == EPI_DGELU) {
+                            if (ch + 2 < Cfg::NCHUNK) {   // refill the consumed window slots for this group's next chunk
+                                const uint4* ap = reinterpret_cast<const uint4*>(aux_row + (ch + 2) * 64 + blk * 16);
+                                aux[2 * blk] = __ldg(ap);
+                                aux[2 * blk + 1] = __ldg(ap + 1);
                             }
-                            if constexpr (EPI == EPI_DGELU) {
-                                const uint32_t uw = reinterpret_cast<const uint32_t*>(aux_cur)[half * 16 + i];
-                                const float2 u = make_float2(__uint_as_float(uw << 16), __uint_as_float(uw & 0xffff0000u));
-                                v = __fmul2_rn(v, gelu_erf_grad2(u));
-                            }
-                            o0[i] = pack_bf16x2(v);
-                            if constexpr (EPI == EPI_BIAS_GELU_DUAL) o1[i] = pack_bf16x2(gelu_erf2(v));
                         }
-                        if (half == 0) {
-                            // the group's previous TMA store must have finished reading the staging buffer
-                            if (issuer) tma_store_wait_read<0>();
-                            named_bar_sync(bar_id, 128);
+                        if (blk == 0) {
+                            if (lane == 0) tma_store_wait_read<0>();   // this warp's previous store has left its slab
+                            __syncwarp();
                         }
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int slot = ((half * 4 + j) ^ sw) << 4;
+                        for (int j = 0; j < 2; ++j) {
+                            const int slot = ((blk * 2 + j) ^ sw) << 4;
                             *reinterpret_cast<uint4*>(my_row + slot) = make_uint4(o0[4 * j], o0[4 * j + 1], o0[4 * j + 2], o0[4 * j + 3]);
                             if constexpr (EPI == EPI_BIAS_GELU_DUAL)
                                 *reinterpret_cast<uint4*>(my_row + kStagingBytes + slot) =
@@ -386,18 +452,14 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                     }
                     fence_proxy_async_smem();
-                    named_bar_sync(bar_id, 128);
-                    if (issuer) {
-                        tma_store_2d(&tmO0, gstage, c.n0 + ch * 64, c.m0);
-                        if constexpr (Cfg::NOUT == 2) tma_store_2d(&tmO1, gstage + kStagingBytes, c.n0 + ch * 64, c.m0);
+                    __syncwarp();
+#ifndef MOE_DBG_NO_STORE
+                    if (lane == 0) {
+                        tma_store_2d(&tmO0, slab, c.n0 + ch * 64, c.m0 + q * 32);
+                        if constexpr (Cfg::NOUT == 2) tma_store_2d(&tmO1, slab + kStagingBytes, c.n0 + ch * 64, c.m0 + q * 32);
                         tma_store_commit();
                     }
-                    if constexpr (EPI == EPI_DGELU) {
-                        if (ch + 2 < Cfg::NCHUNK) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) aux_cur[i] = aux_nxt[i];
-                        }
-                    }
+#endif
                 }
             }
             if (live) {
@@ -409,7 +471,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
         }
-        if (issuer) tma_store_wait_all<0>();
+        if (lane == 0) tma_store_wait_all<0>();
     }
 
     // teardown: neither CTA may exit (or free TMEM) while its peer can still signal or read it

@@ -100,6 +100,8 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
     if (!wgrad && (K % 64 != 0 || K <= 0)) { set_error("grouped gemm: K=%d must be a positive multiple of 64", K); return 1; }
     if (wgrad && (M % 64 != 0 || M <= 0)) { set_error("grouped gemm: M=%d must be a positive multiple of 64", M); return 1; }
     if (rows_cap % MOE_ROW_ALIGN != 0) { set_error("grouped gemm: rows_cap=%lld must be a multiple of %d", (long long)rows_cap, MOE_ROW_ALIGN); return 1; }
+    if ((op == MOE_GEMM_FC1 || op == MOE_GEMM_FC2) && bias == nullptr) { set_error("grouped gemm: fc1 / fc2 need a bias vector"); return 1; }
+    if (op == MOE_GEMM_DGELU && aux == nullptr) { set_error("grouped gemm: dgelu needs the pre-activation (aux)"); return 1; }
     const int bn = wgrad ? pick_bn_wgrad(N) : pick_bn_rows(N);
 
     GemmParams p{};
@@ -118,13 +120,13 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
         // A [rows, K] and B [E*N, K] K-major; each CTA of a pair loads 128 A rows and bn/2 B rows per k-block
         ok = ok && encode_2d(&tA, BF, 2, A, K, R, 64, 128);
         ok = ok && encode_2d(&tB, BF, 2, B, K, static_cast<uint64_t>(E) * N, 64, bn / 2);
-        ok = ok && encode_2d(&tO0, BF, 2, out0, N, R, 64, 128);
-        ok = ok && encode_2d(&tO1, BF, 2, op == MOE_GEMM_FC1 ? out1 : out0, N, R, 64, 128);
+        ok = ok && encode_2d(&tO0, BF, 2, out0, N, R, 64, 32);   // each epilogue warp stores its own 32-row slab
+        ok = ok && encode_2d(&tO1, BF, 2, op == MOE_GEMM_FC1 ? out1 : out0, N, R, 64, 32);
     } else {
         // A [rows, M], B [rows, N] read MN-major in 64 x 64 boxes; out [E, M, N] fp32 in 32-column chunks
         ok = ok && encode_2d(&tA, BF, 2, A, M, R, 64, 64);
         ok = ok && encode_2d(&tB, BF, 2, B, N, R, 64, 64);
-        ok = ok && encode_3d_f32(&tO0, out0, N, M, E, 32, 128);
+        ok = ok && encode_3d_f32(&tO0, out0, N, M, E, 32, 32);
         tO1 = tO0;
     }
     if (!ok) return 1;

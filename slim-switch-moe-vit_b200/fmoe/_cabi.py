@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmoe_b200.so")
+LIB_PATH = os.environ.get("MOE_B200_LIB") or os.path.join(_HERE, "libmoe_b200.so")   # env override: kernel experiments only
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 SCORE_TOPK_SOFTMAX, SCORE_FULL_SOFTMAX = 0, 1
