@@ -77,48 +77,59 @@ struct GemmCfg {
 
 // ------------------------------------------------------------------------------------------------
 // exact-erf GELU and its derivative for the epilogues (coefficients: tools/fit_gelu.py)
-//   gelu(u)  = relu(u) - |u| Q(|u|),       Q(a) = Phi(-a) = g(a) W(a),  g(a) = exp(-a^2/2)
-//   gelu'(u) = 1/2 + copysign(1/2 - m(|u|), u),   m(a) = Phi(-a) - a phi(a) = g(a) w(a)
-// W, w: degree-10 polynomials on [0, 6.5] (|u| is clamped; beyond it both corrections are < 1e-9).
-// Max abs error vs float64 erfc: 1.2e-7 (gelu), 1.3e-7 (gelu') — the level of CUDA's erff — with one
-// MUFU (ex2) per element and packed fp32 FMAs (FFMA2) for the Horner chains: the epilogue of a
-// K = 384 tile has ~12 issue slots per element, erff + expf needs ~3x that.
+//   gelu(u)  = relu(u) - |u| Q(|u|),              Q(a) = Phi(-a) = exp2(P6(a))
+//   gelu'(u) = u < 0 ? m(|u|) : 1 - m(|u|),       m(a) = Phi(-a) - a phi(a) = exp(-a^2/2) w8(a)
+// P6 / w8: polynomials on [0, 6.5] (|u| is clamped; beyond it both corrections are < 1e-9).
+// Max abs error vs float64 erfc: 1.0e-7 (gelu — the level of CUDA's erff), 1.2e-6 (gelu', a factor that is
+// rounded to bf16 right after).  One MUFU (ex2) per element, Horner chains on packed fp32 FMAs (FFMA2).
+// Why not erff/expf: the fp32 pipe retires 128 lane-FMAs per clock per SM, a 128 x 256 tile at K = 384
+// leaves ~20 of them per element; erff + expf + the rest needs about twice that (measured round 1b).
 // ------------------------------------------------------------------------------------------------
 constexpr float kGeluAMax = 6.5f;
 constexpr float kNegHalfLog2e = -0.72134752044448170f;
-__device__ constexpr float kGeluNegW[11] = {  // -W(a)
-    -4.999984264e-01f, 3.988943415e-01f, -2.496126727e-01f, 1.315388586e-01f, -5.946753551e-02f, 2.258705447e-02f,
-    -6.850097529e-03f, 1.548216262e-03f, -2.391936664e-04f, 2.217437910e-05f, -9.204634787e-07f};
-__device__ constexpr float kGeluGradW[11] = {  // w(a)
-    4.999999215e-01f, -7.978779301e-01f, 2.499070795e-01f, -1.324720956e-01f, 6.106562675e-02f, -2.420641669e-02f,
-    7.862224466e-03f, -1.941088571e-03f, 3.311199745e-04f, -3.400798613e-05f, 1.562210311e-06f};
+__device__ constexpr float kGeluLogQ[7] = {  // P6(a) = log2 Phi(-a)
+    -9.999921094e-01f, -1.151212416e+00f, -4.587352391e-01f, -5.346286518e-02f, 8.115032863e-03f, -7.800564408e-04f,
+    3.437071280e-05f};
+__device__ constexpr float kGeluGradW[9] = {  // w8(a)
+    4.999988248e-01f, -7.978099009e-01f, 2.492143745e-01f, -1.297814929e-01f, 5.588059320e-02f, -1.862516973e-02f,
+    4.319766638e-03f, -5.991640005e-04f, 3.660521692e-05f};
 
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float2 v) {
     __nv_bfloat162 b = __float22bfloat162_rn(v);
     return *reinterpret_cast<uint32_t*>(&b);
 }
 
-// g(a) * poly(a) for 8 element pairs at once.  The eight Horner chains are written step-major so
-// that consecutive FFMA2s are independent (a dependent FFMA2 chain is latency-bound: measured
-// round 1b, 0.25 IPC per scheduler with the pair-at-a-time form).
-template <bool GRAD>
-__device__ __forceinline__ void gelu_core8(const float2 (&a)[8], float2 (&out)[8]) {
+// Q(a) = Phi(-a) for 8 element pairs.  The eight Horner chains are written step-major so that
+// consecutive FFMA2s are independent.
+__device__ __forceinline__ void gelu_q8(const float2 (&a)[8], float2 (&q)[8]) {
+    float2 p[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = __ffma2_rn(splat2(kGeluLogQ[6]), a[i], splat2(kGeluLogQ[5]));
+#pragma unroll
+    for (int k = 4; k >= 0; --k) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] = __ffma2_rn(p[i], a[i], splat2(kGeluLogQ[k]));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = make_float2(ex2_approx(p[i].x), ex2_approx(p[i].y));
+}
+// m(a) = Phi(-a) - a phi(a) for 8 element pairs
+__device__ __forceinline__ void gelu_m8(const float2 (&a)[8], float2 (&m)[8]) {
     float2 g[8], p[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] = __fmul2_rn(__fmul2_rn(a[i], splat2(kNegHalfLog2e)), a[i]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] = make_float2(ex2_approx(g[i].x), ex2_approx(g[i].y));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) p[i] = splat2(GRAD ? kGeluGradW[10] : kGeluNegW[10]);
+    for (int i = 0; i < 8; ++i) p[i] = __ffma2_rn(splat2(kGeluGradW[8]), a[i], splat2(kGeluGradW[7]));
 #pragma unroll
-    for (int k = 9; k >= 0; --k) {
+    for (int k = 6; k >= 0; --k) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) p[i] = __ffma2_rn(p[i], a[i], splat2(GRAD ? kGeluGradW[k] : kGeluNegW[k]));
+        for (int i = 0; i < 8; ++i) p[i] = __ffma2_rn(p[i], a[i], splat2(kGeluGradW[k]));
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) out[i] = __fmul2_rn(g[i], p[i]);
+    for (int i = 0; i < 8; ++i) m[i] = __fmul2_rn(g[i], p[i]);
 }
 
 // One block of 16 accumulator columns (8 pairs) of one row through the epilogue.
@@ -150,11 +161,11 @@ __device__ __forceinline__ void epilogue_block16(const uint32_t* acc, uint32_t b
             u[i] = make_float2(__uint_as_float(aux[i] << 16), __uint_as_float(aux[i] & 0xffff0000u));
             a[i] = make_float2(fminf(fabsf(u[i].x), kGeluAMax), fminf(fabsf(u[i].y), kGeluAMax));
         }
-        gelu_core8<true>(a, m);
+        gelu_m8(a, m);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float2 hm = __ffma2_rn(m[i], splat2(-1.0f), splat2(0.5f));  // 1/2 - m
-            const float2 gp = __fadd2_rn(make_float2(copysignf(hm.x, u[i].x), copysignf(hm.y, u[i].y)), splat2(0.5f));
+            const float2 om = __ffma2_rn(m[i], splat2(-1.0f), splat2(1.0f));  // 1 - m
+            const float2 gp = make_float2(u[i].x < 0.0f ? m[i].x : om.x, u[i].y < 0.0f ? m[i].y : om.y);
             o0[i] = pack_bf16x2(__fmul2_rn(v[i], gp));
         }
     } else {
@@ -169,13 +180,13 @@ __device__ __forceinline__ void epilogue_block16(const uint32_t* acc, uint32_t b
     return;
 #endif
     if constexpr (EPI == EPI_BIAS_GELU_DUAL) {
-        float2 a[8], nq[8];
+        float2 a[8], qq[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) a[i] = make_float2(fminf(fabsf(v[i].x), kGeluAMax), fminf(fabsf(v[i].y), kGeluAMax));
-        gelu_core8<false>(a, nq);  // -Q(a)
+        gelu_q8(a, qq);
 #pragma unroll
         for (int i = 0; i < 8; ++i)  // relu(v) - a Q(a)
-            o1[i] = pack_bf16x2(__ffma2_rn(a[i], nq[i], make_float2(fmaxf(v[i].x, 0.0f), fmaxf(v[i].y, 0.0f))));
+            o1[i] = pack_bf16x2(__ffma2_rn(make_float2(-a[i].x, -a[i].y), qq[i], make_float2(fmaxf(v[i].x, 0.0f), fmaxf(v[i].y, 0.0f))));
     }
 }
 

@@ -1,8 +1,9 @@
 """Fits the polynomials used by the GEMM epilogues for exact-erf GELU and its derivative.
 
-  gelu(u)  = relu(u) - |u| * Q(|u|),          Q(a) = Phi(-a) = 0.5 erfc(a / sqrt 2) = g(a) * W(a)
-  gelu'(u) = u < 0 ? m(|u|) : 1 - m(|u|),      m(a) = Phi(-a) - a phi(a)         = g(a) * w(a)
-  g(a) = exp(-a^2 / 2)  (one ex2.approx),  W and w polynomials in a on [0, A_MAX] (a is clamped).
+  gelu(u)  = relu(u) - |u| * Q(|u|),          Q(a) = Phi(-a) = 0.5 erfc(a / sqrt 2) = exp2(P(a))   [shipped: deg 6]
+                                                                                   = g(a) * W(a)   [alternative]
+  gelu'(u) = u < 0 ? m(|u|) : 1 - m(|u|),      m(a) = Phi(-a) - a phi(a)         = g(a) * w(a)   [shipped: deg 8]
+  g(a) = exp(-a^2 / 2)  (one ex2.approx),  P, W and w polynomials in a on [0, A_MAX] (a is clamped).
 
 Weighted least squares on Chebyshev nodes (weight = the factor that multiplies the polynomial in the
 final result), then the fp32 Horner evaluation is checked against float64 erfc on a dense grid.
@@ -56,5 +57,23 @@ def main():
             print("  w:", ", ".join(f"{c:.9e}f" for c in cw))
 
 
+def main_shipped():
+    from scipy.special import log_ndtr
+    a = np.linspace(0, A_MAX, 2_000_001)
+    Q = lambda t: 0.5 * erfc(t / np.sqrt(2.0))
+    P = lambda t: log_ndtr(-t) / np.log(2.0)
+    g = lambda t: np.exp(-0.5 * t * t)
+    w = lambda t: 0.5 * erfcx(t / np.sqrt(2.0)) - t / np.sqrt(2 * np.pi)
+    cP = fit(P, lambda t: np.maximum(t, 0.02) * Q(t), 6)
+    q = np.exp2(horner32(cP, a).astype(np.float64))
+    print(f"P6 : max |gelu err| = {np.abs(a * (q - Q(a))).max():.3e}")
+    print("  kGeluLogQ:", ", ".join(f"{c:.9e}f" for c in cP))
+    cw = fit(w, lambda t: g(t), 8)
+    g32 = np.exp2((-(a.astype(np.float32) ** 2) * np.float32(0.5 * np.log2(np.e))).astype(np.float32)).astype(np.float64)
+    m = g32 * horner32(cw, a)
+    print(f"w8 : max |gelu' err| = {np.abs(m - (Q(a) - a * g(a) / np.sqrt(2 * np.pi))).max():.3e}")
+    print("  kGeluGradW:", ", ".join(f"{c:.9e}f" for c in cw))
+
+
 if __name__ == "__main__":
-    main()
+    main_shipped()

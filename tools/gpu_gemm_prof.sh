@@ -1,8 +1,7 @@
 #!/bin/bash
-# one ncu --set full capture of fc1 / fc2 / dgelu at the config-2 shape (with source-level sampling)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-CMD="python tools/gemm_bench.py --d 384 --E 16 --rows 3152 --iters 1 --no-cublas --ops fc1,fc2,dgelu"
+CMD="python tools/gemm_bench.py --d 384 --E 16 --rows 3152 --iters 1 --no-cublas --ops fc1,dgelu"
 $CMD > gpurun_out/plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:grouped_gemm -c 12 -o gpurun_out/prof_gemm3 -f $CMD > gpurun_out/ncu_full.log 2>&1
-echo "ncu rc=$?"; tail -3 gpurun_out/ncu_full.log
+ncu --set full --clock-control none --import-source on -k regex:grouped_gemm -c 8 -o gpurun_out/prof_gemm4 -f $CMD > gpurun_out/ncu_full.log 2>&1
+echo "ncu rc=$?"; tail -2 gpurun_out/ncu_full.log
