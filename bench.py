@@ -201,7 +201,10 @@ PHASE_BYTES = {
     "moe_dispatch_fwd": lambda T, d, h, E, k, R: T * d * 2 + R * d * 2 + T * k * 4,
     "moe_combine_fwd": lambda T, d, h, E, k, R: R * d * 2 + R * 4 + T * d * 2,
     "moe_combine_bwd": lambda T, d, h, E, k, R: T * d * 2 + 2 * R * d * 2 + 2 * R * 4,
-    "moe_dispatch_bwd": lambda T, d, h, E, k, R: R * d * 2 + T * d * 2 + T * E * 4,
+    "moe_gate_dispatch_bwd": lambda T, d, h, E, k, R: R * d * 2 + T * d * 2 + 2 * T * E * 4 + T * k * 12,
+    "colsum_db1": lambda T, d, h, E, k, R: R * h * 2,
+    "colsum_db2": lambda T, d, h, E, k, R: R * d * 2,
+    "moe_gate_wgrad": lambda T, d, h, E, k, R: T * d * 2 + T * E * 4,
 }
 GEMM_FLOPS = {
     "gemm_fc1": lambda R, d, h: 2 * R * d * h, "gemm_fc2": lambda R, d, h: 2 * R * d * h,

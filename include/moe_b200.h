@@ -37,7 +37,11 @@ extern "C" {
 #define MOE_SCORE_TOPK_SOFTMAX 0 /* NaiveGate / GShardGate: softmax over the k selected logits      */
 #define MOE_SCORE_FULL_SOFTMAX 1 /* SwitchGate: softmax over all experts, score = prob of selection */
 
-#define MOE_TOKEN_TILE 256 /* tokens per routing tile; ntiles = ceil(T / 256) */
+#define MOE_AUX_NONE 0   /* no load-balancing loss (NaiveGate)                                       */
+#define MOE_AUX_SWITCH 1 /* E * sum_e f_e P_e, f_e = share of KEPT pairs, P_e = mean softmax prob      */
+#define MOE_AUX_GSHARD 2 /* mean_e(c_e m_e) * E^2, c_e = share of routed pairs, m_e = mean softmax prob */
+
+#define MOE_TOKEN_TILE 64 /* tokens per routing tile; ntiles = ceil(T / 64) */
 #define MOE_ROW_ALIGN 256  /* segment alignment of the packed buffers = rows of one CTA-pair MMA tile */
 
 /* grouped GEMM ops (moe_grouped_gemm) */
@@ -55,19 +59,24 @@ int64_t moe_rows_cap(int64_t T, int k, int E, int64_t capacity);
 
 /* ---- gate: replaces NaiveGate's nn.Linear + torch.topk + F.softmax and fmoe_cuda.expert_count.
  * logits[T,E] fp32 (LOGIT ORDER v1, bit-identical to oracle/gate_ref.c), idx[T,k] i32,
- * score[T,k] fp32, tile_hist[ntiles,E] i32, tile_psum[ntiles,E] fp32 (only if want_psum). */
+ * score[T,k] fp32, tile_hist[E,ntiles] i32, tile_psum[E,ntiles] fp32 (only if want_psum);
+ * ntiles = ceil(T / MOE_TOKEN_TILE). */
 int moe_gate_fwd(const void *x, int x_dtype, const float *Wg, const float *bg /* nullable */,
                  const float *noise /* nullable [T,E], added to the logits (SwitchGate jitter) */, int64_t T, int d, int E,
                  int k, int score_mode, int want_psum, float *logits, int32_t *idx, float *score, int32_t *tile_hist,
                  float *tile_psum, void *stream);
 
 /* ---- scan: replaces torch.cumsum + .item() + limit_by_capacity (no host sync).
- * tile_base[ntiles,E], count[E], kept[E] = min(count, capacity), seg_start[E+1],
+ * tile_base[E,ntiles], count[E], kept[E] = min(count, capacity), seg_start[E+1],
  * tile_expert[max_mtiles] (expert of each 256-row tile, -1 past the end), num_mtiles[1],
- * psum[E] = sum over tiles of tile_psum (nullable together with tile_psum). */
+ * psum[E] = sum over tiles of tile_psum (nullable together with tile_psum).  With aux_mode != 0 the
+ * load-balancing loss of the gate and its gradient w.r.t. psum are produced here too, so that no
+ * framework-level reduction kernels run per layer. */
 int moe_route_scan(const int32_t *tile_hist, const float *tile_psum, int ntiles, int E, int64_t capacity,
                    int32_t *tile_base, int32_t *count, int32_t *kept, int32_t *seg_start, int32_t *tile_expert,
-                   int32_t *num_mtiles, int max_mtiles, float *psum, void *stream);
+                   int32_t *num_mtiles, int max_mtiles, float *psum,
+                   int aux_mode /* MOE_AUX_* */, int64_t T, int k, float *aux_loss /* [1] */,
+                   float *aux_coef /* [E] = d aux_loss / d psum */, void *stream);
 
 /* ---- dispatch: replaces fmoe_cuda.assign_pos + MOEScatter (deterministic, token order).
  * pos[T,k] row of each (token,slot) or -1 if dropped; row_src[rows_cap] flattened pair index of
@@ -100,7 +109,8 @@ int moe_combine_bwd(const void *dy, int dy_dtype, const void *ybuf, const int32_
 int moe_expert_ffn_bwd(const void *dybuf, const void *xbuf, const void *U, const void *H, const void *W1tb,
                        const void *W2tb, const int32_t *tile_expert, const int32_t *num_mtiles,
                        const int32_t *seg_start, int64_t rows_cap, int d, int h, int E, void *dU, void *dxbuf,
-                       float *dW1, float *db1, float *dW2, float *db2, void *stream);
+                       float *dW1, float *db1, float *dW2, float *db2,
+                       void *colsum_ws /* moe_segment_colsum_workspace_bytes(rows_cap, h) bytes */, void *stream);
 
 /* ---- gate backward: dlogits[T,E] from dscore[T,k] and (nullable) dpsum[E]. */
 int moe_gate_bwd(const float *logits, const int32_t *idx, const float *score, const float *dscore, const float *dpsum,
@@ -112,6 +122,13 @@ int moe_gate_bwd(const float *logits, const int32_t *idx, const float *score, co
 int moe_dispatch_bwd(const void *dxbuf, const int32_t *pos, const float *dlogits, const int32_t *idx, const float *Wg,
                      int64_t T, int d, int E, int k, int dense_dlogits, void *dx, int dx_dtype, void *stream);
 
+/* ---- gate backward + dispatch backward in one pass (what the layer's autograd node calls):
+ * dlogits[T,E] (output, consumed by moe_gate_wgrad) from dscore[T,k] and the nullable dpsum[E];
+ * dx[t] = sum_j dxbuf[pos[t,j]] + dlogits[t] Wg.  dxbuf may be NULL. */
+int moe_gate_dispatch_bwd(const void *dxbuf, const int32_t *pos, const float *logits, const int32_t *idx, const float *score,
+                          const float *dscore, const float *dpsum, const float *Wg, int64_t T, int d, int E, int k,
+                          int score_mode, float *dlogits, void *dx, int dx_dtype, void *stream);
+
 /* ---- gate weight gradient: dWg[E,d] = dlogits^T x, dbg[E] (nullable) = colsum(dlogits).
  * workspace: moe_gate_wgrad_workspace_bytes(T, d, E) bytes. */
 size_t moe_gate_wgrad_workspace_bytes(int64_t T, int d, int E);
@@ -122,7 +139,11 @@ int moe_gate_wgrad(const float *dlogits, const void *x, int x_dtype, int64_t T, 
 int moe_cast_bf16(const float *src, void *dst, int64_t n /* % 8 == 0 */, void *stream);
 /* src[E,R,C] fp32 -> dst[E,R,C] bf16 (nullable) and dst_t[E,C,R] bf16 (transposed per expert); R, C % 32 == 0 */
 int moe_cast_bf16_transposed(const float *src, void *dst, void *dst_t, int E, int R, int C, void *stream);
-int moe_segment_colsum(const void *buf, const int32_t *seg_start, int E, int cols, float *out, void *stream);
+/* out[E,cols] = per-segment column sums of the packed bf16 buffer buf[rows_cap,cols] (bias gradients;
+ * replaces fmoe_cuda's column_reduce).  Two deterministic stages through `workspace`. */
+size_t moe_segment_colsum_workspace_bytes(int64_t rows_cap, int cols);
+int moe_segment_colsum(const void *buf, const int32_t *seg_start, int64_t rows_cap, int E, int cols, void *workspace,
+                       float *out, void *stream);
 
 /* ---- the grouped tcgen05 GEMM itself (building block of the two FFN entry points; exported so
  * each contraction can be tested and timed on its own).  See MOE_GEMM_* for operand shapes. */

@@ -341,6 +341,24 @@ def bruteforce_forward(x, Wg, bg, W1, b1, W2, b2, k: int, score_mode: int, capac
     return y
 
 
+AUX_NONE, AUX_SWITCH, AUX_GSHARD = 0, 1, 2
+
+
+def aux_coef(r: Routing, T: int, aux_mode: int) -> torch.Tensor:
+    """d aux_loss / d psum [E] (fp64): aux_loss = sum_e coef_e * psum_e, coef_e = E / T * share_e with
+    share_e = kept_e / sum(kept) (Switch) or count_e / (T k) (GShard) — SURVEY.md §8a."""
+    E = r.count.shape[0]
+    k = r.idx.shape[1]
+    if aux_mode == AUX_SWITCH:
+        kept = r.kept.double()
+        share = kept / kept.sum().clamp(min=1)
+    elif aux_mode == AUX_GSHARD:
+        share = r.count.double() / float(T * k)
+    else:
+        return torch.zeros(E, dtype=torch.float64)
+    return share * E / T
+
+
 def switch_aux_loss(r: Routing, psum: torch.Tensor, T: int) -> torch.Tensor:
     """E * sum_e f_e * P_e with f_e = kept_e / sum(kept), P_e = psum_e / T."""
     E = psum.shape[0]

@@ -73,10 +73,19 @@ int moe_gate_fwd(const void* x, int x_dtype, const float* Wg, const float* bg, c
 
 int moe_route_scan(const int32_t* tile_hist, const float* tile_psum, int ntiles, int E, int64_t capacity,
                    int32_t* tile_base, int32_t* count, int32_t* kept, int32_t* seg_start, int32_t* tile_expert,
-                   int32_t* num_mtiles, int max_mtiles, float* psum, void* stream) {
+                   int32_t* num_mtiles, int max_mtiles, float* psum, int aux_mode, int64_t T, int k, float* aux_loss,
+                   float* aux_coef, void* stream) {
     if (ntiles <= 0 || E <= 0 || E > 1024 || capacity <= 0) { set_error("moe_route_scan: bad arguments ntiles=%d E=%d capacity=%lld", ntiles, E, (long long)capacity); return 1; }
+    if (aux_mode != MOE_AUX_NONE) {
+        if ((aux_mode != MOE_AUX_SWITCH && aux_mode != MOE_AUX_GSHARD) || tile_psum == nullptr || psum == nullptr ||
+            aux_loss == nullptr || aux_coef == nullptr || T <= 0 || k < 1) {
+            set_error("moe_route_scan: aux_mode %d needs tile_psum, psum, aux_loss, aux_coef, T > 0 and k >= 1", aux_mode);
+            return 1;
+        }
+    }
     return check(launch_route_scan(tile_hist, tile_psum, ntiles, E, capacity, tile_base, count, kept, seg_start,
-                                   tile_expert, num_mtiles, max_mtiles, psum, static_cast<cudaStream_t>(stream)),
+                                   tile_expert, num_mtiles, max_mtiles, psum, aux_mode, T, k, aux_loss, aux_coef,
+                                   static_cast<cudaStream_t>(stream)),
                  "moe_route_scan");
 }
 
@@ -139,9 +148,26 @@ int moe_cast_bf16_transposed(const float* src, void* dst, void* dst_t, int E, in
     return check(launch_cast_bf16_transposed(src, dst, dst_t, E, R, C, static_cast<cudaStream_t>(stream)), "moe_cast_bf16_transposed");
 }
 
-int moe_segment_colsum(const void* buf, const int32_t* seg_start, int E, int cols, float* out, void* stream) {
-    if (E <= 0 || cols <= 0 || cols % 2 != 0) { set_error("moe_segment_colsum: bad shape"); return 1; }
-    return check(launch_segment_colsum(buf, seg_start, E, cols, out, static_cast<cudaStream_t>(stream)), "moe_segment_colsum");
+size_t moe_segment_colsum_workspace_bytes(int64_t rows_cap, int cols) { return segment_colsum_workspace_bytes(rows_cap, cols); }
+
+int moe_segment_colsum(const void* buf, const int32_t* seg_start, int64_t rows_cap, int E, int cols, void* workspace, float* out,
+                       void* stream) {
+    if (E <= 0 || cols <= 0 || cols % 8 != 0 || rows_cap <= 0 || rows_cap % MOE_ROW_ALIGN != 0 || workspace == nullptr) {
+        set_error("moe_segment_colsum: bad arguments (E=%d cols=%d rows_cap=%lld; cols %% 8 == 0, rows_cap %% %d == 0, workspace required)",
+                  E, cols, (long long)rows_cap, MOE_ROW_ALIGN);
+        return 1;
+    }
+    return check(launch_segment_colsum(buf, seg_start, rows_cap, E, cols, workspace, out, static_cast<cudaStream_t>(stream)),
+                 "moe_segment_colsum");
+}
+
+int moe_gate_dispatch_bwd(const void* dxbuf, const int32_t* pos, const float* logits, const int32_t* idx, const float* score,
+                          const float* dscore, const float* dpsum, const float* Wg, int64_t T, int d, int E, int k, int score_mode,
+                          float* dlogits, void* dx, int dx_dtype, void* stream) {
+    if (!dims_ok("moe_gate_dispatch_bwd", T, d, E, k) || !dtype_ok("moe_gate_dispatch_bwd", dx_dtype)) return 1;
+    return check(launch_gate_dispatch_bwd(dxbuf, pos, logits, idx, score, dscore, dpsum, Wg, T, d, E, k, score_mode, dlogits, dx,
+                                          dx_dtype, static_cast<cudaStream_t>(stream)),
+                 "moe_gate_dispatch_bwd");
 }
 
 int moe_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out1, const float* bias, const void* aux,
@@ -165,7 +191,7 @@ int moe_expert_ffn_fwd(const void* xbuf, const void* W1b, const float* b1, const
 int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* U, const void* H, const void* W1tb,
                        const void* W2tb, const int32_t* tile_expert, const int32_t* num_mtiles,
                        const int32_t* seg_start, int64_t rows_cap, int d, int h, int E, void* dU, void* dxbuf,
-                       float* dW1, float* db1, float* dW2, float* db2, void* stream) {
+                       float* dW1, float* db1, float* dW2, float* db2, void* colsum_ws, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int sms = sm_count();
     int rc;
@@ -185,8 +211,9 @@ int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* U, const
     rc = launch_grouped_gemm(MOE_GEMM_DGRAD, dU, W1tb, dxbuf, nullptr, nullptr, nullptr, tile_expert, num_mtiles, nullptr,
                              rows_cap, E, 0, d, h, sms, st);
     if (rc) return rc;
-    if (check(launch_segment_colsum(dybuf, seg_start, E, d, db2, st), "db2 colsum")) return 1;
-    return check(launch_segment_colsum(dU, seg_start, E, h, db1, st), "db1 colsum");
+    if (colsum_ws == nullptr) { set_error("moe_expert_ffn_bwd: colsum workspace (moe_segment_colsum_workspace_bytes(rows_cap, h)) required"); return 1; }
+    if (check(launch_segment_colsum(dybuf, seg_start, rows_cap, E, d, colsum_ws, db2, st), "db2 colsum")) return 1;
+    return check(launch_segment_colsum(dU, seg_start, rows_cap, E, h, colsum_ws, db1, st), "db1 colsum");
 }
 
 }  // extern "C"

@@ -14,7 +14,8 @@ cudaError_t launch_gate_fwd(const void* x, int x_dtype, const float* Wg, const f
                             float* tile_psum, cudaStream_t st);
 cudaError_t launch_route_scan(const int* tile_hist, const float* tile_psum, int ntiles, int E, long long capacity,
                               int* tile_base, int* count, int* kept, int* seg_start, int* tile_expert, int* num_mtiles,
-                              int max_mtiles, float* psum, cudaStream_t st);
+                              int max_mtiles, float* psum, int aux_mode, long long tokens, int k, float* aux_loss,
+                              float* aux_coef, cudaStream_t st);
 cudaError_t launch_dispatch_fwd(const void* x, int x_dtype, const int* idx, const int* tile_base, const int* seg_start,
                                 const int* kept, int64_t T, int d, int E, int k, long long capacity, int* pos,
                                 int* row_src, void* xbuf, cudaStream_t st);
@@ -34,7 +35,12 @@ cudaError_t launch_gate_wgrad(const float* dlogits, const void* x, int x_dtype, 
                               float* dWg, float* dbg, cudaStream_t st);
 cudaError_t launch_cast_bf16(const float* src, void* dst, int64_t n, int sm_count, cudaStream_t st);
 cudaError_t launch_cast_bf16_transposed(const float* src, void* dst, void* dst_t, int E, int R, int C, cudaStream_t st);
-cudaError_t launch_segment_colsum(const void* buf, const int* seg_start, int E, int cols, float* out, cudaStream_t st);
+size_t segment_colsum_workspace_bytes(int64_t rows_cap, int cols);
+cudaError_t launch_segment_colsum(const void* buf, const int* seg_start, int64_t rows_cap, int E, int cols, void* workspace,
+                                  float* out, cudaStream_t st);
+cudaError_t launch_gate_dispatch_bwd(const void* dxbuf, const int* pos, const float* logits, const int* idx, const float* score,
+                                     const float* dscore, const float* dpsum, const float* Wg, int64_t T, int d, int E, int k,
+                                     int score_mode, float* dlogits, void* dx, int dx_dtype, cudaStream_t st);
 
 // gemm_launch.cu — returns 0 on success, otherwise sets the error string via set_error()
 int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out1, const float* bias, const void* aux,

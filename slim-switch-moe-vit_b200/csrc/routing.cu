@@ -19,7 +19,9 @@
 
 namespace moe {
 
-constexpr int kTokTile = 256;  // tokens per routing tile (one CTA)
+constexpr int kTokTile = MOE_TOKEN_TILE;  // tokens per routing tile (one CTA): small tiles = many CTAs in flight
+constexpr int kTokPerWarp = kTokTile / 8;
+static_assert(kTokTile == 64, "gate / dispatch kernels assume 8 warps x 8 tokens");
 constexpr int kMaxK = 8;
 
 // ------------------------------------------------------------------------------------------------
@@ -88,12 +90,12 @@ __global__ void __launch_bounds__(256)
 gate_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ Wg, const float* __restrict__ bg,
                 const float* __restrict__ noise, int64_t T, int d, int E, int k, int score_mode, int want_psum, float* __restrict__ logits, int* __restrict__ idx,
                 float* __restrict__ score, int* __restrict__ tile_hist, float* __restrict__ tile_psum) {
-    constexpr int NT = 64 / EG;  // tokens per warp pass: NT*EG = 64 accumulators per lane
+    constexpr int NT = 64 / EG;  // tokens per warp pass: NT*EG = 64 accumulators per lane (NT <= kTokPerWarp)
     extern __shared__ float smem_f[];
     float* wg_s = smem_f;                          // [EG][d]
-    float* lg_s = wg_s + EG * d;                   // [256][E+1]
-    float* m_s = lg_s + kTokTile * (E + 1);        // [256] row max
-    float* rz_s = m_s + kTokTile;                  // [256] 1/Z
+    float* lg_s = wg_s + EG * d;                   // [kTokTile][E+1]
+    float* m_s = lg_s + kTokTile * (E + 1);        // [kTokTile] row max
+    float* rz_s = m_s + kTokTile;                  // [kTokTile] 1/Z
     int* hist_s = reinterpret_cast<int*>(rz_s + kTokTile);  // [E]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -114,8 +116,8 @@ gate_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ Wg, const fl
         }
         __syncthreads();
 
-        for (int it = 0; it < 32 / NT; ++it) {
-            const int64_t tok0 = t_base + warp * 32 + it * NT;
+        for (int it = 0; it < kTokPerWarp / NT; ++it) {
+            const int64_t tok0 = t_base + warp * kTokPerWarp + it * NT;
             if (tok0 >= T) break;  // warp-uniform
             float acc[NT * EG];
 #pragma unroll
@@ -123,12 +125,9 @@ gate_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ Wg, const fl
             for (int c = 0; c < n_chunks; ++c) {
                 const int i0 = c * 128 + lane * 4;
                 if (i0 < d) {
-                    float4 xv[NT];
+                    float4 xv[NT];   // rows past T are clamped to the last row: their logits are never stored
 #pragma unroll
-                    for (int n = 0; n < NT; ++n) {
-                        xv[n] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (tok0 + n < T) xv[n] = load_x4(x + (tok0 + n) * d + i0);
-                    }
+                    for (int n = 0; n < NT; ++n) xv[n] = load_x4(x + min(tok0 + n, T - 1) * d + i0);
 #pragma unroll
                     for (int e = 0; e < EG; ++e) {
                         const float4 w = *reinterpret_cast<const float4*>(wg_s + e * d + i0);
@@ -167,7 +166,7 @@ gate_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ Wg, const fl
     // ---- per-token top-k (ties -> lowest index), scores, histogram
     {
         const int64_t tok = t_base + tid;
-        if (tok < T) {
+        if (tid < kTokTile && tok < T) {
             const float* lr = lg_s + tid * ldl;
             int picked[kMaxK];
             float pv[kMaxK];
@@ -203,7 +202,7 @@ gate_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ Wg, const fl
         }
     }
     __syncthreads();
-    for (int e = tid; e < E; e += 256) tile_hist[static_cast<size_t>(blockIdx.x) * E + e] = hist_s[e];
+    for (int e = tid; e < E; e += 256) tile_hist[static_cast<size_t>(e) * gridDim.x + blockIdx.x] = hist_s[e];
 
     if (want_psum) {
         const int n_tok = static_cast<int>(min(static_cast<int64_t>(kTokTile), T - t_base));
@@ -211,7 +210,7 @@ gate_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ Wg, const fl
             float part = 0.0f;
             for (int t = lane; t < n_tok; t += 32) part += expf(lg_s[t * ldl + e] - m_s[t]) / rz_s[t];
             part = warp_sum_xor(part);
-            if (lane == 0) tile_psum[static_cast<size_t>(blockIdx.x) * E + e] = part;
+            if (lane == 0) tile_psum[static_cast<size_t>(e) * gridDim.x + blockIdx.x] = part;
         }
     }
 }
@@ -223,32 +222,49 @@ __global__ void __launch_bounds__(1024)
 route_scan_kernel(const int* __restrict__ tile_hist, const float* __restrict__ tile_psum, int ntiles, int E,
                   long long capacity, int* __restrict__ tile_base, int* __restrict__ count, int* __restrict__ kept,
                   int* __restrict__ seg_start, int* __restrict__ tile_expert, int* __restrict__ num_mtiles,
-                  int max_mtiles, float* __restrict__ psum) {
+                  int max_mtiles, float* __restrict__ psum, int aux_mode, long long tokens, int k, float* __restrict__ aux_loss,
+                  float* __restrict__ aux_coef) {
     extern __shared__ int smem_i[];
     int* cnt_s = smem_i;          // [E]
     int* seg_s = smem_i + E;      // [E+1]
+    float* ps_s = reinterpret_cast<float*>(smem_i + 2 * E + 1);  // [E]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+    // tile_hist / tile_base / tile_psum are [E, ntiles]: warp e walks row e 1024 tiles at a time with coalesced,
+    // fully unrolled loads (tile = g0 + i*32 + lane), then one warp scan per i turns them into exclusive prefixes.
     for (int e = warp; e < E; e += 32) {
-        int running = 0;
-        for (int b0 = 0; b0 < ntiles; b0 += 32) {
-            const int b = b0 + lane;
-            const int v = b < ntiles ? tile_hist[static_cast<size_t>(b) * E + e] : 0;
-            int incl = v;
+        const int* hrow = tile_hist + static_cast<size_t>(e) * ntiles;
+        int* brow = tile_base + static_cast<size_t>(e) * ntiles;
+        int carried = 0;
+        for (int g0 = 0; g0 < ntiles; g0 += 1024) {
+            int v[32];
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, incl, off);
-                if (lane >= off) incl += o;
+            for (int i = 0; i < 32; ++i) {
+                const int b = g0 + i * 32 + lane;
+                v[i] = b < ntiles ? hrow[b] : 0;
             }
-            if (b < ntiles) tile_base[static_cast<size_t>(b) * E + e] = running + incl - v;
-            running += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                int incl = v[i];
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += o;
+                }
+                const int b = g0 + i * 32 + lane;
+                if (b < ntiles) brow[b] = carried + incl - v[i];
+                carried += __shfl_sync(0xffffffffu, incl, 31);
+            }
         }
-        if (lane == 0) cnt_s[e] = running;
+        if (lane == 0) cnt_s[e] = carried;
         if (tile_psum != nullptr && psum != nullptr) {
+            // fixed order: lane-strided partial sums, then the xor butterfly
+            const float* prow = tile_psum + static_cast<size_t>(e) * ntiles;
             float part = 0.0f;
-            for (int b = lane; b < ntiles; b += 32) part += tile_psum[static_cast<size_t>(b) * E + e];
+#pragma unroll 8
+            for (int b = lane; b < ntiles; b += 32) part += prow[b];
             part = warp_sum_xor(part);
-            if (lane == 0) psum[e] = part;
+            if (lane == 0) { psum[e] = part; ps_s[e] = part; }
         }
     }
     __syncthreads();
@@ -266,6 +282,25 @@ route_scan_kernel(const int* __restrict__ tile_hist, const float* __restrict__ t
         seg_s[E] = start;
         seg_start[E] = start;
         *num_mtiles = start / MOE_ROW_ALIGN;
+        // load-balancing loss = sum_e coef_e * psum_e with coef_e = E/T * (share of expert e); the coefficients are
+        // its gradient w.r.t. psum (the shares are integers, not differentiable).
+        //   MOE_AUX_SWITCH: share = kept_e / sum(kept)        (Switch: E * sum_e f_e P_e)
+        //   MOE_AUX_GSHARD: share = count_e / (tokens * k)    (GShard: mean(c_e m_e) * E^2)
+        if (aux_mode != 0 && aux_loss != nullptr) {
+            long long tot_kept = 0;
+            for (int e = 0; e < E; ++e) tot_kept += cnt_s[e] < capacity ? cnt_s[e] : capacity;
+            float loss = 0.0f;
+            for (int e = 0; e < E; ++e) {
+                const long long kp = cnt_s[e] < capacity ? cnt_s[e] : capacity;
+                const float share = aux_mode == MOE_AUX_SWITCH
+                                        ? static_cast<float>(kp) / static_cast<float>(tot_kept > 0 ? tot_kept : 1)
+                                        : static_cast<float>(cnt_s[e]) / static_cast<float>(tokens * k);
+                const float coef = share * static_cast<float>(E) / static_cast<float>(tokens);
+                aux_coef[e] = coef;
+                loss = fmaf(coef, ps_s[e], loss);
+            }
+            *aux_loss = loss;
+        }
     }
     __syncthreads();
     const int nm = seg_s[E] / MOE_ROW_ALIGN;
@@ -335,7 +370,7 @@ dispatch_fwd_kernel(const XT* __restrict__ x, const int* __restrict__ idx, const
     __syncthreads();
     // B: exclusive scan over chunks per expert, seeded with this tile's global base
     for (int e = tid; e < E; e += 256) {
-        int running = tile_base[static_cast<size_t>(blockIdx.x) * E + e];
+        int running = tile_base[static_cast<size_t>(e) * ntiles + blockIdx.x];
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int c = chunk_cnt[ch * E + e];
             chunk_cnt[ch * E + e] = running;
@@ -525,57 +560,303 @@ dispatch_bwd_kernel(const __nv_bfloat16* __restrict__ dxbuf, const int* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// K8: gate weight gradient   dWg = dlogits^T x, dbg = colsum(dlogits)   (two deterministic stages)
+// K7b: gate backward + dispatch backward in one pass (the layer's fused path)
+//   dlogits[t,:] from dscore (+ dpsum)  -> written out for the gate weight gradient
+//   dx[t] = sum_j dXbuf[pos[t,j]] + sum_e dlogits[t,e] * Wg[e]
+// One CTA per 64-token tile: 64 threads compute the tile's dlogits rows into shared memory, then
+// thread (cg, tg) owns 4 consecutive features for every TG-th token.  With dense dlogits and
+// E <= 16 the thread keeps its Wg[:, cg*4..+3] slice in registers for the whole tile.
 // ------------------------------------------------------------------------------------------------
-template <typename XT>
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+}
+
+template <typename OT>
 __global__ void __launch_bounds__(256)
-gate_wgrad_partial_kernel(const float* __restrict__ dlogits, const XT* __restrict__ x, int64_t T, int d, int E,
-                          float* __restrict__ part_w, float* __restrict__ part_b) {
+gate_dispatch_bwd_kernel(const __nv_bfloat16* __restrict__ dxbuf, const int* __restrict__ pos,
+                         const float* __restrict__ logits, const int* __restrict__ idx, const float* __restrict__ score,
+                         const float* __restrict__ dscore, const float* __restrict__ dpsum, const float* __restrict__ Wg,
+                         int64_t T, int d, int E, int k, int score_mode, float* __restrict__ dlogits, OT* __restrict__ dx) {
     extern __shared__ float smem_f[];
-    float* dl_s = smem_f;  // [256][E]
+    float* dl_s = smem_f;                                        // [kTokTile][E]
+    int* pos_s = reinterpret_cast<int*>(smem_f + kTokTile * E);  // [kTokTile][k]
     const int tid = threadIdx.x;
     const int64_t t_base = static_cast<int64_t>(blockIdx.x) * kTokTile;
     const int n_tok = static_cast<int>(min(static_cast<int64_t>(kTokTile), T - t_base));
-    for (int i = tid; i < n_tok * E; i += 256) dl_s[i] = dlogits[t_base * E + i];
-    __syncthreads();
-    float* pw = part_w + static_cast<size_t>(blockIdx.x) * E * d;
-    for (int e0 = 0; e0 < E; e0 += 16) {
-        for (int c = tid; c < d; c += 256) {
-            float acc[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
-            for (int t = 0; t < n_tok; ++t) {
-                const float xv = static_cast<float>(x[(t_base + t) * d + c]);
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (e0 + i < E) acc[i] = fmaf(dl_s[t * E + e0 + i], xv, acc[i]);
+    const bool dense = (score_mode == 1) || (dpsum != nullptr);
+    // rows of this tile's pairs, so that the gathers below do not wait on a dependent index load
+    for (int i = tid; i < n_tok * k; i += 256) pos_s[i] = pos[t_base * k + i];
+
+    {   // dlogits rows of the tile: 4 threads per token, experts strided over the 4 (same formulas as gate_bwd_kernel)
+        const int tl = tid >> 2, part = tid & 3;
+        const bool live = tl < n_tok;
+        const int64_t t = t_base + (live ? tl : 0);
+        const float* lr = logits + t * E;
+        int pk[kMaxK];
+        float sc[kMaxK], g[kMaxK];
+        for (int j = 0; j < k; ++j) { pk[j] = idx[t * k + j]; sc[j] = score[t * k + j]; g[j] = dscore[t * k + j]; }
+        float m = 0.0f, rz = 0.0f, pdot = 0.0f;
+        if (dense) {
+            m = lr[pk[0]];
+            float z = 0.0f;
+#pragma unroll 1
+            for (int e = part; e < E; e += 4) z += expf(lr[e] - m);
+            z += __shfl_xor_sync(0xffffffffu, z, 1);
+            z += __shfl_xor_sync(0xffffffffu, z, 2);
+            rz = 1.0f / z;
+            if (dpsum != nullptr) {
+#pragma unroll 1
+                for (int e = part; e < E; e += 4) pdot += expf(lr[e] - m) * rz * dpsum[e];
+                pdot += __shfl_xor_sync(0xffffffffu, pdot, 1);
+                pdot += __shfl_xor_sync(0xffffffffu, pdot, 2);
             }
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (e0 + i < E) pw[static_cast<size_t>(e0 + i) * d + c] = acc[i];
+        }
+        float inner = 0.0f;
+        for (int j = 0; j < k; ++j) inner += sc[j] * g[j];
+        if (live) {
+            float* dl = dl_s + tl * E;
+#pragma unroll 1
+            for (int e = part; e < E; e += 4) {
+                float v = 0.0f;
+                const float p = dense ? expf(lr[e] - m) * rz : 0.0f;
+                if (score_mode == 0) {
+                    for (int j = 0; j < k; ++j)
+                        if (pk[j] == e) v += sc[j] * (g[j] - inner);
+                } else {
+                    for (int j = 0; j < k; ++j)
+                        if (pk[j] == e) v += g[j] * sc[j];
+                    v -= inner * p;
+                }
+                if (dpsum != nullptr) v += p * (dpsum[e] - pdot);
+                dl[e] = v;
+            }
         }
     }
-    for (int e = tid; e < E; e += 256) {
-        float s = 0.0f;
-        for (int t = 0; t < n_tok; ++t) s += dl_s[t * E + e];
-        part_b[static_cast<size_t>(blockIdx.x) * E + e] = s;
+    __syncthreads();
+    for (int i = tid; i < n_tok * E; i += 256) dlogits[t_base * E + i] = dl_s[i];
+
+    const int CG = d / 4;
+    const int TG = CG >= 256 ? 1 : 256 / CG;
+    for (int cgb = 0; cgb < CG; cgb += 256) {
+        const int cg = CG >= 256 ? cgb + tid : tid % CG;
+        const int tg = CG >= 256 ? 0 : tid / CG;
+        if (cg >= CG || tg >= TG) continue;
+        const bool regs = dense && E <= 16;
+        float4 wg[16];
+        if (regs) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+                wg[e] = e < E ? __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e) * d + cg * 4))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        constexpr int U = 2;    // tokens per batch; the next batch's gathers are issued before this batch's FMAs
+        constexpr int KP = 2;   // slots whose gathers are pipelined (k = 1, 2 cover every shipped gate)
+        float4 nxt[U][KP];
+        float nkeep[U][KP];
+        auto gather = [&](int tl0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int tl = min(tl0 + u * TG, n_tok - 1);
+#pragma unroll
+                for (int j = 0; j < KP; ++j) {
+                    const int row = (j < k && dxbuf != nullptr) ? pos_s[tl * k + j] : -1;
+                    nkeep[u][j] = (row >= 0 && tl0 + u * TG < n_tok) ? 1.0f : 0.0f;
+                    nxt[u][j] = (j < k && dxbuf != nullptr) ? load_x4(dxbuf + static_cast<size_t>(max(row, 0)) * d + cg * 4)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        };
+        gather(tg);
+        for (int tl0 = tg; tl0 < n_tok; tl0 += U * TG) {
+            float4 acc[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < KP; ++j) {
+                    acc[u].x = fmaf(nkeep[u][j], nxt[u][j].x, acc[u].x); acc[u].y = fmaf(nkeep[u][j], nxt[u][j].y, acc[u].y);
+                    acc[u].z = fmaf(nkeep[u][j], nxt[u][j].z, acc[u].z); acc[u].w = fmaf(nkeep[u][j], nxt[u][j].w, acc[u].w);
+                }
+            }
+            if (tl0 + U * TG < n_tok) gather(tl0 + U * TG);
+            if (dxbuf != nullptr) {
+                for (int j = KP; j < k; ++j) {   // un-pipelined tail for k > 2
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int tl = tl0 + u * TG;
+                        const int row = tl < n_tok ? pos_s[tl * k + j] : -1;
+                        if (row >= 0) {
+                            const float4 v = load_x4(dxbuf + static_cast<size_t>(row) * d + cg * 4);
+                            acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int tl = tl0 + u * TG;
+                if (tl >= n_tok) break;
+                const int64_t t = t_base + tl;
+                const float* dr = dl_s + tl * E;
+                if (regs) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const float g = e < E ? dr[e] : 0.0f;
+                        acc[u].x = fmaf(g, wg[e].x, acc[u].x); acc[u].y = fmaf(g, wg[e].y, acc[u].y);
+                        acc[u].z = fmaf(g, wg[e].z, acc[u].z); acc[u].w = fmaf(g, wg[e].w, acc[u].w);
+                    }
+                } else if (dense) {
+                    for (int e = 0; e < E; ++e) {
+                        const float g = dr[e];
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e) * d + cg * 4));
+                        acc[u].x = fmaf(g, w.x, acc[u].x); acc[u].y = fmaf(g, w.y, acc[u].y);
+                        acc[u].z = fmaf(g, w.z, acc[u].z); acc[u].w = fmaf(g, w.w, acc[u].w);
+                    }
+                } else {
+                    for (int j = 0; j < k; ++j) {
+                        const int e = __ldg(idx + t * k + j);
+                        const float g = dr[e];
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e) * d + cg * 4));
+                        acc[u].x = fmaf(g, w.x, acc[u].x); acc[u].y = fmaf(g, w.y, acc[u].y);
+                        acc[u].z = fmaf(g, w.z, acc[u].z); acc[u].w = fmaf(g, w.w, acc[u].w);
+                    }
+                }
+                st4(dx + t * d + cg * 4, acc[u]);
+            }
+        }
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K8: gate weight gradient   dWg = dlogits^T x, dbg = colsum(dlogits)   (two deterministic stages)
+// Stage 1 is persistent: block b owns the 64-token tiles b, b + grid, ... (a fixed assignment, so the
+// summation order never changes) and keeps its [16 experts x 4 columns] accumulators in registers
+// across all of them.  Thread (cg, tg): column group cg = 4 consecutive features, token group tg takes
+// every TG-th token of a tile; the TG partial sums are combined in shared memory in tg order.
+// Stage 2 sums the per-block partials in block order.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgTile = 64;   // tokens per step of the persistent loop
+constexpr int kWgEG = 16;     // experts per register pass
+
+__device__ __forceinline__ float4 ldx4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldx4(const __nv_bfloat16* p) { return load_x4(p); }
+
+template <typename XT>
 __global__ void __launch_bounds__(256)
-gate_wgrad_reduce_kernel(const float* __restrict__ part_w, const float* __restrict__ part_b, int ntiles, int d, int E,
+gate_wgrad_partial_kernel(const float* __restrict__ dlogits, const XT* __restrict__ x, int64_t T, int d, int E,
+                          int ntiles, float* __restrict__ part_w, float* __restrict__ part_b) {
+    extern __shared__ float smem_f[];
+    const int tid = threadIdx.x;
+    const int CG = d / 4;                           // column groups of x
+    const int TG = CG + 1 > 256 ? 1 : 256 / (CG + 1);  // token groups sharing a tile
+    float* dl_s = smem_f;                           // [kWgTile][E]
+    float* red_s = smem_f + kWgTile * E;            // [TG][kWgEG][d + 4] (only used when TG > 1)
+    float* pw = part_w + static_cast<size_t>(blockIdx.x) * E * d;
+
+    // dbg = colsum(dlogits) rides along as one virtual column group (cg == CG) whose x is (1, 0, 0, 0)
+    const int CGX = CG + 1;
+    for (int g0 = 0; g0 < E; g0 += kWgEG) {
+        for (int cgb = 0; cgb < CGX; cgb += 256) {   // more than one sweep only when d >= 1024
+            const int cg = CGX > 256 ? cgb + tid : tid % CGX;
+            const int tg = CGX > 256 ? 0 : tid / CGX;
+            const bool active = cg < CGX && tg < TG;
+            const bool is_bias = cg == CG;
+            float4 acc[kWgEG];
+#pragma unroll
+            for (int i = 0; i < kWgEG; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int64_t t_base = static_cast<int64_t>(tile) * kWgTile;
+                const int n_tok = static_cast<int>(min(static_cast<int64_t>(kWgTile), T - t_base));
+                __syncthreads();   // previous tile's readers are done with dl_s
+                for (int i = tid; i < n_tok * E; i += 256) dl_s[i] = dlogits[t_base * E + i];
+                __syncthreads();
+                if (active) {
+                    constexpr int U = 4;   // tokens per batch; the next batch is loaded before this one is consumed
+                    float4 xn[U];
+                    auto fetch = [&](int t0) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u)   // always load (clamped); slots past the tile get weight 0 below
+                            xn[u] = is_bias ? make_float4(1.f, 0.f, 0.f, 0.f)
+                                            : ldx4(x + (t_base + min(t0 + u * TG, n_tok - 1)) * d + cg * 4);
+                    };
+                    fetch(tg);
+                    for (int t0 = tg; t0 < n_tok; t0 += U * TG) {
+                        float4 xv[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) xv[u] = xn[u];
+                        if (t0 + U * TG < n_tok) fetch(t0 + U * TG);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const bool live = t0 + u * TG < n_tok;
+                            const float* dr = dl_s + min(t0 + u * TG, n_tok - 1) * E + g0;
+#pragma unroll
+                            for (int i = 0; i < kWgEG; ++i) {
+                                const float g = (live && g0 + i < E) ? dr[i] : 0.0f;
+                                acc[i].x = fmaf(g, xv[u].x, acc[i].x);
+                                acc[i].y = fmaf(g, xv[u].y, acc[i].y);
+                                acc[i].z = fmaf(g, xv[u].z, acc[i].z);
+                                acc[i].w = fmaf(g, xv[u].w, acc[i].w);
+                            }
+                        }
+                    }
+                }
+            }
+            float* pb = part_b + static_cast<size_t>(blockIdx.x) * E;
+            if (TG == 1) {
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < kWgEG; ++i) {
+                        if (g0 + i >= E) break;
+                        if (is_bias) pb[g0 + i] = acc[i].x;
+                        else *reinterpret_cast<float4*>(pw + static_cast<size_t>(g0 + i) * d + cg * 4) = acc[i];
+                    }
+                }
+            } else {
+                const int dX = d + 4;   // row of the reduction buffer: d features + the bias group
+                __syncthreads();
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < kWgEG; ++i)
+                        *reinterpret_cast<float4*>(red_s + (static_cast<size_t>(tg) * kWgEG + i) * dX + cg * 4) = acc[i];
+                }
+                __syncthreads();
+                for (int o = tid; o < kWgEG * dX; o += 256) {
+                    const int i = o / dX, c = o - i * dX;
+                    if (g0 + i >= E) break;
+                    if (c > d) continue;
+                    float v = 0.0f;
+                    for (int q = 0; q < TG; ++q) v += red_s[static_cast<size_t>(q) * kWgEG * dX + o];   // tg order
+                    if (c < d) pw[static_cast<size_t>(g0 + i) * d + c] = v;
+                    else pb[g0 + i] = v;
+                }
+            }
+        }
+    }
+}
+
+// out[i] = sum_b part[b][i] in block order; 64 outputs x 4 block-slices per CTA, slices combined in order
+__global__ void __launch_bounds__(256)
+gate_wgrad_reduce_kernel(const float* __restrict__ part_w, const float* __restrict__ part_b, int nparts, int d, int E,
                          float* __restrict__ dWg, float* __restrict__ dbg) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    const int n = E * d;
-    if (i < n) {
-        float s = 0.0f;
-        for (int b = 0; b < ntiles; ++b) s += part_w[static_cast<size_t>(b) * n + i];
-        dWg[i] = s;
-    } else if (i < n + E && dbg != nullptr) {
-        const int e = i - n;
-        float s = 0.0f;
-        for (int b = 0; b < ntiles; ++b) s += part_b[static_cast<size_t>(b) * E + e];
-        dbg[e] = s;
+    __shared__ float red[4][64];
+    const int n = E * d, tot = n + (dbg != nullptr ? E : 0);
+    const int o = blockIdx.x * 64 + (threadIdx.x & 63), sl = threadIdx.x >> 6;
+    const int per = (nparts + 3) / 4;
+    float v = 0.0f;
+    if (o < tot) {
+        const float* src = o < n ? part_w + o : part_b + (o - n);
+        const size_t stride = o < n ? static_cast<size_t>(n) : static_cast<size_t>(E);
+        const int b1 = min(nparts, (sl + 1) * per);
+#pragma unroll 4
+        for (int b = sl * per; b < b1; ++b) v += src[static_cast<size_t>(b) * stride];
+    }
+    red[sl][threadIdx.x & 63] = v;
+    __syncthreads();
+    if (sl == 0 && o < tot) {
+        const float r = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
+        if (o < n) dWg[o] = r;
+        else dbg[o - n] = r;
     }
 }
 
@@ -615,34 +896,57 @@ cast_bf16_transposed_kernel(const float* __restrict__ src, __nv_bfloat16* __rest
     }
 }
 
-// out[e, c] = sum over rows r in [seg_start[e], seg_start[e+1]) of buf[r, c]; block = 32 x 8 threads,
-// each lane owns 2 adjacent columns, the 8 row-lanes stride the segment; fixed-order smem reduction.
+// Per-segment column sums (bias gradients) in two deterministic stages.
+// Stage 1: CTA = 128 rows x 256 columns; warp w reads rows w*16..w*16+15 with all 16 16-byte loads in
+// flight, the 8 warps are combined in shared memory in warp order -> part[rb][c].  128-row blocks never
+// straddle experts (segments are 256-aligned); blocks beyond the last live row exit at once.
+// Stage 2: out[e][c] = sum of the expert's row blocks in order.
 __global__ void __launch_bounds__(256)
-segment_colsum_kernel(const __nv_bfloat16* __restrict__ buf, const int* __restrict__ seg_start, int cols,
-                      float* __restrict__ out) {
-    __shared__ float red[8][64];
-    const int e = blockIdx.y;
-    const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
-    const int c = blockIdx.x * 64 + lane * 2;
-    const int r0 = seg_start[e], r1 = seg_start[e + 1];
-    float a0 = 0.0f, a1 = 0.0f;
+segment_colsum_partial_kernel(const __nv_bfloat16* __restrict__ buf, const int* __restrict__ seg_start, int E, int cols,
+                              float* __restrict__ part) {
+    __shared__ float red[8][256];
+    const int rb = blockIdx.y, row0 = rb * 128;
+    if (row0 >= __ldg(seg_start + E)) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 256 + lane * 8;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
     if (c < cols) {
-        for (int r = r0 + ry; r < r1; r += 8) {
-            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(buf + static_cast<size_t>(r) * cols + c);
-            a0 += __low2float(v);
-            a1 += __high2float(v);
+        uint4 v[16];
+        const __nv_bfloat16* p = buf + static_cast<size_t>(row0 + warp * 16) * cols + c;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = __ldg(reinterpret_cast<const uint4*>(p + static_cast<size_t>(r) * cols));
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[r]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { acc[2 * i] += __low2float(h[i]); acc[2 * i + 1] += __high2float(h[i]); }
         }
     }
-    red[ry][lane * 2] = a0;
-    red[ry][lane * 2 + 1] = a1;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        float s = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
-        const int cc = blockIdx.x * 64 + threadIdx.x;
-        if (cc < cols) out[static_cast<size_t>(e) * cols + cc] = s;
+    for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+    __syncthreads();
+    const int cc = blockIdx.x * 256 + threadIdx.x;
+    if (cc < cols) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
+        part[static_cast<size_t>(rb) * cols + cc] = sum;
     }
+}
+
+__global__ void __launch_bounds__(256)
+segment_colsum_final_kernel(const float* __restrict__ part, const int* __restrict__ seg_start, int cols,
+                            float* __restrict__ out) {
+    const int e = blockIdx.y;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= cols) return;
+    const int b0 = __ldg(seg_start + e) / 128, b1 = __ldg(seg_start + e + 1) / 128;
+    float sum = 0.0f;
+#pragma unroll 4
+    for (int b = b0; b < b1; ++b) sum += part[static_cast<size_t>(b) * cols + c];
+    out[static_cast<size_t>(e) * cols + c] = sum;
 }
 
 // ================================================================================================
@@ -693,10 +997,12 @@ cudaError_t launch_gate_fwd(const void* x, int x_dtype, const float* Wg, const f
 
 cudaError_t launch_route_scan(const int* tile_hist, const float* tile_psum, int ntiles, int E, long long capacity,
                               int* tile_base, int* count, int* kept, int* seg_start, int* tile_expert, int* num_mtiles,
-                              int max_mtiles, float* psum, cudaStream_t st) {
-    const size_t smem = (2 * static_cast<size_t>(E) + 1) * 4;
+                              int max_mtiles, float* psum, int aux_mode, long long tokens, int k, float* aux_loss,
+                              float* aux_coef, cudaStream_t st) {
+    const size_t smem = (3 * static_cast<size_t>(E) + 1) * 4;
     route_scan_kernel<<<1, 1024, smem, st>>>(tile_hist, tile_psum, ntiles, E, capacity, tile_base, count, kept,
-                                             seg_start, tile_expert, num_mtiles, max_mtiles, psum);
+                                             seg_start, tile_expert, num_mtiles, max_mtiles, psum, aux_mode, tokens, k,
+                                             aux_loss, aux_coef);
     return cudaGetLastError();
 }
 
@@ -779,33 +1085,63 @@ cudaError_t launch_dispatch_bwd(const void* dxbuf, const int* pos, const float* 
     return cudaGetLastError();
 }
 
+cudaError_t launch_gate_dispatch_bwd(const void* dxbuf, const int* pos, const float* logits, const int* idx, const float* score,
+                                     const float* dscore, const float* dpsum, const float* Wg, int64_t T, int d, int E, int k,
+                                     int score_mode, float* dlogits, void* dx, int dx_dtype, cudaStream_t st) {
+    const int ntiles = static_cast<int>((T + kTokTile - 1) / kTokTile);
+    const size_t smem = static_cast<size_t>(kTokTile) * (E + k) * 4;
+    auto xb = static_cast<const __nv_bfloat16*>(dxbuf);
+    cudaError_t err;
+    if (dx_dtype == MOE_DTYPE_F32) {
+        auto kfn = gate_dispatch_bwd_kernel<float>;
+        err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        kfn<<<ntiles, 256, smem, st>>>(xb, pos, logits, idx, score, dscore, dpsum, Wg, T, d, E, k, score_mode, dlogits,
+                                       static_cast<float*>(dx));
+    } else {
+        auto kfn = gate_dispatch_bwd_kernel<__nv_bfloat16>;
+        err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        kfn<<<ntiles, 256, smem, st>>>(xb, pos, logits, idx, score, dscore, dpsum, Wg, T, d, E, k, score_mode, dlogits,
+                                       static_cast<__nv_bfloat16*>(dx));
+    }
+    return cudaGetLastError();
+}
+
+static int gate_wgrad_blocks(int64_t T, int sm_count) {
+    const int64_t ntiles = (T + kWgTile - 1) / kWgTile;
+    return static_cast<int>(ntiles < 2LL * sm_count ? ntiles : 2LL * sm_count);
+}
+
 size_t gate_wgrad_workspace_bytes(int64_t T, int d, int E) {
-    const size_t ntiles = static_cast<size_t>((T + kTokTile - 1) / kTokTile);
-    return ntiles * (static_cast<size_t>(E) * d + E) * 4;
+    const size_t nb = static_cast<size_t>(gate_wgrad_blocks(T, sm_count()));
+    return nb * (static_cast<size_t>(E) * d + E) * 4;
 }
 
 cudaError_t launch_gate_wgrad(const float* dlogits, const void* x, int x_dtype, int64_t T, int d, int E, void* workspace,
                               float* dWg, float* dbg, cudaStream_t st) {
-    const int ntiles = static_cast<int>((T + kTokTile - 1) / kTokTile);
+    const int ntiles = static_cast<int>((T + kWgTile - 1) / kWgTile);
+    const int nb = gate_wgrad_blocks(T, sm_count());
     float* part_w = static_cast<float*>(workspace);
-    float* part_b = part_w + static_cast<size_t>(ntiles) * E * d;
-    const size_t smem = static_cast<size_t>(kTokTile) * E * 4;
+    float* part_b = part_w + static_cast<size_t>(nb) * E * d;
+    const int CG = d / 4, TG = CG + 1 > 256 ? 1 : 256 / (CG + 1);
+    const size_t smem = (static_cast<size_t>(kWgTile) * E + (TG > 1 ? static_cast<size_t>(TG) * kWgEG * (d + 4) : 0)) * 4;
     cudaError_t err;
     if (x_dtype == MOE_DTYPE_F32) {
         auto kfn = gate_wgrad_partial_kernel<float>;
         err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        kfn<<<ntiles, 256, smem, st>>>(dlogits, static_cast<const float*>(x), T, d, E, part_w, part_b);
+        kfn<<<nb, 256, smem, st>>>(dlogits, static_cast<const float*>(x), T, d, E, ntiles, part_w, part_b);
     } else {
         auto kfn = gate_wgrad_partial_kernel<__nv_bfloat16>;
         err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        kfn<<<ntiles, 256, smem, st>>>(dlogits, static_cast<const __nv_bfloat16*>(x), T, d, E, part_w, part_b);
+        kfn<<<nb, 256, smem, st>>>(dlogits, static_cast<const __nv_bfloat16*>(x), T, d, E, ntiles, part_w, part_b);
     }
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     const int n = E * d + E;
-    gate_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part_w, part_b, ntiles, d, E, dWg, dbg);
+    gate_wgrad_reduce_kernel<<<(n + 63) / 64, 256, 0, st>>>(part_w, part_b, nb, d, E, dWg, dbg);
     return cudaGetLastError();
 }
 
@@ -822,9 +1158,19 @@ cudaError_t launch_cast_bf16_transposed(const float* src, void* dst, void* dst_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_segment_colsum(const void* buf, const int* seg_start, int E, int cols, float* out, cudaStream_t st) {
-    dim3 grid((cols + 63) / 64, E);
-    segment_colsum_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(buf), seg_start, cols, out);
+size_t segment_colsum_workspace_bytes(int64_t rows_cap, int cols) {
+    return static_cast<size_t>(rows_cap / 128) * cols * 4;
+}
+
+cudaError_t launch_segment_colsum(const void* buf, const int* seg_start, int64_t rows_cap, int E, int cols, void* workspace,
+                                  float* out, cudaStream_t st) {
+    float* part = static_cast<float*>(workspace);
+    dim3 g1((cols + 255) / 256, static_cast<unsigned>(rows_cap / 128));
+    segment_colsum_partial_kernel<<<g1, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(buf), seg_start, E, cols, part);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    dim3 g2((cols + 255) / 256, E);
+    segment_colsum_final_kernel<<<g2, 256, 0, st>>>(part, seg_start, cols, out);
     return cudaGetLastError();
 }
 

@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("MOE_B200_LIB") or os.path.join(_HERE, "libmoe_b200.so
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 SCORE_TOPK_SOFTMAX, SCORE_FULL_SOFTMAX = 0, 1
-TOKEN_TILE, ROW_ALIGN = 256, 256
+AUX_NONE, AUX_SWITCH, AUX_GSHARD = 0, 1, 2
+TOKEN_TILE, ROW_ALIGN = 64, 256
 GEMM_FC1, GEMM_FC2, GEMM_DGELU, GEMM_DGRAD, GEMM_WGRAD = range(5)
 
 _p, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
@@ -26,19 +27,21 @@ SIGNATURES = {
     "moe_version": (_i, []),
     "moe_rows_cap": (_i64, [_i64, _i, _i, _i64]),
     "moe_gate_fwd": (_i, [_p, _i, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
-    "moe_route_scan": (_i, [_p, _p, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
+    "moe_route_scan": (_i, [_p, _p, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _i, _p, _i, _i64, _i, _p, _p, _p]),
     "moe_dispatch_fwd": (_i, [_p, _i, _p, _p, _p, _p, _i64, _i, _i, _i, _i64, _p, _p, _p, _p]),
     "moe_expert_ffn_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p, _p]),
     "moe_combine_fwd": (_i, [_p, _p, _p, _i64, _i, _i, _p, _i, _p]),
     "moe_combine_bwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p]),
-    "moe_expert_ffn_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "moe_expert_ffn_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "moe_gate_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p]),
     "moe_dispatch_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _i, _p]),
     "moe_gate_wgrad_workspace_bytes": (_sz, [_i64, _i, _i]),
     "moe_gate_wgrad": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p, _p]),
     "moe_cast_bf16": (_i, [_p, _p, _i64, _p]),
     "moe_cast_bf16_transposed": (_i, [_p, _p, _p, _i, _i, _i, _p]),
-    "moe_segment_colsum": (_i, [_p, _p, _i, _i, _p, _p]),
+    "moe_segment_colsum_workspace_bytes": (_sz, [_i64, _i]),
+    "moe_segment_colsum": (_i, [_p, _p, _i64, _i, _i, _p, _p, _p]),
+    "moe_gate_dispatch_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _i, _p]),
     "moe_grouped_gemm": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
 }
 
@@ -66,8 +69,8 @@ class MoeB200Error(RuntimeError):
 # kernels launched by each entry point (for the launch count the bench reports)
 KERNELS_PER_CALL = {
     "moe_gate_fwd": 1, "moe_route_scan": 1, "moe_dispatch_fwd": 1, "moe_expert_ffn_fwd": 2, "moe_combine_fwd": 1,
-    "moe_combine_bwd": 1, "moe_expert_ffn_bwd": 6, "moe_gate_bwd": 1, "moe_dispatch_bwd": 1, "moe_gate_wgrad": 2,
-    "moe_cast_bf16": 1, "moe_cast_bf16_transposed": 1, "moe_segment_colsum": 1, "moe_grouped_gemm": 1,
+    "moe_combine_bwd": 1, "moe_expert_ffn_bwd": 8, "moe_gate_bwd": 1, "moe_dispatch_bwd": 1, "moe_gate_dispatch_bwd": 1,
+    "moe_gate_wgrad": 2, "moe_cast_bf16": 1, "moe_cast_bf16_transposed": 1, "moe_segment_colsum": 2, "moe_grouped_gemm": 1,
 }
 
 

@@ -20,7 +20,11 @@ class RouteSpec:
     top_k: int
     score_mode: int          # C.SCORE_TOPK_SOFTMAX | C.SCORE_FULL_SOFTMAX
     capacity: int            # rows per expert (>= T*k means unlimited)
-    want_psum: bool          # also return sum_t softmax(logits)[e] (for load-balancing losses)
+    aux_mode: int            # C.AUX_NONE | C.AUX_SWITCH | C.AUX_GSHARD: load-balancing loss computed by the scan kernel
+
+    @property
+    def want_psum(self) -> bool:   # sum_t softmax(logits)[e] is needed exactly when there is an aux loss
+        return int(self.aux_mode) != C.AUX_NONE
 
 
 class Bf16WeightCache:
@@ -77,21 +81,24 @@ def route(x, Wg, bg, spec: RouteSpec, noise=None):
     max_mtiles = rows_cap // C.ROW_ALIGN
     r = dict(
         logits=_f32((T, E), dev), idx=_i32((T, k), dev), score=_f32((T, k), dev),
-        tile_hist=_i32((ntiles, E), dev), tile_base=_i32((ntiles, E), dev),
+        tile_hist=_i32((E, ntiles), dev), tile_base=_i32((E, ntiles), dev),
         count=_i32(E, dev), kept=_i32(E, dev), seg_start=_i32(E + 1, dev),
         tile_expert=_i32(max_mtiles, dev), num_mtiles=_i32(1, dev),
         pos=_i32((T, k), dev), row_src=_i32(rows_cap, dev),
         xbuf=torch.empty((rows_cap, d), dtype=torch.bfloat16, device=dev),
         rows_cap=rows_cap,
     )
-    tile_psum = _f32((ntiles, E), dev) if spec.want_psum else None
+    tile_psum = _f32((E, ntiles), dev) if spec.want_psum else None
     r["psum"] = _f32(E, dev) if spec.want_psum else None
+    r["aux_loss"] = _f32(1, dev) if spec.want_psum else None
+    r["aux_coef"] = _f32(E, dev) if spec.want_psum else None
     C.call("moe_gate_fwd", C.ptr(x), C.dtype_code(x), C.ptr(Wg), C.ptr(bg), C.ptr(noise), T, d, E, k,
            spec.score_mode, int(spec.want_psum), C.ptr(r["logits"]), C.ptr(r["idx"]), C.ptr(r["score"]),
            C.ptr(r["tile_hist"]), C.ptr(tile_psum), st)
     C.call("moe_route_scan", C.ptr(r["tile_hist"]), C.ptr(tile_psum), ntiles, E, spec.capacity,
            C.ptr(r["tile_base"]), C.ptr(r["count"]), C.ptr(r["kept"]), C.ptr(r["seg_start"]),
-           C.ptr(r["tile_expert"]), C.ptr(r["num_mtiles"]), max_mtiles, C.ptr(r["psum"]), st)
+           C.ptr(r["tile_expert"]), C.ptr(r["num_mtiles"]), max_mtiles, C.ptr(r["psum"]), int(spec.aux_mode), T, k,
+           C.ptr(r["aux_loss"]), C.ptr(r["aux_coef"]), st)
     C.call("moe_dispatch_fwd", C.ptr(x), C.dtype_code(x), C.ptr(r["idx"]), C.ptr(r["tile_base"]),
            C.ptr(r["seg_start"]), C.ptr(r["kept"]), T, d, E, k, spec.capacity, C.ptr(r["pos"]),
            C.ptr(r["row_src"]), C.ptr(r["xbuf"]), st)
@@ -99,10 +106,11 @@ def route(x, Wg, bg, spec: RouteSpec, noise=None):
 
 
 class MoEFunction(torch.autograd.Function):
-    """y, psum, count, kept = MoE(x; Wg, bg, W1, b1, W2, b2).
+    """y, aux_loss, count, kept = MoE(x; Wg, bg, W1, b1, W2, b2).
 
     x [T,d] fp32|bf16; Wg [E,d], bg [E]|None, W1 [E,h,d], b1 [E,h], W2 [E,d,h], b2 [E,d] fp32.
-    y has x's dtype.  psum [E] (fp32, differentiable) is None unless spec.want_psum.
+    y has x's dtype.  aux_loss is the gate's load-balancing loss (fp32 scalar, differentiable w.r.t.
+    x / Wg / bg; an empty tensor when spec.aux_mode is AUX_NONE).
     count/kept [E] int32 are the per-expert routed / kept pair counts (not differentiable).
     """
 
@@ -139,21 +147,23 @@ class MoEFunction(torch.autograd.Function):
         ctx.spec = spec
         ctx.has_bg = bg is not None
         ctx.rows_cap = rows_cap
+        coef = r["aux_coef"] if spec.want_psum else torch.empty(0, dtype=torch.float32, device=dev)
         ctx.save_for_backward(x, Wg_c, r["logits"], r["idx"], r["score"], r["pos"], r["seg_start"], r["kept"],
-                              r["tile_expert"], r["num_mtiles"], r["xbuf"], U, H, Y, W1tb, W2tb)
+                              r["tile_expert"], r["num_mtiles"], r["xbuf"], U, H, Y, W1tb, W2tb, coef)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(r["count"], r["kept"])
-        psum = r["psum"]
-        if psum is None:
-            psum = torch.empty(0, dtype=torch.float32, device=dev)
-            ctx.mark_non_differentiable(psum)
-        return y, psum, r["count"], r["kept"]
+        if spec.want_psum:
+            aux = r["aux_loss"].reshape(())
+        else:
+            aux = torch.empty(0, dtype=torch.float32, device=dev)
+            ctx.mark_non_differentiable(aux)
+        return y, aux, r["count"], r["kept"]
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, dy, dpsum, _dcount, _dkept):
+    def backward(ctx, dy, daux, _dcount, _dkept):
         (x, Wg, logits, idx, score, pos, seg_start, kept, tile_expert, num_mtiles, xbuf, U, H, Y, W1tb,
-         W2tb) = ctx.saved_tensors
+         W2tb, coef) = ctx.saved_tensors
         spec: RouteSpec = ctx.spec
         T, d = x.shape
         E, h = W1tb.shape[0], W1tb.shape[2]
@@ -164,10 +174,8 @@ class MoEFunction(torch.autograd.Function):
         if dy is None:
             dy = torch.zeros_like(x)
         dy = _as_kernel_input(dy)
-        if not spec.want_psum:
-            dpsum = None
-        elif dpsum is not None:
-            dpsum = dpsum.float().contiguous()
+        # aux_loss = sum_e coef_e psum_e  =>  d aux / d psum = coef (the shares inside coef are integers)
+        dpsum = (coef * daux.float()).contiguous() if (spec.want_psum and daux is not None) else None
 
         dybuf = torch.empty((rows_cap, d), dtype=torch.bfloat16, device=dev)
         dscore = _f32((T, k), dev)
@@ -188,15 +196,14 @@ class MoEFunction(torch.autograd.Function):
                None, None, sg, rows_cap, E, h, d, 0, st, tag="gemm_wgrad1")
         C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1tb), C.ptr(dxbuf), None, None, None,
                te, nm, None, rows_cap, E, 0, d, h, st, tag="gemm_dgrad")
-        C.call("moe_segment_colsum", C.ptr(dybuf), sg, E, d, C.ptr(db2), st, tag="colsum_db2")
-        C.call("moe_segment_colsum", C.ptr(dU), sg, E, h, C.ptr(db1), st, tag="colsum_db1")
+        cws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, h), dtype=torch.uint8, device=dev)
+        C.call("moe_segment_colsum", C.ptr(dybuf), sg, rows_cap, E, d, C.ptr(cws), C.ptr(db2), st, tag="colsum_db2")
+        C.call("moe_segment_colsum", C.ptr(dU), sg, rows_cap, E, h, C.ptr(cws), C.ptr(db1), st, tag="colsum_db1")
+        # gate backward (dlogits) + un-permute of dX + dlogits Wg in one pass
         dlogits = _f32((T, E), dev)
-        C.call("moe_gate_bwd", C.ptr(logits), C.ptr(idx), C.ptr(score), C.ptr(dscore), C.ptr(dpsum), T, E, k,
-               spec.score_mode, C.ptr(dlogits), st)
-        dense = int(spec.score_mode == C.SCORE_FULL_SOFTMAX or dpsum is not None)
         dx = torch.empty_like(x)
-        C.call("moe_dispatch_bwd", C.ptr(dxbuf), C.ptr(pos), C.ptr(dlogits), C.ptr(idx), C.ptr(Wg), T, d, E, k,
-               dense, C.ptr(dx), C.dtype_code(dx), st)
+        C.call("moe_gate_dispatch_bwd", C.ptr(dxbuf), C.ptr(pos), C.ptr(logits), C.ptr(idx), C.ptr(score), C.ptr(dscore),
+               C.ptr(dpsum), C.ptr(Wg), T, d, E, k, spec.score_mode, C.ptr(dlogits), C.ptr(dx), C.dtype_code(dx), st)
         ws = torch.empty(C.lib.moe_gate_wgrad_workspace_bytes(T, d, E), dtype=torch.uint8, device=dev)
         dWg = _f32((E, d), dev)
         dbg = _f32(E, dev) if ctx.has_bg else None
@@ -217,8 +224,8 @@ class GateFunction(torch.autograd.Function):
         st = C.stream_ptr()
         ntiles = (T + C.TOKEN_TILE - 1) // C.TOKEN_TILE
         logits, idx, score = _f32((T, E), dev), _i32((T, spec.top_k), dev), _f32((T, spec.top_k), dev)
-        tile_hist = _i32((ntiles, E), dev)
-        tile_psum = _f32((ntiles, E), dev) if spec.want_psum else None
+        tile_hist = _i32((E, ntiles), dev)
+        tile_psum = _f32((E, ntiles), dev) if spec.want_psum else None
         Wg_c = Wg.detach().contiguous()
         bg_c = None if bg is None else bg.detach().contiguous()
         C.call("moe_gate_fwd", C.ptr(x), C.dtype_code(x), C.ptr(Wg_c), C.ptr(bg_c), C.ptr(noise), T, d, E,

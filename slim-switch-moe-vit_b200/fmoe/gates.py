@@ -51,7 +51,7 @@ class BaseGate(nn.Module):
     def make_noise(self, x):  # optional additive logit jitter [T, tot_expert] fp32
         return None
 
-    def finish(self, num_tokens, count, kept, psum):  # called after routing; sets the aux loss
+    def finish(self, aux_loss):  # called after the fused forward with the kernel-computed load-balancing loss
         raise NotImplementedError
 
 
@@ -66,10 +66,10 @@ class NaiveGate(BaseGate):
             raise ValueError(f"top_k={top_k} unsupported (1 <= top_k <= min(8, experts))")
 
     def route_spec(self, num_tokens):
-        return RouteSpec(self.top_k, C.SCORE_TOPK_SOFTMAX, num_tokens * self.top_k, False)
+        return RouteSpec(self.top_k, C.SCORE_TOPK_SOFTMAX, num_tokens * self.top_k, C.AUX_NONE)
 
-    def finish(self, num_tokens, count, kept, psum):
-        self.set_loss(torch.zeros(1, requires_grad=True, device=count.device))
+    def finish(self, aux_loss):
+        self.set_loss(torch.zeros(1, requires_grad=True, device=aux_loss.device))
 
     def forward(self, inp, return_all_scores=False):
         spec = self.route_spec(inp.shape[0])
@@ -104,7 +104,7 @@ class SwitchGate(NaiveGate):
 
     def route_spec(self, num_tokens):
         cap = _capacity(self._cf(), num_tokens, 1, self.tot_expert)
-        return RouteSpec(1, C.SCORE_FULL_SOFTMAX, cap, True)
+        return RouteSpec(1, C.SCORE_FULL_SOFTMAX, cap, C.AUX_SWITCH)
 
     def make_noise(self, x):
         if not self.training or not self.switch_eps:
@@ -112,10 +112,8 @@ class SwitchGate(NaiveGate):
         noise = torch.rand(x.shape[0], self.tot_expert, device=x.device, dtype=torch.float32)
         return noise * (2 * self.switch_eps) + (1.0 - self.switch_eps)
 
-    def finish(self, num_tokens, count, kept, psum):
-        keptf = kept.to(torch.float32)
-        frac = keptf / keptf.sum().clamp(min=1.0)
-        self.set_loss((frac * (psum / num_tokens)).sum() * self.tot_expert)
+    def finish(self, aux_loss):
+        self.set_loss(aux_loss)   # E * sum_e f_e P_e, computed (with its gradient) by the scan kernel
 
     def forward(self, inp):
         spec = self.route_spec(inp.shape[0])
@@ -138,12 +136,10 @@ class GShardGate(NaiveGate):
 
     def route_spec(self, num_tokens):
         cap = _capacity(self.capacity[0 if self.training else 1], num_tokens, 2, self.tot_expert)
-        return RouteSpec(2, C.SCORE_TOPK_SOFTMAX, cap, True)
+        return RouteSpec(2, C.SCORE_TOPK_SOFTMAX, cap, C.AUX_GSHARD)
 
-    def finish(self, num_tokens, count, kept, psum):
-        c_e = count.to(torch.float32) / float(num_tokens * self.top_k)
-        m_e = psum / num_tokens
-        self.set_loss(torch.mean(c_e * m_e) * (self.tot_expert ** 2))
+    def finish(self, aux_loss):
+        self.set_loss(aux_loss)   # mean_e(c_e m_e) * E^2, computed (with its gradient) by the scan kernel
 
     def forward(self, inp):
         spec = self.route_spec(inp.shape[0])

@@ -69,8 +69,8 @@ class FMoE(nn.Module):
         W1, b1, W2, b2 = self._expert_params()
         gate = self.gate
         spec = gate.route_spec(T)
-        y, psum, count, kept = MoEFunction.apply(moe_inp, gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec,
-                                                 self._bf16_cache, gate.make_noise(moe_inp))
-        gate.finish(T, count, kept, psum)
+        y, aux, count, kept = MoEFunction.apply(moe_inp, gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec,
+                                                self._bf16_cache, gate.make_noise(moe_inp))
+        gate.finish(aux)
         self.last_count, self.last_kept = count, kept   # load-balance statistics (device tensors, no sync)
         return y

@@ -53,7 +53,7 @@ def test_routing_and_dispatch_bit_exact(case):
     _, C, Fn = _fm()
     x, Wg, bg, *_ = make_problem(T, d, h, E, seed=1, x_dtype=xdt, skew=skew)
     cap = _cap(T, k, E, cf)
-    spec = Fn.RouteSpec(k, mode, cap, True)
+    spec = Fn.RouteSpec(k, mode, cap, C.AUX_SWITCH)
     r = Fn.route(x.cuda(), Wg.cuda(), bg.cuda(), spec)
     torch.cuda.synchronize()
 
@@ -92,24 +92,26 @@ def test_layer_forward_backward_vs_oracle(case):
     prob = make_problem(T, d, h, E, seed=2, x_dtype=xdt, skew=skew)
     x, Wg, bg, W1, b1, W2, b2 = prob
     cap = _cap(T, k, E, cf)
-    spec = Fn.RouteSpec(k, mode, cap, True)
+    spec = Fn.RouteSpec(k, mode, cap, C.AUX_SWITCH if mode == 1 else C.AUX_GSHARD)
 
     g = torch.Generator().manual_seed(3)
     dy = torch.randn(T, d, generator=g).to(xdt)
-    dps = torch.randn(E, generator=g) * 0.01
+    aux_w = 0.37   # weight of the load-balancing loss in the scalar that is differentiated
 
     dev = [t.cuda().requires_grad_() for t in prob]
-    y, psum, count, kept = Fn.MoEFunction.apply(*dev, spec, Fn.Bf16WeightCache(), None)
-    loss = (y.float() * dy.cuda().float()).sum() + (psum * dps.cuda()).sum()
+    y, aux, count, kept = Fn.MoEFunction.apply(*dev, spec, Fn.Bf16WeightCache(), None)
+    loss = (y.float() * dy.cuda().float()).sum() + aux_w * aux
     loss.backward()
     torch.cuda.synchronize()
 
     ym, sv = O.forward_model(x, Wg, bg, W1, b1, W2, b2, k, mode, cap)
-    gm = O.backward_model(sv, dy, Wg, dps)
+    coef = O.aux_coef(sv.r, T, spec.aux_mode)
+    gm = O.backward_model(sv, dy, Wg, aux_w * coef)
     scale = float(ym.float().abs().max())
     assert rel_err(y, ym) <= MODEL_REL, "forward vs arithmetic model"
     assert max_abs(y, ym) <= scale / 64 + 1e-6
     assert torch.equal(count.cpu(), sv.r.count) and torch.equal(kept.cpu(), sv.r.kept)
+    assert abs(float(aux) - float((coef * sv.r.psum).sum())) <= 1e-5, "load-balancing loss (scan kernel) vs oracle"
 
     names = ["dx", "dWg", "dbg", "dW1", "db1", "dW2", "db2"]
     for name, t in zip(names, dev):
@@ -119,7 +121,7 @@ def test_layer_forward_backward_vs_oracle(case):
     # fp64 ideal with the same routing: bounds the error of the whole bf16 design, not just the kernels
     xs = [t.clone().double().requires_grad_() for t in prob]
     yi, psi = O.ideal_forward(*xs, sv.r, mode)
-    ((yi * dy.double()).sum() + (psi * dps.double()).sum()).backward()
+    ((yi * dy.double()).sum() + aux_w * (psi * coef).sum()).backward()
     assert rel_err(y, yi) <= IDEAL_REL
     for name, t, ref in zip(names, dev, xs):
         assert rel_err(t.grad, ref.grad) <= IDEAL_REL, f"{name} vs fp64 ideal: {rel_err(t.grad, ref.grad)}"
@@ -130,7 +132,7 @@ def test_ffn_intermediates_vs_model():
     T, d, h, E, k, mode = 900, 192, 768, 8, 2, 0
     _, C, Fn = _fm()
     x, Wg, bg, W1, b1, W2, b2 = make_problem(T, d, h, E, seed=5)
-    spec = Fn.RouteSpec(k, mode, T * k, False)
+    spec = Fn.RouteSpec(k, mode, T * k, C.AUX_NONE)
     r = Fn.route(x.cuda(), Wg.cuda(), bg.cuda(), spec)
     W1b, W2b, W1tb, W2tb = Fn.Bf16WeightCache().get(W1.cuda(), W2.cuda())
     rows_cap = r["rows_cap"]
@@ -158,9 +160,9 @@ def test_deterministic_bits():
     outs = []
     for _ in range(2):
         dev = [t.cuda().requires_grad_() for t in prob]
-        spec = Fn.RouteSpec(k, 0, O.capacity_from_factor(1.0, T, k, E), True)
-        y, psum, _, _ = Fn.MoEFunction.apply(*dev, spec, Fn.Bf16WeightCache(), None)
-        (y.sum() + psum.sum()).backward()
+        spec = Fn.RouteSpec(k, 0, O.capacity_from_factor(1.0, T, k, E), C.AUX_GSHARD)
+        y, aux, _, _ = Fn.MoEFunction.apply(*dev, spec, Fn.Bf16WeightCache(), None)
+        (y.sum() + aux).backward()
         outs.append([y.detach().clone()] + [t.grad.clone() for t in dev])
     for a, b in zip(*outs):
         assert torch.equal(a, b)

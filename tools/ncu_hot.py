@@ -3,7 +3,8 @@ usage: python tools/ncu_hot.py <report.ncu-rep> <kernel-id e.g. ::regex:grouped_
 import csv, io, subprocess, sys
 rep, kid = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", kid], capture_output=True, text=True).stdout
+cmd = ["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-id", kid] if kid != "x" else [])
+out = subprocess.run(cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 # the page may hold several kernels, each with its own "Kernel Name" + header rows: take section `sec`
 sec = int(sys.argv[4]) if len(sys.argv) > 4 else 0
