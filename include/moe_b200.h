@@ -76,7 +76,22 @@ int moe_route_scan(const int32_t *tile_hist, const float *tile_psum, int ntiles,
                    int32_t *tile_base, int32_t *count, int32_t *kept, int32_t *seg_start, int32_t *tile_expert,
                    int32_t *num_mtiles, int max_mtiles, float *psum,
                    int aux_mode /* MOE_AUX_* */, int64_t T, int k, float *aux_loss /* [1] */,
-                   float *aux_coef /* [E] = d aux_loss / d psum */, void *stream);
+                   float *aux_coef /* [E] = d aux_loss / d psum */,
+                   int64_t slab_rows /* 0: packed segments; > 0: every expert gets a fixed slab of this many rows
+                                        (expert-parallel send layout, multiple of MOE_ROW_ALIGN, >= capacity) */,
+                   void *stream);
+
+/* ---- expert parallelism, receive side: replaces fmoe_cuda.expert_exchange + the receive half of
+ * global_scatter / global_gather.  The all-to-all itself is issued by the host (NCCL) on fixed slabs
+ * [W, E_local, slab_rows, d]; kept_recv[W, E_local] are the live rows of each received slab.
+ * moe_ep_tables: packed layout of the local experts (sources in rank order inside each segment):
+ *   slab_dst[W,E_local] first packed row of each slab, kept_local[E_local], seg_start[E_local+1],
+ *   tile_expert[max_mtiles], num_mtiles[1].
+ * moe_ep_repack: to_packed = 1 slabs -> packed rows (pad rows zeroed); to_packed = 0 packed rows -> slabs. */
+int moe_ep_tables(const int32_t *kept_recv, int W, int E_local, int32_t *slab_dst, int32_t *kept_local, int32_t *seg_start,
+                  int32_t *tile_expert, int32_t *num_mtiles, int max_mtiles, void *stream);
+int moe_ep_repack(const void *src, void *dst, const int32_t *kept_recv, const int32_t *slab_dst, const int32_t *seg_start,
+                  const int32_t *kept_local, int W, int E_local, int64_t slab_rows, int d, int to_packed, void *stream);
 
 /* ---- dispatch: replaces fmoe_cuda.assign_pos + MOEScatter (deterministic, token order).
  * pos[T,k] row of each (token,slot) or -1 if dropped; row_src[rows_cap] flattened pair index of

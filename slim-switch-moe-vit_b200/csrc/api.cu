@@ -74,7 +74,12 @@ int moe_gate_fwd(const void* x, int x_dtype, const float* Wg, const float* bg, c
 int moe_route_scan(const int32_t* tile_hist, const float* tile_psum, int ntiles, int E, int64_t capacity,
                    int32_t* tile_base, int32_t* count, int32_t* kept, int32_t* seg_start, int32_t* tile_expert,
                    int32_t* num_mtiles, int max_mtiles, float* psum, int aux_mode, int64_t T, int k, float* aux_loss,
-                   float* aux_coef, void* stream) {
+                   float* aux_coef, int64_t slab_rows, void* stream) {
+    if (slab_rows < 0 || slab_rows % MOE_ROW_ALIGN != 0 || (slab_rows > 0 && slab_rows < capacity)) {
+        set_error("moe_route_scan: slab_rows=%lld must be 0 (packed) or a multiple of %d that is >= capacity=%lld", (long long)slab_rows,
+                  MOE_ROW_ALIGN, (long long)capacity);
+        return 1;
+    }
     if (ntiles <= 0 || E <= 0 || E > 1024 || capacity <= 0) { set_error("moe_route_scan: bad arguments ntiles=%d E=%d capacity=%lld", ntiles, E, (long long)capacity); return 1; }
     if (aux_mode != MOE_AUX_NONE) {
         if ((aux_mode != MOE_AUX_SWITCH && aux_mode != MOE_AUX_GSHARD) || tile_psum == nullptr || psum == nullptr ||
@@ -84,9 +89,28 @@ int moe_route_scan(const int32_t* tile_hist, const float* tile_psum, int ntiles,
         }
     }
     return check(launch_route_scan(tile_hist, tile_psum, ntiles, E, capacity, tile_base, count, kept, seg_start,
-                                   tile_expert, num_mtiles, max_mtiles, psum, aux_mode, T, k, aux_loss, aux_coef,
+                                   tile_expert, num_mtiles, max_mtiles, psum, aux_mode, T, k, aux_loss, aux_coef, slab_rows,
                                    static_cast<cudaStream_t>(stream)),
                  "moe_route_scan");
+}
+
+int moe_ep_tables(const int32_t* kept_recv, int W, int E_local, int32_t* slab_dst, int32_t* kept_local, int32_t* seg_start,
+                  int32_t* tile_expert, int32_t* num_mtiles, int max_mtiles, void* stream) {
+    if (W < 1 || E_local < 1 || E_local > 1024 || max_mtiles < 1) { set_error("moe_ep_tables: bad arguments W=%d E_local=%d", W, E_local); return 1; }
+    return check(launch_ep_tables(kept_recv, W, E_local, slab_dst, kept_local, seg_start, tile_expert, num_mtiles, max_mtiles,
+                                  static_cast<cudaStream_t>(stream)),
+                 "moe_ep_tables");
+}
+
+int moe_ep_repack(const void* src, void* dst, const int32_t* kept_recv, const int32_t* slab_dst, const int32_t* seg_start,
+                  const int32_t* kept_local, int W, int E_local, int64_t slab_rows, int d, int to_packed, void* stream) {
+    if (W < 1 || E_local < 1 || slab_rows <= 0 || slab_rows % MOE_ROW_ALIGN != 0 || d <= 0 || d % 8 != 0) {
+        set_error("moe_ep_repack: bad arguments W=%d E_local=%d slab_rows=%lld d=%d", W, E_local, (long long)slab_rows, d);
+        return 1;
+    }
+    return check(launch_ep_repack(src, dst, kept_recv, slab_dst, seg_start, kept_local, W, E_local, slab_rows, d, to_packed,
+                                  static_cast<cudaStream_t>(stream)),
+                 "moe_ep_repack");
 }
 
 int moe_dispatch_fwd(const void* x, int x_dtype, const int32_t* idx, const int32_t* tile_base, const int32_t* seg_start,

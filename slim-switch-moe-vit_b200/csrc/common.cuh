@@ -15,7 +15,11 @@ cudaError_t launch_gate_fwd(const void* x, int x_dtype, const float* Wg, const f
 cudaError_t launch_route_scan(const int* tile_hist, const float* tile_psum, int ntiles, int E, long long capacity,
                               int* tile_base, int* count, int* kept, int* seg_start, int* tile_expert, int* num_mtiles,
                               int max_mtiles, float* psum, int aux_mode, long long tokens, int k, float* aux_loss,
-                              float* aux_coef, cudaStream_t st);
+                              float* aux_coef, long long slab_rows, cudaStream_t st);
+cudaError_t launch_ep_tables(const int* kept_recv, int W, int El, int* slab_dst, int* kept_loc, int* seg_start,
+                             int* tile_expert, int* num_mtiles, int max_mtiles, cudaStream_t st);
+cudaError_t launch_ep_repack(const void* src, void* dst, const int* kept_recv, const int* slab_dst, const int* seg_start,
+                             const int* kept_loc, int W, int El, long long slab_rows, int d, int to_packed, cudaStream_t st);
 cudaError_t launch_dispatch_fwd(const void* x, int x_dtype, const int* idx, const int* tile_base, const int* seg_start,
                                 const int* kept, int64_t T, int d, int E, int k, long long capacity, int* pos,
                                 int* row_src, void* xbuf, cudaStream_t st);

@@ -223,7 +223,7 @@ route_scan_kernel(const int* __restrict__ tile_hist, const float* __restrict__ t
                   long long capacity, int* __restrict__ tile_base, int* __restrict__ count, int* __restrict__ kept,
                   int* __restrict__ seg_start, int* __restrict__ tile_expert, int* __restrict__ num_mtiles,
                   int max_mtiles, float* __restrict__ psum, int aux_mode, long long tokens, int k, float* __restrict__ aux_loss,
-                  float* __restrict__ aux_coef) {
+                  float* __restrict__ aux_coef, long long slab_rows) {
     extern __shared__ int smem_i[];
     int* cnt_s = smem_i;          // [E]
     int* seg_s = smem_i + E;      // [E+1]
@@ -277,7 +277,9 @@ route_scan_kernel(const int* __restrict__ tile_hist, const float* __restrict__ t
             kept[e] = kp;
             seg_s[e] = start;
             seg_start[e] = start;
-            start += (kp + MOE_ROW_ALIGN - 1) / MOE_ROW_ALIGN * MOE_ROW_ALIGN;
+            // packed layout: the segment is as long as the expert needs; expert-parallel layout: fixed slabs, so that
+            // the all-to-all that follows has static message sizes (no host round trip for the counts)
+            start += slab_rows > 0 ? static_cast<int>(slab_rows) : (kp + MOE_ROW_ALIGN - 1) / MOE_ROW_ALIGN * MOE_ROW_ALIGN;
         }
         seg_s[E] = start;
         seg_start[E] = start;
@@ -949,6 +951,72 @@ segment_colsum_final_kernel(const float* __restrict__ part, const int* __restric
     out[static_cast<size_t>(e) * cols + c] = sum;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Expert parallelism (receive side).  After the dispatch all-to-all a rank holds, for each source rank s
+// and each LOCAL expert e, a fixed slab recv[s][e][slab_rows][d] of which the first kept_recv[s][e] rows
+// are live.  ep_tables turns the W x E_local counts into the standard packed layout (expert-contiguous,
+// 256-aligned segments, sources in rank order inside a segment) and ep_repack moves rows between the two
+// layouts, so the expert FFN kernels run unchanged on the packed buffer.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ep_tables_kernel(const int* __restrict__ kept_recv, int W, int El, int* __restrict__ slab_dst, int* __restrict__ kept_loc,
+                 int* __restrict__ seg_start, int* __restrict__ tile_expert, int* __restrict__ num_mtiles, int max_mtiles) {
+    extern __shared__ int smem_i[];
+    int* seg_s = smem_i;  // [El + 1]
+    if (threadIdx.x == 0) {
+        int start = 0;
+        for (int e = 0; e < El; ++e) {
+            seg_s[e] = start;
+            seg_start[e] = start;
+            int tot = 0;
+            for (int s = 0; s < W; ++s) {
+                slab_dst[s * El + e] = start + tot;   // first packed row of source s inside expert e's segment
+                tot += kept_recv[s * El + e];
+            }
+            kept_loc[e] = tot;
+            start += (tot + MOE_ROW_ALIGN - 1) / MOE_ROW_ALIGN * MOE_ROW_ALIGN;
+        }
+        seg_s[El] = start;
+        seg_start[El] = start;
+        *num_mtiles = start / MOE_ROW_ALIGN;
+    }
+    __syncthreads();
+    const int nm = seg_s[El] / MOE_ROW_ALIGN;
+    for (int m = threadIdx.x; m < max_mtiles; m += 256) {
+        int e = -1;
+        if (m < nm) {
+            const int row = m * MOE_ROW_ALIGN;
+            e = 0;
+            while (e + 1 < El && seg_s[e + 1] <= row) ++e;
+        }
+        tile_expert[m] = e;
+    }
+}
+
+// to_packed = 1: packed[slab_dst[s,e] + i] = slabs[(s*El + e)*slab_rows + i] for i < kept_recv[s,e]; pad rows of
+//                every packed segment are zeroed (blocks >= W*El do that).
+// to_packed = 0: the inverse copy; rows of a slab beyond kept are left untouched (the receiver never reads them).
+__global__ void __launch_bounds__(256)
+ep_repack_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, const int* __restrict__ kept_recv,
+                 const int* __restrict__ slab_dst, const int* __restrict__ seg_start, const int* __restrict__ kept_loc,
+                 int W, int El, long long slab_rows, int d, int to_packed, int row_blocks) {
+    const int pair = blockIdx.x / row_blocks, rb = blockIdx.x - pair * row_blocks;
+    if (pair >= W * El) {
+        if (to_packed && rb == 0) zero_pad_rows(dst, d, seg_start, kept_loc, pair - W * El, nullptr);
+        return;
+    }
+    const int n = kept_recv[pair];
+    const size_t slab0 = static_cast<size_t>(pair) * slab_rows, pk0 = static_cast<size_t>(slab_dst[pair]);
+    const int per_row = d / 8;
+    const int r0 = rb * 64, r1 = min(n, r0 + 64);
+    for (int it = threadIdx.x; it < (r1 - r0) * per_row; it += 256) {
+        const int r = r0 + it / per_row, c = (it % per_row) * 8;
+        const size_t a = (slab0 + r) * d + c, b = (pk0 + r) * d + c;
+        if (to_packed) *reinterpret_cast<uint4*>(dst + b) = __ldg(reinterpret_cast<const uint4*>(src + a));
+        else *reinterpret_cast<uint4*>(dst + a) = __ldg(reinterpret_cast<const uint4*>(src + b));
+    }
+}
+
 // ================================================================================================
 // host launchers (C++ linkage; the extern "C" surface lives in api.cu)
 // ================================================================================================
@@ -998,11 +1066,11 @@ cudaError_t launch_gate_fwd(const void* x, int x_dtype, const float* Wg, const f
 cudaError_t launch_route_scan(const int* tile_hist, const float* tile_psum, int ntiles, int E, long long capacity,
                               int* tile_base, int* count, int* kept, int* seg_start, int* tile_expert, int* num_mtiles,
                               int max_mtiles, float* psum, int aux_mode, long long tokens, int k, float* aux_loss,
-                              float* aux_coef, cudaStream_t st) {
+                              float* aux_coef, long long slab_rows, cudaStream_t st) {
     const size_t smem = (3 * static_cast<size_t>(E) + 1) * 4;
     route_scan_kernel<<<1, 1024, smem, st>>>(tile_hist, tile_psum, ntiles, E, capacity, tile_base, count, kept,
                                              seg_start, tile_expert, num_mtiles, max_mtiles, psum, aux_mode, tokens, k,
-                                             aux_loss, aux_coef);
+                                             aux_loss, aux_coef, slab_rows);
     return cudaGetLastError();
 }
 
@@ -1171,6 +1239,22 @@ cudaError_t launch_segment_colsum(const void* buf, const int* seg_start, int64_t
     if (err != cudaSuccess) return err;
     dim3 g2((cols + 255) / 256, E);
     segment_colsum_final_kernel<<<g2, 256, 0, st>>>(part, seg_start, cols, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ep_tables(const int* kept_recv, int W, int El, int* slab_dst, int* kept_loc, int* seg_start,
+                             int* tile_expert, int* num_mtiles, int max_mtiles, cudaStream_t st) {
+    ep_tables_kernel<<<1, 256, (El + 1) * sizeof(int), st>>>(kept_recv, W, El, slab_dst, kept_loc, seg_start, tile_expert,
+                                                            num_mtiles, max_mtiles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ep_repack(const void* src, void* dst, const int* kept_recv, const int* slab_dst, const int* seg_start,
+                             const int* kept_loc, int W, int El, long long slab_rows, int d, int to_packed, cudaStream_t st) {
+    const int row_blocks = static_cast<int>((slab_rows + 63) / 64);
+    const int grid = W * El * row_blocks + (to_packed ? El * row_blocks : 0);
+    ep_repack_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), kept_recv,
+                                           slab_dst, seg_start, kept_loc, W, El, slab_rows, d, to_packed, row_blocks);
     return cudaGetLastError();
 }
 

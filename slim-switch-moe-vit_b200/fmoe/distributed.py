@@ -1,0 +1,217 @@
+"""Expert parallelism for the B200 MoE layer (FastMoE's `world_size > 1` mode, which the
+reference never switches on — /root/reference/models/resMoE.py:27-29 leaves world_size at 1 — and which
+BASELINE.json configs[2..3] ask for).
+
+Layout: global expert g lives on rank g // E_local.  Every rank routes its own tokens over all
+E = W * E_local experts with a per-source-rank capacity C = ceil(cf * T_local * k / E), so routing needs no
+cross-rank traffic and stays bit-exact against a single-process oracle run on the rank's token shard.
+The dispatch kernel writes FIXED slabs [E, slab_rows, d] (slab_rows = C rounded up to 256), which makes
+both all-to-alls static-size — no `.item()` / `.cpu()` round trip for the counts as in upstream:
+
+    forward   gate+scan+dispatch -> a2a(counts) + a2a(slabs) -> repack -> expert FFN -> unpack -> a2a -> combine
+    backward  combine_bwd -> a2a -> repack -> expert FFN backward -> unpack -> a2a -> gate/dispatch backward
+
+Gates without a capacity (NaiveGate, what the reference configures) would need slabs of T_local*k rows
+per expert; they are refused under expert parallelism — use SwitchGate / GShardGate.
+The collectives are `torch.distributed.all_to_all_single` on the layer's `moe_group` (NCCL over NVLink on
+the GPU box; gloo in the CPU tests of the host logic).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi as C
+from .functions import Bf16WeightCache, RouteSpec, _as_kernel_input, _f32, _i32, route
+
+
+def slab_rows_for(capacity: int) -> int:
+    """Rows of one (source rank, expert) slab: the capacity rounded up to the GEMM tile height."""
+    return (int(capacity) + C.ROW_ALIGN - 1) // C.ROW_ALIGN * C.ROW_ALIGN
+
+
+def all_to_all_slabs(send: torch.Tensor, group=None) -> torch.Tensor:
+    """send[W, ...] -> recv[W, ...]: chunk j of rank r becomes chunk r of rank j (equal, static sizes)."""
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    return recv
+
+
+def expert_parameters(model: torch.nn.Module):
+    """(name, parameter) of every expert weight of every expert-parallel MoE layer in `model`."""
+    from .layers import FMoE
+    out = []
+    for mod_name, mod in model.named_modules():
+        if isinstance(mod, FMoE) and mod.world_size > 1 and mod.experts is not None:
+            for n, p in mod.experts.named_parameters():
+                out.append((f"{mod_name}.experts.{n}" if mod_name else f"experts.{n}", p))
+    return out
+
+
+def mark_expert_parallel(model: torch.nn.Module, world_size: int | None = None) -> list[str]:
+    """Prepares `model` for `torch.nn.parallel.DistributedDataParallel` (reference main.py:610-612):
+    expert parameters are sharded, not replicated, so they are excluded from DDP's all-reduce
+    (`_ddp_params_and_buffers_to_ignore`) and their gradients — which already hold the contributions of
+    every rank's tokens after the backward all-to-all — are divided by W, the same 1/W DDP applies to
+    the replicated parameters (so the optimised objective is the mean of the ranks' losses everywhere).
+    Returns the ignored parameter names."""
+    names = []
+    for name, p in expert_parameters(model):
+        names.append(name)
+        if not getattr(p, "_moe_ep_hooked", False):
+            w = float(world_size if world_size is not None else dist.get_world_size())
+            p.register_hook(lambda g, w=w: g / w)
+            p._moe_ep_hooked = True
+    ignored = list(getattr(model, "_ddp_params_and_buffers_to_ignore", []))
+    model._ddp_params_and_buffers_to_ignore = sorted(set(ignored) | set(names))
+    return names
+
+
+def wrap_ddp(model: torch.nn.Module, local_rank: int, **kw):
+    mark_expert_parallel(model)
+    return torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], **kw)
+
+
+class DistributedGroupedDataParallel(torch.nn.parallel.DistributedDataParallel):
+    """Name-compatible stand-in for `fmoe.DistributedGroupedDataParallel`: plain DDP over the data-parallel
+    group with the expert parameters left out of the all-reduce."""
+
+    def __init__(self, module, **kw):
+        mark_expert_parallel(module)
+        super().__init__(module, **kw)
+
+
+class EPMoEFunction(torch.autograd.Function):
+    """y, aux_loss, count, kept = expert-parallel MoE(x; Wg, bg, local W1, b1, W2, b2)."""
+
+    @staticmethod
+    def forward(ctx, x, Wg, bg, W1, b1, W2, b2, spec: RouteSpec, cache: Bf16WeightCache, noise, group, world):
+        x = _as_kernel_input(x)
+        T, d = x.shape
+        El, h = W1.shape[0], W1.shape[1]
+        E, k, W = Wg.shape[0], spec.top_k, world
+        assert E == El * W, "gate must score world_size * num_expert experts"
+        dev, st = x.device, C.stream_ptr()
+        slab = slab_rows_for(spec.capacity)
+        Wg_c, W1_c, W2_c = Wg.detach().contiguous(), W1.detach().contiguous(), W2.detach().contiguous()
+        bg_c = None if bg is None else bg.detach().contiguous()
+
+        r = route(x, Wg_c, bg_c, spec, noise, slab_rows=slab)                       # send slabs [E, slab, d]
+        kept_recv = all_to_all_slabs(r["kept"].view(W, El), group)                   # [W(src), El]
+        recv_x = all_to_all_slabs(r["xbuf"].view(W, El * slab * d), group)           # [W(src), El, slab, d]
+
+        rows_cap = C.rows_cap(W * El * slab, 1, El, W * El * slab)                   # every received row could be live
+        max_mtiles = rows_cap // C.ROW_ALIGN
+        tb = dict(slab_dst=_i32((W, El), dev), kept=_i32(El, dev), seg_start=_i32(El + 1, dev),
+                  tile_expert=_i32(max_mtiles, dev), num_mtiles=_i32(1, dev))
+        C.call("moe_ep_tables", C.ptr(kept_recv), W, El, C.ptr(tb["slab_dst"]), C.ptr(tb["kept"]), C.ptr(tb["seg_start"]),
+               C.ptr(tb["tile_expert"]), C.ptr(tb["num_mtiles"]), max_mtiles, st)
+        bf = torch.bfloat16
+        xbuf = torch.empty((rows_cap, d), dtype=bf, device=dev)
+        C.call("moe_ep_repack", C.ptr(recv_x), C.ptr(xbuf), C.ptr(kept_recv), C.ptr(tb["slab_dst"]), C.ptr(tb["seg_start"]),
+               C.ptr(tb["kept"]), W, El, slab, d, 1, st)
+
+        W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c)
+        U = torch.empty((rows_cap, h), dtype=bf, device=dev)
+        H = torch.empty((rows_cap, h), dtype=bf, device=dev)
+        Y = torch.empty((rows_cap, d), dtype=bf, device=dev)
+        b1_c, b2_c = b1.detach().contiguous(), b2.detach().contiguous()
+        te, nm = C.ptr(tb["tile_expert"]), C.ptr(tb["num_mtiles"])
+        C.call("moe_grouped_gemm", C.GEMM_FC1, C.ptr(xbuf), C.ptr(W1b), C.ptr(U), C.ptr(H), C.ptr(b1_c), None,
+               te, nm, None, rows_cap, El, 0, h, d, st, tag="gemm_fc1")
+        C.call("moe_grouped_gemm", C.GEMM_FC2, C.ptr(H), C.ptr(W2b), C.ptr(Y), None, C.ptr(b2_c), None,
+               te, nm, None, rows_cap, El, 0, d, h, st, tag="gemm_fc2")
+
+        send_y = torch.empty((W, El * slab * d), dtype=bf, device=dev)
+        C.call("moe_ep_repack", C.ptr(Y), C.ptr(send_y), C.ptr(kept_recv), C.ptr(tb["slab_dst"]), C.ptr(tb["seg_start"]),
+               C.ptr(tb["kept"]), W, El, slab, d, 0, st)
+        ybuf = all_to_all_slabs(send_y, group).view(E * slab, d)                    # this rank's pairs, slab layout
+        y = torch.empty_like(x)
+        C.call("moe_combine_fwd", C.ptr(ybuf), C.ptr(r["pos"]), C.ptr(r["score"]), T, d, k, C.ptr(y), C.dtype_code(y), st)
+
+        ctx.spec, ctx.has_bg, ctx.group, ctx.world, ctx.slab, ctx.rows_cap = spec, bg is not None, group, W, slab, rows_cap
+        coef = r["aux_coef"] if spec.want_psum else torch.empty(0, dtype=torch.float32, device=dev)
+        ctx.save_for_backward(x, Wg_c, r["logits"], r["idx"], r["score"], r["pos"], r["seg_start"], r["kept"], kept_recv,
+                              tb["slab_dst"], tb["seg_start"], tb["kept"], tb["tile_expert"], tb["num_mtiles"], xbuf, U, H,
+                              ybuf, W1tb, W2tb, coef)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(r["count"], r["kept"])
+        if spec.want_psum:
+            aux = r["aux_loss"].reshape(())
+        else:
+            aux = torch.empty(0, dtype=torch.float32, device=dev)
+            ctx.mark_non_differentiable(aux)
+        return y, aux, r["count"], r["kept"]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy, daux, _dcount, _dkept):
+        (x, Wg, logits, idx, score, pos, seg_send, kept_send, kept_recv, slab_dst, seg_loc, kept_loc, tile_expert,
+         num_mtiles, xbuf, U, H, ybuf, W1tb, W2tb, coef) = ctx.saved_tensors
+        spec, W, slab, rows_cap, group = ctx.spec, ctx.world, ctx.slab, ctx.rows_cap, ctx.group
+        T, d = x.shape
+        El, h = W1tb.shape[0], W1tb.shape[2]
+        E, k = El * W, spec.top_k
+        dev, st, bf = x.device, C.stream_ptr(), torch.bfloat16
+        if dy is None:
+            dy = torch.zeros_like(x)
+        dy = _as_kernel_input(dy)
+        dpsum = (coef * daux.float()).contiguous() if (spec.want_psum and daux is not None) else None
+
+        send_dy = torch.empty((E * slab, d), dtype=bf, device=dev)                   # slab layout, pads zeroed
+        dscore = _f32((T, k), dev)
+        C.call("moe_combine_bwd", C.ptr(dy), C.dtype_code(dy), C.ptr(ybuf), C.ptr(pos), C.ptr(score), C.ptr(seg_send),
+               C.ptr(kept_send), T, d, k, E, C.ptr(send_dy), C.ptr(dscore), st)
+        recv_dy = all_to_all_slabs(send_dy.view(W, El * slab * d), group)
+        dybuf = torch.empty((rows_cap, d), dtype=bf, device=dev)
+        C.call("moe_ep_repack", C.ptr(recv_dy), C.ptr(dybuf), C.ptr(kept_recv), C.ptr(slab_dst), C.ptr(seg_loc),
+               C.ptr(kept_loc), W, El, slab, d, 1, st)
+
+        dU = torch.empty((rows_cap, h), dtype=bf, device=dev)
+        dxbuf = torch.empty((rows_cap, d), dtype=bf, device=dev)
+        dW1, db1 = _f32((El, h, d), dev), _f32((El, h), dev)
+        dW2, db2 = _f32((El, d, h), dev), _f32((El, d), dev)
+        te, nm, sg = C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_loc)
+        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), None, None, C.ptr(U),
+               te, nm, None, rows_cap, El, 0, h, d, st, tag="gemm_dgelu")
+        C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dybuf), C.ptr(H), C.ptr(dW2), None, None, None,
+               None, None, sg, rows_cap, El, d, h, 0, st, tag="gemm_wgrad2")
+        C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dU), C.ptr(xbuf), C.ptr(dW1), None, None, None,
+               None, None, sg, rows_cap, El, h, d, 0, st, tag="gemm_wgrad1")
+        C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1tb), C.ptr(dxbuf), None, None, None,
+               te, nm, None, rows_cap, El, 0, d, h, st, tag="gemm_dgrad")
+        cws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, h), dtype=torch.uint8, device=dev)
+        C.call("moe_segment_colsum", C.ptr(dybuf), sg, rows_cap, El, d, C.ptr(cws), C.ptr(db2), st, tag="colsum_db2")
+        C.call("moe_segment_colsum", C.ptr(dU), sg, rows_cap, El, h, C.ptr(cws), C.ptr(db1), st, tag="colsum_db1")
+
+        send_dx = torch.empty((W, El * slab * d), dtype=bf, device=dev)
+        C.call("moe_ep_repack", C.ptr(dxbuf), C.ptr(send_dx), C.ptr(kept_recv), C.ptr(slab_dst), C.ptr(seg_loc),
+               C.ptr(kept_loc), W, El, slab, d, 0, st)
+        dx_slabs = all_to_all_slabs(send_dx, group).view(E * slab, d)
+
+        dlogits = _f32((T, E), dev)
+        dx = torch.empty_like(x)
+        C.call("moe_gate_dispatch_bwd", C.ptr(dx_slabs), C.ptr(pos), C.ptr(logits), C.ptr(idx), C.ptr(score), C.ptr(dscore),
+               C.ptr(dpsum), C.ptr(Wg), T, d, E, k, spec.score_mode, C.ptr(dlogits), C.ptr(dx), C.dtype_code(dx), st)
+        ws = torch.empty(C.lib.moe_gate_wgrad_workspace_bytes(T, d, E), dtype=torch.uint8, device=dev)
+        dWg = _f32((E, d), dev)
+        dbg = _f32(E, dev) if ctx.has_bg else None
+        C.call("moe_gate_wgrad", C.ptr(dlogits), C.ptr(x), C.dtype_code(x), T, d, E, C.ptr(ws), C.ptr(dWg), C.ptr(dbg), st)
+        return dx, dWg, dbg, dW1, db1, dW2, db2, None, None, None, None, None
+
+
+def ep_forward(layer, moe_inp: torch.Tensor) -> torch.Tensor:
+    """`FMoE.forward` for world_size > 1."""
+    gate = layer.gate
+    T = moe_inp.shape[0]
+    spec = gate.route_spec(T)
+    if spec.capacity >= T * spec.top_k:
+        raise NotImplementedError(
+            f"{type(gate).__name__} has no per-expert capacity: expert parallelism exchanges fixed-size slabs and needs a "
+            "capacity-limited gate (SwitchGate / GShardGate)")
+    W1, b1, W2, b2 = layer._expert_params()
+    y, aux, count, kept = EPMoEFunction.apply(moe_inp, gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec,
+                                              layer._bf16_cache, gate.make_noise(moe_inp), layer.moe_group, layer.world_size)
+    gate.finish(aux)
+    layer.last_count, layer.last_kept = count, kept
+    return y

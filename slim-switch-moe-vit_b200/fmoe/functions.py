@@ -69,15 +69,16 @@ def _f32(n, dev):
     return torch.empty(n, dtype=torch.float32, device=dev)
 
 
-def route(x, Wg, bg, spec: RouteSpec, noise=None):
-    """gate + scan + dispatch.  Returns a dict of device tensors (no host sync)."""
+def route(x, Wg, bg, spec: RouteSpec, noise=None, slab_rows: int = 0):
+    """gate + scan + dispatch.  Returns a dict of device tensors (no host sync).
+    slab_rows > 0 selects the expert-parallel send layout: expert e owns rows [e*slab_rows, (e+1)*slab_rows)."""
     T, d = x.shape
     E = Wg.shape[0]
     k = spec.top_k
     dev = x.device
     st = C.stream_ptr()
     ntiles = (T + C.TOKEN_TILE - 1) // C.TOKEN_TILE
-    rows_cap = C.rows_cap(T, k, E, spec.capacity)
+    rows_cap = E * slab_rows if slab_rows else C.rows_cap(T, k, E, spec.capacity)
     max_mtiles = rows_cap // C.ROW_ALIGN
     r = dict(
         logits=_f32((T, E), dev), idx=_i32((T, k), dev), score=_f32((T, k), dev),
@@ -98,7 +99,7 @@ def route(x, Wg, bg, spec: RouteSpec, noise=None):
     C.call("moe_route_scan", C.ptr(r["tile_hist"]), C.ptr(tile_psum), ntiles, E, spec.capacity,
            C.ptr(r["tile_base"]), C.ptr(r["count"]), C.ptr(r["kept"]), C.ptr(r["seg_start"]),
            C.ptr(r["tile_expert"]), C.ptr(r["num_mtiles"]), max_mtiles, C.ptr(r["psum"]), int(spec.aux_mode), T, k,
-           C.ptr(r["aux_loss"]), C.ptr(r["aux_coef"]), st)
+           C.ptr(r["aux_loss"]), C.ptr(r["aux_coef"]), slab_rows, st)
     C.call("moe_dispatch_fwd", C.ptr(x), C.dtype_code(x), C.ptr(r["idx"]), C.ptr(r["tile_base"]),
            C.ptr(r["seg_start"]), C.ptr(r["kept"]), T, d, E, k, spec.capacity, C.ptr(r["pos"]),
            C.ptr(r["row_src"]), C.ptr(r["xbuf"]), st)

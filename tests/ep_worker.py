@@ -1,0 +1,72 @@
+"""Expert-parallel parity worker: run under torch.distributed.run with W ranks (one GPU each, NCCL).
+Every rank checks its own outputs / gradients against the single-process CPU oracle evaluated with
+ALL experts on that rank's token shard (per-source-rank capacity keeps the routing identical).
+Prints `EP_OK rank=<r>` on success."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "slim-switch-moe-vit_b200"), os.path.dirname(os.path.abspath(__file__))]
+import torch
+import torch.distributed as dist
+
+from _util import make_problem, rel_err
+from oracle import moe_oracle as O
+
+
+def main():
+    rank, W = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl")
+    from fmoe import _cabi as C
+    from fmoe import functions as Fn
+    from fmoe.distributed import EPMoEFunction
+
+    for (T, d, h, E, k, mode, cf, aux_mode) in [(1000, 128, 256, 8, 1, 1, 1.25, C.AUX_SWITCH),
+                                                (777, 192, 768, 4 * W, 2, 0, 1.0, C.AUX_GSHARD),
+                                                (2500, 384, 1536, 16, 1, 1, 1.25, C.AUX_SWITCH)]:
+        El = E // W
+        # the same global problem on every rank (seeded), each rank's tokens seeded by its rank
+        _, Wg, bg, W1, b1, W2, b2 = make_problem(T, d, h, E, seed=11, skew=1.0)
+        xs, dys = [], []
+        for r in range(W):
+            g = torch.Generator().manual_seed(100 + r)
+            xs.append(torch.randn(T, d, generator=g))
+            dys.append(torch.randn(T, d, generator=g))
+        cap = O.capacity_from_factor(cf, T, k, E)
+        spec = Fn.RouteSpec(k, mode, cap, aux_mode)
+        sl = slice(rank * El, (rank + 1) * El)
+        dev = [t.cuda().requires_grad_() for t in (xs[rank], Wg, bg, W1[sl].contiguous(), b1[sl].contiguous(),
+                                                   W2[sl].contiguous(), b2[sl].contiguous())]
+        y, aux, count, kept = EPMoEFunction.apply(*dev, spec, Fn.Bf16WeightCache(), None, None, W)
+        aux_w = 0.37
+        ((y * dys[rank].cuda()).sum() + aux_w * aux).backward()
+        torch.cuda.synchronize()
+
+        exp = {}
+        for r in range(W):   # oracle of every rank's shard (expert gradients sum over the source ranks)
+            ym, sv = O.forward_model(xs[r], Wg, bg, W1, b1, W2, b2, k, mode, cap)
+            coef = O.aux_coef(sv.r, T, aux_mode)
+            gm = O.backward_model(sv, dys[r], Wg, aux_w * coef)
+            for n in ("dW1", "db1", "dW2", "db2"):
+                exp[n] = exp.get(n, 0) + gm[n]
+            if r == rank:
+                mine, mine_y, mine_sv, mine_coef = gm, ym, sv, coef
+        assert torch.equal(count.cpu(), mine_sv.r.count) and torch.equal(kept.cpu(), mine_sv.r.kept), "routing counts"
+        assert rel_err(y, mine_y) <= 3e-3, f"y {rel_err(y, mine_y)}"
+        assert abs(float(aux) - float((mine_coef * mine_sv.r.psum).sum())) <= 1e-5
+        for name, t, want in (("dx", dev[0], mine["dx"]), ("dWg", dev[1], mine["dWg"]), ("dbg", dev[2], mine["dbg"]),
+                              ("dW1", dev[3], exp["dW1"][sl]), ("db1", dev[4], exp["db1"][sl]),
+                              ("dW2", dev[5], exp["dW2"][sl]), ("db2", dev[6], exp["db2"][sl])):
+            e = rel_err(t.grad, want)
+            assert e <= 6e-3, f"{name}: {e} (T={T} E={E} k={k})"
+        dropped = int((mine_sv.r.pos < 0).sum())
+        if rank == 0:
+            print(f"case T={T} d={d} E={E} k={k}: ok (dropped pairs on rank 0: {dropped})", flush=True)
+    dist.barrier()
+    print(f"EP_OK rank={rank}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
