@@ -37,6 +37,15 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+# stdout carries exactly ONE line (the JSON): everything libraries print (NCCL's version banner, warnings) goes to stderr
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 import torch  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
@@ -189,7 +198,7 @@ def run_reference_arm(args):
         "e2e": {"value": r["images_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -417,7 +426,7 @@ def main():
             r = cpu_reference_run(steps=1000, warmup=1, budget_s=20.0)
             line["cpu_baseline"] = {"value": r["images_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

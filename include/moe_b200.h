@@ -150,6 +150,18 @@ size_t moe_gate_wgrad_workspace_bytes(int64_t T, int d, int E);
 int moe_gate_wgrad(const float *dlogits, const void *x, int x_dtype, int64_t T, int d, int E, void *workspace,
                    float *dWg, float *dbg, void *stream);
 
+/* ---- block-level fusion around the layer (reference models/vision_transformer.py:319-322):
+ * x_out = x_in + delta (delta nullable: x_out untouched), n = LayerNorm(x_out) * gamma + beta.
+ * The residual stream x is fp32; delta and n are fp32 or bf16; mean / rstd [T] fp32 are saved for backward.
+ * Backward: dx_in = dx_out (nullable) + LN'(dn), d_delta (nullable) = dx_in in delta's dtype, dgamma / dbeta [d]
+ * through a two-stage deterministic reduction (workspace: moe_addln_bwd_workspace_bytes).  d % 4 == 0, d <= 1024. */
+int moe_addln_fwd(const float *x_in, const void *delta, int delta_dtype, const float *gamma, const float *beta, float eps,
+                  int64_t T, int d, float *x_out, void *n, int n_dtype, float *mean, float *rstd, void *stream);
+size_t moe_addln_bwd_workspace_bytes(int64_t T, int d);
+int moe_addln_bwd(const void *dn, int n_dtype, const float *dx_out, const float *x, const float *mean, const float *rstd,
+                  const float *gamma, int64_t T, int d, float *dx_in, void *d_delta, int delta_dtype, void *workspace,
+                  float *dgamma, float *dbeta, void *stream);
+
 /* ---- utilities */
 int moe_cast_bf16(const float *src, void *dst, int64_t n /* % 8 == 0 */, void *stream);
 /* src[E,R,C] fp32 -> dst[E,R,C] bf16 (nullable) and dst_t[E,C,R] bf16 (transposed per expert); R, C % 32 == 0 */

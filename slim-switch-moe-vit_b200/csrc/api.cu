@@ -194,6 +194,32 @@ int moe_gate_dispatch_bwd(const void* dxbuf, const int32_t* pos, const float* lo
                  "moe_gate_dispatch_bwd");
 }
 
+size_t moe_addln_bwd_workspace_bytes(int64_t T, int d) { return addln_bwd_workspace_bytes(T, d); }
+
+static bool addln_ok(const char* fn, int64_t T, int d) {
+    if (T <= 0 || d <= 0 || d % 4 != 0 || d > 1024) { set_error("%s: unsupported shape T=%lld d=%d (need d %% 4 == 0, d <= 1024)", fn, (long long)T, d); return false; }
+    return true;
+}
+
+int moe_addln_fwd(const float* x_in, const void* delta, int delta_dtype, const float* gamma, const float* beta, float eps, int64_t T,
+                  int d, float* x_out, void* n, int n_dtype, float* mean, float* rstd, void* stream) {
+    if (!addln_ok("moe_addln_fwd", T, d) || !dtype_ok("moe_addln_fwd", n_dtype) || (delta != nullptr && !dtype_ok("moe_addln_fwd", delta_dtype))) return 1;
+    if (delta != nullptr && x_out == nullptr) { set_error("moe_addln_fwd: x_out is required when delta is given"); return 1; }
+    return check(launch_addln_fwd(x_in, delta, delta_dtype, gamma, beta, eps, T, d, x_out, n, n_dtype, mean, rstd,
+                                  static_cast<cudaStream_t>(stream)),
+                 "moe_addln_fwd");
+}
+
+int moe_addln_bwd(const void* dn, int n_dtype, const float* dx_out, const float* x, const float* mean, const float* rstd,
+                  const float* gamma, int64_t T, int d, float* dx_in, void* d_delta, int delta_dtype, void* workspace, float* dgamma,
+                  float* dbeta, void* stream) {
+    if (!addln_ok("moe_addln_bwd", T, d) || !dtype_ok("moe_addln_bwd", n_dtype) || (d_delta != nullptr && !dtype_ok("moe_addln_bwd", delta_dtype))) return 1;
+    if (workspace == nullptr) { set_error("moe_addln_bwd: workspace (moe_addln_bwd_workspace_bytes) required"); return 1; }
+    return check(launch_addln_bwd(dn, n_dtype, dx_out, x, mean, rstd, gamma, T, d, dx_in, d_delta, delta_dtype, workspace, dgamma, dbeta,
+                                  static_cast<cudaStream_t>(stream)),
+                 "moe_addln_bwd");
+}
+
 int moe_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out1, const float* bias, const void* aux,
                      const int32_t* tile_expert, const int32_t* num_mtiles, const int32_t* seg_start, int64_t rows_cap,
                      int E, int M, int N, int K, void* stream) {

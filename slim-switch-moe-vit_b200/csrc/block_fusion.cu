@@ -1,0 +1,246 @@
+// block_fusion.cu — the two HBM passes around the MoE layer in the hosting transformer block, fused:
+//   x_out = x_in + delta ;  n = LayerNorm(x_out) * gamma + beta          (one kernel instead of add + LN + cast)
+// and its backward.  In the reference block (/root/reference/models/vision_transformer.py:319-322) these are
+// `x + drop_path(self.mlp(self.norm2(x)))` -> the residual add that consumes the layer's output and the
+// pre-norm that produces the next layer's input.  The residual stream stays fp32
+// (what autocast does in the reference, engine.py:52); the normalised output is written directly in bf16,
+// the dtype the MoE dispatch / attention projections read, so no separate cast kernel runs.
+//
+// One warp per row, the whole row in registers (d <= 1024, d % 4 == 0), two-pass mean / variance.
+// Backward is persistent: every lane owns fixed columns, so the dgamma / dbeta partial sums live in
+// registers across all rows of the CTA, are combined over the CTA's 8 warps in shared memory in warp order
+// and written as one partial per CTA; a second kernel adds the partials in CTA order (deterministic).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace moe {
+
+constexpr int kLnMaxV = 8;  // float4 per lane: d <= 32 * 4 * 8 = 1024 (kernels are instantiated for NV = 2, 3, 6, 8)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld_f4(const __nv_bfloat16* p) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st_f4(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+
+// delta (nullable): x_out = x_in + delta is written to x_out; otherwise x_out is not touched and x_in is normalised.
+template <typename DT, typename NT, int NV>
+__global__ void __launch_bounds__(256)
+addln_fwd_kernel(const float* __restrict__ x_in, const DT* __restrict__ delta, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, int64_t T, int d, float* __restrict__ x_out, NT* __restrict__ n,
+                 float* __restrict__ mean, float* __restrict__ rstd) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= T) return;
+    const int nv = d / 4;
+    float4 v[NV];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (i * 32 + lane < nv) {
+            v[i] = ld_f4(x_in + row * d + c);
+            if (delta != nullptr) {
+                const float4 dl = ld_f4(delta + row * d + c);
+                v[i].x += dl.x; v[i].y += dl.y; v[i].z += dl.z; v[i].w += dl.w;
+                st_f4(x_out + row * d + c, v[i]);
+            }
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mu = warp_sum(s) / static_cast<float>(d);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        if (i * 32 + lane < nv) {
+            const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, e = v[i].w - mu;
+            q += (a * a + b * b) + (c * c + e * e);
+        }
+    }
+    const float rs = rsqrtf(warp_sum(q) / static_cast<float>(d) + eps);
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (i * 32 + lane < nv) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c)), b = __ldg(reinterpret_cast<const float4*>(beta + c));
+            float4 o;
+            o.x = (v[i].x - mu) * rs * g.x + b.x; o.y = (v[i].y - mu) * rs * g.y + b.y;
+            o.z = (v[i].z - mu) * rs * g.z + b.z; o.w = (v[i].w - mu) * rs * g.w + b.w;
+            st_f4(n + row * d + c, o);
+        }
+    }
+}
+
+// dx_in = (dx_out or 0) + LN'(dn);  d_delta (nullable) = dx_in in the delta dtype;  partial dgamma / dbeta per CTA.
+template <typename NT, typename DT, int NV>
+__global__ void __launch_bounds__(256)
+addln_bwd_kernel(const NT* __restrict__ dn, const float* __restrict__ dx_out, const float* __restrict__ x, const float* __restrict__ mean,
+                 const float* __restrict__ rstd, const float* __restrict__ gamma, int64_t T, int d, float* __restrict__ dx_in,
+                 DT* __restrict__ d_delta, float* __restrict__ part /* [grid][2][d] */) {
+    extern __shared__ float red[];  // [8][2*d]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nv = d / 4;
+    float4 gam[NV], dg[NV], db[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gam[i] = (i * 32 + lane < nv) ? __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float inv_d = 1.0f / static_cast<float>(d);
+    for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < T; row += static_cast<int64_t>(gridDim.x) * 8) {
+        const float mu = mean[row], rs = rstd[row];
+        float4 xh[NV], g[NV];
+        float c1 = 0.0f, c2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (i * 32 + lane < nv) {
+                const float4 xv = ld_f4(x + row * d + c), gv = ld_f4(dn + row * d + c);
+                xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                dg[i].x += gv.x * xh[i].x; dg[i].y += gv.y * xh[i].y; dg[i].z += gv.z * xh[i].z; dg[i].w += gv.w * xh[i].w;
+                db[i].x += gv.x; db[i].y += gv.y; db[i].z += gv.z; db[i].w += gv.w;
+                g[i] = make_float4(gv.x * gam[i].x, gv.y * gam[i].y, gv.z * gam[i].z, gv.w * gam[i].w);
+                c1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+                c2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+            }
+        }
+        c1 = warp_sum(c1) * inv_d;
+        c2 = warp_sum(c2) * inv_d;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (i * 32 + lane < nv) {
+                float4 o;
+                o.x = rs * (g[i].x - c1 - xh[i].x * c2); o.y = rs * (g[i].y - c1 - xh[i].y * c2);
+                o.z = rs * (g[i].z - c1 - xh[i].z * c2); o.w = rs * (g[i].w - c1 - xh[i].w * c2);
+                if (dx_out != nullptr) {
+                    const float4 r = ld_f4(dx_out + row * d + c);
+                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
+                st_f4(dx_in + row * d + c, o);
+                if (d_delta != nullptr) st_f4(d_delta + row * d + c, o);
+            }
+        }
+    }
+    // combine the 8 warps of the CTA in warp order
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (i * 32 + lane < nv) {
+            st_f4(red + warp * 2 * d + c, dg[i]);
+            st_f4(red + warp * 2 * d + d + c, db[i]);
+        }
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 2 * d; o += 256) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += red[w * 2 * d + o];
+        part[static_cast<size_t>(blockIdx.x) * 2 * d + o] = sum;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+addln_bwd_reduce_kernel(const float* __restrict__ part, int nparts, int d, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float red[4][64];
+    const int o = blockIdx.x * 64 + (threadIdx.x & 63), sl = threadIdx.x >> 6;
+    const int per = (nparts + 3) / 4;
+    float v = 0.0f;
+    if (o < 2 * d) {
+        const int b1 = min(nparts, (sl + 1) * per);
+#pragma unroll 4
+        for (int b = sl * per; b < b1; ++b) v += part[static_cast<size_t>(b) * 2 * d + o];
+    }
+    red[sl][threadIdx.x & 63] = v;
+    __syncthreads();
+    if (sl == 0 && o < 2 * d) {
+        const float r = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
+        if (o < d) dgamma[o] = r;
+        else dbeta[o - d] = r;
+    }
+}
+
+static int addln_bwd_blocks(int64_t T) {
+    const int64_t want = (T + 7) / 8;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+    return static_cast<int>(want < cap ? want : cap);
+}
+
+size_t addln_bwd_workspace_bytes(int64_t T, int d) { return static_cast<size_t>(addln_bwd_blocks(T)) * 2 * d * 4; }
+
+cudaError_t launch_addln_fwd(const float* x_in, const void* delta, int delta_dtype, const float* gamma, const float* beta, float eps,
+                             int64_t T, int d, float* x_out, void* n, int n_dtype, float* mean, float* rstd, cudaStream_t st) {
+    const int grid = static_cast<int>((T + 7) / 8);
+#define MOE_LN_FWD_NV(DT, NT, NVV)                                                                                      \
+    addln_fwd_kernel<DT, NT, NVV><<<grid, 256, 0, st>>>(x_in, static_cast<const DT*>(delta), gamma, beta, eps, T, d, x_out, \
+                                                        static_cast<NT*>(n), mean, rstd)
+#define MOE_LN_FWD(DT, NT)                                                                                              \
+    {                                                                                                                   \
+        if (d <= 256) MOE_LN_FWD_NV(DT, NT, 2);                                                                         \
+        else if (d <= 384) MOE_LN_FWD_NV(DT, NT, 3);                                                                    \
+        else if (d <= 768) MOE_LN_FWD_NV(DT, NT, 6);                                                                    \
+        else MOE_LN_FWD_NV(DT, NT, 8);                                                                                  \
+    }
+    const bool dbf = delta != nullptr && delta_dtype == MOE_DTYPE_BF16, nbf = n_dtype == MOE_DTYPE_BF16;
+    if (dbf && nbf) MOE_LN_FWD(__nv_bfloat16, __nv_bfloat16)
+    else if (dbf) MOE_LN_FWD(__nv_bfloat16, float)
+    else if (nbf) MOE_LN_FWD(float, __nv_bfloat16)
+    else MOE_LN_FWD(float, float)
+#undef MOE_LN_FWD
+#undef MOE_LN_FWD_NV
+    return cudaGetLastError();
+}
+
+cudaError_t launch_addln_bwd(const void* dn, int n_dtype, const float* dx_out, const float* x, const float* mean, const float* rstd,
+                             const float* gamma, int64_t T, int d, float* dx_in, void* d_delta, int delta_dtype, void* workspace,
+                             float* dgamma, float* dbeta, cudaStream_t st) {
+    const int grid = addln_bwd_blocks(T);
+    float* part = static_cast<float*>(workspace);
+    const size_t smem = static_cast<size_t>(8) * 2 * d * 4;
+    cudaError_t err = cudaSuccess;
+#define MOE_LN_BWD_NV(NT, DT, NVV)                                                                                          \
+    {                                                                                                                       \
+        auto kfn = addln_bwd_kernel<NT, DT, NVV>;                                                                           \
+        err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                            \
+        if (err != cudaSuccess) return err;                                                                                 \
+        kfn<<<grid, 256, smem, st>>>(static_cast<const NT*>(dn), dx_out, x, mean, rstd, gamma, T, d, dx_in,                \
+                                     static_cast<DT*>(d_delta), part);                                                      \
+    }
+#define MOE_LN_BWD(NT, DT)                                                                                                  \
+    {                                                                                                                       \
+        if (d <= 256) MOE_LN_BWD_NV(NT, DT, 2)                                                                              \
+        else if (d <= 384) MOE_LN_BWD_NV(NT, DT, 3)                                                                         \
+        else if (d <= 768) MOE_LN_BWD_NV(NT, DT, 6)                                                                         \
+        else MOE_LN_BWD_NV(NT, DT, 8)                                                                                       \
+    }
+    const bool nbf = n_dtype == MOE_DTYPE_BF16, dbf = d_delta != nullptr && delta_dtype == MOE_DTYPE_BF16;
+    if (nbf && dbf) MOE_LN_BWD(__nv_bfloat16, __nv_bfloat16)
+    else if (nbf) MOE_LN_BWD(__nv_bfloat16, float)
+    else if (dbf) MOE_LN_BWD(float, __nv_bfloat16)
+    else MOE_LN_BWD(float, float)
+#undef MOE_LN_BWD
+#undef MOE_LN_BWD_NV
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    addln_bwd_reduce_kernel<<<(2 * d + 63) / 64, 256, 0, st>>>(part, grid, d, dgamma, dbeta);
+    return cudaGetLastError();
+}
+
+}  // namespace moe

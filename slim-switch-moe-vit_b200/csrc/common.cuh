@@ -46,6 +46,14 @@ cudaError_t launch_gate_dispatch_bwd(const void* dxbuf, const int* pos, const fl
                                      const float* dscore, const float* dpsum, const float* Wg, int64_t T, int d, int E, int k,
                                      int score_mode, float* dlogits, void* dx, int dx_dtype, cudaStream_t st);
 
+// block_fusion.cu
+size_t addln_bwd_workspace_bytes(int64_t T, int d);
+cudaError_t launch_addln_fwd(const float* x_in, const void* delta, int delta_dtype, const float* gamma, const float* beta, float eps,
+                             int64_t T, int d, float* x_out, void* n, int n_dtype, float* mean, float* rstd, cudaStream_t st);
+cudaError_t launch_addln_bwd(const void* dn, int n_dtype, const float* dx_out, const float* x, const float* mean, const float* rstd,
+                             const float* gamma, int64_t T, int d, float* dx_in, void* d_delta, int delta_dtype, void* workspace,
+                             float* dgamma, float* dbeta, cudaStream_t st);
+
 // gemm_launch.cu — returns 0 on success, otherwise sets the error string via set_error()
 int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out1, const float* bias, const void* aux,
                         const int* tile_expert, const int* num_mtiles, const int* seg_start, int64_t rows_cap, int E,

@@ -91,16 +91,29 @@ class Mlp(nn.Module):
 
 
 class Block(nn.Module):
-    def __init__(self, dim, heads, mlp: nn.Module):
+    """Pre-norm block of the reference (vision_transformer.py:319-322): x + attn(norm1(x)), then x + mlp(norm2(x))."""
+
+    def __init__(self, dim, heads, mlp: nn.Module, norm=nn.LayerNorm):
         super().__init__()
-        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.norm1 = norm(dim, eps=1e-6)
         self.attn = Attention(dim, heads)
-        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.norm2 = norm(dim, eps=1e-6)
         self.mlp = mlp
 
     def forward(self, x):
         x = x + self.attn(self.norm1(x))
         return x + self.mlp(self.norm2(x))
+
+    def forward_fused(self, x, delta):
+        """Same arithmetic with every residual add folded into the LayerNorm that follows it
+        (fmoe.AddLayerNorm).  `delta` is the previous sub-layer's output that has not been added to the
+        fp32 residual stream `x` yet; returns (x, pending delta)."""
+        if delta is None:
+            n1 = self.norm1(x)
+        else:
+            x, n1 = self.norm1(x, delta)
+        x, n2 = self.norm2(x, self.attn(n1))
+        return x, self.mlp(n2)
 
 
 def _b200_moe_mlp(cfg: MoEViTConfig, dim: int, hidden: int) -> nn.Module:
@@ -125,17 +138,25 @@ def _b200_moe_mlp(cfg: MoEViTConfig, dim: int, hidden: int) -> nn.Module:
 
 
 class MoEViT(nn.Module):
-    def __init__(self, cfg: MoEViTConfig, moe_mlp=None):
+    def __init__(self, cfg: MoEViTConfig, moe_mlp=None, fused_norm: bool | None = None):
+        """`moe_mlp(dim, hidden)` builds the MoE module (default: the B200 layer).  `fused_norm` selects the
+        fused residual-add + LayerNorm kernels around the sub-layers (default: on with the B200 layer, off
+        otherwise — the CPU baseline runs the stock block)."""
         super().__init__()
         self.cfg = cfg
         dim, depth, heads = cfg.dims
+        self.fused_norm = (moe_mlp is None) if fused_norm is None else fused_norm
+        norm = nn.LayerNorm
+        if self.fused_norm:
+            from fmoe import AddLayerNorm
+            norm = AddLayerNorm
         moe_mlp = moe_mlp or partial(_b200_moe_mlp, cfg)
         n_patches = (cfg.img_size // cfg.patch) ** 2
         self.patch_embed = nn.Conv2d(3, dim, kernel_size=cfg.patch, stride=cfg.patch)
         self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
         self.pos_embed = nn.Parameter(torch.zeros(1, n_patches + 1, dim))
         self.blocks = nn.ModuleList(
-            Block(dim, heads, moe_mlp(dim, 4 * dim) if cfg.is_moe_block(i) else Mlp(dim, 4 * dim)) for i in range(depth))
+            Block(dim, heads, moe_mlp(dim, 4 * dim) if cfg.is_moe_block(i) else Mlp(dim, 4 * dim), norm) for i in range(depth))
         self.norm = nn.LayerNorm(dim, eps=1e-6)
         self.head = nn.Linear(dim, cfg.num_classes)
         nn.init.trunc_normal_(self.pos_embed, std=0.02)
@@ -153,9 +174,15 @@ class MoEViT(nn.Module):
     def forward(self, img):
         x = self.patch_embed(img).flatten(2).transpose(1, 2)
         x = torch.cat((self.cls_token.expand(x.shape[0], -1, -1), x), dim=1) + self.pos_embed
+        if not self.fused_norm:
+            for blk in self.blocks:
+                x = blk(x)
+            return self.head(self.norm(x)[:, 0])
+        x, delta = x.float(), None
         for blk in self.blocks:
-            x = blk(x)
-        return self.head(self.norm(x)[:, 0])
+            x, delta = blk.forward_fused(x, delta)
+        cls = x[:, 0] + delta[:, 0].float()       # only the class token reaches the head
+        return self.head(F.layer_norm(cls, self.norm.normalized_shape, self.norm.weight, self.norm.bias, self.norm.eps))
 
     def train_flops_per_image(self, kept_fraction: float = 1.0) -> float:
         """fwd+bwd (3x forward) matmul flops per image, SURVEY.md §8d formula."""

@@ -10,6 +10,7 @@ Bars (stated per assertion):
   * everything vs the un-rounded fp64 ideal: relative Frobenius error <= 2e-2 (bf16 operands).
 """
 import copy
+import os
 
 import pytest
 import torch
@@ -231,3 +232,61 @@ def test_rejects_cpu_and_bad_config():
     layer = fmoe.FMoETransformerMLP(4, 64, 256, torch.nn.GELU(), top_k=2)
     with pytest.raises(RuntimeError):
         layer(torch.randn(3, 64))
+
+
+@pytest.mark.parametrize("d,dt", [(384, torch.bfloat16), (192, torch.float32), (768, torch.bfloat16), (1024, torch.bfloat16), (64, torch.float32)])
+def test_add_layer_norm_vs_torch(d, dt):
+    """Fused residual-add + LayerNorm (fmoe.AddLayerNorm) against plain PyTorch fp32 (a floating-point kernel:
+    the torch fp32 reference is its oracle).  fp32 outputs: rel 1e-5; bf16 outputs: 4e-3 (bf16 rounding)."""
+    fmoe, C, Fn = _fm()
+    torch.manual_seed(3)
+    B, N = 5, 197
+    ln = fmoe.AddLayerNorm(d, eps=1e-6).cuda()
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5); ln.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(B, N, d, device="cuda", requires_grad=True)
+    delta = (torch.randn(B, N, d, device="cuda") * 0.5).to(dt).requires_grad_()
+    gx, gn = torch.randn(B, N, d, device="cuda"), torch.randn(B, N, d, device="cuda").to(dt)
+    x_out, n = fmoe.add_layer_norm(x, delta, ln.weight, ln.bias, ln.eps, out_dtype=dt)
+    assert x_out.dtype == torch.float32 and n.dtype == dt
+    torch.autograd.backward([x_out, n], [gx, gn])
+    got = [x_out.detach(), n.detach(), x.grad, delta.grad, ln.weight.grad, ln.bias.grad]
+    xr = x.detach().clone().requires_grad_(); dr = delta.detach().float().requires_grad_()
+    wr, br = ln.weight.detach().clone().requires_grad_(), ln.bias.detach().clone().requires_grad_()
+    xo = xr + dr
+    nr = torch.nn.functional.layer_norm(xo, (d,), wr, br, 1e-6)
+    torch.autograd.backward([xo, nr], [gx, gn.float()])
+    want = [xo.detach(), nr.detach(), xr.grad, dr.grad, wr.grad, br.grad]
+    tol = 1e-5 if dt == torch.float32 else 4e-3
+    for name, a, b in zip(["x_out", "n", "dx", "ddelta", "dgamma", "dbeta"], got, want):
+        lim = 1e-5 if name in ("x_out", "dx") and dt == torch.float32 else tol
+        if name in ("dgamma", "dbeta", "dx"):
+            lim = max(lim, 2e-5)
+        assert rel_err(a, b) <= lim, f"{name}: {rel_err(a, b)}"
+    # no pending delta: plain LayerNorm
+    n2 = ln(x.detach())
+    assert rel_err(n2, torch.nn.functional.layer_norm(x.detach(), (d,), ln.weight, ln.bias, 1e-6)) <= 1e-5
+
+
+def test_fused_block_model_matches_stock_blocks():
+    """MoEViT with the fused residual+LayerNorm path == the same model running the stock block code."""
+    sys_path_pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "slim-switch-moe-vit_b200")
+    import sys
+    if sys_path_pkg not in sys.path:
+        sys.path.insert(0, sys_path_pkg)
+    from moe_vit import MoEViT, MoEViTConfig
+    cfg = MoEViTConfig(size="tiny", num_experts=8, top_k=1, capacity_factor=1.25, moe_stride=2, num_classes=10)
+    torch.manual_seed(0)
+    fused = MoEViT(cfg).cuda()
+    stock = MoEViT(cfg, fused_norm=False).cuda()
+    stock.load_state_dict(fused.state_dict())
+    img = torch.randn(4, 3, 224, 224, device="cuda")
+    outs = []
+    for m in (fused, stock):
+        m.zero_grad()
+        out = m(img)
+        (out.square().mean() + 0.01 * m.aux_loss()).backward()
+        outs.append((out.detach(), m.blocks[0].attn.qkv.weight.grad.clone(), m.blocks[1].mlp.experts.htoh4.weight.grad.clone(),
+                     m.blocks[3].norm2.weight.grad.clone()))
+    for a, b in zip(*outs):
+        assert rel_err(a, b) <= 2e-3, rel_err(a, b)
