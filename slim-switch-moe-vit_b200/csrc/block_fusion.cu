@@ -89,7 +89,7 @@ addln_fwd_kernel(const float* __restrict__ x_in, const DT* __restrict__ delta, c
 
 // dx_in = (dx_out or 0) + LN'(dn);  d_delta (nullable) = dx_in in the delta dtype;  partial dgamma / dbeta per CTA.
 template <typename NT, typename DT, int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NV <= 6 ? 2 : 1)
 addln_bwd_kernel(const NT* __restrict__ dn, const float* __restrict__ dx_out, const float* __restrict__ x, const float* __restrict__ mean,
                  const float* __restrict__ rstd, const float* __restrict__ gamma, int64_t T, int d, float* __restrict__ dx_in,
                  DT* __restrict__ d_delta, float* __restrict__ part /* [grid][2][d] */) {
@@ -177,9 +177,11 @@ addln_bwd_reduce_kernel(const float* __restrict__ part, int nparts, int d, float
     }
 }
 
+// persistent grid: 2 CTAs per SM always fit (<= 128 registers per thread for every instantiation up to NV = 6; the
+// NV = 8 instantiation runs one CTA per SM and simply takes two passes), so no partial last wave
 static int addln_bwd_blocks(int64_t T) {
     const int64_t want = (T + 7) / 8;
-    const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 2;
     return static_cast<int>(want < cap ? want : cap);
 }
 

@@ -74,8 +74,9 @@ class Attention(nn.Module):
 
     def forward(self, x):
         B, N, C = x.shape
-        qkv = self.qkv(x).reshape(B, N, 3, self.heads, C // self.heads).permute(2, 0, 3, 1, 4)
-        out = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])
+        # q, k, v as strided [B, H, N, D] views of the projection output: no permute copies in either direction
+        q, k, v = self.qkv(x).view(B, N, 3, self.heads, C // self.heads).unbind(2)
+        out = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2))
         return self.proj(out.transpose(1, 2).reshape(B, N, C))
 
 
@@ -171,8 +172,16 @@ class MoEViT(nn.Module):
         losses = [m.gate.get_loss() for m in self.moe_layers if m.gate.has_loss]
         return sum(l.sum() for l in losses) if losses else None
 
+    def _patchify(self, img):
+        """Patch embedding (reference: timm PatchEmbed = Conv2d(3, d, 16, stride 16)) evaluated as one GEMM over
+        flattened patches — identical arithmetic and parameters, without the slow strided-convolution kernels."""
+        pe, p = self.patch_embed, self.cfg.patch
+        B, Cin, Hh, Ww = img.shape
+        patches = img.view(B, Cin, Hh // p, p, Ww // p, p).permute(0, 2, 4, 1, 3, 5).reshape(B, (Hh // p) * (Ww // p), Cin * p * p)
+        return F.linear(patches, pe.weight.view(pe.weight.shape[0], -1), pe.bias)
+
     def forward(self, img):
-        x = self.patch_embed(img).flatten(2).transpose(1, 2)
+        x = self._patchify(img) if img.is_cuda else self.patch_embed(img).flatten(2).transpose(1, 2)
         x = torch.cat((self.cls_token.expand(x.shape[0], -1, -1), x), dim=1) + self.pos_embed
         if not self.fused_norm:
             for blk in self.blocks:
