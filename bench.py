@@ -127,7 +127,7 @@ def synthetic_batch(batch: int, seed: int, pin: bool):
     return img, lab
 
 
-def train_step(model, opt, img, lab, autocast_dtype):
+def train_step(model, opt, img, lab, autocast_dtype, zero_grad=True):
     if autocast_dtype is not None:
         with torch.autocast("cuda", dtype=autocast_dtype):
             logits = model(img)
@@ -140,7 +140,8 @@ def train_step(model, opt, img, lab, autocast_dtype):
     total = loss if aux is None else loss + AUX_COEF * aux
     total.backward()
     opt.step()
-    opt.zero_grad(set_to_none=True)
+    if zero_grad:   # (a captured step keeps its static .grad tensors: backward overwrites them on every replay)
+        opt.zero_grad(set_to_none=True)
     return loss
 
 
@@ -292,6 +293,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-layer", action="store_true", help="skip the isolated-layer breakdown (profiling runs)")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of replaying the captured training step")
     ap.add_argument("--profile-window", action="store_true",
                     help="cudaProfilerStart/Stop around the device-resident timed region (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -310,6 +312,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # whole-step CUDA graph capture with NCCL inside needs the watchdog's async error handling off
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from fmoe import _cabi as C
@@ -319,11 +323,21 @@ def main():
     cfg = make_cfg(world)
     torch.manual_seed(0)           # same dense/gate init on every rank; experts differ per rank below
     model = MoEViT(cfg).cuda()
+    use_graph = not args.no_graph
     if world > 1:
         from fmoe.distributed import wrap_ddp
-        model = wrap_ddp(model, local_rank)
+        torch.manual_seed(1 + rank)    # experts are sharded, not replicated: every rank initialises its own
+        for lyr in model.moe_layers:
+            lyr.experts.htoh4.reset_parameters()
+            lyr.experts.h4toh.reset_parameters()
+        side0 = torch.cuda.Stream()    # DDP built on a side stream so that its collectives can be graph-captured later
+        side0.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side0):
+            model = wrap_ddp(model, local_rank)
+        torch.cuda.current_stream().wait_stream(side0)
+        args.warmup = max(args.warmup, 11) if use_graph else args.warmup   # DDP needs 11 eager iterations before capture
     inner = model.module if hasattr(model, "module") else model
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.05, fused=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.05, fused=True, capturable=use_graph)
 
     B = PER_GPU_BATCH
     img_h, lab_h = synthetic_batch(B, 1000 + rank, pin=True)
@@ -339,34 +353,92 @@ def main():
         train_step(model, opt, img_d, lab_d, bf16)
     barrier()
 
-    # ---- timed region 1: inputs resident in HBM
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # ---- per-kernel timing pass (eager): CUDA events around every C-ABI call of the same training step.
+    # (Events cannot be recorded inside a captured graph, so this pass directly precedes the timed region.)
+    prof_steps = min(args.steps, 5)
     C.PROF.reset()
     C.PROF.enabled = True
+    for _ in range(prof_steps):
+        train_step(model, opt, img_d, lab_d, bf16)
+    barrier()
+    C.PROF.enabled = False
+    launches_per_step = C.PROF.launches // prof_steps
+    kern = C.PROF.summary_ms()
+    kept = [int(m.last_kept.sum()) for m in inner.moe_layers]
+
+    # ---- the whole training step as ONE CUDA graph (single GPU): the layer never synchronises the host and all
+    # its buffers are static functions of the shapes, so forward + backward + fused AdamW capture as they are.
+    graph, static_loss, mode = None, None, "eager"
+    if use_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                train_step(model, opt, img_d, lab_d, bf16)        # one step on the capture stream (allocator warm-up)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = train_step(model, opt, img_d, lab_d, bf16, zero_grad=False)
+            for _ in range(2):
+                graph.replay()
+            torch.cuda.synchronize()
+            if not bool(torch.isfinite(static_loss)):
+                raise RuntimeError("non-finite loss after graph replay")
+            mode = "cuda_graph"
+        except Exception as e:  # noqa: BLE001 — fall back to eager launches, say so in the JSON line
+            print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+            return static_loss
+        return train_step(model, opt, img_d, lab_d, bf16)
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if args.profile_window:
         torch.cuda.cudart().cudaProfilerStart()
     ev0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
-        train_step(model, opt, img_d, lab_d, bf16)
+        run_step()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # ~= ms_per_step means the host is the bottleneck
     ev1.record()
     barrier()
     if args.profile_window:
         torch.cuda.cudart().cudaProfilerStop()
-    C.PROF.enabled = False
-    launches = C.PROF.launches
+    launches = launches_per_step * args.steps
     ms_total = ev0.elapsed_time(ev1)
-    kern = C.PROF.summary_ms()
-    kept = [int(m.last_kept.sum()) for m in inner.moe_layers]
 
-    # ---- timed region 2: end to end from host buffers
+    # ---- timed region 2: end to end from host buffers.  Every step's batch is copied from pinned host memory inside
+    # the timed region; the copy of batch i+1 runs on a copy stream while step i computes (a prefetching loader),
+    # lands in a staging buffer and is moved into the step's static input by a device-to-device copy.
+    copy_stream = torch.cuda.Stream()
+    img_stage, lab_stage = torch.empty_like(img_d), torch.empty_like(lab_d)
+    staged = torch.cuda.Event()
+
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            img_stage.copy_(img_h, non_blocking=True)
+            lab_stage.copy_(lab_h, non_blocking=True)
+            staged.record(copy_stream)
+
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        img_d.copy_(img_h, non_blocking=True)
-        lab_d.copy_(lab_h, non_blocking=True)
-        loss = train_step(model, opt, img_d, lab_d, bf16)
+    prefetch()
+    for i in range(args.steps):
+        torch.cuda.current_stream().wait_event(staged)
+        img_d.copy_(img_stage, non_blocking=True)
+        lab_d.copy_(lab_stage, non_blocking=True)
+        copy_stream.wait_stream(torch.cuda.current_stream())   # staging buffers are free again
+        if i + 1 < args.steps:
+            prefetch()
+        loss = run_step()
         loss_host = loss.item()      # device -> host read of the step's result
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -396,18 +468,20 @@ def main():
                     "achieved": round(achieved, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                     "frac": round(achieved / peaks["tf_sustained"], 4), "traffic": None,
                     "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                    "timing": f"CUDA events around each launch in {prof_steps} eager steps of the same loop directly before the timed region",
                     "launches_timed": gemm_calls, "avg_launch_ms": round(gemm_ms / max(1, gemm_calls), 4),
                     "flops_per_launch": flops_per_launch,
-                    "share_of_step": round(gemm_ms / ms_total, 4),
+                    "share_of_step": round(gemm_ms / prof_steps / (ms_total / args.steps), 4),
                     "per_op_ms": {t_: round(kern[t_][1], 4) for t_ in sorted(gemm_tags)}}
         moe_ms = sum(n * m for n, m in kern.values())
         flops_img = inner.train_flops_per_image(kept_fraction=sum(kept) / max(1, n_moe) / (B * 197 * cfg.top_k))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": cfg.describe() + ", full training step (fwd + CE + aux loss + bwd + fused AdamW)",
                        "global_batch": global_batch, "per_gpu_batch": B, "tokens_per_moe_layer_per_gpu": B * 197,
+                       "launch": mode,
                        "parallelism": "1 GPU" if world == 1 else f"dp{world} dense blocks + ep{world} experts (all-to-all)",
                        "cache": "inputs and activations larger than L2 (154 MB fp32 image batch, >1 GB activations per step)"},
             "clocks": clocks,
@@ -418,7 +492,7 @@ def main():
             "roofline": roofline,
             "model_roofline": {"train_flops_per_image": flops_img, "achieved_tflops": round(flops_img * value / 1e12, 1),
                                "frac_of_sustained_bf16": round(flops_img * value / 1e12 / (peaks["tf_sustained"] * world), 4),
-                               "moe_kernels_share_of_step": round(moe_ms / ms_total, 4)},
+                               "moe_kernels_share_of_step": round(moe_ms / prof_steps / (ms_total / args.steps), 4)},
         }
         if not args.no_layer:
             line["moe_layer"] = layer_bench(peaks)
@@ -428,8 +502,11 @@ def main():
                                     "sample": r["sample"]}
         emit(line)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # no barrier / destroy_process_group here: tearing NCCL down after its collectives were captured into a CUDA
+        # graph can block forever (seen once on 2 GPUs, round 1); every rank is already past its last collective.
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
