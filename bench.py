@@ -473,6 +473,25 @@ def main():
                     "flops_per_launch": flops_per_launch,
                     "share_of_step": round(gemm_ms / prof_steps / (ms_total / args.steps), 4),
                     "per_op_ms": {t_: round(kern[t_][1], 4) for t_ in sorted(gemm_tags)}}
+        # each launch against ITS roofline: min(tensor peak, arithmetic intensity x HBM bandwidth).  Algorithmic bytes
+        # (DESIGN.md §4): operands read once, outputs written once, bf16 activations / weights, fp32 weight gradients.
+        Rk, El_ = sum(kept) / max(1, n_moe), cfg.num_experts // world
+        act_d, act_h, wts = Rk * d * 2, Rk * h * 2, El_ * d * h * 2
+        op_bytes = {"gemm_fc1": act_d + wts + 2 * act_h, "gemm_fc2": act_h + wts + act_d, "gemm_dgelu": act_d + wts + 2 * act_h,
+                    "gemm_dgrad": act_h + wts + act_d, "gemm_wgrad1": act_h + act_d + 2 * wts, "gemm_wgrad2": act_d + act_h + 2 * wts}
+        per_op, ideal_ms, actual_ms = {}, 0.0, 0.0
+        for t_ in sorted(gemm_tags):
+            ms_ = kern[t_][1]
+            t_tensor = flops_per_launch / (peaks["tf_sustained"] * 1e12) * 1e3
+            t_hbm = op_bytes.get(t_, 0.0) / (peaks["hbm"] * 1e9) * 1e3
+            floor = max(t_tensor, t_hbm)
+            per_op[t_] = {"ms": round(ms_, 4), "tflops": round(flops_per_launch / (ms_ * 1e-3) / 1e12, 1),
+                          "gbs": round(op_bytes.get(t_, 0.0) / (ms_ * 1e-3) / 1e9, 1), "bound": "hbm" if t_hbm > t_tensor else "tensor",
+                          "floor_ms": round(floor, 4), "frac_of_its_roofline": round(floor / ms_, 3)}
+            ideal_ms += floor
+            actual_ms += ms_
+        roofline["per_op"] = per_op
+        roofline["frac_vs_per_op_roofline"] = round(ideal_ms / actual_ms, 4) if actual_ms > 0 else None
         moe_ms = sum(n * m for n, m in kern.values())
         flops_img = inner.train_flops_per_image(kept_fraction=sum(kept) / max(1, n_moe) / (B * 197 * cfg.top_k))
         line = {

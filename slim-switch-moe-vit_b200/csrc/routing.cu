@@ -575,7 +575,7 @@ __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
 }
 
 template <typename OT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 gate_dispatch_bwd_kernel(const __nv_bfloat16* __restrict__ dxbuf, const int* __restrict__ pos,
                          const float* __restrict__ logits, const int* __restrict__ idx, const float* __restrict__ score,
                          const float* __restrict__ dscore, const float* __restrict__ dpsum, const float* __restrict__ Wg,
@@ -695,6 +695,24 @@ gate_dispatch_bwd_kernel(const __nv_bfloat16* __restrict__ dxbuf, const int* __r
                     }
                 }
             }
+            if (dense && !regs) {
+                for (int e0 = 0; e0 < E; e0 += 16) {   // Wg slice of 16 experts: L1/L2-resident, amortised over the batch
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        wg[e] = e0 + e < E ? __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e0 + e) * d + cg * 4))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float* dr = dl_s + min(tl0 + u * TG, n_tok - 1) * E + e0;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const float g = e0 + e < E ? dr[e] : 0.0f;
+                            acc[u].x = fmaf(g, wg[e].x, acc[u].x); acc[u].y = fmaf(g, wg[e].y, acc[u].y);
+                            acc[u].z = fmaf(g, wg[e].z, acc[u].z); acc[u].w = fmaf(g, wg[e].w, acc[u].w);
+                        }
+                    }
+                }
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int tl = tl0 + u * TG;
@@ -708,14 +726,7 @@ gate_dispatch_bwd_kernel(const __nv_bfloat16* __restrict__ dxbuf, const int* __r
                         acc[u].x = fmaf(g, wg[e].x, acc[u].x); acc[u].y = fmaf(g, wg[e].y, acc[u].y);
                         acc[u].z = fmaf(g, wg[e].z, acc[u].z); acc[u].w = fmaf(g, wg[e].w, acc[u].w);
                     }
-                } else if (dense) {
-                    for (int e = 0; e < E; ++e) {
-                        const float g = dr[e];
-                        const float4 w = __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e) * d + cg * 4));
-                        acc[u].x = fmaf(g, w.x, acc[u].x); acc[u].y = fmaf(g, w.y, acc[u].y);
-                        acc[u].z = fmaf(g, w.z, acc[u].z); acc[u].w = fmaf(g, w.w, acc[u].w);
-                    }
-                } else {
+                } else if (!dense) {
                     for (int j = 0; j < k; ++j) {
                         const int e = __ldg(idx + t * k + j);
                         const float g = dr[e];
