@@ -249,19 +249,36 @@ def layer_bench(peaks, iters=20, warmup=5, T=PER_GPU_BATCH * 197, d=384, E=16, k
     for _ in range(warmup):
         it()
     torch.cuda.synchronize()
+    # per-kernel times: CUDA events around every launch of an eager pass
     C.PROF.reset()
     C.PROF.enabled = True
+    for _ in range(iters):
+        it()
+    torch.cuda.synchronize()
+    C.PROF.enabled = False
+    prof = C.PROF.summary_ms()
+    # total: the same iteration captured as one CUDA graph and replayed (pure device time, no launch gaps)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        it()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        it()
+    g.replay()
+    torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(iters):
-        it()
+        g.replay()
     b.record()
     torch.cuda.synchronize()
-    C.PROF.enabled = False
     ms = a.elapsed_time(b) / iters
     R = int(layer.last_kept.sum())
     phases = {}
-    for tag, (n, mean_ms) in sorted(C.PROF.summary_ms().items()):
+    for tag, (n, mean_ms) in sorted(prof.items()):
         ent = {"ms": round(mean_ms, 4), "calls_per_iter": n // iters}
         if tag in PHASE_BYTES:
             gbs = PHASE_BYTES[tag](T, d, h, E, k, R) / (mean_ms * 1e-3) / 1e9
@@ -274,7 +291,7 @@ def layer_bench(peaks, iters=20, warmup=5, T=PER_GPU_BATCH * 197, d=384, E=16, k
     flops = 12.0 * R * d * h
     return {
         "shape": {"T": T, "d": d, "h": h, "E": E, "k": k, "capacity_factor": cf, "kept_pairs": R},
-        "tokens_per_s_fwd_bwd": T / (ms * 1e-3), "ms_fwd_bwd": round(ms, 4),
+        "tokens_per_s_fwd_bwd": T / (ms * 1e-3), "ms_fwd_bwd": round(ms, 4), "timing": "CUDA-graph replay of fwd+bwd (total); CUDA events per launch, eager (kernels)",
         "ffn_tflops_fwd_bwd": round(flops / (gemm_ms * 1e-3) / 1e12, 1),
         "ffn_frac_of_burst_peak": round(flops / (gemm_ms * 1e-3) / 1e12 / peaks["tf_burst"], 3),
         "layer_tflops": round(flops / (ms * 1e-3) / 1e12, 1),

@@ -89,7 +89,7 @@ addln_fwd_kernel(const float* __restrict__ x_in, const DT* __restrict__ delta, c
 
 // dx_in = (dx_out or 0) + LN'(dn);  d_delta (nullable) = dx_in in the delta dtype;  partial dgamma / dbeta per CTA.
 template <typename NT, typename DT, int NV>
-__global__ void __launch_bounds__(256, NV <= 6 ? 2 : 1)
+__global__ void __launch_bounds__(256, NV <= 3 ? 3 : (NV <= 6 ? 2 : 1))
 addln_bwd_kernel(const NT* __restrict__ dn, const float* __restrict__ dx_out, const float* __restrict__ x, const float* __restrict__ mean,
                  const float* __restrict__ rstd, const float* __restrict__ gamma, int64_t T, int d, float* __restrict__ dx_in,
                  DT* __restrict__ d_delta, float* __restrict__ part /* [grid][2][d] */) {
@@ -157,35 +157,30 @@ addln_bwd_kernel(const NT* __restrict__ dn, const float* __restrict__ dx_out, co
     }
 }
 
+// out[o] = sum_b part[b][o]: one warp per output, lanes stride the partials (independent loads), xor butterfly
 __global__ void __launch_bounds__(256)
 addln_bwd_reduce_kernel(const float* __restrict__ part, int nparts, int d, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    __shared__ float red[4][64];
-    const int o = blockIdx.x * 64 + (threadIdx.x & 63), sl = threadIdx.x >> 6;
-    const int per = (nparts + 3) / 4;
+    const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (o >= 2 * d) return;
     float v = 0.0f;
-    if (o < 2 * d) {
-        const int b1 = min(nparts, (sl + 1) * per);
 #pragma unroll 4
-        for (int b = sl * per; b < b1; ++b) v += part[static_cast<size_t>(b) * 2 * d + o];
-    }
-    red[sl][threadIdx.x & 63] = v;
-    __syncthreads();
-    if (sl == 0 && o < 2 * d) {
-        const float r = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
-        if (o < d) dgamma[o] = r;
-        else dbeta[o - d] = r;
+    for (int b = lane; b < nparts; b += 32) v += part[static_cast<size_t>(b) * 2 * d + o];
+    v = warp_sum(v);
+    if (lane == 0) {
+        if (o < d) dgamma[o] = v;
+        else dbeta[o - d] = v;
     }
 }
 
-// persistent grid: 2 CTAs per SM always fit (<= 128 registers per thread for every instantiation up to NV = 6; the
-// NV = 8 instantiation runs one CTA per SM and simply takes two passes), so no partial last wave
-static int addln_bwd_blocks(int64_t T) {
+// persistent grid sized to what is resident at once (3 / 2 / 1 CTAs per SM for NV <= 3 / <= 6 / 8), so no partial last wave
+static int addln_bwd_blocks(int64_t T, int d) {
     const int64_t want = (T + 7) / 8;
-    const int64_t cap = static_cast<int64_t>(sm_count()) * 2;
+    const int per_sm = d <= 384 ? 3 : (d <= 768 ? 2 : 1);   // matches the kernels' __launch_bounds__ residency
+    const int64_t cap = static_cast<int64_t>(sm_count()) * per_sm;
     return static_cast<int>(want < cap ? want : cap);
 }
 
-size_t addln_bwd_workspace_bytes(int64_t T, int d) { return static_cast<size_t>(addln_bwd_blocks(T)) * 2 * d * 4; }
+size_t addln_bwd_workspace_bytes(int64_t T, int d) { return static_cast<size_t>(addln_bwd_blocks(T, d)) * 2 * d * 4; }
 
 cudaError_t launch_addln_fwd(const float* x_in, const void* delta, int delta_dtype, const float* gamma, const float* beta, float eps,
                              int64_t T, int d, float* x_out, void* n, int n_dtype, float* mean, float* rstd, cudaStream_t st) {
@@ -213,7 +208,7 @@ cudaError_t launch_addln_fwd(const float* x_in, const void* delta, int delta_dty
 cudaError_t launch_addln_bwd(const void* dn, int n_dtype, const float* dx_out, const float* x, const float* mean, const float* rstd,
                              const float* gamma, int64_t T, int d, float* dx_in, void* d_delta, int delta_dtype, void* workspace,
                              float* dgamma, float* dbeta, cudaStream_t st) {
-    const int grid = addln_bwd_blocks(T);
+    const int grid = addln_bwd_blocks(T, d);
     float* part = static_cast<float*>(workspace);
     const size_t smem = static_cast<size_t>(8) * 2 * d * 4;
     cudaError_t err = cudaSuccess;
@@ -241,7 +236,7 @@ cudaError_t launch_addln_bwd(const void* dn, int n_dtype, const float* dx_out, c
 #undef MOE_LN_BWD_NV
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    addln_bwd_reduce_kernel<<<(2 * d + 63) / 64, 256, 0, st>>>(part, grid, d, dgamma, dbeta);
+    addln_bwd_reduce_kernel<<<(2 * d + 7) / 8, 256, 0, st>>>(part, grid, d, dgamma, dbeta);
     return cudaGetLastError();
 }
 

@@ -848,28 +848,23 @@ gate_wgrad_partial_kernel(const float* __restrict__ dlogits, const XT* __restric
     }
 }
 
-// out[i] = sum_b part[b][i] in block order; 64 outputs x 4 block-slices per CTA, slices combined in order
+// out[i] = sum_b part[b][i]: one warp per output, lanes stride the per-block partials (independent loads), then the
+// xor butterfly — a fixed order, so the result is reproducible bit for bit
 __global__ void __launch_bounds__(256)
 gate_wgrad_reduce_kernel(const float* __restrict__ part_w, const float* __restrict__ part_b, int nparts, int d, int E,
                          float* __restrict__ dWg, float* __restrict__ dbg) {
-    __shared__ float red[4][64];
     const int n = E * d, tot = n + (dbg != nullptr ? E : 0);
-    const int o = blockIdx.x * 64 + (threadIdx.x & 63), sl = threadIdx.x >> 6;
-    const int per = (nparts + 3) / 4;
+    const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (o >= tot) return;
+    const float* src = o < n ? part_w + o : part_b + (o - n);
+    const size_t stride = o < n ? static_cast<size_t>(n) : static_cast<size_t>(E);
     float v = 0.0f;
-    if (o < tot) {
-        const float* src = o < n ? part_w + o : part_b + (o - n);
-        const size_t stride = o < n ? static_cast<size_t>(n) : static_cast<size_t>(E);
-        const int b1 = min(nparts, (sl + 1) * per);
 #pragma unroll 4
-        for (int b = sl * per; b < b1; ++b) v += src[static_cast<size_t>(b) * stride];
-    }
-    red[sl][threadIdx.x & 63] = v;
-    __syncthreads();
-    if (sl == 0 && o < tot) {
-        const float r = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
-        if (o < n) dWg[o] = r;
-        else dbg[o - n] = r;
+    for (int b = lane; b < nparts; b += 32) v += src[static_cast<size_t>(b) * stride];
+    v = warp_sum_xor(v);
+    if (lane == 0) {
+        if (o < n) dWg[o] = v;
+        else dbg[o - n] = v;
     }
 }
 
@@ -1220,7 +1215,7 @@ cudaError_t launch_gate_wgrad(const float* dlogits, const void* x, int x_dtype, 
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     const int n = E * d + E;
-    gate_wgrad_reduce_kernel<<<(n + 63) / 64, 256, 0, st>>>(part_w, part_b, nb, d, E, dWg, dbg);
+    gate_wgrad_reduce_kernel<<<(n + 7) / 8, 256, 0, st>>>(part_w, part_b, nb, d, E, dWg, dbg);
     return cudaGetLastError();
 }
 
