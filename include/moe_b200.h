@@ -162,6 +162,11 @@ int moe_addln_bwd(const void *dn, int n_dtype, const float *dx_out, const float 
                   const float *gamma, int64_t T, int d, float *dx_in, void *d_delta, int delta_dtype, void *workspace,
                   float *dgamma, float *dbeta, void *stream);
 
+/* out[cols] (fp32) = column sums of buf[rows, cols] (fp32 or bf16): bias gradient of the block's dense projections,
+ * two deterministic stages (workspace: moe_colsum_workspace_bytes).  cols % 8 == 0. */
+size_t moe_colsum_workspace_bytes(int64_t rows, int cols);
+int moe_colsum(const void *buf, int dtype, int64_t rows, int cols, void *workspace, float *out, void *stream);
+
 /* ---- utilities */
 int moe_cast_bf16(const float *src, void *dst, int64_t n /* % 8 == 0 */, void *stream);
 /* src[E,R,C] fp32 -> dst[E,R,C] bf16 (nullable) and dst_t[E,C,R] bf16 (transposed per expert); R, C % 32 == 0 */

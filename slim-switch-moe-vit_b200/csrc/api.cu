@@ -220,6 +220,16 @@ int moe_addln_bwd(const void* dn, int n_dtype, const float* dx_out, const float*
                  "moe_addln_bwd");
 }
 
+size_t moe_colsum_workspace_bytes(int64_t rows, int cols) { return colsum_workspace_bytes(rows, cols); }
+
+int moe_colsum(const void* buf, int dtype, int64_t rows, int cols, void* workspace, float* out, void* stream) {
+    if (rows <= 0 || cols <= 0 || cols % 8 != 0 || workspace == nullptr || !dtype_ok("moe_colsum", dtype)) {
+        if (rows <= 0 || cols <= 0 || cols % 8 != 0 || workspace == nullptr) set_error("moe_colsum: need rows > 0, cols %% 8 == 0 and a workspace (rows=%lld cols=%d)", (long long)rows, cols);
+        return 1;
+    }
+    return check(launch_colsum(buf, dtype, rows, cols, workspace, out, static_cast<cudaStream_t>(stream)), "moe_colsum");
+}
+
 int moe_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out1, const float* bias, const void* aux,
                      const int32_t* tile_expert, const int32_t* num_mtiles, const int32_t* seg_start, int64_t rows_cap,
                      int E, int M, int N, int K, void* stream) {

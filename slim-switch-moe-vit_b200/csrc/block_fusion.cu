@@ -173,6 +173,73 @@ addln_bwd_reduce_kernel(const float* __restrict__ part, int nparts, int d, float
 }
 
 // persistent grid sized to what is resident at once (3 / 2 / 1 CTAs per SM for NV <= 3 / <= 6 / 8), so no partial last wave
+// ------------------------------------------------------------------------------------------------
+// Plain column sum out[c] = sum_r buf[r, c] of a [rows, cols] bf16 / fp32 matrix (bias gradient of the dense
+// projections of the hosting block), same two deterministic stages as segment_colsum: 128 rows x 256 columns per
+// CTA with every load in flight, warps combined in order, then one warp per output column over the row blocks.
+// ------------------------------------------------------------------------------------------------
+template <typename XT>
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const XT* __restrict__ buf, int64_t rows, int cols, float* __restrict__ part) {
+    __shared__ float red[8][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row0 = static_cast<int64_t>(blockIdx.y) * 128 + warp * 16;
+    const int c = blockIdx.x * 256 + lane * 8;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    if (c < cols) {
+        float4 lo[16], hi[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int64_t rr = row0 + r < rows ? row0 + r : rows - 1;   // clamped load, masked below
+            lo[r] = ld_f4(buf + rr * cols + c);
+            hi[r] = ld_f4(buf + rr * cols + c + 4);
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float m = row0 + r < rows ? 1.0f : 0.0f;
+            acc[0] = fmaf(m, lo[r].x, acc[0]); acc[1] = fmaf(m, lo[r].y, acc[1]); acc[2] = fmaf(m, lo[r].z, acc[2]); acc[3] = fmaf(m, lo[r].w, acc[3]);
+            acc[4] = fmaf(m, hi[r].x, acc[4]); acc[5] = fmaf(m, hi[r].y, acc[5]); acc[6] = fmaf(m, hi[r].z, acc[6]); acc[7] = fmaf(m, hi[r].w, acc[7]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+    __syncthreads();
+    const int cc = blockIdx.x * 256 + threadIdx.x;
+    if (cc < cols) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
+        part[static_cast<size_t>(blockIdx.y) * cols + cc] = sum;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ part, int nparts, int cols, float* __restrict__ out) {
+    const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (o >= cols) return;
+    float v = 0.0f;
+#pragma unroll 4
+    for (int b = lane; b < nparts; b += 32) v += part[static_cast<size_t>(b) * cols + o];
+    v = warp_sum(v);
+    if (lane == 0) out[o] = v;
+}
+
+size_t colsum_workspace_bytes(int64_t rows, int cols) { return static_cast<size_t>((rows + 127) / 128) * cols * 4; }
+
+cudaError_t launch_colsum(const void* buf, int dtype, int64_t rows, int cols, void* workspace, float* out, cudaStream_t st) {
+    const int nb = static_cast<int>((rows + 127) / 128);
+    dim3 g1((cols + 255) / 256, nb);
+    float* part = static_cast<float*>(workspace);
+    if (dtype == MOE_DTYPE_BF16) colsum_partial_kernel<__nv_bfloat16><<<g1, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(buf), rows, cols, part);
+    else colsum_partial_kernel<float><<<g1, 256, 0, st>>>(static_cast<const float*>(buf), rows, cols, part);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    colsum_final_kernel<<<(cols + 7) / 8, 256, 0, st>>>(part, nb, cols, out);
+    return cudaGetLastError();
+}
+
 static int addln_bwd_blocks(int64_t T, int d) {
     const int64_t want = (T + 7) / 8;
     const int per_sm = d <= 384 ? 3 : (d <= 768 ? 2 : 1);   // matches the kernels' __launch_bounds__ residency

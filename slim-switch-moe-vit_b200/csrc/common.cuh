@@ -54,6 +54,9 @@ cudaError_t launch_addln_bwd(const void* dn, int n_dtype, const float* dx_out, c
                              const float* gamma, int64_t T, int d, float* dx_in, void* d_delta, int delta_dtype, void* workspace,
                              float* dgamma, float* dbeta, cudaStream_t st);
 
+size_t colsum_workspace_bytes(int64_t rows, int cols);
+cudaError_t launch_colsum(const void* buf, int dtype, int64_t rows, int cols, void* workspace, float* out, cudaStream_t st);
+
 // gemm_launch.cu — returns 0 on success, otherwise sets the error string via set_error()
 int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out1, const float* bias, const void* aux,
                         const int* tile_expert, const int* num_mtiles, const int* seg_start, int64_t rows_cap, int E,

@@ -3,7 +3,7 @@
 hand-written sm_100a kernels behind the C ABI in include/moe_b200.h (libmoe_b200.so)."""
 from . import _cabi  # noqa: F401  (fails loudly if libmoe_b200.so is not built)
 from .distributed import DistributedGroupedDataParallel  # noqa: F401
-from .fused import AddLayerNorm, add_layer_norm  # noqa: F401
+from .fused import AddLayerNorm, Linear, add_layer_norm, fast_linear  # noqa: F401
 from .gates import BaseGate, GShardGate, NaiveGate, SwitchGate  # noqa: F401
 from .layers import FMoE  # noqa: F401
 from .linear import FMoELinear  # noqa: F401

@@ -47,6 +47,8 @@ SIGNATURES = {
     "moe_addln_fwd": (_i, [_p, _p, _i, _p, _p, ctypes.c_float, _i64, _i, _p, _p, _i, _p, _p, _p]),
     "moe_addln_bwd_workspace_bytes": (_sz, [_i64, _i]),
     "moe_addln_bwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _p]),
+    "moe_colsum_workspace_bytes": (_sz, [_i64, _i]),
+    "moe_colsum": (_i, [_p, _i, _i64, _i, _p, _p, _p]),
     "moe_grouped_gemm": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
 }
 
@@ -75,7 +77,7 @@ class MoeB200Error(RuntimeError):
 KERNELS_PER_CALL = {
     "moe_gate_fwd": 1, "moe_route_scan": 1, "moe_ep_tables": 1, "moe_ep_repack": 1, "moe_dispatch_fwd": 1, "moe_expert_ffn_fwd": 2, "moe_combine_fwd": 1,
     "moe_combine_bwd": 1, "moe_expert_ffn_bwd": 8, "moe_gate_bwd": 1, "moe_dispatch_bwd": 1, "moe_gate_dispatch_bwd": 1,
-    "moe_gate_wgrad": 2, "moe_addln_fwd": 1, "moe_addln_bwd": 2, "moe_cast_bf16": 1, "moe_cast_bf16_transposed": 1, "moe_segment_colsum": 2, "moe_grouped_gemm": 1,
+    "moe_gate_wgrad": 2, "moe_addln_fwd": 1, "moe_addln_bwd": 2, "moe_colsum": 2, "moe_cast_bf16": 1, "moe_cast_bf16_transposed": 1, "moe_segment_colsum": 2, "moe_grouped_gemm": 1,
 }
 
 

@@ -97,3 +97,49 @@ class AddLayerNorm(nn.LayerNorm):
 
     def forward(self, x_in, delta=None):
         return add_layer_norm(x_in, delta, self.weight, self.bias, self.eps)
+
+
+class _LinearFastBiasGrad(torch.autograd.Function):
+    """y = x W^T + b with the library GEMMs (cuBLAS) for y, dx and dW, and the two-stage deterministic column-sum
+    kernel for db — the framework's generic reduction takes 60 us per projection at 50 K rows (11 % of the step)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.bfloat16)
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        N, K = w.shape
+        dy2 = dy.reshape(-1, N)
+        if dy2.dtype not in (torch.float32, torch.bfloat16):
+            dy2 = dy2.float()
+        dy2 = dy2.contiguous()
+        dx = (dy2 @ w).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = dy2.t() @ x.reshape(-1, K)
+        db = None
+        if ctx.has_bias:
+            rows = dy2.shape[0]
+            ws = torch.empty(C.lib.moe_colsum_workspace_bytes(rows, N), dtype=torch.uint8, device=dy2.device)
+            db32 = torch.empty(N, dtype=torch.float32, device=dy2.device)
+            C.call("moe_colsum", C.ptr(dy2), C.dtype_code(dy2), rows, N, C.ptr(ws), C.ptr(db32), C.stream_ptr())
+            db = db32.to(w.dtype)
+        return dx, dw, db
+
+
+def fast_linear(x, weight, bias):
+    """Drop-in for F.linear on CUDA tensors whose output features are a multiple of 8."""
+    if x.is_cuda and weight.shape[0] % 8 == 0:
+        return _LinearFastBiasGrad.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
+
+
+class Linear(nn.Linear):
+    """`nn.Linear` (same parameters / state_dict) with the fast bias-gradient backward."""
+
+    def forward(self, x):
+        return fast_linear(x, self.weight, self.bias)

@@ -63,29 +63,44 @@ class MoEViTConfig:
                 f"cf{self.capacity_factor:g} gate={self.gate} moe_blocks={n_moe}/{depth}")
 
 
+class _SplitQKV(torch.autograd.Function):
+    """q, k, v = qkv.unbind(2) as views, with ONE stacked gradient in backward.  (Plain `unbind` makes autograd
+    build the gradient of the projection output from three zero-filled tensors and two adds per block —
+    3.7 ms of a 20 ms training step at batch 256, profiles/r01b_step_launches.md.)"""
+
+    @staticmethod
+    def forward(ctx, qkv):                     # [B, N, 3, H, D]
+        q, k, v = qkv.unbind(2)
+        return q, k, v
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        return torch.stack((dq, dk, dv), dim=2)
+
+
 class Attention(nn.Module):
     """Dense multi-head self-attention (reference models/vision_transformer.py:260-280); stock SDPA."""
 
-    def __init__(self, dim, heads):
+    def __init__(self, dim, heads, linear=nn.Linear):
         super().__init__()
         self.heads = heads
-        self.qkv = nn.Linear(dim, dim * 3)
-        self.proj = nn.Linear(dim, dim)
+        self.qkv = linear(dim, dim * 3)
+        self.proj = linear(dim, dim)
 
     def forward(self, x):
         B, N, C = x.shape
         # q, k, v as strided [B, H, N, D] views of the projection output: no permute copies in either direction
-        q, k, v = self.qkv(x).view(B, N, 3, self.heads, C // self.heads).unbind(2)
+        q, k, v = _SplitQKV.apply(self.qkv(x).view(B, N, 3, self.heads, C // self.heads))
         out = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2))
         return self.proj(out.transpose(1, 2).reshape(B, N, C))
 
 
 class Mlp(nn.Module):
-    def __init__(self, dim, hidden):
+    def __init__(self, dim, hidden, linear=nn.Linear):
         super().__init__()
-        self.fc1 = nn.Linear(dim, hidden)
+        self.fc1 = linear(dim, hidden)
         self.act = nn.GELU()
-        self.fc2 = nn.Linear(hidden, dim)
+        self.fc2 = linear(hidden, dim)
 
     def forward(self, x):
         return self.fc2(self.act(self.fc1(x)))
@@ -94,10 +109,10 @@ class Mlp(nn.Module):
 class Block(nn.Module):
     """Pre-norm block of the reference (vision_transformer.py:319-322): x + attn(norm1(x)), then x + mlp(norm2(x))."""
 
-    def __init__(self, dim, heads, mlp: nn.Module, norm=nn.LayerNorm):
+    def __init__(self, dim, heads, mlp: nn.Module, norm=nn.LayerNorm, linear=nn.Linear):
         super().__init__()
         self.norm1 = norm(dim, eps=1e-6)
-        self.attn = Attention(dim, heads)
+        self.attn = Attention(dim, heads, linear)
         self.norm2 = norm(dim, eps=1e-6)
         self.mlp = mlp
 
@@ -147,17 +162,18 @@ class MoEViT(nn.Module):
         self.cfg = cfg
         dim, depth, heads = cfg.dims
         self.fused_norm = (moe_mlp is None) if fused_norm is None else fused_norm
-        norm = nn.LayerNorm
+        norm, linear = nn.LayerNorm, nn.Linear
         if self.fused_norm:
-            from fmoe import AddLayerNorm
-            norm = AddLayerNorm
+            from fmoe import AddLayerNorm, Linear
+            norm, linear = AddLayerNorm, Linear     # same parameters; fused residual+LN and the fast bias-gradient backward
         moe_mlp = moe_mlp or partial(_b200_moe_mlp, cfg)
         n_patches = (cfg.img_size // cfg.patch) ** 2
         self.patch_embed = nn.Conv2d(3, dim, kernel_size=cfg.patch, stride=cfg.patch)
         self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
         self.pos_embed = nn.Parameter(torch.zeros(1, n_patches + 1, dim))
         self.blocks = nn.ModuleList(
-            Block(dim, heads, moe_mlp(dim, 4 * dim) if cfg.is_moe_block(i) else Mlp(dim, 4 * dim), norm) for i in range(depth))
+            Block(dim, heads, moe_mlp(dim, 4 * dim) if cfg.is_moe_block(i) else Mlp(dim, 4 * dim, linear), norm, linear)
+            for i in range(depth))
         self.norm = nn.LayerNorm(dim, eps=1e-6)
         self.head = nn.Linear(dim, cfg.num_classes)
         nn.init.trunc_normal_(self.pos_embed, std=0.02)
@@ -178,7 +194,11 @@ class MoEViT(nn.Module):
         pe, p = self.patch_embed, self.cfg.patch
         B, Cin, Hh, Ww = img.shape
         patches = img.view(B, Cin, Hh // p, p, Ww // p, p).permute(0, 2, 4, 1, 3, 5).reshape(B, (Hh // p) * (Ww // p), Cin * p * p)
-        return F.linear(patches, pe.weight.view(pe.weight.shape[0], -1), pe.bias)
+        w = pe.weight.view(pe.weight.shape[0], -1)
+        if self.fused_norm:
+            from fmoe import fast_linear
+            return fast_linear(patches, w, pe.bias)
+        return F.linear(patches, w, pe.bias)
 
     def forward(self, img):
         x = self._patchify(img) if img.is_cuda else self.patch_embed(img).flatten(2).transpose(1, 2)

@@ -343,3 +343,32 @@ def test_ragged_empty_and_overloaded_experts_end_to_end():
     import runpy
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     runpy.run_path(os.path.join(root, "tools", "sanitize_case.py"), run_name="__main__")
+
+
+@pytest.mark.parametrize("rows,K,N", [(50432, 384, 1152), (1000, 192, 768), (257, 64, 8)])
+def test_linear_fast_bias_grad_vs_torch(rows, K, N):
+    """fmoe.Linear = nn.Linear whose bias gradient comes from the two-stage column-sum kernel (fp32 accumulation)."""
+    fmoe, C, Fn = _fm()
+    torch.manual_seed(0)
+    lin = fmoe.Linear(K, N).cuda()
+    ref = torch.nn.Linear(K, N).cuda()
+    ref.load_state_dict(lin.state_dict())
+    x = torch.randn(rows, K, device="cuda")
+    dy = torch.randn(rows, N, device="cuda")
+    for m in (lin, ref):
+        xi = x.clone().requires_grad_()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = m(xi)
+        y.backward(dy.to(y.dtype))
+        m._out = (y.detach().float(), xi.grad, m.weight.grad, m.bias.grad)
+    for name, a, b in zip(("y", "dx", "dW", "db"), lin._out, ref._out):
+        assert a.dtype == b.dtype and rel_err(a, b) <= 4e-3, f"{name}: {rel_err(a, b)}"
+    # the column sum against fp64: accumulated in fp32, but autocast hands the function a bf16 bias, so the gradient
+    # is rounded to bf16 on its way back (same as the stock path); the kernel itself is checked tightly below
+    want = dy.to(torch.bfloat16).double().sum(0)
+    assert rel_err(lin.bias.grad, want) <= 4e-3
+    dyb = dy.to(torch.bfloat16).contiguous()
+    ws = torch.empty(C.lib.moe_colsum_workspace_bytes(rows, N), dtype=torch.uint8, device="cuda")
+    out = torch.empty(N, dtype=torch.float32, device="cuda")
+    C.call("moe_colsum", C.ptr(dyb), C.dtype_code(dyb), rows, N, C.ptr(ws), C.ptr(out), C.stream_ptr())
+    assert rel_err(out, want) <= 1e-5
