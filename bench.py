@@ -530,6 +530,14 @@ def main():
                                "frac_of_sustained_bf16": round(flops_img * value / 1e12 / (peaks["tf_sustained"] * world), 4),
                                "moe_kernels_share_of_step": round(moe_ms / prof_steps / (ms_total / args.steps), 4)},
         }
+        if world > 1:   # expert-parallel exchange: per-call CUDA-event times of the eager profiling pass (rank 0)
+            ep_tags = [t_ for t_ in kern if t_.startswith("a2a_") or t_ == "moe_ep_repack" or t_ == "moe_ep_tables"]
+            slab_mb = None
+            line["expert_parallel"] = {
+                "per_call_ms": {t_: round(kern[t_][1], 4) for t_ in sorted(ep_tags)},
+                "calls_per_step": {t_: kern[t_][0] // prof_steps for t_ in sorted(ep_tags)},
+                "ms_per_step": round(sum(kern[t_][0] * kern[t_][1] for t_ in ep_tags) / prof_steps, 3),
+                "note": "NCCL all_to_all_single on fixed slabs [W, E_local, slab_rows, d] bf16; not overlapped with the expert GEMMs yet"}
         if not args.no_layer:
             line["moe_layer"] = layer_bench(peaks)
         if world == 1 and not args.no_cpu_baseline:

@@ -30,10 +30,17 @@ def slab_rows_for(capacity: int) -> int:
     return (int(capacity) + C.ROW_ALIGN - 1) // C.ROW_ALIGN * C.ROW_ALIGN
 
 
-def all_to_all_slabs(send: torch.Tensor, group=None) -> torch.Tensor:
+def all_to_all_slabs(send: torch.Tensor, group=None, tag: str = "a2a") -> torch.Tensor:
     """send[W, ...] -> recv[W, ...]: chunk j of rank r becomes chunk r of rank j (equal, static sizes)."""
     recv = torch.empty_like(send)
-    dist.all_to_all_single(recv, send, group=group)
+    if C.PROF.enabled and send.is_cuda:   # same per-call CUDA-event timing as the C-ABI launches (bench.py)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        dist.all_to_all_single(recv, send, group=group)
+        b.record()
+        C.PROF.events.setdefault(tag, []).append((a, b))
+    else:
+        dist.all_to_all_single(recv, send, group=group)
     return recv
 
 
@@ -97,8 +104,14 @@ class EPMoEFunction(torch.autograd.Function):
         bg_c = None if bg is None else bg.detach().contiguous()
 
         r = route(x, Wg_c, bg_c, spec, noise, slab_rows=slab)                       # send slabs [E, slab, d]
-        kept_recv = all_to_all_slabs(r["kept"].view(W, El), group)                   # [W(src), El]
-        recv_x = all_to_all_slabs(r["xbuf"].view(W, El * slab * d), group)           # [W(src), El, slab, d]
+        # both exchanges run on NCCL's stream while this stream refreshes the bf16 weight copies (after an optimizer step)
+        kept_recv = torch.empty((W, El), dtype=torch.int32, device=dev)
+        recv_x = torch.empty((W, El * slab * d), dtype=torch.bfloat16, device=dev)
+        w1 = dist.all_to_all_single(kept_recv, r["kept"].view(W, El), group=group, async_op=True)     # [W(src), El]
+        w2 = dist.all_to_all_single(recv_x, r["xbuf"].view(W, El * slab * d), group=group, async_op=True)  # [W(src), El, slab, d]
+        W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c)
+        w1.wait()
+        w2.wait()
 
         rows_cap = C.rows_cap(W * El * slab, 1, El, W * El * slab)                   # every received row could be live
         max_mtiles = rows_cap // C.ROW_ALIGN
@@ -111,7 +124,6 @@ class EPMoEFunction(torch.autograd.Function):
         C.call("moe_ep_repack", C.ptr(recv_x), C.ptr(xbuf), C.ptr(kept_recv), C.ptr(tb["slab_dst"]), C.ptr(tb["seg_start"]),
                C.ptr(tb["kept"]), W, El, slab, d, 1, st)
 
-        W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c)
         U = torch.empty((rows_cap, h), dtype=bf, device=dev)
         H = torch.empty((rows_cap, h), dtype=bf, device=dev)
         Y = torch.empty((rows_cap, d), dtype=bf, device=dev)
@@ -125,7 +137,7 @@ class EPMoEFunction(torch.autograd.Function):
         send_y = torch.empty((W, El * slab * d), dtype=bf, device=dev)
         C.call("moe_ep_repack", C.ptr(Y), C.ptr(send_y), C.ptr(kept_recv), C.ptr(tb["slab_dst"]), C.ptr(tb["seg_start"]),
                C.ptr(tb["kept"]), W, El, slab, d, 0, st)
-        ybuf = all_to_all_slabs(send_y, group).view(E * slab, d)                    # this rank's pairs, slab layout
+        ybuf = all_to_all_slabs(send_y, group, "a2a_combine_fwd").view(E * slab, d)                    # this rank's pairs, slab layout
         y = torch.empty_like(x)
         C.call("moe_combine_fwd", C.ptr(ybuf), C.ptr(r["pos"]), C.ptr(r["score"]), T, d, k, C.ptr(y), C.dtype_code(y), st)
 
@@ -162,7 +174,7 @@ class EPMoEFunction(torch.autograd.Function):
         dscore = _f32((T, k), dev)
         C.call("moe_combine_bwd", C.ptr(dy), C.dtype_code(dy), C.ptr(ybuf), C.ptr(pos), C.ptr(score), C.ptr(seg_send),
                C.ptr(kept_send), T, d, k, E, C.ptr(send_dy), C.ptr(dscore), st)
-        recv_dy = all_to_all_slabs(send_dy.view(W, El * slab * d), group)
+        recv_dy = all_to_all_slabs(send_dy.view(W, El * slab * d), group, "a2a_combine_bwd")
         dybuf = torch.empty((rows_cap, d), dtype=bf, device=dev)
         C.call("moe_ep_repack", C.ptr(recv_dy), C.ptr(dybuf), C.ptr(kept_recv), C.ptr(slab_dst), C.ptr(seg_loc),
                C.ptr(kept_loc), W, El, slab, d, 1, st)
@@ -174,20 +186,24 @@ class EPMoEFunction(torch.autograd.Function):
         te, nm, sg = C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_loc)
         C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), None, None, C.ptr(U),
                te, nm, None, rows_cap, El, 0, h, d, st, tag="gemm_dgelu")
+        C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1tb), C.ptr(dxbuf), None, None, None,
+               te, nm, None, rows_cap, El, 0, d, h, st, tag="gemm_dgrad")
+        # dX goes back to the token owners while the weight / bias gradients (which nobody waits for) are computed:
+        # the all-to-all runs on NCCL's stream, the four kernels below on ours
+        send_dx = torch.empty((W, El * slab * d), dtype=bf, device=dev)
+        C.call("moe_ep_repack", C.ptr(dxbuf), C.ptr(send_dx), C.ptr(kept_recv), C.ptr(slab_dst), C.ptr(seg_loc),
+               C.ptr(kept_loc), W, El, slab, d, 0, st)
+        dx_recv = torch.empty_like(send_dx)
+        work = dist.all_to_all_single(dx_recv, send_dx, group=group, async_op=True)
         C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dybuf), C.ptr(H), C.ptr(dW2), None, None, None,
                None, None, sg, rows_cap, El, d, h, 0, st, tag="gemm_wgrad2")
         C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dU), C.ptr(xbuf), C.ptr(dW1), None, None, None,
                None, None, sg, rows_cap, El, h, d, 0, st, tag="gemm_wgrad1")
-        C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1tb), C.ptr(dxbuf), None, None, None,
-               te, nm, None, rows_cap, El, 0, d, h, st, tag="gemm_dgrad")
         cws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, h), dtype=torch.uint8, device=dev)
         C.call("moe_segment_colsum", C.ptr(dybuf), sg, rows_cap, El, d, C.ptr(cws), C.ptr(db2), st, tag="colsum_db2")
         C.call("moe_segment_colsum", C.ptr(dU), sg, rows_cap, El, h, C.ptr(cws), C.ptr(db1), st, tag="colsum_db1")
-
-        send_dx = torch.empty((W, El * slab * d), dtype=bf, device=dev)
-        C.call("moe_ep_repack", C.ptr(dxbuf), C.ptr(send_dx), C.ptr(kept_recv), C.ptr(slab_dst), C.ptr(seg_loc),
-               C.ptr(kept_loc), W, El, slab, d, 0, st)
-        dx_slabs = all_to_all_slabs(send_dx, group).view(E * slab, d)
+        work.wait()
+        dx_slabs = dx_recv.view(E * slab, d)
 
         dlogits = _f32((T, E), dev)
         dx = torch.empty_like(x)
