@@ -257,6 +257,13 @@ def layer_bench(peaks, iters=20, warmup=5, T=PER_GPU_BATCH * 197, d=384, E=16, k
     torch.cuda.synchronize()
     C.PROF.enabled = False
     prof = C.PROF.summary_ms()
+    # host cost of one eager fwd+bwd (Python + ctypes + allocator), profiling off: what an eager training loop pays
+    torch.cuda.synchronize()
+    t_h = time.perf_counter()
+    for _ in range(iters):
+        it()
+    host_ms = (time.perf_counter() - t_h) * 1e3 / iters
+    torch.cuda.synchronize()
     # total: the same iteration captured as one CUDA graph and replayed (pure device time, no launch gaps)
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -291,7 +298,8 @@ def layer_bench(peaks, iters=20, warmup=5, T=PER_GPU_BATCH * 197, d=384, E=16, k
     flops = 12.0 * R * d * h
     return {
         "shape": {"T": T, "d": d, "h": h, "E": E, "k": k, "capacity_factor": cf, "kept_pairs": R},
-        "tokens_per_s_fwd_bwd": T / (ms * 1e-3), "ms_fwd_bwd": round(ms, 4), "timing": "CUDA-graph replay of fwd+bwd (total); CUDA events per launch, eager (kernels)",
+        "tokens_per_s_fwd_bwd": T / (ms * 1e-3), "ms_fwd_bwd": round(ms, 4), "host_enqueue_ms_fwd_bwd_eager": round(host_ms, 4),
+        "timing": "CUDA-graph replay of fwd+bwd (total); CUDA events per launch, eager (kernels)",
         "ffn_tflops_fwd_bwd": round(flops / (gemm_ms * 1e-3) / 1e12, 1),
         "ffn_frac_of_burst_peak": round(flops / (gemm_ms * 1e-3) / 1e12 / peaks["tf_burst"], 3),
         "layer_tflops": round(flops / (ms * 1e-3) / 1e12, 1),
