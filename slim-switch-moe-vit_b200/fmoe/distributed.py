@@ -88,6 +88,40 @@ class DistributedGroupedDataParallel(torch.nn.parallel.DistributedDataParallel):
         super().__init__(module, **kw)
 
 
+def full_state_dict(model: torch.nn.Module, group=None) -> dict:
+    """EP-aware `state_dict()`: expert parameters are all-gathered over the expert-parallel group
+    into their global `[W * E_local, ...]` shape, everything else is taken as is.  The result is what a
+    single-process (world_size = 1) model — or a FastMoE checkpoint of the same architecture — holds, so the
+    reference's rank-0 `utils.save_on_master` (/root/reference/utils.py:264-266) no longer loses remote experts.
+    Collective: every rank of the group must call it; every rank gets the full dict."""
+    sd = model.state_dict()
+    expert_names = {n for n, _ in expert_parameters(model)}
+    W = dist.get_world_size(group)
+    out = {}
+    for name, t in sd.items():
+        if name in expert_names and W > 1:
+            parts = [torch.empty_like(t) for _ in range(W)]
+            dist.all_gather(parts, t.contiguous(), group=group)
+            out[name] = torch.cat(parts, dim=0)
+        else:
+            out[name] = t
+    return out
+
+
+def load_full_state_dict(model: torch.nn.Module, full: dict, group=None, strict: bool = True):
+    """Inverse of `full_state_dict`: every rank keeps rows [r * E_local, (r + 1) * E_local) of the expert tensors."""
+    expert_names = {n for n, _ in expert_parameters(model)}
+    W, r = dist.get_world_size(group), dist.get_rank(group)
+    local = {}
+    for name, t in full.items():
+        if name in expert_names and W > 1:
+            El = t.shape[0] // W
+            local[name] = t[r * El:(r + 1) * El]
+        else:
+            local[name] = t
+    return model.load_state_dict(local, strict=strict)
+
+
 class EPMoEFunction(torch.autograd.Function):
     """y, aux_loss, count, kept = expert-parallel MoE(x; Wg, bg, local W1, b1, W2, b2)."""
 

@@ -50,6 +50,17 @@ def _cpu_worker(rank, world, port, q):
         g = model.head.weight
         (g.sum() * float(rank + 1)).backward()
 
+        # 2b. EP-aware checkpointing: the gathered state dict has global expert shapes and round-trips
+        full = D.full_state_dict(model)
+        w_name = "blocks.1.mlp.experts.htoh4.weight"
+        assert full[w_name].shape[0] == 8 and torch.equal(full[w_name][rank * 4:(rank + 1) * 4], layer.experts.htoh4.weight)
+        single = MoEViT(MoEViTConfig(size="tiny", num_experts=8, top_k=1, capacity_factor=1.25, moe_stride=2, world_size=1))
+        single.load_state_dict(full)            # what rank 0 saves loads into a single-process model unchanged
+        with torch.no_grad():
+            layer.experts.htoh4.weight.zero_()
+        D.load_full_state_dict(model, full)
+        assert torch.equal(layer.experts.htoh4.weight, full[w_name][rank * 4:(rank + 1) * 4])
+
         # 3. gates without a capacity are refused under expert parallelism, before any kernel is touched
         naive = fmoe.FMoETransformerMLP(2, 64, 256, torch.nn.GELU(), top_k=2, world_size=world)
         try:
