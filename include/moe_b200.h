@@ -60,9 +60,14 @@ int64_t moe_rows_cap(int64_t T, int k, int E, int64_t capacity);
 /* ---- gate: replaces NaiveGate's nn.Linear + torch.topk + F.softmax and fmoe_cuda.expert_count.
  * logits[T,E] fp32 (LOGIT ORDER v1, bit-identical to oracle/gate_ref.c), idx[T,k] i32,
  * score[T,k] fp32, tile_hist[E,ntiles] i32, tile_psum[E,ntiles] fp32 (only if want_psum);
- * ntiles = ceil(T / MOE_TOKEN_TILE). */
+ * ntiles = ceil(T / MOE_TOKEN_TILE).
+ * token_mask (nullable, uint8 [T]): the token-skip mask of the residual-MoE block
+ * (/root/reference/models/resMoE.py:126-145, `tk = x * mask[:, :, 1]`).  A token with mask 0 is not routed at
+ * all: idx = -1 and score = 0 in every slot, no histogram entry (it takes no capacity), no share in psum; every
+ * downstream kernel treats idx / pos = -1 as "no row" (zero output, zero gradient). */
 int moe_gate_fwd(const void *x, int x_dtype, const float *Wg, const float *bg /* nullable */,
-                 const float *noise /* nullable [T,E], added to the logits (SwitchGate jitter) */, int64_t T, int d, int E,
+                 const float *noise /* nullable [T,E], added to the logits (SwitchGate jitter) */,
+                 const uint8_t *token_mask /* nullable [T] */, int64_t T, int d, int E,
                  int k, int score_mode, int want_psum, float *logits, int32_t *idx, float *score, int32_t *tile_hist,
                  float *tile_psum, void *stream);
 

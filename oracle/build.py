@@ -39,7 +39,7 @@ def load():
         i64, i32, p = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
         lib.moe_oracle_gate_logits.argtypes = [p, i64, i32, p, p, p, i32, p]
         lib.moe_oracle_gate_logits.restype = None
-        lib.moe_oracle_route.argtypes = [p, i64, i32, i32, i32, i64, i32, p, p, p, p, p, p, p]
+        lib.moe_oracle_route.argtypes = [p, i64, i32, i32, i32, i64, i32, p, p, p, p, p, p, p, p]
         lib.moe_oracle_route.restype = None
         _lib = lib
     return _lib

@@ -65,12 +65,15 @@ void moe_oracle_gate_logits(const float *x, int64_t T, int d, const float *Wg, c
  *   score_mode 1: full-softmax probability of the selected expert (FastMoE SwitchGate)
  *   capacity    : per-expert row limit C (pairs with rank >= C are dropped, pos = -1)
  *   align       : every expert's segment in the packed buffer starts at a multiple of `align`
+ *   token_mask  : NULL, or uint8[T]: a token with mask 0 is skipped (the residual-MoE block's token gate,
+ *                 /root/reference/models/resMoE.py:126-145): idx = -1, score = 0, pos = -1 in every slot, it is
+ *                 not counted, takes no capacity and adds nothing to psum
  * Outputs: idx[T*k] i32, score[T*k] f32, count[E], kept[E], seg_start[E+1], pos[T*k] (-1 = dropped),
  *          psum[E] = sum_t softmax(logits[t,:])[e] (double accumulated; may be NULL).
  */
 void moe_oracle_route(const float *logits, int64_t T, int E, int k, int score_mode,
                       int64_t capacity, int align, int32_t *idx, float *score, int32_t *count,
-                      int32_t *kept, int32_t *seg_start, int32_t *pos, double *psum)
+                      int32_t *kept, int32_t *seg_start, int32_t *pos, double *psum, const uint8_t *token_mask)
 {
     int64_t *rank = (int64_t *)calloc((size_t)E, sizeof(int64_t));
     for (int e = 0; e < E; ++e) count[e] = 0;
@@ -79,6 +82,10 @@ void moe_oracle_route(const float *logits, int64_t T, int E, int k, int score_mo
 
     for (int64_t t = 0; t < T; ++t) {
         const float *lr = logits + t * E;
+        if (token_mask && token_mask[t] == 0) {
+            for (int j = 0; j < k; ++j) { idx[t * k + j] = -1; score[t * k + j] = 0.0f; rk[t * k + j] = 0; }
+            continue;
+        }
         int picked[64];
         float pv[64];
         for (int j = 0; j < k; ++j) {
@@ -125,7 +132,7 @@ void moe_oracle_route(const float *logits, int64_t T, int E, int k, int score_mo
     seg_start[E] = (int32_t)start;
     for (int64_t i = 0; i < T * k; ++i) {
         int e = idx[i];
-        pos[i] = (rk[i] < capacity) ? seg_start[e] + rk[i] : -1;
+        pos[i] = (e >= 0 && rk[i] < capacity) ? seg_start[e] + rk[i] : -1;
     }
     free(rk);
     free(rank);

@@ -87,8 +87,10 @@ class Routing:
         return int(self.seg_start[-1])
 
 
-def route(logits: torch.Tensor, k: int, score_mode: int, capacity: int, align: int = ALIGN) -> Routing:
+def route(logits: torch.Tensor, k: int, score_mode: int, capacity: int, align: int = ALIGN, token_mask=None) -> Routing:
+    """token_mask [T] (optional, non-zero = keep): skipped tokens get idx = pos = -1, score = 0 and are not counted."""
     lib = _build.load()
+    tm = None if token_mask is None else np.ascontiguousarray((token_mask.detach().reshape(-1).cpu() != 0).numpy().astype(np.uint8))
     lg = np.ascontiguousarray(logits.detach().to(torch.float32).cpu().numpy())
     T, E = lg.shape
     idx = np.empty((T, k), np.int32)
@@ -99,18 +101,22 @@ def route(logits: torch.Tensor, k: int, score_mode: int, capacity: int, align: i
     pos = np.empty((T, k), np.int32)
     psum = np.empty(E, np.float64)
     lib.moe_oracle_route(_ptr(lg), T, E, k, score_mode, int(capacity), align, _ptr(idx), _ptr(score),
-                         _ptr(count), _ptr(kept), _ptr(seg), _ptr(pos), _ptr(psum))
+                         _ptr(count), _ptr(kept), _ptr(seg), _ptr(pos), _ptr(psum), None if tm is None else _ptr(tm))
     tn = torch.from_numpy
     return Routing(tn(idx), tn(score), tn(count), tn(kept), tn(seg), tn(pos), tn(psum), int(capacity))
 
 
-def route_python(logits: torch.Tensor, k: int, score_mode: int, capacity: int, align: int = ALIGN) -> Routing:
+def route_python(logits: torch.Tensor, k: int, score_mode: int, capacity: int, align: int = ALIGN, token_mask=None) -> Routing:
     """Independent pure-Python restatement of `route` (small cases only) — pins the C code."""
     lg = logits.detach().to(torch.float32)
     T, E = lg.shape
     idx = torch.zeros(T, k, dtype=torch.int32)
     score = torch.zeros(T, k, dtype=torch.float32)
+    live = [True] * T if token_mask is None else [bool(v) for v in (token_mask.reshape(-1) != 0).tolist()]
     for t in range(T):
+        if not live[t]:
+            idx[t] = -1
+            continue
         row = lg[t].tolist()
         order = sorted(range(E), key=lambda e: (-row[e], e))[:k]  # desc value, ties -> low index
         idx[t] = torch.tensor(order, dtype=torch.int32)
@@ -122,6 +128,9 @@ def route_python(logits: torch.Tensor, k: int, score_mode: int, capacity: int, a
     seen = [0] * E
     rank = []
     for e in flat:
+        if e < 0:
+            rank.append(capacity)   # skipped token: never kept
+            continue
         rank.append(seen[e])
         seen[e] += 1
     count = torch.tensor(seen, dtype=torch.int32)
@@ -129,8 +138,8 @@ def route_python(logits: torch.Tensor, k: int, score_mode: int, capacity: int, a
     seg = [0]
     for e in range(E):
         seg.append(seg[-1] + (int(kept[e]) + align - 1) // align * align)
-    pos = torch.tensor([seg[e] + r if r < capacity else -1 for e, r in zip(flat, rank)], dtype=torch.int32)
-    psum = torch.softmax(lg.double(), dim=-1).sum(0)
+    pos = torch.tensor([seg[e] + r if (e >= 0 and r < capacity) else -1 for e, r in zip(flat, rank)], dtype=torch.int32)
+    psum = (torch.softmax(lg.double(), dim=-1) * torch.tensor(live, dtype=torch.float64).unsqueeze(1)).sum(0)
     return Routing(idx, score, count, kept, torch.tensor(seg, dtype=torch.int32), pos.reshape(T, k), psum, capacity)
 
 

@@ -60,13 +60,13 @@ int64_t moe_rows_cap(int64_t T, int k, int E, int64_t capacity) {
     return (pairs + MOE_ROW_ALIGN - 1) / MOE_ROW_ALIGN * MOE_ROW_ALIGN + static_cast<int64_t>(MOE_ROW_ALIGN) * E;
 }
 
-int moe_gate_fwd(const void* x, int x_dtype, const float* Wg, const float* bg, const float* noise, int64_t T, int d, int E, int k,
+int moe_gate_fwd(const void* x, int x_dtype, const float* Wg, const float* bg, const float* noise, const uint8_t* token_mask, int64_t T, int d, int E, int k,
                  int score_mode, int want_psum, float* logits, int32_t* idx, float* score, int32_t* tile_hist,
                  float* tile_psum, void* stream) {
     if (!dims_ok("moe_gate_fwd", T, d, E, k) || !dtype_ok("moe_gate_fwd", x_dtype)) return 1;
     if (score_mode != MOE_SCORE_TOPK_SOFTMAX && score_mode != MOE_SCORE_FULL_SOFTMAX) { set_error("moe_gate_fwd: bad score_mode %d", score_mode); return 1; }
     if (want_psum && tile_psum == nullptr) { set_error("moe_gate_fwd: want_psum needs tile_psum"); return 1; }
-    return check(launch_gate_fwd(x, x_dtype, Wg, bg, noise, T, d, E, k, score_mode, want_psum, logits, idx, score, tile_hist,
+    return check(launch_gate_fwd(x, x_dtype, Wg, bg, noise, token_mask, T, d, E, k, score_mode, want_psum, logits, idx, score, tile_hist,
                                  tile_psum, static_cast<cudaStream_t>(stream)),
                  "moe_gate_fwd");
 }

@@ -9,7 +9,7 @@
 namespace moe {
 
 // routing.cu
-cudaError_t launch_gate_fwd(const void* x, int x_dtype, const float* Wg, const float* bg, const float* noise, int64_t T, int d, int E, int k,
+cudaError_t launch_gate_fwd(const void* x, int x_dtype, const float* Wg, const float* bg, const float* noise, const uint8_t* token_mask, int64_t T, int d, int E, int k,
                             int score_mode, int want_psum, float* logits, int* idx, float* score, int* tile_hist,
                             float* tile_psum, cudaStream_t st);
 cudaError_t launch_route_scan(const int* tile_hist, const float* tile_psum, int ntiles, int E, long long capacity,

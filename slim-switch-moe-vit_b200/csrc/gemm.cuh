@@ -55,8 +55,11 @@ constexpr int kPairM = 256;  // rows per pair tile (UMMA M with cta_group::2)
 constexpr int kBK = 64;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
-constexpr int kStagingBytes = 16384;  // 128 rows x 128 B
 constexpr int kSmemLimit = 232448;    // 227 KB
+#ifndef MOE_PREFETCH_DIST
+#define MOE_PREFETCH_DIST 8
+#endif
+constexpr int kPrefetchDist = MOE_PREFETCH_DIST;  // k-blocks the L2 prefetch cursor runs ahead of the smem ring
 
 template <int BN, int EPI>
 struct GemmCfg {
@@ -64,13 +67,19 @@ struct GemmCfg {
     static constexpr int B_BYTES = (BN / 2) * kBK * 2;  // this CTA's half of the B tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int NOUT = (EPI == EPI_BIAS_GELU_DUAL) ? 2 : 1;
-    static constexpr int NBUF = 2 * NOUT;  // one staging buffer per epilogue group and output
-    static constexpr int CHUNK_COLS = (EPI == EPI_F32) ? 32 : 64;
-    static constexpr int NCHUNK = BN / CHUNK_COLS;
-    static constexpr int BAR_BYTES = 256 + kEpiWarps * 128 * 4;  // mbarriers + TMEM slot, then the per-warp bias copies
-    static constexpr int STAGES_RAW = (kSmemLimit - 1024 - BAR_BYTES - NBUF * kStagingBytes) / STAGE_BYTES;
+    // The epilogue works in chunks of 32 accumulator columns.  Every epilogue warp owns one 32-row slab per output
+    // (32 x 64 B of bf16, 64-byte swizzle; 32 x 128 B of fp32 for WGRAD, 128-byte swizzle) that it fills and TMA-stores
+    // on its own, and for DGELU two more 2 KB slabs into which it TMA-loads its rows of the pre-activation U one
+    // chunk ahead.  Small slabs leave the shared memory to the operand ring.
+    static constexpr int NCHUNK = BN / 32;
+    static constexpr int SLAB_BYTES = (EPI == EPI_F32) ? 4096 : 2048;
+    static constexpr int OUT_BYTES = kEpiWarps * NOUT * SLAB_BYTES;
+    static constexpr int AUX_BYTES = (EPI == EPI_DGELU) ? kEpiWarps * 2 * 2048 : 0;
+    static constexpr int STAGING_BYTES = OUT_BYTES + AUX_BYTES;
+    static constexpr int BAR_BYTES = 512 + kEpiWarps * 128 * 4;  // mbarriers + TMEM slot, then the per-warp bias copies
+    static constexpr int STAGES_RAW = (kSmemLimit - 1024 - BAR_BYTES - STAGING_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + NBUF * kStagingBytes + BAR_BYTES;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
     static_assert(STAGES >= 3, "not enough shared memory for a pipelined tile");
     static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64, at most 256");
 };
@@ -190,6 +199,18 @@ __device__ __forceinline__ void epilogue_block16(const uint32_t* acc, uint32_t b
     }
 }
 
+// -DMOE_DBG_TIMELINE (kernel experiments only): per-tile clock64 stamps of the three roles of CTA 0 / CTA 1
+//   g_tl[cta][role][tile][event]; role 0 = TMA producer, 1 = MMA issuer, 2 = epilogue warp 2, 3 = epilogue warp 6
+#ifdef MOE_DBG_TIMELINE
+__device__ long long g_tl[2][4][64][4];
+#define MOE_TL(role, ti, ev)                                                                        \
+    do {                                                                                            \
+        if (blockIdx.x < 2 && (ti) < 64) g_tl[blockIdx.x][role][ti][ev] = clock64();                \
+    } while (0)
+#else
+#define MOE_TL(role, ti, ev) do { } while (0)
+#endif
+
 struct TileCoord {
     int e;      // expert (weight index)
     int m0;     // ROWS: first packed row of THIS CTA's half.  WGRAD: first output row of this CTA's half
@@ -226,7 +247,7 @@ template <int BN, int EPI, bool WGRAD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
     using Cfg = GemmCfg<BN, EPI>;
     constexpr int STAGES = Cfg::STAGES;
     static_assert(WGRAD == (EPI == EPI_F32), "WGRAD <=> fp32 output");
@@ -235,12 +256,13 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::NBUF * kStagingBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    [[maybe_unused]] float* bias_s = reinterpret_cast<float*>(staging + Cfg::NBUF * kStagingBytes + 256);  // [8 warps][128]
+    [[maybe_unused]] uint64_t* aux_bar = tempty_bar + 2;                                  // [8 warps][2]  (DGELU)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * kEpiWarps);
+    [[maybe_unused]] float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES + 512);  // [8 warps][128]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -251,6 +273,10 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmO0);
         if constexpr (Cfg::NOUT == 2) tma_prefetch_desc(&tmO1);
+        if constexpr (EPI == EPI_DGELU) {
+            tma_prefetch_desc(&tmAux);
+            for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(aux_bar + i, 1);
+        }
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar + s, 1);   // leader's producer arrive.expect_tx; bytes from both CTAs
             mbar_init(empty_bar + s, 1);  // one multicast tcgen05.commit
@@ -279,29 +305,69 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp == 0) {
         // ================================ TMA producer (one thread per CTA) =========================
+        // -DMOE_L2_PREFETCH (experiment, off): a second cursor runs kPrefetchDist k-blocks ahead of the loads and pulls
+        // those boxes into L2 (cp.async.bulk.prefetch.tensor).  Measured round 1e: 20-35 % SLOWER on every op (fc2
+        // 68 -> 84 us) — the mainloop is bound by L2 -> SM request throughput, not by HBM latency, and the
+        // prefetches double the requests.
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+            [[maybe_unused]] int ti = 0;
+            auto issue = [&](const TileCoord& c, int kb, uint8_t* sa, uint64_t* bar) {   // sa == nullptr: L2 prefetch only
+                uint8_t* const sb = sa != nullptr ? sa + Cfg::A_BYTES : nullptr;
+                if constexpr (!WGRAD) {
+                    const int ca = kb * kBK, ra = c.m0, rb = c.e * p.N + c.n0 + rank * (BN / 2);
+                    if (sa == nullptr) { tma_prefetch_2d(&tmA, ca, ra); tma_prefetch_2d(&tmB, ca, rb); return; }
+                    tma_load_2d_pair(sa, &tmA, bar, ca, ra);
+                    tma_load_2d_pair(sb, &tmB, bar, ca, rb);
+                } else {
+                    const int krow = c.row0 + kb * kBK;
+                    if (sa == nullptr) {
+                        tma_prefetch_2d(&tmA, c.m0, krow);
+                        tma_prefetch_2d(&tmA, c.m0 + 64, krow);
+#pragma unroll
+                        for (int i = 0; i < BN / 128; ++i) tma_prefetch_2d(&tmB, c.n0 + rank * (BN / 2) + i * 64, krow);
+                        return;
+                    }
+                    tma_load_2d_pair(sa, &tmA, bar, c.m0, krow);
+                    tma_load_2d_pair(sa + 8192, &tmA, bar, c.m0 + 64, krow);
+#pragma unroll
+                    for (int i = 0; i < BN / 128; ++i)
+                        tma_load_2d_pair(sb + i * 8192, &tmB, bar, c.n0 + rank * (BN / 2) + i * 64, krow);
+                }
+            };
+            // prefetch cursor
+            int ptile = first_tile, pkb = 0;
+            TileCoord pc{};
+            if (ptile < total_tiles) pc = decode_tile<BN, WGRAD>(p, ptile, n_ntiles, rank);
+            [[maybe_unused]] auto prefetch_next = [&]() {
+                while (ptile < total_tiles && pkb >= pc.kb) {   // next non-empty tile
+                    ptile += tile_stride;
+                    pkb = 0;
+                    if (ptile < total_tiles) pc = decode_tile<BN, WGRAD>(p, ptile, n_ntiles, rank);
+                }
+                if (ptile >= total_tiles) return;
+                issue(pc, pkb, nullptr, nullptr);
+                ++pkb;
+            };
+#ifdef MOE_L2_PREFETCH
+            for (int i = 0; i < STAGES + kPrefetchDist; ++i) prefetch_next();
+#endif
+            for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++ti) {
                 const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
+                MOE_TL(0, ti, 0);
                 for (int kb = 0; kb < c.kb; ++kb) {
                     mbar_wait(empty_bar + s, ph ^ 1);
+                    if (kb == 0) MOE_TL(0, ti, 1);
                     uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-                    uint8_t* sb = sa + Cfg::A_BYTES;
                     if (rank == 0) mbar_arrive_expect_tx(full_bar + s, 2 * Cfg::STAGE_BYTES);
-                    if constexpr (!WGRAD) {
-                        tma_load_2d_pair(sa, &tmA, full_bar + s, kb * kBK, c.m0);
-                        tma_load_2d_pair(sb, &tmB, full_bar + s, kb * kBK, c.e * p.N + c.n0 + rank * (BN / 2));
-                    } else {
-                        const int krow = c.row0 + kb * kBK;
-                        tma_load_2d_pair(sa, &tmA, full_bar + s, c.m0, krow);
-                        tma_load_2d_pair(sa + 8192, &tmA, full_bar + s, c.m0 + 64, krow);
-#pragma unroll
-                        for (int i = 0; i < BN / 128; ++i)
-                            tma_load_2d_pair(sb + i * 8192, &tmB, full_bar + s, c.n0 + rank * (BN / 2) + i * 64, krow);
-                    }
+                    issue(c, kb, sa, full_bar + s);
+#ifdef MOE_L2_PREFETCH
+                    prefetch_next();
+#endif
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
+                MOE_TL(0, ti, 2);
             }
         }
         __syncwarp();
@@ -311,15 +377,19 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             constexpr uint32_t idesc = umma_idesc_bf16(kPairM, BN, WGRAD, WGRAD);
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
-            for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+            [[maybe_unused]] int ti = 0;
+            for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++ti) {
                 const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
                 if (c.kb == 0) continue;
+                MOE_TL(1, ti, 0);
                 mbar_wait(tempty_bar + as, aph ^ 1);
                 tc_fence_after();
+                MOE_TL(1, ti, 1);
                 const uint32_t tmem_d = tmem_base + as * 256;
                 for (int kb = 0; kb < c.kb; ++kb) {
                     mbar_wait(full_bar + s, ph);
                     tc_fence_after();
+                    if (kb == 0) MOE_TL(1, ti, 2);
                     const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
                     const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
@@ -334,58 +404,42 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
                 umma_commit_pair(tfull_bar + as);  // accumulator complete -> epilogues of both CTAs
+                MOE_TL(1, ti, 3);
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
         }
         __syncwarp();
     } else {
         // ================================ epilogue (2 groups x 4 warps) ============================
-        // Every warp is independent: it owns 32 accumulator rows (its TMEM lane quarter), stages them in
-        // its own 32-row slab of the group's staging buffer and issues its own TMA stores, so there is
-        // no CTA-level barrier anywhere in the epilogue.
+        // Every warp is independent: it owns 32 accumulator rows (its TMEM lane quarter; thread = row), the two groups
+        // take alternate 32-column chunks, and each warp stages and TMA-stores its own slabs, so there is no CTA-level
+        // barrier anywhere in the epilogue.
         const int q = warp & 3;                  // TMEM lane quarter this warp may touch
         const int grp = (warp - 2) >> 2;         // column-chunk parity this group owns
-        const int r = q * 32 + lane;             // row inside this CTA's 128-row half
-        uint8_t* const gstage = staging + grp * Cfg::NOUT * kStagingBytes;
-        uint8_t* const slab = gstage + q * 4096;           // this warp's 32 rows x 128 B
-        uint8_t* const my_row = gstage + r * 128;
-        const int sw = r & 7;
-        float* const wbias = bias_s + (warp - 2) * 128;     // this warp's copy of the bias values of its chunks
+        const int ew = warp - 2;                 // 0..7
+        float* const wbias = bias_s + ew * 128;  // this warp's copy of the bias values of its chunks
         int as = 0;
         uint32_t aph = 0;
-        for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
-            const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
-            const bool live = c.kb != 0;
-            if constexpr (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS) {
-                // lane l fetches 4 consecutive bias values of the group's (at most two) chunks
-                const int lc = grp + 2 * (lane >> 4);       // chunk the lane's values belong to
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lc < Cfg::NCHUNK)
-                    bv = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(c.e) * p.N + c.n0 + lc * 64) + (lane & 15));
-                __syncwarp();                                // previous tile's reads of wbias are done
-                *reinterpret_cast<float4*>(wbias + lane * 4) = bv;
-                __syncwarp();
-            }
-            // DGELU: this row's pre-activations, 64 columns ahead of their use (rotating register window)
-            [[maybe_unused]] uint4 aux[8];
-            [[maybe_unused]] const __nv_bfloat16* aux_row = nullptr;
-            if constexpr (EPI == EPI_DGELU) {
-                aux_row = p.aux + static_cast<size_t>(c.m0 + r) * p.N + c.n0;
-                if (grp < Cfg::NCHUNK) {
-                    const uint4* ap = reinterpret_cast<const uint4*>(aux_row + grp * 64);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) aux[i] = __ldg(ap + i);
+        [[maybe_unused]] int ti = 0;
+        [[maybe_unused]] const int tl_role = warp == 2 ? 2 : 3;
+        [[maybe_unused]] const bool tl_on = (warp == 2 || warp == 6) && lane == 0;
+        if constexpr (EPI == EPI_F32) {
+            uint8_t* const slab = staging + ew * Cfg::SLAB_BYTES;     // 32 rows x 128 B, 128-byte swizzle
+            uint8_t* const my_row = slab + lane * 128;
+            const int sw = lane & 7;
+            for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++ti) {
+                const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
+                const bool live = c.kb != 0;
+                if (tl_on) MOE_TL(tl_role, ti, 0);
+                if (live) {
+                    mbar_wait(tfull_bar + as, aph);
+                    tc_fence_after();
                 }
-            }
-            if (live) {
-                mbar_wait(tfull_bar + as, aph);
-                tc_fence_after();
-            }
-            const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
+                if (tl_on) MOE_TL(tl_role, ti, 1);
+                const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
 #pragma unroll 1
-            for (int ch = grp; ch < Cfg::NCHUNK; ch += 2) {
-                const bool last_chunk = (ch + 2 >= Cfg::NCHUNK);
-                if constexpr (EPI == EPI_F32) {
+                for (int ch = grp; ch < Cfg::NCHUNK; ch += 2) {
+                    const bool last_chunk = (ch + 2 >= Cfg::NCHUNK);
                     uint32_t acc[32];
                     if (live) {
                         tmem_ld32(tmem_row + ch * 32, acc);
@@ -394,6 +448,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive_cluster(tempty_bar + as, 0);
+                            if (tl_on) MOE_TL(tl_role, ti, 2);
                         }
                     } else {
 #pragma unroll
@@ -411,7 +466,54 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         tma_store_3d(&tmO0, slab, c.n0 + ch * 32, c.m0 + q * 32, c.e);
                         tma_store_commit();
                     }
-                } else {
+                }
+                if (tl_on) MOE_TL(tl_role, ti, 3);
+                if (live && ++as == 2) { as = 0; aph ^= 1; }
+            }
+        } else {
+            // bf16 outputs: slab rows are 64 B (four 16-byte units), unit u of row r lives at unit u ^ ((r >> 1) & 3)
+            // (CU_TENSOR_MAP_SWIZZLE_64B); a quarter-warp then touches all 32 banks exactly once.
+            const uint32_t out_s = smem_u32(staging) + ew * Cfg::NOUT * 2048;                 // this warp's output slab(s)
+            const uint32_t my_out = out_s + lane * 64;
+            const int sw = (lane >> 1) & 3;
+            [[maybe_unused]] const uint32_t aux_s = smem_u32(staging) + Cfg::OUT_BYTES + ew * 4096;   // two 2 KB slabs
+            [[maybe_unused]] uint64_t* const my_aux_bar = aux_bar + ew * 2;
+            [[maybe_unused]] uint32_t aux_issued = 0, aux_used = 0;   // running chunk counters of this warp (slab = n & 1)
+            constexpr int MYCH = Cfg::NCHUNK / 2;                     // chunks of one group per tile
+            // DGELU: TMA-load this warp's 32 rows x 32 columns of U for chunk `ch` of the tile at `c`
+            [[maybe_unused]] auto issue_aux = [&](const TileCoord& c, int ch) {
+                if (lane == 0) {
+                    uint64_t* bar = my_aux_bar + (aux_issued & 1);
+                    mbar_arrive_expect_tx(bar, 2048);
+                    tma_load_2d_s(aux_s + (aux_issued & 1) * 2048, &tmAux, bar, c.n0 + ch * 32, c.m0 + q * 32);
+                }
+                ++aux_issued;
+            };
+            for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++ti) {
+                const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
+                const bool live = c.kb != 0;
+                if (tl_on) MOE_TL(tl_role, ti, 0);
+                if constexpr (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS) {
+                    // lane l fetches 4 consecutive bias values of the group's (at most four) chunks
+                    const int lc = grp + 2 * (lane >> 3);       // chunk the lane's values belong to
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lc < Cfg::NCHUNK)
+                        bv = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(c.e) * p.N + c.n0 + lc * 32) + (lane & 7));
+                    __syncwarp();                                // previous tile's reads of wbias are done
+                    *reinterpret_cast<float4*>(wbias + lane * 4) = bv;
+                    __syncwarp();
+                }
+                if constexpr (EPI == EPI_DGELU) issue_aux(c, grp);   // lands while this warp waits for the accumulator
+                if (live) {
+                    mbar_wait(tfull_bar + as, aph);
+                    tc_fence_after();
+                }
+                if (tl_on) MOE_TL(tl_role, ti, 1);
+                const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
+#pragma unroll 1
+                for (int i = 0; i < MYCH; ++i) {
+                    const int ch = grp + 2 * i;
+                    const bool last_chunk = (i + 1 == MYCH);
 #ifdef MOE_DBG_NO_EPI
                     if (last_chunk) {
                         tc_fence_before();
@@ -420,66 +522,72 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     continue;
 #endif
-                    const uint32_t cbias = smem_u32(wbias) + ((ch - grp) >> 1) * 256;
+                    [[maybe_unused]] uint32_t aux_rd = 0;
+                    if constexpr (EPI == EPI_DGELU) {
+                        // the other aux slab is free (its chunk was consumed in the previous iteration): prefetch the next chunk
+                        if (!last_chunk) {
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            issue_aux(c, ch + 2);
+                        }
+                        mbar_wait(my_aux_bar + (aux_used & 1), (aux_used >> 1) & 1);
+                        aux_rd = aux_s + (aux_used & 1) * 2048 + lane * 64;
+                        ++aux_used;
+                    }
+                    const uint32_t cbias = smem_u32(wbias) + i * 128;
                     uint32_t acc[2][16];
-                    tmem_ld16(tmem_row + ch * 64, acc[0]);
+                    tmem_ld16(tmem_row + ch * 32, acc[0]);
 #pragma unroll
-                    for (int blk = 0; blk < 4; ++blk) {   // 16 accumulator columns at a time
+                    for (int blk = 0; blk < 2; ++blk) {   // 16 accumulator columns at a time
                         tmem_ld_wait();
-                        if (blk < 3) {
-                            tmem_ld16(tmem_row + ch * 64 + (blk + 1) * 16, acc[(blk + 1) & 1]);
+                        if (blk == 0) {
+                            tmem_ld16(tmem_row + ch * 32 + 16, acc[1]);
                         } else if (last_chunk) {
                             // every TMEM read of this accumulator stage by this warp is done -> hand it back
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive_cluster(tempty_bar + as, 0);
+                            if (tl_on) MOE_TL(tl_role, ti, 2);
                         }
-                        // keep the block just loaded in its own registers: its consumers may not move above
-                        // the next tcgen05.ld (which would make ptxas reuse one register set and serialise)
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(acc[blk & 1][i]));
+                        for (int r = 0; r < 16; ++r) asm volatile("" : "+r"(acc[blk][r]));
+                        [[maybe_unused]] uint32_t aux[8];
+                        if constexpr (EPI == EPI_DGELU) {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(aux[4 * j]), "=r"(aux[4 * j + 1]), "=r"(aux[4 * j + 2]), "=r"(aux[4 * j + 3])
+                                             : "r"(aux_rd + (((blk * 2 + j) ^ sw) << 4)));
+                        }
                         uint32_t o0[8];                       // 16 columns of output 0, packed bf16x2
                         [[maybe_unused]] uint32_t o1[8];      // 16 columns of output 1 (fc1: gelu)
-                        epilogue_block16<EPI>(acc[blk & 1], cbias + blk * 64,
-                                              reinterpret_cast<const uint32_t*>(aux) + blk * 8, o0, o1);
-                        if constexpr (EPI == EPI_DGELU) {
-                            if (ch + 2 < Cfg::NCHUNK) {   // refill the consumed window slots for this group's next chunk
-                                const uint4* ap = reinterpret_cast<const uint4*>(aux_row + (ch + 2) * 64 + blk * 16);
-                                aux[2 * blk] = __ldg(ap);
-                                aux[2 * blk + 1] = __ldg(ap + 1);
-                            }
-                        }
+                        epilogue_block16<EPI>(acc[blk], cbias + blk * 64, aux, o0, o1);
                         if (blk == 0) {
-                            if (lane == 0) tma_store_wait_read<0>();   // this warp's previous store has left its slab
+                            if (lane == 0) tma_store_wait_read<0>();   // this warp's previous store has left its slab(s)
                             __syncwarp();
                         }
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            const int slot = ((blk * 2 + j) ^ sw) << 4;
-                            *reinterpret_cast<uint4*>(my_row + slot) = make_uint4(o0[4 * j], o0[4 * j + 1], o0[4 * j + 2], o0[4 * j + 3]);
+                            const uint32_t slot = my_out + (((blk * 2 + j) ^ sw) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "r"(o0[4 * j]), "r"(o0[4 * j + 1]),
+                                         "r"(o0[4 * j + 2]), "r"(o0[4 * j + 3]) : "memory");
                             if constexpr (EPI == EPI_BIAS_GELU_DUAL)
-                                *reinterpret_cast<uint4*>(my_row + kStagingBytes + slot) =
-                                    make_uint4(o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 2048), "r"(o1[4 * j]),
+                                             "r"(o1[4 * j + 1]), "r"(o1[4 * j + 2]), "r"(o1[4 * j + 3]) : "memory");
                         }
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
 #ifndef MOE_DBG_NO_STORE
                     if (lane == 0) {
-                        tma_store_2d(&tmO0, slab, c.n0 + ch * 64, c.m0 + q * 32);
-                        if constexpr (Cfg::NOUT == 2) tma_store_2d(&tmO1, slab + kStagingBytes, c.n0 + ch * 64, c.m0 + q * 32);
+                        tma_store_2d_s(&tmO0, out_s, c.n0 + ch * 32, c.m0 + q * 32);
+                        if constexpr (Cfg::NOUT == 2) tma_store_2d_s(&tmO1, out_s + 2048, c.n0 + ch * 32, c.m0 + q * 32);
                         tma_store_commit();
                     }
 #endif
                 }
-            }
-            if (live) {
-                if (grp >= Cfg::NCHUNK) {  // a group without chunks (BN = 64) still has to release the stage
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(tempty_bar + as, 0);
-                }
-                if (++as == 2) { as = 0; aph ^= 1; }
+                if (tl_on) MOE_TL(tl_role, ti, 3);
+                if (live && ++as == 2) { as = 0; aph ^= 1; }
             }
         }
         if (lane == 0) tma_store_wait_all<0>();

@@ -23,9 +23,9 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
-// 2-D row-major tensor [outer, inner] of `esz`-byte elements, 128-byte swizzle
+// 2-D row-major tensor [outer, inner] of `esz`-byte elements; 128-byte swizzle unless told otherwise
 bool encode_2d(CUtensorMap* m, CUtensorMapDataType dt, int esz, const void* base, uint64_t inner, uint64_t outer,
-               uint32_t box_inner, uint32_t box_outer) {
+               uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     auto fn = get_encode_fn();
     if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
     cuuint64_t dims[2] = {inner, outer};
@@ -33,7 +33,7 @@ bool encode_2d(CUtensorMap* m, CUtensorMapDataType dt, int esz, const void* base
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(2d) failed: CUresult %d (inner=%llu outer=%llu box=%u x %u)", (int)r,
                   (unsigned long long)inner, (unsigned long long)outer, box_inner, box_outer);
@@ -59,7 +59,7 @@ bool encode_3d_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, u
 
 template <int BN, int EPI, bool WGRAD>
 int launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tO0, const CUtensorMap& tO1,
-               const GemmParams& p, int grid, cudaStream_t st) {
+               const CUtensorMap& tAux, const GemmParams& p, int grid, cudaStream_t st) {
     using Cfg = GemmCfg<BN, EPI>;
     auto kfn = grouped_gemm_kernel<BN, EPI, WGRAD>;
     static bool configured = false;  // per instantiation
@@ -69,7 +69,7 @@ int launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& 
         configured = true;
     }
     // the kernel carries __cluster_dims__(2,1,1): the grid is a whole number of CTA pairs
-    kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(tA, tB, tO0, tO1, p);
+    kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(tA, tB, tO0, tO1, tAux, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("grouped_gemm launch: %s", cudaGetErrorString(e)); return 1; }
     return 0;
@@ -114,7 +114,7 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
     p.aux = static_cast<const __nv_bfloat16*>(aux);
     p.E = E; p.M = M; p.N = N; p.K = K;
 
-    CUtensorMap tA, tB, tO0, tO1;
+    CUtensorMap tA, tB, tO0, tO1, tAux;
     const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const uint64_t R = static_cast<uint64_t>(rows_cap);
     bool ok = true;
@@ -122,24 +122,28 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
         // A [rows, K] and B [E*N, K] K-major; each CTA of a pair loads 128 A rows and bn/2 B rows per k-block
         ok = ok && encode_2d(&tA, BF, 2, A, K, R, 64, 128);
         ok = ok && encode_2d(&tB, BF, 2, B, K, static_cast<uint64_t>(E) * N, 64, bn / 2);
-        ok = ok && encode_2d(&tO0, BF, 2, out0, N, R, 64, 32);   // each epilogue warp stores its own 32-row slab
-        ok = ok && encode_2d(&tO1, BF, 2, op == MOE_GEMM_FC1 ? out1 : out0, N, R, 64, 32);
+        // each epilogue warp stores (and, for dgelu, loads its rows of the pre-activation as) 32-row x 32-column slabs
+        const auto S64 = CU_TENSOR_MAP_SWIZZLE_64B;
+        ok = ok && encode_2d(&tO0, BF, 2, out0, N, R, 32, 32, S64);
+        ok = ok && encode_2d(&tO1, BF, 2, op == MOE_GEMM_FC1 ? out1 : out0, N, R, 32, 32, S64);
+        ok = ok && encode_2d(&tAux, BF, 2, op == MOE_GEMM_DGELU ? aux : out0, N, R, 32, 32, S64);
     } else {
         // A [rows, M], B [rows, N] read MN-major in 64 x 64 boxes; out [E, M, N] fp32 in 32-column chunks
         ok = ok && encode_2d(&tA, BF, 2, A, M, R, 64, 64);
         ok = ok && encode_2d(&tB, BF, 2, B, N, R, 64, 64);
         ok = ok && encode_3d_f32(&tO0, out0, N, M, E, 32, 32);
         tO1 = tO0;
+        tAux = tO0;
     }
     if (!ok) return 1;
     const int grid = (sm_count / 2) * 2;
 
 #define MOE_BN_ROWS(EPI)                                                                  \
     switch (bn) {                                                                         \
-        case 256: return launch_one<256, EPI, false>(tA, tB, tO0, tO1, p, grid, st);      \
-        case 192: return launch_one<192, EPI, false>(tA, tB, tO0, tO1, p, grid, st);      \
-        case 128: return launch_one<128, EPI, false>(tA, tB, tO0, tO1, p, grid, st);      \
-        default: return launch_one<64, EPI, false>(tA, tB, tO0, tO1, p, grid, st);        \
+        case 256: return launch_one<256, EPI, false>(tA, tB, tO0, tO1, tAux, p, grid, st);      \
+        case 192: return launch_one<192, EPI, false>(tA, tB, tO0, tO1, tAux, p, grid, st);      \
+        case 128: return launch_one<128, EPI, false>(tA, tB, tO0, tO1, tAux, p, grid, st);      \
+        default: return launch_one<64, EPI, false>(tA, tB, tO0, tO1, tAux, p, grid, st);        \
     }
     switch (op) {
         case MOE_GEMM_FC1: MOE_BN_ROWS(EPI_BIAS_GELU_DUAL)
@@ -147,10 +151,17 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
         case MOE_GEMM_DGELU: MOE_BN_ROWS(EPI_DGELU)
         case MOE_GEMM_DGRAD: MOE_BN_ROWS(EPI_PLAIN)
         default:
-            if (bn == 256) return launch_one<256, EPI_F32, true>(tA, tB, tO0, tO1, p, grid, st);
-            return launch_one<128, EPI_F32, true>(tA, tB, tO0, tO1, p, grid, st);
+            if (bn == 256) return launch_one<256, EPI_F32, true>(tA, tB, tO0, tO1, tAux, p, grid, st);
+            return launch_one<128, EPI_F32, true>(tA, tB, tO0, tO1, tAux, p, grid, st);
     }
 #undef MOE_BN_ROWS
 }
 
 }  // namespace moe
+
+#ifdef MOE_DBG_TIMELINE
+// kernel experiments only: copy the timeline stamps of the last launch to the host (2*4*64*4 long longs)
+extern "C" int moe_debug_timeline(long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, moe::g_tl, sizeof(moe::g_tl)) == cudaSuccess ? 0 : 1;
+}
+#endif

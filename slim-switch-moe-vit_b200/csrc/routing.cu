@@ -88,14 +88,15 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
 template <typename XT, int EG>
 __global__ void __launch_bounds__(256)
 gate_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ Wg, const float* __restrict__ bg,
-                const float* __restrict__ noise, int64_t T, int d, int E, int k, int score_mode, int want_psum, float* __restrict__ logits, int* __restrict__ idx,
+                const float* __restrict__ noise, const uint8_t* __restrict__ token_mask, int64_t T, int d, int E, int k, int score_mode,
+                int want_psum, float* __restrict__ logits, int* __restrict__ idx,
                 float* __restrict__ score, int* __restrict__ tile_hist, float* __restrict__ tile_psum) {
     constexpr int NT = 64 / EG;  // tokens per warp pass: NT*EG = 64 accumulators per lane (NT <= kTokPerWarp)
     extern __shared__ float smem_f[];
     float* wg_s = smem_f;                          // [EG][d]
     float* lg_s = wg_s + EG * d;                   // [kTokTile][E+1]
     float* m_s = lg_s + kTokTile * (E + 1);        // [kTokTile] row max
-    float* rz_s = m_s + kTokTile;                  // [kTokTile] 1/Z
+    float* rz_s = m_s + kTokTile;                  // [kTokTile] Z
     int* hist_s = reinterpret_cast<int*>(rz_s + kTokTile);  // [E]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -166,7 +167,13 @@ gate_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ Wg, const fl
     // ---- per-token top-k (ties -> lowest index), scores, histogram
     {
         const int64_t tok = t_base + tid;
-        if (tid < kTokTile && tok < T) {
+        if (tid < kTokTile && tok < T && token_mask != nullptr && token_mask[tok] == 0) {
+            // token-skip mask (reference models/resMoE.py:126-145): the token is not routed at all —
+            // idx = -1, score = 0, no histogram entry, no share in psum (exp(l - inf) = 0)
+            for (int j = 0; j < k; ++j) { idx[tok * k + j] = -1; score[tok * k + j] = 0.0f; }
+            m_s[tid] = INFINITY;
+            rz_s[tid] = 1.0f;
+        } else if (tid < kTokTile && tok < T) {
             const float* lr = lg_s + tid * ldl;
             int picked[kMaxK];
             float pv[kMaxK];
@@ -359,10 +366,10 @@ dispatch_fwd_kernel(const XT* __restrict__ x, const int* __restrict__ idx, const
     // A: per-32-entry chunk: rank inside the chunk + per-chunk expert counts
     for (int ch = warp; ch < n_chunks; ch += 8) {
         const int il = ch * 32 + lane;
-        const bool valid = il < n_ent;
+        const int e = il < n_ent ? idx[i_base + il] : -1;   // -1: past the end, or a masked (skipped) token
+        const bool valid = e >= 0;
         const unsigned act = __ballot_sync(0xffffffffu, valid);
         if (valid) {
-            const int e = idx[i_base + il];
             const unsigned peers = __match_any_sync(act, e);
             const int rk = __popc(peers & ((1u << lane) - 1u));
             if (rk == 0) chunk_cnt[ch * E + e] = __popc(peers);
@@ -383,7 +390,7 @@ dispatch_fwd_kernel(const XT* __restrict__ x, const int* __restrict__ idx, const
     // C: final positions
     for (int il = tid; il < n_ent; il += 256) {
         const int e = idx[i_base + il];
-        const long long rank = static_cast<long long>(chunk_cnt[(il >> 5) * E + e]) + ent_row[il];
+        const long long rank = e >= 0 ? static_cast<long long>(chunk_cnt[(il >> 5) * E + e]) + ent_row[il] : capacity;
         const int row = rank < capacity ? seg_start[e] + static_cast<int>(rank) : -1;
         pos[i_base + il] = row;
         if (row >= 0) row_src[row] = static_cast<int>(i_base + il);
@@ -483,8 +490,9 @@ gate_bwd_kernel(const float* __restrict__ logits, const int* __restrict__ idx, c
     for (int j = 0; j < k; ++j) { pk[j] = idx[t * k + j]; s[j] = score[t * k + j]; g[j] = dscore[t * k + j]; }
     const bool need_p = (score_mode == 1) || (dpsum != nullptr);
     float m = 0.0f, rz = 0.0f, pdot = 0.0f;
+    const bool masked = pk[0] < 0;   // token-skip mask: no gate gradient at all
     if (need_p) {
-        m = lr[pk[0]];
+        m = lr[max(pk[0], 0)];
         float z = 0.0f;
         for (int e = 0; e < E; ++e) z += expf(lr[e] - m);
         rz = 1.0f / z;
@@ -506,7 +514,7 @@ gate_bwd_kernel(const float* __restrict__ logits, const int* __restrict__ idx, c
             v -= inner * p;
         }
         if (dpsum != nullptr) v += p * (dpsum[e] - pdot);
-        dl[e] = v;
+        dl[e] = masked ? 0.0f : v;
     }
 }
 
@@ -549,6 +557,7 @@ dispatch_bwd_kernel(const __nv_bfloat16* __restrict__ dxbuf, const int* __restri
             } else {
                 for (int j = 0; j < k; ++j) {
                     const int e = __ldg(idx + t * k + j);
+                    if (e < 0) continue;   // masked (skipped) token
                     const float g = __ldg(dlogits + t * E + e);
                     float w[8];
                     load8(Wg + static_cast<size_t>(e) * d + c, w);
@@ -599,8 +608,9 @@ gate_dispatch_bwd_kernel(const __nv_bfloat16* __restrict__ dxbuf, const int* __r
         float sc[kMaxK], g[kMaxK];
         for (int j = 0; j < k; ++j) { pk[j] = idx[t * k + j]; sc[j] = score[t * k + j]; g[j] = dscore[t * k + j]; }
         float m = 0.0f, rz = 0.0f, pdot = 0.0f;
+        const bool masked = pk[0] < 0;   // token-skip mask: no gate gradient at all
         if (dense) {
-            m = lr[pk[0]];
+            m = lr[max(pk[0], 0)];
             float z = 0.0f;
 #pragma unroll 1
             for (int e = part; e < E; e += 4) z += expf(lr[e] - m);
@@ -631,7 +641,7 @@ gate_dispatch_bwd_kernel(const __nv_bfloat16* __restrict__ dxbuf, const int* __r
                     v -= inner * p;
                 }
                 if (dpsum != nullptr) v += p * (dpsum[e] - pdot);
-                dl[e] = v;
+                dl[e] = masked ? 0.0f : v;
             }
         }
     }
@@ -729,6 +739,7 @@ gate_dispatch_bwd_kernel(const __nv_bfloat16* __restrict__ dxbuf, const int* __r
                 } else if (!dense) {
                     for (int j = 0; j < k; ++j) {
                         const int e = __ldg(idx + t * k + j);
+                        if (e < 0) continue;
                         const float g = dr[e];
                         const float4 w = __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e) * d + cg * 4));
                         acc[u].x = fmaf(g, w.x, acc[u].x); acc[u].y = fmaf(g, w.y, acc[u].y);
@@ -1033,7 +1044,7 @@ static int pick_eg(int E, int d) {
 }
 
 template <typename XT>
-static cudaError_t launch_gate_fwd_t(const XT* x, const float* Wg, const float* bg, const float* noise, int64_t T, int d, int E, int k,
+static cudaError_t launch_gate_fwd_t(const XT* x, const float* Wg, const float* bg, const float* noise, const uint8_t* token_mask, int64_t T, int d, int E, int k,
                                      int score_mode, int want_psum, float* logits, int* idx, float* score,
                                      int* tile_hist, float* tile_psum, cudaStream_t st) {
     const int ntiles = static_cast<int>((T + kTokTile - 1) / kTokTile);
@@ -1045,7 +1056,7 @@ static cudaError_t launch_gate_fwd_t(const XT* x, const float* Wg, const float* 
         auto kfn = gate_fwd_kernel<XT, EGV>;                                                                       \
         cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         if (err != cudaSuccess) return err;                                                                        \
-        kfn<<<ntiles, 256, smem, st>>>(x, Wg, bg, noise, T, d, E, k, score_mode, want_psum, logits, idx, score, tile_hist, \
+        kfn<<<ntiles, 256, smem, st>>>(x, Wg, bg, noise, token_mask, T, d, E, k, score_mode, want_psum, logits, idx, score, tile_hist, \
                                        tile_psum);                                                                 \
         break;                                                                                                     \
     }
@@ -1059,13 +1070,13 @@ static cudaError_t launch_gate_fwd_t(const XT* x, const float* Wg, const float* 
     return cudaGetLastError();
 }
 
-cudaError_t launch_gate_fwd(const void* x, int x_dtype, const float* Wg, const float* bg, const float* noise, int64_t T, int d, int E, int k,
+cudaError_t launch_gate_fwd(const void* x, int x_dtype, const float* Wg, const float* bg, const float* noise, const uint8_t* token_mask, int64_t T, int d, int E, int k,
                             int score_mode, int want_psum, float* logits, int* idx, float* score, int* tile_hist,
                             float* tile_psum, cudaStream_t st) {
     if (x_dtype == MOE_DTYPE_F32)
-        return launch_gate_fwd_t(static_cast<const float*>(x), Wg, bg, noise, T, d, E, k, score_mode, want_psum, logits, idx,
+        return launch_gate_fwd_t(static_cast<const float*>(x), Wg, bg, noise, token_mask, T, d, E, k, score_mode, want_psum, logits, idx,
                                  score, tile_hist, tile_psum, st);
-    return launch_gate_fwd_t(static_cast<const __nv_bfloat16*>(x), Wg, bg, noise, T, d, E, k, score_mode, want_psum, logits,
+    return launch_gate_fwd_t(static_cast<const __nv_bfloat16*>(x), Wg, bg, noise, token_mask, T, d, E, k, score_mode, want_psum, logits,
                              idx, score, tile_hist, tile_psum, st);
 }
 

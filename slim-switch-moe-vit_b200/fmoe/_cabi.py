@@ -26,7 +26,7 @@ SIGNATURES = {
     "moe_last_error": (ctypes.c_char_p, []),
     "moe_version": (_i, []),
     "moe_rows_cap": (_i64, [_i64, _i, _i, _i64]),
-    "moe_gate_fwd": (_i, [_p, _i, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "moe_gate_fwd": (_i, [_p, _i, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "moe_route_scan": (_i, [_p, _p, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _i, _p, _i, _i64, _i, _p, _p, _i64, _p]),
     "moe_ep_tables": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "moe_ep_repack": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _i, _i, _p]),

@@ -69,9 +69,10 @@ def _f32(n, dev):
     return torch.empty(n, dtype=torch.float32, device=dev)
 
 
-def route(x, Wg, bg, spec: RouteSpec, noise=None, slab_rows: int = 0):
+def route(x, Wg, bg, spec: RouteSpec, noise=None, slab_rows: int = 0, token_mask=None):
     """gate + scan + dispatch.  Returns a dict of device tensors (no host sync).
-    slab_rows > 0 selects the expert-parallel send layout: expert e owns rows [e*slab_rows, (e+1)*slab_rows)."""
+    slab_rows > 0 selects the expert-parallel send layout: expert e owns rows [e*slab_rows, (e+1)*slab_rows).
+    token_mask (uint8 [T], optional): tokens with mask 0 are not routed (idx = pos = -1, no capacity taken)."""
     T, d = x.shape
     E = Wg.shape[0]
     k = spec.top_k
@@ -93,7 +94,7 @@ def route(x, Wg, bg, spec: RouteSpec, noise=None, slab_rows: int = 0):
     r["psum"] = _f32(E, dev) if spec.want_psum else None
     r["aux_loss"] = _f32(1, dev) if spec.want_psum else None
     r["aux_coef"] = _f32(E, dev) if spec.want_psum else None
-    C.call("moe_gate_fwd", C.ptr(x), C.dtype_code(x), C.ptr(Wg), C.ptr(bg), C.ptr(noise), T, d, E, k,
+    C.call("moe_gate_fwd", C.ptr(x), C.dtype_code(x), C.ptr(Wg), C.ptr(bg), C.ptr(noise), C.ptr(token_mask), T, d, E, k,
            spec.score_mode, int(spec.want_psum), C.ptr(r["logits"]), C.ptr(r["idx"]), C.ptr(r["score"]),
            C.ptr(r["tile_hist"]), C.ptr(tile_psum), st)
     C.call("moe_route_scan", C.ptr(r["tile_hist"]), C.ptr(tile_psum), ntiles, E, spec.capacity,
@@ -116,7 +117,7 @@ class MoEFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, Wg, bg, W1, b1, W2, b2, spec: RouteSpec, cache: Bf16WeightCache, noise):
+    def forward(ctx, x, Wg, bg, W1, b1, W2, b2, spec: RouteSpec, cache: Bf16WeightCache, noise, token_mask=None):
         x = _as_kernel_input(x)
         T, d = x.shape
         E, h = W1.shape[0], W1.shape[1]
@@ -128,7 +129,7 @@ class MoEFunction(torch.autograd.Function):
             if w.dtype != torch.float32:
                 raise C.MoeB200Error("expert / gate parameters must be fp32 (master weights)")
         bg_c = None if bg is None else bg.detach().contiguous()
-        r = route(x, Wg_c, bg_c, spec, noise)
+        r = route(x, Wg_c, bg_c, spec, noise, token_mask=token_mask)
         rows_cap = r["rows_cap"]
         W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c)
         U = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
@@ -210,7 +211,61 @@ class MoEFunction(torch.autograd.Function):
         dbg = _f32(E, dev) if ctx.has_bg else None
         C.call("moe_gate_wgrad", C.ptr(dlogits), C.ptr(x), C.dtype_code(x), T, d, E, C.ptr(ws), C.ptr(dWg),
                C.ptr(dbg), st)
-        return dx, dWg, dbg, dW1, db1, dW2, db2, None, None, None
+        return dx, dWg, dbg, dW1, db1, dW2, db2, None, None, None, None
+
+
+class SkipFill(torch.autograd.Function):
+    """Token-skip semantics of the reference's residual-MoE block (/root/reference/models/resMoE.py:126-145):
+    there a skipped token enters the layer as `x * 0`, so its output is the constant c = mlp(0) and the gradient
+    with respect to its (zero) input row is J0^T dy, J0 = d mlp / d z at z = 0.  The fused layer never routes such
+    tokens; this node restores both terms:  out = keep ? y : c,  d inp[skipped] = dy J0,  dc = sum over skipped dy."""
+
+    @staticmethod
+    def forward(ctx, y, inp, keep, c, J0):
+        ctx.save_for_backward(keep, J0)
+        ctx.inp_dtype = inp.dtype
+        return torch.where(keep.bool().unsqueeze(1), y, c.to(y.dtype).unsqueeze(0))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        keep, J0 = ctx.saved_tensors
+        kb = keep.bool().unsqueeze(1)
+        dskip = torch.where(kb, torch.zeros((), dtype=torch.float32, device=dout.device), dout.float())   # rows of skipped tokens
+        dy = torch.where(kb, dout, torch.zeros((), dtype=dout.dtype, device=dout.device))
+        dinp = (dskip @ J0).to(ctx.inp_dtype) if ctx.needs_input_grad[1] else None
+        dc = dskip.sum(0) if ctx.needs_input_grad[3] else None
+        return dy, dinp, None, dc, None
+
+
+def zero_token_path(gate_w, gate_b, W1, b1, W2, b2, top_k: int, score_mode: int):
+    """c = mlp(0) [d] (differentiable w.r.t. the parameters) and J0 = d mlp(z) / d z at z = 0 [d_out, d_in] (detached)
+    for one all-zero token — a handful of small fp32 ops on the expert(s) the gate bias selects; no host sync.
+    Selection follows the layer's canonical rule (descending logit, ties -> lowest index)."""
+    E, d = gate_w.shape
+    bg = gate_b if gate_b is not None else torch.zeros(E, dtype=torch.float32, device=gate_w.device)
+    vals, e_idx = torch.sort(bg.float(), descending=True, stable=True)
+    vals, e_idx = vals[:top_k], e_idx[:top_k]
+    if score_mode == C.SCORE_TOPK_SOFTMAX:
+        s = torch.softmax(vals, dim=0)                                         # [k]
+    else:
+        p = torch.softmax(bg.float(), dim=0)
+        s = p[e_idx]
+    W1s, b1s, W2s, b2s = W1[e_idx], b1[e_idx], W2[e_idx], b2[e_idx]           # [k,h,d] [k,h] [k,d,h] [k,d]
+    act = torch.nn.functional.gelu(b1s)                                        # exact erf
+    E0 = torch.einsum("kdh,kh->kd", W2s, act) + b2s                            # expert outputs at z = 0
+    c = (s.unsqueeze(1) * E0).sum(0)
+    with torch.no_grad():
+        u = b1s.float()
+        dact = 0.5 * (1.0 + torch.erf(u * 0.7071067811865476)) + u * torch.exp(-0.5 * u * u) * 0.3989422804014327
+        J0 = torch.einsum("k,kdh,khi->di", s, W2s.float() * dact.unsqueeze(1), W1s.float())   # sum_j s_j W2 diag(gelu') W1
+        Wg_sel = gate_w.float()[e_idx]                                                       # [k, d_in]
+        if score_mode == C.SCORE_TOPK_SOFTMAX:
+            ds = s.unsqueeze(1) * (Wg_sel - (s.unsqueeze(1) * Wg_sel).sum(0, keepdim=True))  # d s_j / d z
+        else:
+            ds = s.unsqueeze(1) * (Wg_sel - (p.unsqueeze(1) * gate_w.float()).sum(0, keepdim=True))
+        J0 = J0 + E0.float().t() @ ds
+    return c, J0
 
 
 class GateFunction(torch.autograd.Function):
@@ -229,7 +284,7 @@ class GateFunction(torch.autograd.Function):
         tile_psum = _f32((E, ntiles), dev) if spec.want_psum else None
         Wg_c = Wg.detach().contiguous()
         bg_c = None if bg is None else bg.detach().contiguous()
-        C.call("moe_gate_fwd", C.ptr(x), C.dtype_code(x), C.ptr(Wg_c), C.ptr(bg_c), C.ptr(noise), T, d, E,
+        C.call("moe_gate_fwd", C.ptr(x), C.dtype_code(x), C.ptr(Wg_c), C.ptr(bg_c), C.ptr(noise), None, T, d, E,
                spec.top_k, spec.score_mode, int(spec.want_psum), C.ptr(logits), C.ptr(idx), C.ptr(score),
                C.ptr(tile_hist), C.ptr(tile_psum), st)
         ctx.spec, ctx.has_bg = spec, bg is not None

@@ -13,7 +13,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .functions import Bf16WeightCache, MoEFunction
+from .functions import Bf16WeightCache, MoEFunction, SkipFill, zero_token_path
 from .gates import BaseGate, NaiveGate
 
 
@@ -58,19 +58,36 @@ class FMoE(nn.Module):
     def _expert_params(self):
         raise NotImplementedError
 
-    def forward(self, moe_inp: torch.Tensor) -> torch.Tensor:
-        """moe_inp [T, d_model] -> [T, d_model]; sets `self.gate`'s aux loss as a side effect."""
+    def forward(self, moe_inp: torch.Tensor, token_mask: torch.Tensor | None = None) -> torch.Tensor:
+        """moe_inp [T, d_model] -> [T, d_model]; sets `self.gate`'s aux loss as a side effect.
+
+        token_mask [T] (optional; non-zero = keep): the token-skip mask of the reference's residual-MoE block
+        (/root/reference/models/resMoE.py:126-145 calls `self.mlp(x * mask)`).  `layer(x * m, token_mask=m)` returns
+        what `layer(x * m)` returns for a 0/1 mask — skipped rows get the constant mlp(0), their input gradient is
+        J0^T dy — but skipped tokens are never routed: they cost no dispatch, expert-FFN or combine work and take no
+        expert capacity (with a capacity-limited gate that is where the two differ: upstream would let them compete
+        for the slots of the expert the gate bias favours).  Rows of moe_inp under a zero mask are not read."""
         if moe_inp.dim() != 2 or moe_inp.shape[1] != self.d_model:
             raise ValueError(f"expected [tokens, {self.d_model}] input, got {tuple(moe_inp.shape)}")
         if self.world_size > 1:
+            if token_mask is not None:
+                raise NotImplementedError("token_mask under expert parallelism: mlp(0) of a skipped token may live on a remote rank")
             from .distributed import ep_forward
             return ep_forward(self, moe_inp)
         T = moe_inp.shape[0]
         W1, b1, W2, b2 = self._expert_params()
         gate = self.gate
         spec = gate.route_spec(T)
+        keep = None
+        if token_mask is not None:
+            if token_mask.numel() != T:
+                raise ValueError(f"token_mask has {token_mask.numel()} entries for {T} tokens")
+            keep = (token_mask.reshape(T) != 0).to(torch.uint8)
         y, aux, count, kept = MoEFunction.apply(moe_inp, gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec,
-                                                self._bf16_cache, gate.make_noise(moe_inp))
+                                                self._bf16_cache, gate.make_noise(moe_inp), keep)
+        if keep is not None:
+            c, J0 = zero_token_path(gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec.top_k, spec.score_mode)
+            y = SkipFill.apply(y, moe_inp, keep, c, J0)
         gate.finish(aux)
         self.last_count, self.last_kept = count, kept   # load-balance statistics (device tensors, no sync)
         return y

@@ -62,8 +62,9 @@ class FMoETransformerMLP(FMoE):
         e = self.experts
         return e.htoh4.weight, e.htoh4.bias, e.h4toh.weight, e.h4toh.bias
 
-    def forward(self, inp: torch.Tensor):
+    def forward(self, inp: torch.Tensor, token_mask: torch.Tensor | None = None):
+        """inp [..., d_model] -> same shape.  token_mask [...] (optional): see `FMoE.forward` and `fmoe.residual`."""
         original_shape = inp.shape
         inp = inp.reshape(-1, self.d_model)
-        output = super().forward(inp)
+        output = super().forward(inp, None if token_mask is None else token_mask.reshape(-1))
         return output.reshape(original_shape)

@@ -27,3 +27,22 @@ def rel_err(a, b):
 
 def max_abs(a, b):
     return float((a.double().cpu() - b.double().cpu()).abs().max())
+
+
+class TokenGate(torch.nn.Module):
+    """Test-side restatement of the reference's token-skip `Gate` in its hard mode
+    (/root/reference/models/resMoE.py:60-84): returns [B, N, 2] = (skip, keep) 0/1 weights with the straight-through
+    terms `+ p.detach() - p`.  Pinned by the `mask` array of tests/golden/ref_resmoe_skip*.npz."""
+
+    def __init__(self, d, threshold):
+        super().__init__()
+        self.head = torch.nn.Sequential(torch.nn.Dropout(p=0.0), torch.nn.Linear(d, 1))
+        self.threshold = float(threshold)
+        self.is_hard, self.disable = True, False
+
+    def forward(self, x):
+        prob = torch.sigmoid(self.head(x))
+        inv = 1 - prob
+        skip = (prob > self.threshold).float() + inv.detach() - inv
+        keep = (prob <= self.threshold).float() + prob.detach() - prob
+        return torch.cat([skip, keep], dim=-1)

@@ -372,3 +372,129 @@ def test_linear_fast_bias_grad_vs_torch(rows, K, N):
     out = torch.empty(N, dtype=torch.float32, device="cuda")
     C.call("moe_colsum", C.ptr(dyb), C.dtype_code(dyb), rows, N, C.ptr(ws), C.ptr(out), C.stream_ptr())
     assert rel_err(out, want) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# token-skip mask (reference models/resMoE.py:126-145)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,mode,cf,xdt", [(1, 0, 0.0, torch.float32), (2, 0, 0.0, torch.bfloat16), (1, 1, 1.25, torch.float32), (2, 1, 0.5, torch.float32)])
+def test_routing_with_token_mask_bit_exact(k, mode, cf, xdt):
+    """Skipped tokens: idx = pos = -1, score 0, not counted, no capacity taken, nothing in psum — bit-exact vs the oracle."""
+    _, C, Fn = _fm()
+    T, d, h, E = 1000, 192, 768, 8
+    x, Wg, bg, *_ = make_problem(T, d, h, E, seed=5, x_dtype=xdt, skew=1.0)
+    mask = torch.rand(T, generator=torch.Generator().manual_seed(6)) < 0.55
+    mask[128:192] = False        # one routing tile without a single live token
+    mask[-3:] = False            # ragged last tile ends on skipped tokens
+    cap = _cap(T, k, E, cf)
+    spec = Fn.RouteSpec(k, mode, cap, C.AUX_SWITCH)
+    r = Fn.route(x.cuda(), Wg.cuda(), bg.cuda(), spec, token_mask=mask.to(torch.uint8).cuda())
+    torch.cuda.synchronize()
+    logits = O.gate_logits(x, Wg, bg)
+    ref = O.route(logits, k, mode, cap, token_mask=mask)
+    assert torch.equal(r["logits"].cpu(), logits)
+    for f in ("idx", "count", "kept", "seg_start", "pos"):
+        assert torch.equal(r[f].cpu(), getattr(ref, f)), f
+    assert (r["idx"].cpu()[~mask] == -1).all() and (r["pos"].cpu()[~mask] == -1).all()
+    assert max_abs(r["score"], ref.score) <= 2e-6 and max_abs(r["psum"], ref.psum) <= 2e-6 * T
+    assert int(r["num_mtiles"].item()) == ref.rows // C.ROW_ALIGN
+    row_src, _ = O._row_tables(ref, E)
+    rows = ref.rows
+    assert torch.equal(r["row_src"].cpu()[:rows].long(), row_src)
+    want = torch.zeros(rows, d)
+    live = row_src >= 0
+    want[live] = O.bf16_round(x.float()[row_src[live] // k])
+    assert torch.equal(r["xbuf"].cpu()[:rows].float(), want)
+
+
+@pytest.mark.parametrize("k,gate_name", [(2, "NaiveGate"), (1, "SwitchGate")])
+def test_masked_layer_equals_layer_on_kept_tokens(k, gate_name):
+    """layer(x * m, token_mask=m): kept rows are what the layer computes for the kept tokens alone, skipped rows are
+    mlp(0), the input gradient of a skipped row is dy J0, and no gate / expert gradient comes from skipped rows
+    except through mlp(0)."""
+    fmoe, C, Fn = _fm()
+    T, d, h, E = 600, 128, 512, 8
+    torch.manual_seed(0)
+    gate_cls = getattr(fmoe, gate_name)
+    layer = fmoe.FMoETransformerMLP(E, d, h, torch.nn.GELU(), top_k=k, gate=gate_cls).cuda()
+    if gate_name == "SwitchGate":
+        layer.gate.capacity = (1e9, 1e9)                                                # no drops: tokens stay independent
+        layer.eval()                                                                    # no train-time jitter
+    with torch.no_grad():
+        for p in layer.experts.parameters():
+            if p.dim() == 2:
+                p.uniform_(-0.1, 0.1)     # non-zero expert biases: mlp(0) != 0
+    x = torch.randn(T, d, device="cuda")
+    keep = torch.rand(T, device="cuda") < 0.5
+    dy = torch.randn(T, d, device="cuda")
+
+    xa = (x * keep.unsqueeze(1)).requires_grad_()
+    ya = layer(xa, token_mask=keep)
+    (ya * dy).sum().backward()
+    ga = {n: p.grad.clone() for n, p in layer.named_parameters()}
+    layer.zero_grad()
+
+    xb = x[keep].clone().requires_grad_()
+    yb = layer(xb)                                           # the kept tokens alone
+    c, J0 = Fn.zero_token_path(layer.gate.gate.weight, layer.gate.gate.bias, *layer._expert_params(), k,
+                               layer.gate.route_spec(T).score_mode)
+    ((yb * dy[keep]).sum() + (c * dy[~keep].sum(0)).sum()).backward()
+    assert rel_err(ya[keep], yb) <= 1e-6 and rel_err(xa.grad[keep], xb.grad) <= 1e-6
+    assert rel_err(ya[~keep], c.detach().expand(int((~keep).sum()), d)) <= 1e-6
+    assert rel_err(xa.grad[~keep], dy[~keep] @ J0) <= 1e-5
+    for n, p in layer.named_parameters():
+        assert rel_err(ga[n], p.grad) <= 2e-3, n                # same sums, different row order inside the GEMMs
+    # mlp(0) from the small fp32 path agrees with pushing a zero token through the kernels (bf16 operands)
+    y0 = layer(torch.zeros(64, d, device="cuda"))
+    assert rel_err(y0[0], c) <= 1e-2
+
+
+@pytest.mark.parametrize("name", ["ref_resmoe_skip", "ref_resmoe_skip_top1"])
+def test_residual_moe_block_vs_reference_golden(name):
+    """`fmoe.residual.forward_residual_moe` (skipped tokens really skipped) against what the reference's own
+    `forward_residule_moe` + `Gate` + `CustomizedMoEMLP` produced on the CPU (tests/golden/make_golden_resmoe.py):
+    bf16-level tolerance on outputs and gradients, exact keep mask."""
+    import numpy as np
+    import sys
+    fmoe, C, Fn = _fm()
+    from fmoe.residual import forward_residual_moe
+    from _util import TokenGate
+    golden = os.path.join(os.path.dirname(__file__), "golden")
+    sys.path.insert(0, golden)
+    from make_golden_params import build_params, weights_digest
+    z = np.load(os.path.join(golden, name + ".npz"))
+    d, hid, E, k, B, N = [int(v) for v in z["meta"]]
+    sd = build_params(d, hid, E)
+    assert weights_digest(sd) == str(z["weights_sha256"])
+
+    class _Zero(torch.nn.Module):
+        def forward(self, t):
+            return torch.zeros_like(t)
+
+    blk = torch.nn.Module()
+    blk.norm1, blk.norm2, blk.drop_path, blk.attn = torch.nn.Identity(), torch.nn.Identity(), torch.nn.Identity(), _Zero()
+    blk.dense_gate = TokenGate(d, 2.0)                      # threshold above 1: keeps everything (the reference's disabled gate)
+    blk.moe_gate = TokenGate(d, float(z["threshold"]))
+    blk.moe_gate.head[1].weight.data.copy_(torch.from_numpy(z["param.moe_gate.head.1.weight"]))
+    blk.moe_gate.head[1].bias.data.copy_(torch.from_numpy(z["param.moe_gate.head.1.bias"]))
+    blk.mlp = fmoe.FMoETransformerMLP(E, d, hid, torch.nn.Sequential(torch.nn.GELU(), torch.nn.Dropout(0.0)), top_k=k)
+    blk.mlp.load_state_dict(sd)
+    blk = blk.cuda().train()
+    x = torch.from_numpy(z["x"]).cuda().requires_grad_()
+    with torch.no_grad():
+        # same tokens skipped as in the reference run (the mask values themselves are 0/1 up to an ulp of `1 + p - p`)
+        assert np.array_equal(np.round(blk.moe_gate(x).cpu().numpy()), np.round(z["mask"]))
+    out = forward_residual_moe(blk, x)
+    (out * torch.from_numpy(z["dy"]).cuda()).sum().backward()
+    kept_pairs = int(blk.mlp.last_count.sum())
+    assert kept_pairs == int(z["mask"][..., 1].sum()) * k                         # skipped tokens never reached the experts
+    assert rel_err(out, torch.from_numpy(z["out"])) <= IDEAL_REL
+    assert rel_err(x.grad, torch.from_numpy(z["dx"])) <= IDEAL_REL
+    assert rel_err(blk.moe_gate.head[1].weight.grad, torch.from_numpy(z["grad.moe_gate.head.1.weight"])) <= IDEAL_REL
+    assert rel_err(blk.moe_gate.head[1].bias.grad, torch.from_numpy(z["grad.moe_gate.head.1.bias"])) <= IDEAL_REL
+    for pn, p in blk.mlp.named_parameters():
+        if "grad.mlp." + pn in z.files:
+            assert rel_err(p.grad, torch.from_numpy(z["grad.mlp." + pn])) <= IDEAL_REL, pn
+        else:
+            got = torch.stack([p.grad[i].norm() for i in range(E)]).double()
+            assert rel_err(got, torch.from_numpy(z["gradnorm.mlp." + pn])) <= IDEAL_REL, pn

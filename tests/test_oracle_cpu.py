@@ -31,7 +31,8 @@ def load_golden(name):
     return z, sd, (d, hid, E, k, B, N)
 
 
-GOLDEN_NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+GOLDEN_NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "ref_wrapper_*.npz")))
+RESMOE_NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "ref_resmoe_*.npz")))
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
@@ -81,6 +82,74 @@ def test_c_routing_matches_python_restatement(k, mode, cf):
     assert (a.psum - b.psum).abs().max() <= 1e-4
     if cf:
         assert int(a.kept.max()) <= cap and (a.pos < 0).any()
+
+
+@pytest.mark.parametrize("k,mode,cf", [(1, 0, 0.0), (2, 0, 0.0), (1, 1, 1.25), (2, 1, 0.5)])
+def test_c_routing_with_token_mask_matches_python_restatement(k, mode, cf):
+    """Token-skip mask: skipped tokens are never routed (idx = pos = -1), take no capacity and add nothing to psum."""
+    T, d, E = 333, 64, 8
+    x, Wg, bg, *_ = make_problem(T, d, 128, E, seed=12, skew=1.0)
+    mask = (torch.rand(T, generator=torch.Generator().manual_seed(5)) < 0.6)
+    mask[64:128] = False                       # a whole 64-token routing tile without live tokens
+    logits = O.gate_logits(x, Wg, bg)
+    cap = O.capacity_from_factor(cf, T, k, E)
+    a, b = O.route(logits, k, mode, cap, token_mask=mask), O.route_python(logits, k, mode, cap, token_mask=mask)
+    for f in ("idx", "count", "kept", "seg_start", "pos"):
+        assert torch.equal(getattr(a, f), getattr(b, f)), f
+    assert (a.score - b.score).abs().max() <= 1e-6 and (a.psum - b.psum).abs().max() <= 1e-4
+    assert (a.idx[~mask] == -1).all() and (a.pos[~mask] == -1).all() and (a.score[~mask] == 0).all()
+    assert int(a.count.sum()) == int(mask.sum()) * k
+    # the kept tokens route exactly as they would in a batch that only holds them (capacity aside)
+    sub = O.route(logits[mask], k, mode, T * k)
+    assert torch.equal(a.idx[mask], sub.idx) and torch.equal(a.count, sub.count)
+
+
+def load_resmoe(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d, hid, E, k, B, N = [int(v) for v in z["meta"]]
+    sd = build_params(d, hid, E)
+    assert weights_digest(sd) == str(z["weights_sha256"]), "torch CPU RNG drifted: regenerate the fixtures"
+    return z, sd, (d, hid, E, k, B, N)
+
+
+@pytest.mark.parametrize("name", RESMOE_NAMES)
+def test_skip_formulation_matches_reference_residual_moe(name):
+    """The product never routes skipped tokens and restores mlp(0) / the J0^T dy input gradient analytically
+    (fmoe.functions.zero_token_path + SkipFill, pure torch).  Here that formulation is evaluated on the CPU with the
+    oracle layer standing in for the CUDA kernels, and compared with what the reference's own
+    `forward_residule_moe` + `Gate` produced (tests/golden/make_golden_resmoe.py)."""
+    from _util import TokenGate
+    from fmoe.functions import SkipFill, zero_token_path
+    from oracle import fmoe_cpu
+    z, sd, (d, hid, E, k, B, N) = load_resmoe(name)
+    T = B * N
+    layer = fmoe_cpu.FMoETransformerMLP(E, d, hid, torch.nn.GELU(), top_k=k)
+    layer.load_state_dict(sd)
+    gate = TokenGate(d, float(z["threshold"]))
+    gate.head[1].weight.data.copy_(torch.from_numpy(z["param.moe_gate.head.1.weight"]))
+    gate.head[1].bias.data.copy_(torch.from_numpy(z["param.moe_gate.head.1.bias"]))
+    x = torch.from_numpy(z["x"]).clone().requires_grad_()
+    w = gate(x)
+    assert np.array_equal(w.detach().numpy(), z["mask"])                         # the Gate restatement is exact
+    keep = (w[..., 1] != 0).reshape(T)
+    assert 0 < int(keep.sum()) < T
+    tk, skip_tk = x * w[..., 1:2], x * w[..., 0:1]
+    tk2 = tk.reshape(T, d)
+    y = torch.zeros(T, d).index_put((keep.nonzero().squeeze(1),), layer(tk2[keep]))   # kept tokens only
+    g, e = layer.gate.gate, layer.experts
+    c, J0 = zero_token_path(g.weight, g.bias, e.htoh4.weight, e.htoh4.bias, e.h4toh.weight, e.h4toh.bias, k, 0)
+    out = SkipFill.apply(y, tk2, keep.to(torch.uint8), c, J0).reshape(B, N, d) + tk + skip_tk
+    (out * torch.from_numpy(z["dy"])).sum().backward()
+    assert rel_err(out, torch.from_numpy(z["out"])) <= 1e-5
+    assert rel_err(x.grad, torch.from_numpy(z["dx"])) <= 1e-4
+    assert rel_err(gate.head[1].weight.grad, torch.from_numpy(z["grad.moe_gate.head.1.weight"])) <= 1e-4
+    assert rel_err(gate.head[1].bias.grad, torch.from_numpy(z["grad.moe_gate.head.1.bias"])) <= 1e-4
+    for pn, p in layer.named_parameters():
+        if "grad.mlp." + pn in z.files:
+            assert rel_err(p.grad, torch.from_numpy(z["grad.mlp." + pn])) <= 1e-4, pn
+        else:
+            got = torch.stack([p.grad[i].norm() for i in range(E)]).double()
+            assert rel_err(got, torch.from_numpy(z["gradnorm.mlp." + pn])) <= 1e-4, pn
 
 
 def test_ties_resolve_to_lowest_index_and_edge_cases():
