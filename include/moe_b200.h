@@ -14,7 +14,7 @@
  *     asynchronously, nothing synchronises the host.
  *   - return value: 0 = OK, non-zero = error; moe_last_error() (thread-local) describes it.
  *   - dtype codes: MOE_DTYPE_F32 = 0, MOE_DTYPE_BF16 = 1.
- *   - packed row buffers ("xbuf", "U", "H", "Y", ...) are [rows_cap, cols] bf16 row-major;
+ *   - packed row buffers ("xbuf", "G", "H", "Y", ...) are [rows_cap, cols] bf16 row-major;
  *     expert e owns rows [seg_start[e], seg_start[e+1]), each segment start is a multiple of 256
  *     (one CTA-pair MMA tile; MOE_ROW_ALIGN),
  *     rows [seg_start[e] + kept[e], seg_start[e+1]) are padding.
@@ -45,9 +45,9 @@ extern "C" {
 #define MOE_ROW_ALIGN 256  /* segment alignment of the packed buffers = rows of one CTA-pair MMA tile */
 
 /* grouped GEMM ops (moe_grouped_gemm) */
-#define MOE_GEMM_FC1 0   /* out0 = U = A W^T + b, out1 = gelu_erf(U)    A[rows,K] B[E,N,K]            */
+#define MOE_GEMM_FC1 0   /* U = A W^T + b: out0 = gelu_erf'(U), out1 = gelu_erf(U)   A[rows,K] B[E,N,K] */
 #define MOE_GEMM_FC2 1   /* out0 = A W^T + b                            A[rows,K] B[E,N,K]            */
-#define MOE_GEMM_DGELU 2 /* out0 = (A Wt^T) * gelu'(aux)                A[rows,K] B[E,N,K] aux[rows,N] */
+#define MOE_GEMM_DGELU 2 /* out0 = (A Wt^T) * aux  (aux = FC1's out0)       A[rows,K] B[E,N,K] aux[rows,N] */
 #define MOE_GEMM_DGRAD 3 /* out0 = A Wt^T                               A[rows,K] B[E,N,K]            */
 #define MOE_GEMM_WGRAD 4 /* out0[e] (fp32 [E,M,N]) = A_e^T B_e          A[rows,M] B[rows,N]           */
 
@@ -107,10 +107,11 @@ int moe_dispatch_fwd(const void *x, int x_dtype, const int32_t *idx, const int32
 
 /* ---- expert FFN forward: replaces _Expert.forward = fmoe_cuda.linear_forward x2 + GELU.
  * W1b[E,h,d], W2b[E,d,h] bf16 copies of the fp32 parameters; b1[E,h], b2[E,d] fp32.
- * Writes U (pre-activation), H = gelu_erf(U), Y, all bf16 [rows_cap, .]. */
+ * With U = X W1^T + b1 (fp32, never stored): writes G = gelu_erf'(U) — all that backward needs of U —,
+ * H = gelu_erf(U) and Y = H W2^T + b2, all bf16 [rows_cap, .]. */
 int moe_expert_ffn_fwd(const void *xbuf, const void *W1b, const float *b1, const void *W2b, const float *b2,
                        const int32_t *tile_expert, const int32_t *num_mtiles, int64_t rows_cap, int d, int h, int E,
-                       void *U, void *H, void *Y, void *stream);
+                       void *G, void *H, void *Y, void *stream);
 
 /* ---- combine: replaces MOEGather + torch.bmm(gate_score, expert_out). out[T,d] in out_dtype. */
 int moe_combine_fwd(const void *ybuf, const int32_t *pos, const float *score, int64_t T, int d, int k, void *out,
@@ -126,7 +127,7 @@ int moe_combine_bwd(const void *dy, int dy_dtype, const void *ybuf, const int32_
  * (moe_cast_bf16_transposed), so that every row-mode contraction reads K-major operands.
  * dU[rows_cap,h] and dxbuf[rows_cap,d] are bf16 outputs (dU doubles as workspace);
  * dW1[E,h,d], db1[E,h], dW2[E,d,h], db2[E,d] are fp32 and are overwritten. */
-int moe_expert_ffn_bwd(const void *dybuf, const void *xbuf, const void *U, const void *H, const void *W1tb,
+int moe_expert_ffn_bwd(const void *dybuf, const void *xbuf, const void *G, const void *H, const void *W1tb,
                        const void *W2tb, const int32_t *tile_expert, const int32_t *num_mtiles,
                        const int32_t *seg_start, int64_t rows_cap, int d, int h, int E, void *dU, void *dxbuf,
                        float *dW1, float *db1, float *dW2, float *db2,

@@ -10,7 +10,7 @@ Three independent restatements live here, each checked against the others in tes
 
 * `forward_model` / `backward_model`  — the *arithmetic model* of the CUDA path: same routing
   (bit-exact, via oracle/gate_ref.c), and bf16 rounding at exactly the points where the
-  kernels round (dispatch buffer, weights, pre-activation U, hidden H, expert output Y and
+  kernels round (dispatch buffer, weights, activation derivative G = gelu'(U), hidden H, expert output Y and
   the backward buffers).  CUDA results are compared with this under a tight tolerance.
 * `ideal_forward` — plain differentiable PyTorch (fp32/fp64) of the same function with the
   routing held fixed: `F.linear -> F.gelu(approximate='none') -> F.linear`, index_add combine.
@@ -165,7 +165,7 @@ class Saved:
     row_src: torch.Tensor   # int64 [rows] flattened pair index t*k+j of each buffer row, -1 = pad
     row_exp: torch.Tensor   # int64 [rows] expert owning the row (pads included)
     Xb: torch.Tensor
-    Ub: torch.Tensor
+    Gb: torch.Tensor        # bf16(gelu'(U)) of the fp32 pre-activation U (U itself is never stored)
     Hb: torch.Tensor
     Yb: torch.Tensor
     W1b: torch.Tensor
@@ -213,7 +213,7 @@ def forward_model(x, Wg, bg, W1, b1, W2, b2, k: int, score_mode: int, capacity: 
     Xb[valid] = bf16_round(xf[row_src[valid] // k])
     W1b, W2b = bf16_round(W1.detach()), bf16_round(W2.detach())
     U = _grouped_linear(Xb, W1b, b1.detach().float(), row_exp, r.seg_start)
-    Ub = bf16_round(U)
+    Gb = bf16_round(gelu_erf_grad(U))
     Hb = bf16_round(gelu_erf(U))
     Y = _grouped_linear(Hb, W2b, b2.detach().float(), row_exp, r.seg_start)
     Yb = bf16_round(Y)
@@ -222,7 +222,7 @@ def forward_model(x, Wg, bg, W1, b1, W2, b2, k: int, score_mode: int, capacity: 
         p = r.pos[:, j].to(torch.int64)
         m = p >= 0
         y[m] += r.score[m, j].unsqueeze(1) * Yb[p[m]]
-    saved = Saved(xf, logits, r, row_src, row_exp, Xb, Ub, Hb, Yb, W1b, W2b, score_mode, k)
+    saved = Saved(xf, logits, r, row_src, row_exp, Xb, Gb, Hb, Yb, W1b, W2b, score_mode, k)
     return y.to(x.dtype), saved
 
 
@@ -273,7 +273,7 @@ def backward_model(sv: Saved, dy, Wg, dpsum=None):
     for e in range(E):
         s, t = int(r.seg_start[e]), int(r.seg_start[e + 1])
         dH[s:t] = dYb[s:t] @ sv.W2b[e]
-    dUb = bf16_round(dH * gelu_erf_grad(sv.Ub))
+    dUb = bf16_round(dH * sv.Gb)
     dXb = torch.empty(rows, d, dtype=torch.float32)
     for e in range(E):
         s, t = int(r.seg_start[e]), int(r.seg_start[e + 1])

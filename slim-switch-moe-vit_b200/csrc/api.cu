@@ -239,24 +239,24 @@ int moe_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out
 
 int moe_expert_ffn_fwd(const void* xbuf, const void* W1b, const float* b1, const void* W2b, const float* b2,
                        const int32_t* tile_expert, const int32_t* num_mtiles, int64_t rows_cap, int d, int h, int E,
-                       void* U, void* H, void* Y, void* stream) {
+                       void* G, void* H, void* Y, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = launch_grouped_gemm(MOE_GEMM_FC1, xbuf, W1b, U, H, b1, nullptr, tile_expert, num_mtiles, nullptr, rows_cap,
+    int rc = launch_grouped_gemm(MOE_GEMM_FC1, xbuf, W1b, G, H, b1, nullptr, tile_expert, num_mtiles, nullptr, rows_cap,
                                  E, 0, h, d, sm_count(), st);
     if (rc) return rc;
     return launch_grouped_gemm(MOE_GEMM_FC2, H, W2b, Y, nullptr, b2, nullptr, tile_expert, num_mtiles, nullptr, rows_cap,
                                E, 0, d, h, sm_count(), st);
 }
 
-int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* U, const void* H, const void* W1tb,
+int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* G, const void* H, const void* W1tb,
                        const void* W2tb, const int32_t* tile_expert, const int32_t* num_mtiles,
                        const int32_t* seg_start, int64_t rows_cap, int d, int h, int E, void* dU, void* dxbuf,
                        float* dW1, float* db1, float* dW2, float* db2, void* colsum_ws, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int sms = sm_count();
     int rc;
-    // dU = (dY W2) * gelu'(U)                     [rows, h]   K = d, B = W2^T [E, h, d] K-major
-    rc = launch_grouped_gemm(MOE_GEMM_DGELU, dybuf, W2tb, dU, nullptr, nullptr, U, tile_expert, num_mtiles, nullptr,
+    // dU = (dY W2) * G, G = gelu'(U)                   [rows, h]   K = d, B = W2^T [E, h, d] K-major
+    rc = launch_grouped_gemm(MOE_GEMM_DGELU, dybuf, W2tb, dU, nullptr, nullptr, G, tile_expert, num_mtiles, nullptr,
                              rows_cap, E, 0, h, d, sms, st);
     if (rc) return rc;
     // dW2[e] = dY_e^T H_e                          [d, h]

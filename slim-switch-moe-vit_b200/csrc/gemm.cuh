@@ -5,9 +5,9 @@
 // `fmoe_cuda.linear_forward/backward`, reached from /root/reference/models/resMoE.py:27-29):
 //
 //   ROWS mode  (M = packed token rows, one weight matrix per 256-row pair tile; A and B K-major):
-//     fc1   : U = X  W1^T + b1, H = gelu_erf(U)     B = W1   [E, h, d]      EPI_BIAS_GELU_DUAL
+//     fc1   : U = X  W1^T + b1 -> G = gelu_erf'(U), H = gelu_erf(U)   B = W1   [E, h, d]   EPI_BIAS_GELU_DUAL
 //     fc2   : Y = H  W2^T + b2                      B = W2   [E, d, h]      EPI_BIAS
-//     dgelu : dU = (dY W2) * gelu'(U)               B = W2^T [E, h, d]      EPI_DGELU
+//     dgelu : dU = (dY W2) * G                      B = W2^T [E, h, d]      EPI_DGELU
 //     dgrad : dX = dU W1                            B = W1^T [E, d, h]      EPI_PLAIN
 //   WGRAD mode (K = the rows of one expert's segment, fp32 output per expert; A and B MN-major):
 //     dW2[e] = dY_e^T H_e , dW1[e] = dU_e^T X_e                             EPI_F32
@@ -22,13 +22,25 @@
 // pair (`tcgen05.mma.cta_group::2`, UMMA 256 x BN x 16) shares B: each CTA loads its own 128 A
 // rows and HALF of the B tile, 0.0078 B/flop at BN = 256.
 //
-// CTA = 320 threads: warp 0 = TMA producer, warp 1 = TMEM owner (+ single-thread MMA issuer in
-// the leader CTA), warps 2..9 = epilogue: two groups of four warps (one TMEM lane quarter each),
-// the groups take alternate column chunks of the accumulator; every warp stages and TMA-stores its own
-// 32-row slab, so the epilogue has no CTA-level barrier.  Pipelines: smem ring full/empty
-// (TMA <-> MMA; `full` lives in the leader and is credited by both CTAs' TMA loads, `empty` is
-// multicast to both CTAs by tcgen05.commit), two TMEM accumulator stages full/empty
-// (MMA <-> epilogue of both CTAs), one store-staging buffer per group and output drained by TMA.
+// CTA = 64 + 32 W threads: warp 0 = TMA producer, warp 1 = TMEM owner (+ single-thread MMA issuer in the leader
+// CTA), W epilogue warps (8; 12 for fc1) in groups of four (one TMEM lane quarter each); the groups take alternate
+// 32-column chunks of the accumulator, and every warp stages and TMA-stores its own 32-row slab, so the epilogue
+// has no CTA-level barrier.  Pipelines: smem ring full/empty (TMA <-> MMA; `full` lives in the leader and is
+// credited by both CTAs' TMA loads, `empty` is multicast to both CTAs by tcgen05.commit), two TMEM accumulator
+// stages full/empty (MMA <-> epilogue of both CTAs), per-warp store slabs drained by TMA.
+//
+// What bounds it (round 1e, -DMOE_DBG_TIMELINE stamps + tools/ubench/tmem_mma_ld.cu):
+//   * tcgen05.ld does NOT contend with tcgen05.mma: 128 KB of accumulator read in ~410 clocks (320 B/clk/SM) with
+//     or without MMAs in flight.
+//   * the mainloop runs at ~1 000 clocks per 64-deep k-block against 512 clocks of MMA issue: operand feed.  An L2
+//     prefetch cursor ahead of the ring made every op 20-35 % slower, and keeping the weight tile resident in shared
+//     memory for the K = 384 ops (half the L2 -> SM traffic) made them 7-10 % slower: it is neither HBM latency nor
+//     L2 bandwidth.  Per tile the shared memory moves the TMA fill, the UMMA operand reads (A 4 KB + B 8 KB per
+//     MMA and SM, the B half served twice) and the epilogue's staging + TMA-store reads — ~740 KB for an fc1 tile,
+//     5 800 clocks at 128 B/clk, which is what a tile takes.
+//   * epilogues: gelu' moved from dgelu into fc1 (one shared exp + polynomial), dgelu reads G through TMA
+//     most of a tile ahead (per-lane row loads cost 4 000 LSU cycles per tile, a one-chunk-ahead TMA exposed its
+//     ~1 500-clock latency four times per tile), fc1 runs 12 epilogue warps.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -43,7 +55,7 @@ struct GemmParams {
     const int* num_mtiles;   // ROWS: number of live 256-row tiles (device scalar)
     const int* seg_start;    // WGRAD: first row of each expert segment      [E+1]
     const float* bias;       // [E, N] fp32 or nullptr
-    const __nv_bfloat16* aux;  // EPI_DGELU: pre-activation U [rows_cap, N]
+    const __nv_bfloat16* aux;  // EPI_DGELU: G = gelu'(U) [rows_cap, N] (read through its tensor map)
     int E;
     int M;  // WGRAD: output rows per expert
     int N;  // output columns (per expert)
@@ -53,30 +65,35 @@ struct GemmParams {
 constexpr int kBM = 128;     // accumulator rows per CTA
 constexpr int kPairM = 256;  // rows per pair tile (UMMA M with cta_group::2)
 constexpr int kBK = 64;
-constexpr int kEpiWarps = 8;
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
-constexpr int kSmemLimit = 232448;    // 227 KB
-#ifndef MOE_PREFETCH_DIST
-#define MOE_PREFETCH_DIST 8
+// epilogue warps per CTA (a multiple of 4: one warp per TMEM lane quarter and column group).  The fc1 epilogue
+// evaluates gelu and gelu' (~13 instructions per element) and is latency-bound at two warps per scheduler
+// (measured: 6 300 clocks per tile against a 6 600-clock mainloop); a third group of four warps hides that.
+#ifndef MOE_FC1_EPI_WARPS
+#define MOE_FC1_EPI_WARPS 12
 #endif
-constexpr int kPrefetchDist = MOE_PREFETCH_DIST;  // k-blocks the L2 prefetch cursor runs ahead of the smem ring
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == 0 /* EPI_BIAS_GELU_DUAL */ ? MOE_FC1_EPI_WARPS : 8; }
+constexpr int kSmemLimit = 232448;    // 227 KB
 
 template <int BN, int EPI>
 struct GemmCfg {
     static constexpr int A_BYTES = kBM * kBK * 2;
-    static constexpr int B_BYTES = (BN / 2) * kBK * 2;  // this CTA's half of the B tile
+    static constexpr int B_BYTES = (BN / 2) * kBK * 2;  // this CTA's half of the B tile (one k-block)
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int NOUT = (EPI == EPI_BIAS_GELU_DUAL) ? 2 : 1;
+    static constexpr int EPI_WARPS = epi_warps(EPI);
+    static constexpr int NGRP = EPI_WARPS / 4;          // column groups: group g takes chunks g, g + NGRP, ...
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;  // warp 0 = TMA producer, warp 1 = TMEM owner / MMA issuer
     // The epilogue works in chunks of 32 accumulator columns.  Every epilogue warp owns one 32-row slab per output
     // (32 x 64 B of bf16, 64-byte swizzle; 32 x 128 B of fp32 for WGRAD, 128-byte swizzle) that it fills and TMA-stores
-    // on its own, and for DGELU two more 2 KB slabs into which it TMA-loads its rows of the pre-activation U one
-    // chunk ahead.  Small slabs leave the shared memory to the operand ring.
+    // on its own.  DGELU works in place: a warp has one slab per chunk of its tile share, TMA-loads its rows of
+    // G = gelu'(U) into it most of a tile ahead (a TMA round trip is ~1 500 clocks, four times a chunk's arithmetic),
+    // multiplies in place and stores the same slab.  Small slabs leave the shared memory to the operand ring.
     static constexpr int NCHUNK = BN / 32;
+    static constexpr int MAXCH = (NCHUNK + NGRP - 1) / NGRP;   // chunks of one warp per tile
     static constexpr int SLAB_BYTES = (EPI == EPI_F32) ? 4096 : 2048;
-    static constexpr int OUT_BYTES = kEpiWarps * NOUT * SLAB_BYTES;
-    static constexpr int AUX_BYTES = (EPI == EPI_DGELU) ? kEpiWarps * 2 * 2048 : 0;
-    static constexpr int STAGING_BYTES = OUT_BYTES + AUX_BYTES;
-    static constexpr int BAR_BYTES = 512 + kEpiWarps * 128 * 4;  // mbarriers + TMEM slot, then the per-warp bias copies
+    static constexpr int OUT_BYTES = EPI_WARPS * SLAB_BYTES * (EPI == EPI_DGELU ? MAXCH : NOUT);
+    static constexpr int STAGING_BYTES = OUT_BYTES;
+    static constexpr int BAR_BYTES = 512 + EPI_WARPS * 128 * 4;  // mbarriers + TMEM slot, then the per-warp bias copies
     static constexpr int STAGES_RAW = (kSmemLimit - 1024 - BAR_BYTES - STAGING_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
@@ -85,23 +102,22 @@ struct GemmCfg {
 };
 
 // ------------------------------------------------------------------------------------------------
-// exact-erf GELU and its derivative for the epilogues (coefficients: tools/fit_gelu.py)
-//   gelu(u)  = relu(u) - |u| Q(|u|),              Q(a) = Phi(-a) = exp2(P6(a))
-//   gelu'(u) = u < 0 ? m(|u|) : 1 - m(|u|),       m(a) = Phi(-a) - a phi(a) = exp(-a^2/2) w8(a)
-// P6 / w8: polynomials on [0, 6.5] (|u| is clamped; beyond it both corrections are < 1e-9).
-// Max abs error vs float64 erfc: 1.0e-7 (gelu — the level of CUDA's erff), 1.2e-6 (gelu', a factor that is
-// rounded to bf16 right after).  One MUFU (ex2) per element, Horner chains on packed fp32 FMAs (FFMA2).
-// Why not erff/expf: the fp32 pipe retires 128 lane-FMAs per clock per SM, a 128 x 256 tile at K = 384
-// leaves ~20 of them per element; erff + expf + the rest needs about twice that (measured round 1b).
+// exact-erf GELU and its derivative, both in the fc1 epilogue (coefficients: tools/fit_gelu.py)
+//   a = min(|u|, 6.5),  g = exp(-a^2 / 2) (one ex2.approx),  W(a) = Phi(-a) / g = 0.5 erfcx(a / sqrt 2): degree-7 polynomial
+//   gelu(u)  = relu(u) - a g W(a)
+//   gelu'(u) = u < 0 ? m : 1 - m,   m = Phi(-a) - a phi(a) = g (W(a) - a / sqrt(2 pi))
+// fc1 writes H = gelu(U) and G = gelu'(U) (bf16) instead of the pre-activation itself: backward needs U only
+// through gelu'(U), so the dgelu epilogue shrinks to one multiply per element, and gelu' is evaluated from the fp32
+// pre-activation, not from its bf16 rounding.  Max abs error vs float64 erfc: 5.3e-6 (gelu), 1.2e-5 (gelu') — both
+// far below the bf16 rounding of the stored values (2^-9 relative).  One MUFU per element, the Horner chain on packed
+// fp32 FMAs (FFMA2).
 // ------------------------------------------------------------------------------------------------
 constexpr float kGeluAMax = 6.5f;
 constexpr float kNegHalfLog2e = -0.72134752044448170f;
-__device__ constexpr float kGeluLogQ[7] = {  // P6(a) = log2 Phi(-a)
-    -9.999921094e-01f, -1.151212416e+00f, -4.587352391e-01f, -5.346286518e-02f, 8.115032863e-03f, -7.800564408e-04f,
-    3.437071280e-05f};
-__device__ constexpr float kGeluGradW[9] = {  // w8(a)
-    4.999988248e-01f, -7.978099009e-01f, 2.492143745e-01f, -1.297814929e-01f, 5.588059320e-02f, -1.862516973e-02f,
-    4.319766638e-03f, -5.991640005e-04f, 3.660521692e-05f};
+constexpr float kNegInvSqrt2Pi = -0.39894228040143268f;
+__device__ constexpr float kGeluW[8] = {  // W(a) = 0.5 erfcx(a / sqrt 2) on [0, 6.5]
+    4.999879883e-01f, -3.984107670e-01f, 2.460856669e-01f, -1.217100563e-01f, 4.573317066e-02f, -1.176512435e-02f,
+    1.782060358e-03f, -1.172508184e-04f};
 
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float2 v) {
@@ -109,41 +125,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float2 v) {
     return *reinterpret_cast<uint32_t*>(&b);
 }
 
-// Q(a) = Phi(-a) for 8 element pairs.  The eight Horner chains are written step-major so that
-// consecutive FFMA2s are independent.
-__device__ __forceinline__ void gelu_q8(const float2 (&a)[8], float2 (&q)[8]) {
-    float2 p[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) p[i] = __ffma2_rn(splat2(kGeluLogQ[6]), a[i], splat2(kGeluLogQ[5]));
-#pragma unroll
-    for (int k = 4; k >= 0; --k) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) p[i] = __ffma2_rn(p[i], a[i], splat2(kGeluLogQ[k]));
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = make_float2(ex2_approx(p[i].x), ex2_approx(p[i].y));
-}
-// m(a) = Phi(-a) - a phi(a) for 8 element pairs
-__device__ __forceinline__ void gelu_m8(const float2 (&a)[8], float2 (&m)[8]) {
-    float2 g[8], p[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = __fmul2_rn(__fmul2_rn(a[i], splat2(kNegHalfLog2e)), a[i]);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = make_float2(ex2_approx(g[i].x), ex2_approx(g[i].y));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) p[i] = __ffma2_rn(splat2(kGeluGradW[8]), a[i], splat2(kGeluGradW[7]));
-#pragma unroll
-    for (int k = 6; k >= 0; --k) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) p[i] = __ffma2_rn(p[i], a[i], splat2(kGeluGradW[k]));
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] = __fmul2_rn(g[i], p[i]);
-}
-
 // One block of 16 accumulator columns (8 pairs) of one row through the epilogue.
-//   acc: 16 fp32 accumulators; bias_saddr: shared-memory address of 16 fp32 (BIAS epilogues); aux: 8 packed bf16x2 of U (DGELU)
-//   o0 / o1: 8 packed bf16x2 outputs each (o1 = gelu, fc1 only)
+//   acc: 16 fp32 accumulators; bias_saddr: shared-memory address of 16 fp32 (BIAS epilogues); aux: 8 packed bf16x2 of G (DGELU)
+//   o0 / o1: 8 packed bf16x2 outputs each (fc1: o0 = gelu'(u), o1 = gelu(u))
 template <int EPI>
 __device__ __forceinline__ void epilogue_block16(const uint32_t* acc, uint32_t bias_saddr, const uint32_t* aux,
                                                  uint32_t* o0, uint32_t* o1) {
@@ -164,38 +148,42 @@ __device__ __forceinline__ void epilogue_block16(const uint32_t* acc, uint32_t b
         for (int i = 0; i < 8; ++i) v[i] = __fadd2_rn(v[i], b[i]);
     }
     if constexpr (EPI == EPI_DGELU) {
-        float2 u[8], a[8], m[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            u[i] = make_float2(__uint_as_float(aux[i] << 16), __uint_as_float(aux[i] & 0xffff0000u));
-            a[i] = make_float2(fminf(fabsf(u[i].x), kGeluAMax), fminf(fabsf(u[i].y), kGeluAMax));
-        }
-        gelu_m8(a, m);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float2 om = __ffma2_rn(m[i], splat2(-1.0f), splat2(1.0f));  // 1 - m
-            const float2 gp = make_float2(u[i].x < 0.0f ? m[i].x : om.x, u[i].y < 0.0f ? m[i].y : om.y);
+        for (int i = 0; i < 8; ++i) {   // dU = (dY W2) * gelu'(U)
+            const float2 gp = make_float2(__uint_as_float(aux[i] << 16), __uint_as_float(aux[i] & 0xffff0000u));
             o0[i] = pack_bf16x2(__fmul2_rn(v[i], gp));
+        }
+    } else if constexpr (EPI == EPI_BIAS_GELU_DUAL) {
+#ifdef MOE_DBG_NO_GELU
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o0[i] = o1[i] = pack_bf16x2(v[i]);
+        return;
+#endif
+        float2 a[8], g[8], w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = make_float2(fminf(fabsf(v[i].x), kGeluAMax), fminf(fabsf(v[i].y), kGeluAMax));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = __fmul2_rn(__fmul2_rn(a[i], splat2(kNegHalfLog2e)), a[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = make_float2(ex2_approx(g[i].x), ex2_approx(g[i].y));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = __ffma2_rn(splat2(kGeluW[7]), a[i], splat2(kGeluW[6]));
+#pragma unroll
+        for (int k = 5; k >= 0; --k) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = __ffma2_rn(w[i], a[i], splat2(kGeluW[k]));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 q = __fmul2_rn(g[i], w[i]);                                                   // Phi(-a)
+            o1[i] = pack_bf16x2(__ffma2_rn(make_float2(-a[i].x, -a[i].y), q, make_float2(fmaxf(v[i].x, 0.0f), fmaxf(v[i].y, 0.0f))));
+            const float2 m = __fmul2_rn(g[i], __ffma2_rn(a[i], splat2(kNegInvSqrt2Pi), w[i]));          // Phi(-a) - a phi(a)
+            const float2 om = __ffma2_rn(m, splat2(-1.0f), splat2(1.0f));
+            o0[i] = pack_bf16x2(make_float2(v[i].x < 0.0f ? m.x : om.x, v[i].y < 0.0f ? m.y : om.y));
         }
     } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) o0[i] = pack_bf16x2(v[i]);
-    }
-#ifdef MOE_DBG_NO_GELU
-    if constexpr (EPI == EPI_BIAS_GELU_DUAL) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o1[i] = pack_bf16x2(v[i]);
-    }
-    return;
-#endif
-    if constexpr (EPI == EPI_BIAS_GELU_DUAL) {
-        float2 a[8], qq[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = make_float2(fminf(fabsf(v[i].x), kGeluAMax), fminf(fabsf(v[i].y), kGeluAMax));
-        gelu_q8(a, qq);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)  // relu(v) - a Q(a)
-            o1[i] = pack_bf16x2(__ffma2_rn(make_float2(-a[i].x, -a[i].y), qq[i], make_float2(fmaxf(v[i].x, 0.0f), fmaxf(v[i].y, 0.0f))));
     }
 }
 
@@ -244,7 +232,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
 }
 
 template <int BN, int EPI, bool WGRAD>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((GemmCfg<BN, EPI>::THREADS), 1)
 grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                     const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
@@ -260,8 +248,8 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    [[maybe_unused]] uint64_t* aux_bar = tempty_bar + 2;                                  // [8 warps][2]  (DGELU)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * kEpiWarps);
+    [[maybe_unused]] uint64_t* aux_bar = tempty_bar + 2;                                  // [warps][MAXCH]  (DGELU)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + Cfg::EPI_WARPS * Cfg::MAXCH);
     [[maybe_unused]] float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES + 512);  // [8 warps][128]
 
     const int warp = threadIdx.x >> 5;
@@ -275,7 +263,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if constexpr (Cfg::NOUT == 2) tma_prefetch_desc(&tmO1);
         if constexpr (EPI == EPI_DGELU) {
             tma_prefetch_desc(&tmAux);
-            for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(aux_bar + i, 1);
+            for (int i = 0; i < Cfg::EPI_WARPS * Cfg::MAXCH; ++i) mbar_init(aux_bar + i, 1);
         }
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar + s, 1);   // leader's producer arrive.expect_tx; bytes from both CTAs
@@ -283,7 +271,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar + s, 1);                // one multicast tcgen05.commit
-            mbar_init(tempty_bar + s, 2 * kEpiWarps);   // every epilogue warp of both CTAs (leader's copy is used)
+            mbar_init(tempty_bar + s, 2 * Cfg::EPI_WARPS);   // every epilogue warp of both CTAs (leader's copy is used)
         }
         fence_mbar_init();
     }
@@ -300,59 +288,15 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int total_tiles;
     if constexpr (WGRAD) total_tiles = p.E * ((p.M + kPairM - 1) / kPairM) * n_ntiles;
     else total_tiles = __ldg(p.num_mtiles) * n_ntiles;
-    const int first_tile = blockIdx.x >> 1;
+    const int first_tile = blockIdx.x >> 1;   // pair p takes tiles p, p + npairs, ...
     const int tile_stride = gridDim.x >> 1;
 
     if (warp == 0) {
         // ================================ TMA producer (one thread per CTA) =========================
-        // -DMOE_L2_PREFETCH (experiment, off): a second cursor runs kPrefetchDist k-blocks ahead of the loads and pulls
-        // those boxes into L2 (cp.async.bulk.prefetch.tensor).  Measured round 1e: 20-35 % SLOWER on every op (fc2
-        // 68 -> 84 us) — the mainloop is bound by L2 -> SM request throughput, not by HBM latency, and the
-        // prefetches double the requests.
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
             [[maybe_unused]] int ti = 0;
-            auto issue = [&](const TileCoord& c, int kb, uint8_t* sa, uint64_t* bar) {   // sa == nullptr: L2 prefetch only
-                uint8_t* const sb = sa != nullptr ? sa + Cfg::A_BYTES : nullptr;
-                if constexpr (!WGRAD) {
-                    const int ca = kb * kBK, ra = c.m0, rb = c.e * p.N + c.n0 + rank * (BN / 2);
-                    if (sa == nullptr) { tma_prefetch_2d(&tmA, ca, ra); tma_prefetch_2d(&tmB, ca, rb); return; }
-                    tma_load_2d_pair(sa, &tmA, bar, ca, ra);
-                    tma_load_2d_pair(sb, &tmB, bar, ca, rb);
-                } else {
-                    const int krow = c.row0 + kb * kBK;
-                    if (sa == nullptr) {
-                        tma_prefetch_2d(&tmA, c.m0, krow);
-                        tma_prefetch_2d(&tmA, c.m0 + 64, krow);
-#pragma unroll
-                        for (int i = 0; i < BN / 128; ++i) tma_prefetch_2d(&tmB, c.n0 + rank * (BN / 2) + i * 64, krow);
-                        return;
-                    }
-                    tma_load_2d_pair(sa, &tmA, bar, c.m0, krow);
-                    tma_load_2d_pair(sa + 8192, &tmA, bar, c.m0 + 64, krow);
-#pragma unroll
-                    for (int i = 0; i < BN / 128; ++i)
-                        tma_load_2d_pair(sb + i * 8192, &tmB, bar, c.n0 + rank * (BN / 2) + i * 64, krow);
-                }
-            };
-            // prefetch cursor
-            int ptile = first_tile, pkb = 0;
-            TileCoord pc{};
-            if (ptile < total_tiles) pc = decode_tile<BN, WGRAD>(p, ptile, n_ntiles, rank);
-            [[maybe_unused]] auto prefetch_next = [&]() {
-                while (ptile < total_tiles && pkb >= pc.kb) {   // next non-empty tile
-                    ptile += tile_stride;
-                    pkb = 0;
-                    if (ptile < total_tiles) pc = decode_tile<BN, WGRAD>(p, ptile, n_ntiles, rank);
-                }
-                if (ptile >= total_tiles) return;
-                issue(pc, pkb, nullptr, nullptr);
-                ++pkb;
-            };
-#ifdef MOE_L2_PREFETCH
-            for (int i = 0; i < STAGES + kPrefetchDist; ++i) prefetch_next();
-#endif
             for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++ti) {
                 const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
                 MOE_TL(0, ti, 0);
@@ -360,11 +304,19 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_wait(empty_bar + s, ph ^ 1);
                     if (kb == 0) MOE_TL(0, ti, 1);
                     uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
                     if (rank == 0) mbar_arrive_expect_tx(full_bar + s, 2 * Cfg::STAGE_BYTES);
-                    issue(c, kb, sa, full_bar + s);
-#ifdef MOE_L2_PREFETCH
-                    prefetch_next();
-#endif
+                    if constexpr (!WGRAD) {
+                        tma_load_2d_pair(sa, &tmA, full_bar + s, kb * kBK, c.m0);
+                        tma_load_2d_pair(sb, &tmB, full_bar + s, kb * kBK, c.e * p.N + c.n0 + rank * (BN / 2));
+                    } else {
+                        const int krow = c.row0 + kb * kBK;
+                        tma_load_2d_pair(sa, &tmA, full_bar + s, c.m0, krow);
+                        tma_load_2d_pair(sa + 8192, &tmA, full_bar + s, c.m0 + 64, krow);
+#pragma unroll
+                        for (int i = 0; i < BN / 128; ++i)
+                            tma_load_2d_pair(sb + i * 8192, &tmB, full_bar + s, c.n0 + rank * (BN / 2) + i * 64, krow);
+                    }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
                 MOE_TL(0, ti, 2);
@@ -415,7 +367,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // take alternate 32-column chunks, and each warp stages and TMA-stores its own slabs, so there is no CTA-level
         // barrier anywhere in the epilogue.
         const int q = warp & 3;                  // TMEM lane quarter this warp may touch
-        const int grp = (warp - 2) >> 2;         // column-chunk parity this group owns
+        const int grp = (warp - 2) >> 2;         // column group this warp belongs to
         const int ew = warp - 2;                 // 0..7
         float* const wbias = bias_s + ew * 128;  // this warp's copy of the bias values of its chunks
         int as = 0;
@@ -438,8 +390,8 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (tl_on) MOE_TL(tl_role, ti, 1);
                 const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
 #pragma unroll 1
-                for (int ch = grp; ch < Cfg::NCHUNK; ch += 2) {
-                    const bool last_chunk = (ch + 2 >= Cfg::NCHUNK);
+                for (int ch = grp; ch < Cfg::NCHUNK; ch += Cfg::NGRP) {
+                    const bool last_chunk = (ch + Cfg::NGRP >= Cfg::NCHUNK);
                     uint32_t acc[32];
                     if (live) {
                         tmem_ld32(tmem_row + ch * 32, acc);
@@ -473,29 +425,29 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         } else {
             // bf16 outputs: slab rows are 64 B (four 16-byte units), unit u of row r lives at unit u ^ ((r >> 1) & 3)
             // (CU_TENSOR_MAP_SWIZZLE_64B); a quarter-warp then touches all 32 banks exactly once.
-            const uint32_t out_s = smem_u32(staging) + ew * Cfg::NOUT * 2048;                 // this warp's output slab(s)
-            const uint32_t my_out = out_s + lane * 64;
+            // this warp's slab(s): [output 0][output 1] — or, DGELU, one in-place slab per chunk
+            const uint32_t out_s = smem_u32(staging) + ew * (EPI == EPI_DGELU ? Cfg::MAXCH : Cfg::NOUT) * 2048;
             const int sw = (lane >> 1) & 3;
-            [[maybe_unused]] const uint32_t aux_s = smem_u32(staging) + Cfg::OUT_BYTES + ew * 4096;   // two 2 KB slabs
-            [[maybe_unused]] uint64_t* const my_aux_bar = aux_bar + ew * 2;
-            [[maybe_unused]] uint32_t aux_issued = 0, aux_used = 0;   // running chunk counters of this warp (slab = n & 1)
-            constexpr int MYCH = Cfg::NCHUNK / 2;                     // chunks of one group per tile
-            // DGELU: TMA-load this warp's 32 rows x 32 columns of U for chunk `ch` of the tile at `c`
-            [[maybe_unused]] auto issue_aux = [&](const TileCoord& c, int ch) {
-                if (lane == 0) {
-                    uint64_t* bar = my_aux_bar + (aux_issued & 1);
-                    mbar_arrive_expect_tx(bar, 2048);
-                    tma_load_2d_s(aux_s + (aux_issued & 1) * 2048, &tmAux, bar, c.n0 + ch * 32, c.m0 + q * 32);
-                }
-                ++aux_issued;
+            [[maybe_unused]] uint64_t* const my_aux_bar = aux_bar + ew * Cfg::MAXCH;
+            // DGELU: TMA-load this warp's 32 rows x 32 columns of G for its i-th chunk of the tile at `c` into slab i
+            [[maybe_unused]] auto issue_aux = [&](const TileCoord& c, int i) {
+                mbar_arrive_expect_tx(my_aux_bar + i, 2048);
+                tma_load_2d_s(out_s + i * 2048, &tmAux, my_aux_bar + i, c.n0 + (grp + Cfg::NGRP * i) * 32, c.m0 + q * 32);
             };
+            [[maybe_unused]] uint32_t it = 0;   // tiles done by this warp
+            if constexpr (EPI == EPI_DGELU) {
+                if (lane == 0 && first_tile < total_tiles) {
+                    const TileCoord c0 = decode_tile<BN, WGRAD>(p, first_tile, n_ntiles, rank);
+                    for (int i = 0; grp + Cfg::NGRP * i < Cfg::NCHUNK; ++i) issue_aux(c0, i);
+                }
+            }
             for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++ti) {
                 const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
                 const bool live = c.kb != 0;
                 if (tl_on) MOE_TL(tl_role, ti, 0);
                 if constexpr (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS) {
                     // lane l fetches 4 consecutive bias values of the group's (at most four) chunks
-                    const int lc = grp + 2 * (lane >> 3);       // chunk the lane's values belong to
+                    const int lc = grp + Cfg::NGRP * (lane >> 3);   // chunk the lane's values belong to
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (lc < Cfg::NCHUNK)
                         bv = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(c.e) * p.N + c.n0 + lc * 32) + (lane & 7));
@@ -503,17 +455,31 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     *reinterpret_cast<float4*>(wbias + lane * 4) = bv;
                     __syncwarp();
                 }
-                if constexpr (EPI == EPI_DGELU) issue_aux(c, grp);   // lands while this warp waits for the accumulator
+                [[maybe_unused]] TileCoord cn{};                  // DGELU: next tile of this pair, whose G slabs are prefetched
+                [[maybe_unused]] bool have_next = false;
+                if constexpr (EPI == EPI_DGELU) {
+                    have_next = tile + tile_stride < total_tiles;
+                    if (have_next) cn = decode_tile<BN, WGRAD>(p, tile + tile_stride, n_ntiles, rank);
+                    if (it > 0 && lane == 0) {   // the last slab of the previous tile: its store was the last group committed
+                        tma_store_wait_read<0>();
+                        issue_aux(c, (Cfg::NCHUNK - 1 - grp) / Cfg::NGRP);
+                    }
+                }
                 if (live) {
                     mbar_wait(tfull_bar + as, aph);
                     tc_fence_after();
                 }
                 if (tl_on) MOE_TL(tl_role, ti, 1);
                 const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
+                if (Cfg::NGRP > Cfg::NCHUNK && grp >= Cfg::NCHUNK) {   // a group without chunks (narrow tile) still releases the stage
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tempty_bar + as, 0);
+                }
 #pragma unroll 1
-                for (int i = 0; i < MYCH; ++i) {
-                    const int ch = grp + 2 * i;
-                    const bool last_chunk = (i + 1 == MYCH);
+                for (int i = 0; grp + Cfg::NGRP * i < Cfg::NCHUNK; ++i) {
+                    const int ch = grp + Cfg::NGRP * i;
+                    const bool last_chunk = (ch + Cfg::NGRP >= Cfg::NCHUNK);
 #ifdef MOE_DBG_NO_EPI
                     if (last_chunk) {
                         tc_fence_before();
@@ -522,18 +488,8 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     continue;
 #endif
-                    [[maybe_unused]] uint32_t aux_rd = 0;
-                    if constexpr (EPI == EPI_DGELU) {
-                        // the other aux slab is free (its chunk was consumed in the previous iteration): prefetch the next chunk
-                        if (!last_chunk) {
-                            fence_proxy_async_smem();
-                            __syncwarp();
-                            issue_aux(c, ch + 2);
-                        }
-                        mbar_wait(my_aux_bar + (aux_used & 1), (aux_used >> 1) & 1);
-                        aux_rd = aux_s + (aux_used & 1) * 2048 + lane * 64;
-                        ++aux_used;
-                    }
+                    const uint32_t my_out = out_s + (EPI == EPI_DGELU ? i * 2048 : 0) + lane * 64;   // this lane's row of the slab
+                    if constexpr (EPI == EPI_DGELU) mbar_wait(my_aux_bar + i, it & 1);                  // G rows of this chunk have landed
                     const uint32_t cbias = smem_u32(wbias) + i * 128;
                     uint32_t acc[2][16];
                     tmem_ld16(tmem_row + ch * 32, acc[0]);
@@ -557,12 +513,12 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             for (int j = 0; j < 2; ++j)
                                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                                              : "=r"(aux[4 * j]), "=r"(aux[4 * j + 1]), "=r"(aux[4 * j + 2]), "=r"(aux[4 * j + 3])
-                                             : "r"(aux_rd + (((blk * 2 + j) ^ sw) << 4)));
+                                             : "r"(my_out + (((blk * 2 + j) ^ sw) << 4)));
                         }
                         uint32_t o0[8];                       // 16 columns of output 0, packed bf16x2
                         [[maybe_unused]] uint32_t o1[8];      // 16 columns of output 1 (fc1: gelu)
                         epilogue_block16<EPI>(acc[blk], cbias + blk * 64, aux, o0, o1);
-                        if (blk == 0) {
+                        if (EPI != EPI_DGELU && blk == 0) {
                             if (lane == 0) tma_store_wait_read<0>();   // this warp's previous store has left its slab(s)
                             __syncwarp();
                         }
@@ -580,13 +536,21 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     __syncwarp();
 #ifndef MOE_DBG_NO_STORE
                     if (lane == 0) {
-                        tma_store_2d_s(&tmO0, out_s, c.n0 + ch * 32, c.m0 + q * 32);
+                        tma_store_2d_s(&tmO0, my_out - lane * 64, c.n0 + ch * 32, c.m0 + q * 32);
                         if constexpr (Cfg::NOUT == 2) tma_store_2d_s(&tmO1, out_s + 2048, c.n0 + ch * 32, c.m0 + q * 32);
                         tma_store_commit();
+                        if constexpr (EPI == EPI_DGELU) {
+                            // slab i-1 was stored one chunk ago: once that store has read it, refill it for the next tile
+                            if (i >= 1 && have_next) {
+                                tma_store_wait_read<1>();
+                                issue_aux(cn, i - 1);
+                            }
+                        }
                     }
 #endif
                 }
                 if (tl_on) MOE_TL(tl_role, ti, 3);
+                ++it;
                 if (live && ++as == 2) { as = 0; aph ^= 1; }
             }
         }

@@ -69,7 +69,7 @@ int launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& 
         configured = true;
     }
     // the kernel carries __cluster_dims__(2,1,1): the grid is a whole number of CTA pairs
-    kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(tA, tB, tO0, tO1, tAux, p);
+    kfn<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tA, tB, tO0, tO1, tAux, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("grouped_gemm launch: %s", cudaGetErrorString(e)); return 1; }
     return 0;

@@ -158,12 +158,12 @@ class EPMoEFunction(torch.autograd.Function):
         C.call("moe_ep_repack", C.ptr(recv_x), C.ptr(xbuf), C.ptr(kept_recv), C.ptr(tb["slab_dst"]), C.ptr(tb["seg_start"]),
                C.ptr(tb["kept"]), W, El, slab, d, 1, st)
 
-        U = torch.empty((rows_cap, h), dtype=bf, device=dev)
+        G = torch.empty((rows_cap, h), dtype=bf, device=dev)
         H = torch.empty((rows_cap, h), dtype=bf, device=dev)
         Y = torch.empty((rows_cap, d), dtype=bf, device=dev)
         b1_c, b2_c = b1.detach().contiguous(), b2.detach().contiguous()
         te, nm = C.ptr(tb["tile_expert"]), C.ptr(tb["num_mtiles"])
-        C.call("moe_grouped_gemm", C.GEMM_FC1, C.ptr(xbuf), C.ptr(W1b), C.ptr(U), C.ptr(H), C.ptr(b1_c), None,
+        C.call("moe_grouped_gemm", C.GEMM_FC1, C.ptr(xbuf), C.ptr(W1b), C.ptr(G), C.ptr(H), C.ptr(b1_c), None,
                te, nm, None, rows_cap, El, 0, h, d, st, tag="gemm_fc1")
         C.call("moe_grouped_gemm", C.GEMM_FC2, C.ptr(H), C.ptr(W2b), C.ptr(Y), None, C.ptr(b2_c), None,
                te, nm, None, rows_cap, El, 0, d, h, st, tag="gemm_fc2")
@@ -178,7 +178,7 @@ class EPMoEFunction(torch.autograd.Function):
         ctx.spec, ctx.has_bg, ctx.group, ctx.world, ctx.slab, ctx.rows_cap = spec, bg is not None, group, W, slab, rows_cap
         coef = r["aux_coef"] if spec.want_psum else torch.empty(0, dtype=torch.float32, device=dev)
         ctx.save_for_backward(x, Wg_c, r["logits"], r["idx"], r["score"], r["pos"], r["seg_start"], r["kept"], kept_recv,
-                              tb["slab_dst"], tb["seg_start"], tb["kept"], tb["tile_expert"], tb["num_mtiles"], xbuf, U, H,
+                              tb["slab_dst"], tb["seg_start"], tb["kept"], tb["tile_expert"], tb["num_mtiles"], xbuf, G, H,
                               ybuf, W1tb, W2tb, coef)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(r["count"], r["kept"])
@@ -193,7 +193,7 @@ class EPMoEFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy, daux, _dcount, _dkept):
         (x, Wg, logits, idx, score, pos, seg_send, kept_send, kept_recv, slab_dst, seg_loc, kept_loc, tile_expert,
-         num_mtiles, xbuf, U, H, ybuf, W1tb, W2tb, coef) = ctx.saved_tensors
+         num_mtiles, xbuf, G, H, ybuf, W1tb, W2tb, coef) = ctx.saved_tensors
         spec, W, slab, rows_cap, group = ctx.spec, ctx.world, ctx.slab, ctx.rows_cap, ctx.group
         T, d = x.shape
         El, h = W1tb.shape[0], W1tb.shape[2]
@@ -218,7 +218,7 @@ class EPMoEFunction(torch.autograd.Function):
         dW1, db1 = _f32((El, h, d), dev), _f32((El, h), dev)
         dW2, db2 = _f32((El, d, h), dev), _f32((El, d), dev)
         te, nm, sg = C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_loc)
-        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), None, None, C.ptr(U),
+        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), None, None, C.ptr(G),
                te, nm, None, rows_cap, El, 0, h, d, st, tag="gemm_dgelu")
         C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1tb), C.ptr(dxbuf), None, None, None,
                te, nm, None, rows_cap, El, 0, d, h, st, tag="gemm_dgrad")

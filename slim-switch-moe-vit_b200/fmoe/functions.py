@@ -132,13 +132,13 @@ class MoEFunction(torch.autograd.Function):
         r = route(x, Wg_c, bg_c, spec, noise, token_mask=token_mask)
         rows_cap = r["rows_cap"]
         W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c)
-        U = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
+        G = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
         H = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
         Y = torch.empty((rows_cap, d), dtype=torch.bfloat16, device=dev)
         # the two forward GEMMs (same kernels as the bundled moe_expert_ffn_fwd entry point)
         b1_c, b2_c = b1.detach().contiguous(), b2.detach().contiguous()
         te, nm = C.ptr(r["tile_expert"]), C.ptr(r["num_mtiles"])
-        C.call("moe_grouped_gemm", C.GEMM_FC1, C.ptr(r["xbuf"]), C.ptr(W1b), C.ptr(U), C.ptr(H), C.ptr(b1_c), None,
+        C.call("moe_grouped_gemm", C.GEMM_FC1, C.ptr(r["xbuf"]), C.ptr(W1b), C.ptr(G), C.ptr(H), C.ptr(b1_c), None,
                te, nm, None, rows_cap, E, 0, h, d, st, tag="gemm_fc1")
         C.call("moe_grouped_gemm", C.GEMM_FC2, C.ptr(H), C.ptr(W2b), C.ptr(Y), None, C.ptr(b2_c), None,
                te, nm, None, rows_cap, E, 0, d, h, st, tag="gemm_fc2")
@@ -151,7 +151,7 @@ class MoEFunction(torch.autograd.Function):
         ctx.rows_cap = rows_cap
         coef = r["aux_coef"] if spec.want_psum else torch.empty(0, dtype=torch.float32, device=dev)
         ctx.save_for_backward(x, Wg_c, r["logits"], r["idx"], r["score"], r["pos"], r["seg_start"], r["kept"],
-                              r["tile_expert"], r["num_mtiles"], r["xbuf"], U, H, Y, W1tb, W2tb, coef)
+                              r["tile_expert"], r["num_mtiles"], r["xbuf"], G, H, Y, W1tb, W2tb, coef)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(r["count"], r["kept"])
         if spec.want_psum:
@@ -164,7 +164,7 @@ class MoEFunction(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy, daux, _dcount, _dkept):
-        (x, Wg, logits, idx, score, pos, seg_start, kept, tile_expert, num_mtiles, xbuf, U, H, Y, W1tb,
+        (x, Wg, logits, idx, score, pos, seg_start, kept, tile_expert, num_mtiles, xbuf, G, H, Y, W1tb,
          W2tb, coef) = ctx.saved_tensors
         spec: RouteSpec = ctx.spec
         T, d = x.shape
@@ -190,7 +190,7 @@ class MoEFunction(torch.autograd.Function):
         dW2, db2 = _f32((E, d, h), dev), _f32((E, d), dev)
         # same kernel sequence as the bundled moe_expert_ffn_bwd entry point
         te, nm, sg = C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_start)
-        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), None, None, C.ptr(U),
+        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), None, None, C.ptr(G),
                te, nm, None, rows_cap, E, 0, h, d, st, tag="gemm_dgelu")
         C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dybuf), C.ptr(H), C.ptr(dW2), None, None, None,
                None, None, sg, rows_cap, E, d, h, 0, st, tag="gemm_wgrad2")

@@ -129,7 +129,7 @@ def test_layer_forward_backward_vs_oracle(case):
 
 
 def test_ffn_intermediates_vs_model():
-    """U, H, Y rows of the expert FFN against the arithmetic model (live rows only)."""
+    """G = gelu'(U), H, Y rows of the expert FFN against the arithmetic model (live rows only)."""
     T, d, h, E, k, mode = 900, 192, 768, 8, 2, 0
     _, C, Fn = _fm()
     x, Wg, bg, W1, b1, W2, b2 = make_problem(T, d, h, E, seed=5)
@@ -148,7 +148,7 @@ def test_ffn_intermediates_vs_model():
     rows = sv.r.rows
     assert torch.equal(W1b.cpu().float(), sv.W1b) and torch.equal(W2b.cpu().float(), sv.W2b)
     assert torch.equal(W1tb.cpu().float(), sv.W1b.transpose(1, 2)) and torch.equal(W2tb.cpu().float(), sv.W2b.transpose(1, 2))
-    for name, got, want in (("U", U, sv.Ub), ("H", H, sv.Hb), ("Y", Y, sv.Yb)):
+    for name, got, want in (("G", U, sv.Gb), ("H", H, sv.Hb), ("Y", Y, sv.Yb)):
         assert rel_err(got[:rows], want) <= MODEL_REL, name
         assert max_abs(got[:rows], want) <= float(want.abs().max()) / 64, name
 

@@ -1,8 +1,8 @@
 """Fits the polynomials used by the GEMM epilogues for exact-erf GELU and its derivative.
 
-  gelu(u)  = relu(u) - |u| * Q(|u|),          Q(a) = Phi(-a) = 0.5 erfc(a / sqrt 2) = exp2(P(a))   [shipped: deg 6]
-                                                                                   = g(a) * W(a)   [alternative]
-  gelu'(u) = u < 0 ? m(|u|) : 1 - m(|u|),      m(a) = Phi(-a) - a phi(a)         = g(a) * w(a)   [shipped: deg 8]
+  gelu(u)  = relu(u) - |u| * Q(|u|),          Q(a) = Phi(-a) = 0.5 erfc(a / sqrt 2) = exp2(P(a))   [rounds 1b-1d: deg 6]
+                                                                                   = g(a) * W(a)   [shipped: W deg 7, shared with gelu']
+  gelu'(u) = u < 0 ? m(|u|) : 1 - m(|u|),      m(a) = Phi(-a) - a phi(a)         = g(a) * (W(a) - a / sqrt(2 pi))   [shipped]
   g(a) = exp(-a^2 / 2)  (one ex2.approx),  P, W and w polynomials in a on [0, A_MAX] (a is clamped).
 
 Weighted least squares on Chebyshev nodes (weight = the factor that multiplies the polynomial in the
@@ -57,6 +57,21 @@ def main():
             print("  w:", ", ".join(f"{c:.9e}f" for c in cw))
 
 
+def main_shipped_v2():
+    """Round 1e: gelu and gelu' share g = exp(-a^2/2) and one degree-7 polynomial W(a) = 0.5 erfcx(a / sqrt 2)."""
+    a = np.linspace(0, A_MAX, 2_000_001)
+    g = lambda t: np.exp(-0.5 * t * t)
+    W = lambda t: 0.5 * erfcx(t / np.sqrt(2.0))
+    c0 = 1 / np.sqrt(2 * np.pi)
+    cW = fit(W, lambda t: np.maximum(t, 0.5) * g(t), 7)
+    g32 = np.exp2((-(a.astype(np.float32) ** 2) * np.float32(0.5 * np.log2(np.e))).astype(np.float32)).astype(np.float32)
+    Wv = horner32(cW, a)
+    errQ = np.abs(a * (g32 * Wv - 0.5 * erfc(a / np.sqrt(2))))
+    errm = np.abs(g32 * (Wv - np.float32(c0) * a.astype(np.float32)) - (0.5 * erfc(a / np.sqrt(2)) - a * g(a) * c0))
+    print(f"W7 : max |gelu err| = {errQ.max():.3e}   max |gelu' err| = {errm.max():.3e}")
+    print("  kGeluW:", ", ".join(f"{c:.9e}f" for c in cW))
+
+
 def main_shipped():
     from scipy.special import log_ndtr
     a = np.linspace(0, A_MAX, 2_000_001)
@@ -76,4 +91,4 @@ def main_shipped():
 
 
 if __name__ == "__main__":
-    main_shipped()
+    main_shipped_v2()
