@@ -11,6 +11,7 @@
 // butterfly) so they are bit-identical to oracle/gate_ref.c; top-k ties go to the lowest expert
 // index; pairs are ranked inside an expert by ascending flattened index t*k+j.  No atomics on
 // floating point anywhere; integer shared-memory atomics only where the result is order-free.
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -859,6 +860,131 @@ gate_wgrad_partial_kernel(const float* __restrict__ dlogits, const XT* __restric
     }
 }
 
+// Stage 1 for bf16 activations, on the tensor cores: per 16-expert group dWg^T-partial[16, d] += dlogits^T[16, 8] x[8, d]
+// as m16n8k8 tf32 MMAs (x is exact in tf32, dlogits is rounded to tf32: 2^-11 relative).  T d E fp32 FMAs on the CUDA
+// cores cost ~50 us at the config-2 shape; here the arithmetic disappears and the kernel streams x once per expert
+// group (cp.async, double-buffered 32-token sub-tiles).  Same block -> tile assignment and partial layout as the SIMT
+// kernel, so the result stays reproducible bit for bit.
+constexpr int kWgSub = 32;     // tokens per staged sub-tile
+constexpr int kWgLdl = 24;     // floats per staged dlogits row (16 experts + 8: conflict-free A-fragment reads)
+constexpr int kWgMaxNT = 16;   // 8-column n-tiles per warp at d = 1024
+
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256)
+gate_wgrad_partial_mma_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x, int64_t T, int d, int E,
+                              int ntiles, float* __restrict__ part_w, float* __restrict__ part_b) {
+    extern __shared__ __align__(16) uint8_t smem_wg[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int ldx = d + 8;                                   // staged x row, in bf16 (16-byte multiple, bank-skewed)
+    const size_t xbytes = static_cast<size_t>(kWgSub) * ldx * 2;
+    auto xs = [&](int buf) { return reinterpret_cast<uint16_t*>(smem_wg + buf * xbytes); };
+    auto dls = [&](int buf) { return reinterpret_cast<float*>(smem_wg + 2 * xbytes) + buf * (kWgSub * kWgLdl); };
+    const int fw = d / 8;                                    // features per warp
+    const int nt = fw / 8;                                   // n-tiles per warp
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int steps = my_tiles * (kWgTile / kWgSub);
+    float* pw = part_w + static_cast<size_t>(blockIdx.x) * E * d;
+    const int chunks_per_row = d / 8;                        // 16-byte pieces of one x row
+
+    for (int g0 = 0; g0 < E; g0 += 16) {
+        float acc[kWgMaxNT][4];
+#pragma unroll
+        for (int j = 0; j < kWgMaxNT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
+        float bsum = 0.0f;
+        auto tok_base = [&](int st) {   // first token of step st
+            const int tile = blockIdx.x + (st / (kWgTile / kWgSub)) * gridDim.x;
+            return static_cast<int64_t>(tile) * kWgTile + (st % (kWgTile / kWgSub)) * kWgSub;
+        };
+        auto stage_x = [&](int st, int buf) {   // cp.async: rows past T are clamped (their dlogits are staged as 0)
+            const int64_t t0 = tok_base(st);
+            for (int c = tid; c < kWgSub * chunks_per_row; c += 256) {
+                const int r = c / chunks_per_row, cc = c - r * chunks_per_row;
+                const __nv_bfloat16* src = x + min(t0 + r, T - 1) * d + cc * 8;
+                const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(xs(buf) + static_cast<size_t>(r) * ldx + cc * 8));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        float dreg[2];
+        auto fetch_dl = [&](int st) {   // 32 tokens x 16 experts = 512 values, two per thread
+            const int64_t t0 = tok_base(st);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int idx = tid + i * 256, r = idx >> 4, e = g0 + (idx & 15);
+                dreg[i] = (t0 + r < T && e < E) ? __ldg(dlogits + (t0 + r) * E + e) : 0.0f;
+            }
+        };
+        auto store_dl = [&](int buf) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int idx = tid + i * 256;
+                dls(buf)[(idx >> 4) * kWgLdl + (idx & 15)] = dreg[i];
+            }
+        };
+        if (steps > 0) {
+            stage_x(0, 0);
+            fetch_dl(0);
+            store_dl(0);
+        }
+        for (int st = 0; st < steps; ++st) {
+            const int buf = st & 1;
+            if (st + 1 < steps) {
+                stage_x(st + 1, buf ^ 1);   // that buffer's readers finished at the barrier that closed step st - 1
+                fetch_dl(st + 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();                // x and dlogits of step st are visible to every warp
+            const uint16_t* xb = xs(buf);
+            const float* db = dls(buf);
+#pragma unroll
+            for (int ks = 0; ks < kWgSub / 8; ++ks) {
+                const int k0 = ks * 8;
+                uint32_t a[4];
+                a[0] = to_tf32(db[(k0 + t) * kWgLdl + g]);
+                a[1] = to_tf32(db[(k0 + t) * kWgLdl + g + 8]);
+                a[2] = to_tf32(db[(k0 + t + 4) * kWgLdl + g]);
+                a[3] = to_tf32(db[(k0 + t + 4) * kWgLdl + g + 8]);
+                const uint16_t* r0 = xb + static_cast<size_t>(k0 + t) * ldx + warp * fw + g;
+                const uint16_t* r1 = r0 + 4 * static_cast<size_t>(ldx);
+#pragma unroll
+                for (int j = 0; j < kWgMaxNT; ++j) {
+                    if (j < nt) mma_tf32_16x8x8(acc[j], a, static_cast<uint32_t>(r0[j * 8]) << 16, static_cast<uint32_t>(r1[j * 8]) << 16);
+                }
+            }
+            if (tid < 16) {
+#pragma unroll 8
+                for (int r = 0; r < kWgSub; ++r) bsum += db[r * kWgLdl + tid];
+            }
+            if (st + 1 < steps) store_dl(buf ^ 1);
+            __syncthreads();                // readers of buffer `buf` are done before step st + 2 overwrites it
+        }
+        // C fragment: rows g, g + 8 = experts, columns 2t, 2t + 1 of each n-tile = features
+#pragma unroll
+        for (int j = 0; j < kWgMaxNT; ++j) {
+            if (j < nt) {
+                const int col = warp * fw + j * 8 + 2 * t;
+                if (g0 + g < E) *reinterpret_cast<float2*>(pw + static_cast<size_t>(g0 + g) * d + col) = make_float2(acc[j][0], acc[j][1]);
+                if (g0 + g + 8 < E) *reinterpret_cast<float2*>(pw + static_cast<size_t>(g0 + g + 8) * d + col) = make_float2(acc[j][2], acc[j][3]);
+            }
+        }
+        if (tid < 16 && g0 + tid < E) part_b[static_cast<size_t>(blockIdx.x) * E + g0 + tid] = bsum;
+        __syncthreads();
+    }
+}
+
 // out[i] = sum_b part[b][i]: one warp per output, lanes stride the per-block partials (independent loads), then the
 // xor butterfly — a fixed order, so the result is reproducible bit for bit
 __global__ void __launch_bounds__(256)
@@ -1217,11 +1343,17 @@ cudaError_t launch_gate_wgrad(const float* dlogits, const void* x, int x_dtype, 
         err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
         kfn<<<nb, 256, smem, st>>>(dlogits, static_cast<const float*>(x), T, d, E, ntiles, part_w, part_b);
-    } else {
+    } else if (getenv("MOE_GATE_WGRAD_SIMT") != nullptr) {   // experiment hook: the CUDA-core kernel on bf16 activations
         auto kfn = gate_wgrad_partial_kernel<__nv_bfloat16>;
         err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
         kfn<<<nb, 256, smem, st>>>(dlogits, static_cast<const __nv_bfloat16*>(x), T, d, E, ntiles, part_w, part_b);
+    } else {
+        const size_t smem_mma = 2 * static_cast<size_t>(kWgSub) * (d + 8) * 2 + 2 * static_cast<size_t>(kWgSub) * kWgLdl * 4;
+        auto kfn = gate_wgrad_partial_mma_kernel;
+        err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+        if (err != cudaSuccess) return err;
+        kfn<<<nb, 256, smem_mma, st>>>(dlogits, static_cast<const __nv_bfloat16*>(x), T, d, E, ntiles, part_w, part_b);
     }
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
