@@ -50,6 +50,8 @@ extern "C" {
 #define MOE_GEMM_DGELU 2 /* out0 = (A Wt^T) * aux  (aux = FC1's out0)       A[rows,K] B[E,N,K] aux[rows,N] */
 #define MOE_GEMM_DGRAD 3 /* out0 = A Wt^T                               A[rows,K] B[E,N,K]            */
 #define MOE_GEMM_WGRAD 4 /* out0[e] (fp32 [E,M,N]) = A_e^T B_e          A[rows,M] B[rows,N]           */
+#define MOE_GEMM_WGRAD_T 5 /* out0[e] (fp32 [E,N,M]) = (A_e^T B_e)^T = B_e^T A_e, same tiles as WGRAD, transposed store:
+                              lets the wide dimension be M (256-row tiles) whatever the parameter's layout */
 
 const char *moe_last_error(void);
 int moe_version(void);
@@ -185,6 +187,10 @@ int moe_segment_colsum(const void *buf, const int32_t *seg_start, int64_t rows_c
 
 /* ---- the grouped tcgen05 GEMM itself (building block of the two FFN entry points; exported so
  * each contraction can be tested and timed on its own).  See MOE_GEMM_* for operand shapes. */
+/* MOE_GEMM_WGRAD / MOE_GEMM_WGRAD_T only: bytes of the optional split-K flag workspace passed as `aux` (int32, zero-filled
+ * once by the caller; every launch leaves it zero again; one workspace per stream).  With it each output tile's K range
+ * is computed as two halves on two CTA pairs (second half stored, first half added: bit-reproducible). */
+size_t moe_wgrad_flags_bytes(int E, int M, int N);
 int moe_grouped_gemm(int op, const void *A, const void *B, void *out0, void *out1, const float *bias, const void *aux,
                      const int32_t *tile_expert, const int32_t *num_mtiles, const int32_t *seg_start, int64_t rows_cap,
                      int E, int M, int N, int K, void *stream);

@@ -230,6 +230,11 @@ int moe_colsum(const void* buf, int dtype, int64_t rows, int cols, void* workspa
     return check(launch_colsum(buf, dtype, rows, cols, workspace, out, static_cast<cudaStream_t>(stream)), "moe_colsum");
 }
 
+size_t moe_wgrad_flags_bytes(int E, int M, int N) {
+    // one int per (tile, CTA rank, epilogue warp); tiles counted for the narrowest tile the launcher may pick (128)
+    return static_cast<size_t>(E) * ((M + 255) / 256) * ((N + 127) / 128) * 2 * 8 * sizeof(int32_t);
+}
+
 int moe_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out1, const float* bias, const void* aux,
                      const int32_t* tile_expert, const int32_t* num_mtiles, const int32_t* seg_start, int64_t rows_cap,
                      int E, int M, int N, int K, void* stream) {
@@ -259,9 +264,9 @@ int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* G, const
     rc = launch_grouped_gemm(MOE_GEMM_DGELU, dybuf, W2tb, dU, nullptr, nullptr, G, tile_expert, num_mtiles, nullptr,
                              rows_cap, E, 0, h, d, sms, st);
     if (rc) return rc;
-    // dW2[e] = dY_e^T H_e                          [d, h]
-    rc = launch_grouped_gemm(MOE_GEMM_WGRAD, dybuf, H, dW2, nullptr, nullptr, nullptr, nullptr, nullptr, seg_start,
-                             rows_cap, E, d, h, 0, sms, st);
+    // dW2[e] = dY_e^T H_e = (H_e^T dY_e)^T      [d, h]   computed with M = h, stored transposed
+    rc = launch_grouped_gemm(MOE_GEMM_WGRAD_T, H, dybuf, dW2, nullptr, nullptr, nullptr, nullptr, nullptr, seg_start,
+                             rows_cap, E, h, d, 0, sms, st);
     if (rc) return rc;
     // dW1[e] = dU_e^T X_e                          [h, d]
     rc = launch_grouped_gemm(MOE_GEMM_WGRAD, dU, xbuf, dW1, nullptr, nullptr, nullptr, nullptr, nullptr, seg_start,

@@ -10,7 +10,10 @@
 //     dgelu : dU = (dY W2) * G                      B = W2^T [E, h, d]      EPI_DGELU
 //     dgrad : dX = dU W1                            B = W1^T [E, d, h]      EPI_PLAIN
 //   WGRAD mode (K = the rows of one expert's segment, fp32 output per expert; A and B MN-major):
-//     dW2[e] = dY_e^T H_e , dW1[e] = dU_e^T X_e                             EPI_F32
+//     dW1[e] = dU_e^T X_e   [E, M = h, N = d]                               EPI_F32
+//     dW2[e] = (H_e^T dY_e)^T: computed as [M = h, N = d], stored transposed EPI_F32_T
+//   (both weight gradients then have M = h, N = d: at d = 384 that is six 256-row M tiles and two 192-column N
+//    tiles per expert with no padding, where dW2 as [M = d, N = h] left half of every second M tile empty)
 //
 // Layout contract: the packed row buffers are [rows_cap, cols] bf16, every expert's segment
 // starts at a multiple of 256 rows (so a 256-row pair tile never straddles two experts) and pad
@@ -48,7 +51,7 @@
 
 namespace moe {
 
-enum : int { EPI_BIAS_GELU_DUAL = 0, EPI_BIAS = 1, EPI_DGELU = 2, EPI_PLAIN = 3, EPI_F32 = 4 };
+enum : int { EPI_BIAS_GELU_DUAL = 0, EPI_BIAS = 1, EPI_DGELU = 2, EPI_PLAIN = 3, EPI_F32 = 4, EPI_F32_T = 5 };
 
 struct GemmParams {
     const int* tile_expert;  // ROWS: expert of each 256-row pair tile       [max_mtiles]
@@ -56,6 +59,8 @@ struct GemmParams {
     const int* seg_start;    // WGRAD: first row of each expert segment      [E+1]
     const float* bias;       // [E, N] fp32 or nullptr
     const __nv_bfloat16* aux;  // EPI_DGELU: G = gelu'(U) [rows_cap, N] (read through its tensor map)
+    int* flags;              // WGRAD split-K: one int per (tile, CTA rank, epilogue warp), zero between launches
+    int ksplit;              // WGRAD: 1, or 2 = every tile's K range is done in two halves by two work units
     int E;
     int M;  // WGRAD: output rows per expert
     int N;  // output columns (per expert)
@@ -76,6 +81,13 @@ constexpr int kSmemLimit = 232448;    // 227 KB
 
 template <int BN, int EPI>
 struct GemmCfg {
+    // BN <= 256: one UMMA per k-step and two TMEM accumulator stages (the epilogue of a tile overlaps the next
+    // tile's mainloop).  BN = 384: ONE 384-column accumulator fed by two UMMAs per k-step (N = 256 + N = 128) that
+    // share the A tile: 40 KB of operands per 256 x 384 x 64 block instead of 2 x 28 KB (BN = 192) — the mainloop
+    // is bound by the L2 -> SM operand feed (~35 B/clk/SM measured on every variant), so bytes per flop is what
+    // counts; the epilogue no longer overlaps, which long-K launches (K >= 768, WGRAD) amortise.
+    static constexpr int NSUB = (BN + 255) / 256;
+    static constexpr int ACC_STAGES = BN <= 256 ? 2 : 1;
     static constexpr int A_BYTES = kBM * kBK * 2;
     static constexpr int B_BYTES = (BN / 2) * kBK * 2;  // this CTA's half of the B tile (one k-block)
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -90,15 +102,21 @@ struct GemmCfg {
     // multiplies in place and stores the same slab.  Small slabs leave the shared memory to the operand ring.
     static constexpr int NCHUNK = BN / 32;
     static constexpr int MAXCH = (NCHUNK + NGRP - 1) / NGRP;   // chunks of one warp per tile
-    static constexpr int SLAB_BYTES = (EPI == EPI_F32) ? 4096 : 2048;
+    static constexpr bool F32 = (EPI == EPI_F32 || EPI == EPI_F32_T);
+    // WGRAD reads B MN-major: whole 128-byte swizzle atoms (64 columns) when this CTA's half allows it, else
+    // 64-byte swizzle atoms (32 columns): BN = 192 -> 96 columns per CTA = three 32-column atoms
+    static constexpr int B_ATOM = ((BN / 2) % 64 == 0) ? 64 : 32;
+    static constexpr int SLAB_BYTES = F32 ? 4096 : 2048;
     static constexpr int OUT_BYTES = EPI_WARPS * SLAB_BYTES * (EPI == EPI_DGELU ? MAXCH : NOUT);
     static constexpr int STAGING_BYTES = OUT_BYTES;
-    static constexpr int BAR_BYTES = 512 + EPI_WARPS * 128 * 4;  // mbarriers + TMEM slot, then the per-warp bias copies
+    static constexpr int BIAS_FLOATS = (MAXCH > 4 ? MAXCH : 4) * 32;   // per-warp copy of the bias of its chunks
+    static constexpr int BAR_BYTES = 512 + EPI_WARPS * BIAS_FLOATS * 4;  // mbarriers + TMEM slot, then the bias copies
     static constexpr int STAGES_RAW = (kSmemLimit - 1024 - BAR_BYTES - STAGING_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
     static_assert(STAGES >= 3, "not enough shared memory for a pipelined tile");
-    static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64, at most 256");
+    static_assert(BN % 64 == 0 && (BN <= 256 || BN == 384), "BN must be a multiple of 64, at most 256, or 384");
+    static_assert(BN <= 256 || (EPI != EPI_DGELU && EPI != EPI_BIAS_GELU_DUAL), "wide tiles: fc2 / dgrad / wgrad only");
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -205,7 +223,17 @@ struct TileCoord {
     int n0;     // first output column of the pair tile
     int row0;   // WGRAD: first packed row of the expert segment
     int kb;     // number of 64-deep k-blocks
+    int kb0;    // WGRAD: first k-block of this work unit inside the expert segment
+    int part;   // WGRAD split-K: 1 = early half (plain store, then raises the flags), 0 = late half (waits, reduce-adds); -1 = unsplit
+    int tile;   // WGRAD: output tile index (flags)
 };
+// first B column (inside the pair tile) of this CTA's i-th 64-column block: BN <= 256: this CTA's half;
+// BN = 384: blocks 0, 1 belong to the N = 256 UMMA (columns 0..255), block 2 to the N = 128 UMMA (columns 256..383)
+template <int BN>
+__device__ __forceinline__ int b_block_col(int rank, int i) {
+    if constexpr (BN <= 256) return rank * (BN / 2) + i * 64;
+    else return i < 2 ? rank * 128 + i * 64 : 256 + rank * 64;
+}
 
 template <int BN, bool WGRAD>
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, int n_ntiles, int rank) {
@@ -217,9 +245,17 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
         c.n0 = (tile - m * n_ntiles) * BN;
         c.row0 = 0;
         c.kb = p.K / kBK;
+        c.kb0 = 0; c.part = -1; c.tile = tile;
     } else {
         int m_tiles = (p.M + kPairM - 1) / kPairM;
         int per_e = m_tiles * n_ntiles;
+        c.part = -1;
+        if (p.ksplit == 2) {   // units [0, tiles) are the early halves, [tiles, 2 tiles) the late ones
+            const int ntile = p.E * per_e;
+            c.part = tile < ntile ? 1 : 0;
+            if (tile >= ntile) tile -= ntile;
+        }
+        c.tile = tile;
         c.e = tile / per_e;
         int rem = tile - c.e * per_e;
         int mt = rem / n_ntiles;
@@ -227,6 +263,12 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
         c.n0 = (rem - mt * n_ntiles) * BN;
         c.row0 = __ldg(p.seg_start + c.e);
         c.kb = (__ldg(p.seg_start + c.e + 1) - c.row0) / kBK;
+        c.kb0 = 0;
+        if (c.part >= 0) {
+            const int h0 = c.kb / 2;   // late half: [0, h0); early half: [h0, kb) — never smaller than the late one
+            if (c.part == 0) c.kb = h0;
+            else { c.kb0 = h0; c.kb -= h0; }
+        }
     }
     return c;
 }
@@ -238,8 +280,8 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
     using Cfg = GemmCfg<BN, EPI>;
     constexpr int STAGES = Cfg::STAGES;
-    static_assert(WGRAD == (EPI == EPI_F32), "WGRAD <=> fp32 output");
-    static_assert(!WGRAD || BN % 128 == 0, "MN-major B: each CTA's half must be whole 64-column swizzle atoms");
+    static_assert(WGRAD == Cfg::F32, "WGRAD <=> fp32 output");
+    static_assert(!WGRAD || BN % 64 == 0, "MN-major B: each CTA's half must be whole 32-column swizzle atoms");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -249,7 +291,8 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     [[maybe_unused]] uint64_t* aux_bar = tempty_bar + 2;                                  // [warps][MAXCH]  (DGELU)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + Cfg::EPI_WARPS * Cfg::MAXCH);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + (EPI == EPI_DGELU ? Cfg::EPI_WARPS * Cfg::MAXCH : 0));
+    static_assert((2 * STAGES + 4 + (EPI == EPI_DGELU ? Cfg::EPI_WARPS * Cfg::MAXCH : 0)) * 8 + 4 <= 512, "barrier block overflows its 512 bytes");
     [[maybe_unused]] float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES + 512);  // [8 warps][128]
 
     const int warp = threadIdx.x >> 5;
@@ -269,7 +312,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_init(full_bar + s, 1);   // leader's producer arrive.expect_tx; bytes from both CTAs
             mbar_init(empty_bar + s, 1);  // one multicast tcgen05.commit
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < Cfg::ACC_STAGES; ++s) {
             mbar_init(tfull_bar + s, 1);                // one multicast tcgen05.commit
             mbar_init(tempty_bar + s, 2 * Cfg::EPI_WARPS);   // every epilogue warp of both CTAs (leader's copy is used)
         }
@@ -286,7 +329,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     const int n_ntiles = (p.N + BN - 1) / BN;
     int total_tiles;
-    if constexpr (WGRAD) total_tiles = p.E * ((p.M + kPairM - 1) / kPairM) * n_ntiles;
+    if constexpr (WGRAD) total_tiles = p.E * ((p.M + kPairM - 1) / kPairM) * n_ntiles * p.ksplit;
     else total_tiles = __ldg(p.num_mtiles) * n_ntiles;
     const int first_tile = blockIdx.x >> 1;   // pair p takes tiles p, p + npairs, ...
     const int tile_stride = gridDim.x >> 1;
@@ -308,14 +351,23 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (rank == 0) mbar_arrive_expect_tx(full_bar + s, 2 * Cfg::STAGE_BYTES);
                     if constexpr (!WGRAD) {
                         tma_load_2d_pair(sa, &tmA, full_bar + s, kb * kBK, c.m0);
-                        tma_load_2d_pair(sb, &tmB, full_bar + s, kb * kBK, c.e * p.N + c.n0 + rank * (BN / 2));
+                        if constexpr (BN <= 256) {
+                            tma_load_2d_pair(sb, &tmB, full_bar + s, kb * kBK, c.e * p.N + c.n0 + rank * (BN / 2));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < BN / 128; ++i)   // 64-row boxes
+                                tma_load_2d_pair(sb + i * 8192, &tmB, full_bar + s, kb * kBK,
+                                                 c.e * p.N + c.n0 + b_block_col<BN>(rank, i));
+                        }
                     } else {
-                        const int krow = c.row0 + kb * kBK;
+                        const int krow = c.row0 + (c.kb0 + kb) * kBK;
                         tma_load_2d_pair(sa, &tmA, full_bar + s, c.m0, krow);
                         tma_load_2d_pair(sa + 8192, &tmA, full_bar + s, c.m0 + 64, krow);
 #pragma unroll
-                        for (int i = 0; i < BN / 128; ++i)
-                            tma_load_2d_pair(sb + i * 8192, &tmB, full_bar + s, c.n0 + rank * (BN / 2) + i * 64, krow);
+                        for (int i = 0; i < (BN / 2) / Cfg::B_ATOM; ++i)
+                            tma_load_2d_pair(sb + i * (Cfg::B_ATOM * kBK * 2), &tmB, full_bar + s,
+                                             c.n0 + (Cfg::B_ATOM == 64 ? b_block_col<BN>(rank, i) : rank * (BN / 2) + i * Cfg::B_ATOM),
+                                             krow);
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -326,7 +378,8 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else if (warp == 1) {
         // ================================ MMA issuer (one thread of the leader CTA) =================
         if (rank == 0 && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kPairM, BN, WGRAD, WGRAD);
+            constexpr uint32_t idesc = umma_idesc_bf16(kPairM, BN <= 256 ? BN : 256, WGRAD, WGRAD);
+            [[maybe_unused]] constexpr uint32_t idesc1 = umma_idesc_bf16(kPairM, BN <= 256 ? 16 : BN - 256, WGRAD, WGRAD);
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
             [[maybe_unused]] int ti = 0;
@@ -337,7 +390,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_wait(tempty_bar + as, aph ^ 1);
                 tc_fence_after();
                 MOE_TL(1, ti, 1);
-                const uint32_t tmem_d = tmem_base + as * 256;
+                const uint32_t tmem_d = tmem_base + as * 256;   // wide tiles: one stage, columns [0, BN)
                 for (int kb = 0; kb < c.kb; ++kb) {
                     mbar_wait(full_bar + s, ph);
                     tc_fence_after();
@@ -348,16 +401,19 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int k4 = 0; k4 < kBK / 16; ++k4) {
                         const uint64_t ad = WGRAD ? umma_smem_desc(a_addr + k4 * 2048, 8192, 1024)
                                                   : umma_smem_desc(a_addr + k4 * 32, 16, 1024);
-                        const uint64_t bd = WGRAD ? umma_smem_desc(b_addr + k4 * 2048, 8192, 1024)
-                                                  : umma_smem_desc(b_addr + k4 * 32, 16, 1024);
+                        const uint64_t bd = !WGRAD ? umma_smem_desc(b_addr + k4 * 32, 16, 1024)
+                                            : Cfg::B_ATOM == 64 ? umma_smem_desc(b_addr + k4 * 2048, 8192, 1024)
+                                                                : umma_smem_desc(b_addr + k4 * 1024, 4096, 512, 4);
                         umma_bf16(tmem_d, ad, bd, idesc, (kb | k4) != 0);
+                        if constexpr (Cfg::NSUB == 2)   // second UMMA of the k-step: B blocks past the first 128 rows / columns
+                            umma_bf16(tmem_d + 256, ad, bd + (16384 >> 4), idesc1, (kb | k4) != 0);
                     }
                     umma_commit_pair(empty_bar + s);  // frees the smem slot in both CTAs once these MMAs retire
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
                 umma_commit_pair(tfull_bar + as);  // accumulator complete -> epilogues of both CTAs
                 MOE_TL(1, ti, 3);
-                if (++as == 2) { as = 0; aph ^= 1; }
+                if (++as == Cfg::ACC_STAGES) { as = 0; aph ^= 1; }
             }
         }
         __syncwarp();
@@ -369,13 +425,13 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int q = warp & 3;                  // TMEM lane quarter this warp may touch
         const int grp = (warp - 2) >> 2;         // column group this warp belongs to
         const int ew = warp - 2;                 // 0..7
-        float* const wbias = bias_s + ew * 128;  // this warp's copy of the bias values of its chunks
+        float* const wbias = bias_s + ew * Cfg::BIAS_FLOATS;  // this warp's copy of the bias values of its chunks
         int as = 0;
         uint32_t aph = 0;
         [[maybe_unused]] int ti = 0;
         [[maybe_unused]] const int tl_role = warp == 2 ? 2 : 3;
         [[maybe_unused]] const bool tl_on = (warp == 2 || warp == 6) && lane == 0;
-        if constexpr (EPI == EPI_F32) {
+        if constexpr (Cfg::F32) {
             uint8_t* const slab = staging + ew * Cfg::SLAB_BYTES;     // 32 rows x 128 B, 128-byte swizzle
             uint8_t* const my_row = slab + lane * 128;
             const int sw = lane & 7;
@@ -383,6 +439,23 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
                 const bool live = c.kb != 0;
                 if (tl_on) MOE_TL(tl_role, ti, 0);
+                // split-K: this warp's slabs of the tile are also written by the same warp of the pair that runs the
+                // other half.  The early half stores and then raises its flag; the late half waits for it and
+                // reduce-adds (a + b in one fixed order: bit-reproducible), and leaves the flag cleared.
+                int* const my_flag = c.part >= 0 ? p.flags + (static_cast<size_t>(c.tile) * 2 + rank) * Cfg::EPI_WARPS + ew : nullptr;
+                if (c.part == 0) {
+                    if (lane == 0) {
+                        uint32_t spins = 0;
+                        while (ld_acquire_gpu(my_flag) == 0) {
+                            __nanosleep(64);
+                            if (++spins > (1u << 27)) __trap();
+                        }
+                        *reinterpret_cast<volatile int*>(my_flag) = 0;
+                        fence_proxy_async_all();
+                    }
+                    __syncwarp();
+                    if (!live) continue;   // nothing to add
+                }
                 if (live) {
                     mbar_wait(tfull_bar + as, aph);
                     tc_fence_after();
@@ -408,19 +481,38 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     if (lane == 0) tma_store_wait_read<0>();   // this warp's previous store has left its slab
                     __syncwarp();
+                    if constexpr (EPI == EPI_F32) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) =
-                            make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) =
+                                make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                    } else {
+                        // transposed: slab row j = accumulator column j, this lane's accumulator row is slab column `lane`
+                        uint8_t* const my_col = slab + (lane & 3) * 4;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            *reinterpret_cast<uint32_t*>(my_col + j * 128 + (((lane >> 2) ^ (j & 7)) << 4)) = acc[j];
+                    }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0 && c.m0 + q * 32 < p.M && c.n0 + ch * 32 < p.N) {
-                        tma_store_3d(&tmO0, slab, c.n0 + ch * 32, c.m0 + q * 32, c.e);
+                        const int o_col = EPI == EPI_F32 ? c.n0 + ch * 32 : c.m0 + q * 32;
+                        const int o_row = EPI == EPI_F32 ? c.m0 + q * 32 : c.n0 + ch * 32;
+                        if (c.part == 0) tma_reduce_add_3d(&tmO0, slab, o_col, o_row, c.e);
+                        else tma_store_3d(&tmO0, slab, o_col, o_row, c.e);
                         tma_store_commit();
                     }
                 }
+                if (c.part == 1) {   // early half: its stores are complete and visible before the flag goes up
+                    if (lane == 0) {
+                        tma_store_wait_all<0>();
+                        __threadfence();
+                        st_release_gpu(my_flag, 1);
+                    }
+                    __syncwarp();
+                }
                 if (tl_on) MOE_TL(tl_role, ti, 3);
-                if (live && ++as == 2) { as = 0; aph ^= 1; }
+                if (live && ++as == Cfg::ACC_STAGES) { as = 0; aph ^= 1; }
             }
         } else {
             // bf16 outputs: slab rows are 64 B (four 16-byte units), unit u of row r lives at unit u ^ ((r >> 1) & 3)
@@ -446,13 +538,16 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const bool live = c.kb != 0;
                 if (tl_on) MOE_TL(tl_role, ti, 0);
                 if constexpr (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS) {
-                    // lane l fetches 4 consecutive bias values of the group's (at most four) chunks
-                    const int lc = grp + Cfg::NGRP * (lane >> 3);   // chunk the lane's values belong to
-                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (lc < Cfg::NCHUNK)
-                        bv = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(c.e) * p.N + c.n0 + lc * 32) + (lane & 7));
+                    // lane l fetches 4 consecutive bias values of the group's chunks, four chunks per pass
                     __syncwarp();                                // previous tile's reads of wbias are done
-                    *reinterpret_cast<float4*>(wbias + lane * 4) = bv;
+#pragma unroll
+                    for (int i0 = 0; i0 < Cfg::MAXCH; i0 += 4) {
+                        const int lc = grp + Cfg::NGRP * (i0 + (lane >> 3));   // chunk the lane's values belong to
+                        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (lc < Cfg::NCHUNK)
+                            bv = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(c.e) * p.N + c.n0 + lc * 32) + (lane & 7));
+                        if (i0 + (lane >> 3) < Cfg::BIAS_FLOATS / 32) *reinterpret_cast<float4*>(wbias + i0 * 32 + lane * 4) = bv;
+                    }
                     __syncwarp();
                 }
                 [[maybe_unused]] TileCoord cn{};                  // DGELU: next tile of this pair, whose G slabs are prefetched
@@ -551,7 +646,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 if (tl_on) MOE_TL(tl_role, ti, 3);
                 ++it;
-                if (live && ++as == 2) { as = 0; aph ^= 1; }
+                if (live && ++as == Cfg::ACC_STAGES) { as = 0; aph ^= 1; }
             }
         }
         if (lane == 0) tma_store_wait_all<0>();

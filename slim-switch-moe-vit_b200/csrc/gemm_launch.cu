@@ -75,19 +75,26 @@ int launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& 
     return 0;
 }
 
-// ROWS mode: N must be tiled exactly (the outputs are dense row buffers)
-int pick_bn_rows(int N) {
+// ROWS mode: N must be tiled exactly (the outputs are dense row buffers).  fc2 / dgrad (`wide_ok`) take 384-wide
+// single-accumulator tiles when N allows it and K is long enough to amortise the un-overlapped epilogue.
+int pick_bn_rows(int N, int K, bool wide_ok) {
+    if (wide_ok && getenv("MOE_ROWS_BN")) return atoi(getenv("MOE_ROWS_BN"));   // experiment hook
+    if (wide_ok && N % 384 == 0 && N % 256 != 0 && K >= 768) return 384;
     if (N % 256 == 0) return 256;
     if (N % 192 == 0) return 192;
     if (N % 128 == 0) return 128;
     if (N % 64 == 0) return 64;
     return 0;
 }
-// WGRAD mode: BN in {128, 256} (whole swizzle atoms per CTA half); ragged N is handled by TMA zero-fill /
-// clipping.  256 wins whenever N > 128 even when a quarter of the last tile is padding (N = 384: measured
-// 75 us vs 86 us with three 128-wide tiles): the A tile is re-read once per N tile, and L2 feed is the limit.
+// WGRAD mode: BN in {128, 192, 256}; ragged N is handled by TMA zero-fill / clipping.  Exact tilings first
+// (N = 384 -> two 192-wide tiles, B read through 64-byte-swizzle atoms); otherwise 256 wins whenever N > 128 even
+// when part of the last tile is padding (N = 384: measured 75 us vs 86 us with three 128-wide tiles): the A tile
+// is re-read once per N tile, and operand feed is the limit.
 int pick_bn_wgrad(int N) {
     if (getenv("MOE_WGRAD_BN")) return atoi(getenv("MOE_WGRAD_BN"));   // experiment hook
+    if (N % 384 == 0 && N % 256 != 0) return 384;   // one 384-column accumulator: A is read once per 384 columns
+    if (N % 256 == 0) return 256;
+    if (N % 192 == 0) return 192;
     return N > 128 ? 256 : 128;
 }
 
@@ -96,22 +103,29 @@ int pick_bn_wgrad(int N) {
 int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out1, const float* bias, const void* aux,
                         const int* tile_expert, const int* num_mtiles, const int* seg_start, int64_t rows_cap, int E,
                         int M, int N, int K, int sm_count, cudaStream_t st) {
-    const bool wgrad = op == MOE_GEMM_WGRAD;
-    if (op < MOE_GEMM_FC1 || op > MOE_GEMM_WGRAD) { set_error("grouped gemm: unknown op %d", op); return 1; }
+    const bool wgrad = op == MOE_GEMM_WGRAD || op == MOE_GEMM_WGRAD_T;
+    if (op < MOE_GEMM_FC1 || op > MOE_GEMM_WGRAD_T) { set_error("grouped gemm: unknown op %d", op); return 1; }
     if (N <= 0 || N % 64 != 0) { set_error("grouped gemm: N=%d must be a positive multiple of 64", N); return 1; }
     if (!wgrad && (K % 64 != 0 || K <= 0)) { set_error("grouped gemm: K=%d must be a positive multiple of 64", K); return 1; }
     if (wgrad && (M % 64 != 0 || M <= 0)) { set_error("grouped gemm: M=%d must be a positive multiple of 64", M); return 1; }
     if (rows_cap % MOE_ROW_ALIGN != 0) { set_error("grouped gemm: rows_cap=%lld must be a multiple of %d", (long long)rows_cap, MOE_ROW_ALIGN); return 1; }
     if ((op == MOE_GEMM_FC1 || op == MOE_GEMM_FC2) && bias == nullptr) { set_error("grouped gemm: fc1 / fc2 need a bias vector"); return 1; }
     if (op == MOE_GEMM_DGELU && aux == nullptr) { set_error("grouped gemm: dgelu needs the pre-activation (aux)"); return 1; }
-    const int bn = wgrad ? pick_bn_wgrad(N) : pick_bn_rows(N);
+    const bool wide_ok = op == MOE_GEMM_FC2 || op == MOE_GEMM_DGRAD;
+    const int bn = wgrad ? pick_bn_wgrad(N) : pick_bn_rows(N, K, wide_ok);
+    if (!wgrad && (bn <= 0 || N % bn != 0 || (bn == 384 && !wide_ok))) { set_error("grouped gemm: BN=%d does not tile N=%d for op %d", bn, N, op); return 1; }
 
     GemmParams p{};
     p.tile_expert = tile_expert;
     p.num_mtiles = num_mtiles;
     p.seg_start = seg_start;
     p.bias = bias;
-    p.aux = static_cast<const __nv_bfloat16*>(aux);
+    p.aux = wgrad ? nullptr : static_cast<const __nv_bfloat16*>(aux);
+    // WGRAD: `aux` is the optional split-K flag workspace (moe_wgrad_flags_bytes(E, M, N) bytes, zero-filled once; the
+    // kernel leaves it zero).  With it every tile's K range runs as two work units on two CTA pairs — 96 tiles of
+    // 256 x 384 on 74 pairs would otherwise take two full rounds.
+    p.flags = wgrad ? static_cast<int*>(const_cast<void*>(aux)) : nullptr;
+    p.ksplit = (wgrad && aux != nullptr && getenv("MOE_WGRAD_NO_SPLIT") == nullptr) ? 2 : 1;
     p.E = E; p.M = M; p.N = N; p.K = K;
 
     CUtensorMap tA, tB, tO0, tO1, tAux;
@@ -121,23 +135,34 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
     if (!wgrad) {
         // A [rows, K] and B [E*N, K] K-major; each CTA of a pair loads 128 A rows and bn/2 B rows per k-block
         ok = ok && encode_2d(&tA, BF, 2, A, K, R, 64, 128);
-        ok = ok && encode_2d(&tB, BF, 2, B, K, static_cast<uint64_t>(E) * N, 64, bn / 2);
+        ok = ok && encode_2d(&tB, BF, 2, B, K, static_cast<uint64_t>(E) * N, 64, bn <= 256 ? bn / 2 : 64);
         // each epilogue warp stores (and, for dgelu, loads its rows of the pre-activation as) 32-row x 32-column slabs
         const auto S64 = CU_TENSOR_MAP_SWIZZLE_64B;
         ok = ok && encode_2d(&tO0, BF, 2, out0, N, R, 32, 32, S64);
         ok = ok && encode_2d(&tO1, BF, 2, op == MOE_GEMM_FC1 ? out1 : out0, N, R, 32, 32, S64);
         ok = ok && encode_2d(&tAux, BF, 2, op == MOE_GEMM_DGELU ? aux : out0, N, R, 32, 32, S64);
     } else {
-        // A [rows, M], B [rows, N] read MN-major in 64 x 64 boxes; out [E, M, N] fp32 in 32-column chunks
+        // A [rows, M], B [rows, N] read MN-major in 64 x 64 boxes (B: 32 x 64 boxes, 64-byte swizzle, when the
+        // CTA's half of the tile is not whole 64-column atoms); out [E, M, N] (WGRAD_T: [E, N, M]) fp32, 32 x 32 boxes
+        if (bn != 128 && bn != 192 && bn != 256 && bn != 384) { set_error("grouped gemm: wgrad BN=%d not in {128,192,256,384}", bn); return 1; }
         ok = ok && encode_2d(&tA, BF, 2, A, M, R, 64, 64);
-        ok = ok && encode_2d(&tB, BF, 2, B, N, R, 64, 64);
-        ok = ok && encode_3d_f32(&tO0, out0, N, M, E, 32, 32);
+        if ((bn / 2) % 64 == 0) ok = ok && encode_2d(&tB, BF, 2, B, N, R, 64, 64);
+        else ok = ok && encode_2d(&tB, BF, 2, B, N, R, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (op == MOE_GEMM_WGRAD) ok = ok && encode_3d_f32(&tO0, out0, N, M, E, 32, 32);
+        else ok = ok && encode_3d_f32(&tO0, out0, M, N, E, 32, 32);
         tO1 = tO0;
         tAux = tO0;
     }
     if (!ok) return 1;
     const int grid = (sm_count / 2) * 2;
+    if (wgrad && p.ksplit == 2) {   // with three or more full rounds of tiles the split buys no balance, only epilogue work
+        const int64_t ntile = static_cast<int64_t>(E) * ((M + 255) / 256) * ((N + bn - 1) / bn);
+        if (ntile >= 3LL * (grid / 2)) p.ksplit = 1;
+    }
 
+#define MOE_BN_ROWS_WIDE(EPI)                                                             \
+    if (bn == 384) return launch_one<384, EPI, false>(tA, tB, tO0, tO1, tAux, p, grid, st); \
+    MOE_BN_ROWS(EPI)
 #define MOE_BN_ROWS(EPI)                                                                  \
     switch (bn) {                                                                         \
         case 256: return launch_one<256, EPI, false>(tA, tB, tO0, tO1, tAux, p, grid, st);      \
@@ -147,14 +172,22 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
     }
     switch (op) {
         case MOE_GEMM_FC1: MOE_BN_ROWS(EPI_BIAS_GELU_DUAL)
-        case MOE_GEMM_FC2: MOE_BN_ROWS(EPI_BIAS)
+        case MOE_GEMM_FC2: MOE_BN_ROWS_WIDE(EPI_BIAS)
         case MOE_GEMM_DGELU: MOE_BN_ROWS(EPI_DGELU)
-        case MOE_GEMM_DGRAD: MOE_BN_ROWS(EPI_PLAIN)
-        default:
+        case MOE_GEMM_DGRAD: MOE_BN_ROWS_WIDE(EPI_PLAIN)
+        case MOE_GEMM_WGRAD:
+            if (bn == 384) return launch_one<384, EPI_F32, true>(tA, tB, tO0, tO1, tAux, p, grid, st);
             if (bn == 256) return launch_one<256, EPI_F32, true>(tA, tB, tO0, tO1, tAux, p, grid, st);
+            if (bn == 192) return launch_one<192, EPI_F32, true>(tA, tB, tO0, tO1, tAux, p, grid, st);
             return launch_one<128, EPI_F32, true>(tA, tB, tO0, tO1, tAux, p, grid, st);
+        default:
+            if (bn == 384) return launch_one<384, EPI_F32_T, true>(tA, tB, tO0, tO1, tAux, p, grid, st);
+            if (bn == 256) return launch_one<256, EPI_F32_T, true>(tA, tB, tO0, tO1, tAux, p, grid, st);
+            if (bn == 192) return launch_one<192, EPI_F32_T, true>(tA, tB, tO0, tO1, tAux, p, grid, st);
+            return launch_one<128, EPI_F32_T, true>(tA, tB, tO0, tO1, tAux, p, grid, st);
     }
 #undef MOE_BN_ROWS
+#undef MOE_BN_ROWS_WIDE
 }
 
 }  // namespace moe

@@ -87,6 +87,23 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                  "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+// same box, added (fp32) to what global memory holds
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// orders earlier generic-proxy accesses (any state space) before later async-proxy (TMA) operations of this thread
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
@@ -201,13 +218,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
 //   K-major operand : rows of 64 bf16 (128 B); 8-row groups 1024 B apart  -> SBO = 1024, LBO unused (1)
 //   MN-major operand: K-rows of 64 MN-elements (128 B); 8-K-row groups 1024 B apart -> SBO = 1024,
 //                     64-element MN chunks `lbo_bytes` apart                       -> LBO = lbo_bytes
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// `layout_type`: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B (MN-major: K-rows of 32 MN-elements (64 B), 8-K-row groups 512 B apart).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint64_t layout_type = 2) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= 1ull << 46;  // version = 1
-    d |= 2ull << 61;  // SWIZZLE_128B
+    d |= layout_type << 61;
     return d;
 }
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, M x N, with per-operand major-ness.

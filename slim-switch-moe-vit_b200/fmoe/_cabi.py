@@ -17,7 +17,7 @@ DTYPE_F32, DTYPE_BF16 = 0, 1
 SCORE_TOPK_SOFTMAX, SCORE_FULL_SOFTMAX = 0, 1
 AUX_NONE, AUX_SWITCH, AUX_GSHARD = 0, 1, 2
 TOKEN_TILE, ROW_ALIGN = 64, 256
-GEMM_FC1, GEMM_FC2, GEMM_DGELU, GEMM_DGRAD, GEMM_WGRAD = range(5)
+GEMM_FC1, GEMM_FC2, GEMM_DGELU, GEMM_DGRAD, GEMM_WGRAD, GEMM_WGRAD_T = range(6)
 
 _p, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
 
@@ -49,6 +49,7 @@ SIGNATURES = {
     "moe_addln_bwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _p]),
     "moe_colsum_workspace_bytes": (_sz, [_i64, _i]),
     "moe_colsum": (_i, [_p, _i, _i64, _i, _p, _p, _p]),
+    "moe_wgrad_flags_bytes": (_sz, [_i, _i, _i]),
     "moe_grouped_gemm": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
 }
 
@@ -137,6 +138,23 @@ def dtype_code(t: torch.Tensor) -> int:
 
 def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+_WGRAD_FLAGS: dict = {}
+
+
+def wgrad_flags(E: int, M: int, N: int, dev) -> torch.Tensor:
+    """Zero-filled split-K flag workspace of the weight-gradient GEMMs (`aux` of MOE_GEMM_WGRAD / _T), one per device
+    and stream; every launch leaves it zero, so it is allocated and cleared once."""
+    nbytes = int(lib.moe_wgrad_flags_bytes(E, M, N))
+    key = (torch.device(dev).index, stream_ptr())
+    t = _WGRAD_FLAGS.get(key)
+    if t is None or t.numel() * 4 < nbytes:
+        t = torch.zeros(nbytes // 4, dtype=torch.int32, device=dev)
+        if torch.cuda.is_current_stream_capturing():
+            return t   # lives in the graph's pool (the fill is replayed with the graph): not cached
+        _WGRAD_FLAGS[key] = t
+    return t
 
 
 def rows_cap(T: int, k: int, E: int, capacity: int) -> int:

@@ -229,9 +229,11 @@ class EPMoEFunction(torch.autograd.Function):
                C.ptr(kept_loc), W, El, slab, d, 0, st)
         dx_recv = torch.empty_like(send_dx)
         work = dist.all_to_all_single(dx_recv, send_dx, group=group, async_op=True)
-        C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dybuf), C.ptr(H), C.ptr(dW2), None, None, None,
-               None, None, sg, rows_cap, El, d, h, 0, st, tag="gemm_wgrad2")
-        C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dU), C.ptr(xbuf), C.ptr(dW1), None, None, None,
+        # dW2 = (H^T dY)^T: the wide dimension h is M (256-row tiles), the store is transposed
+        wfl = C.ptr(C.wgrad_flags(El, h, d, dev))   # split-K flags: each tile's K range runs as two halves
+        C.call("moe_grouped_gemm", C.GEMM_WGRAD_T, C.ptr(H), C.ptr(dybuf), C.ptr(dW2), None, None, wfl,
+               None, None, sg, rows_cap, El, h, d, 0, st, tag="gemm_wgrad2")
+        C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dU), C.ptr(xbuf), C.ptr(dW1), None, None, wfl,
                None, None, sg, rows_cap, El, h, d, 0, st, tag="gemm_wgrad1")
         cws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, h), dtype=torch.uint8, device=dev)
         C.call("moe_segment_colsum", C.ptr(dybuf), sg, rows_cap, El, d, C.ptr(cws), C.ptr(db2), st, tag="colsum_db2")

@@ -192,9 +192,11 @@ class MoEFunction(torch.autograd.Function):
         te, nm, sg = C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_start)
         C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), None, None, C.ptr(G),
                te, nm, None, rows_cap, E, 0, h, d, st, tag="gemm_dgelu")
-        C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dybuf), C.ptr(H), C.ptr(dW2), None, None, None,
-               None, None, sg, rows_cap, E, d, h, 0, st, tag="gemm_wgrad2")
-        C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dU), C.ptr(xbuf), C.ptr(dW1), None, None, None,
+        # dW2 = (H^T dY)^T: the wide dimension h is M (256-row tiles), the store is transposed
+        wfl = C.ptr(C.wgrad_flags(E, h, d, dev))   # split-K flags: each tile's K range runs as two halves
+        C.call("moe_grouped_gemm", C.GEMM_WGRAD_T, C.ptr(H), C.ptr(dybuf), C.ptr(dW2), None, None, wfl,
+               None, None, sg, rows_cap, E, h, d, 0, st, tag="gemm_wgrad2")
+        C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dU), C.ptr(xbuf), C.ptr(dW1), None, None, wfl,
                None, None, sg, rows_cap, E, h, d, 0, st, tag="gemm_wgrad1")
         C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1tb), C.ptr(dxbuf), None, None, None,
                te, nm, None, rows_cap, E, 0, d, h, st, tag="gemm_dgrad")

@@ -50,13 +50,15 @@ def main():
     dW1, dW2 = torch.empty(E, h, d, device=dev), torch.empty(E, d, h, device=dev)
     st = C.stream_ptr()
     P = C.ptr
+    FL = C.wgrad_flags(E, h, d, dev)
     ops = {
         "fc1": lambda: C.call("moe_grouped_gemm", C.GEMM_FC1, P(X), P(W1), P(oU), P(oH), P(b1), None, P(tile_e), P(nm), None, rows_cap, E, 0, h, d, st),
         "fc2": lambda: C.call("moe_grouped_gemm", C.GEMM_FC2, P(Hh), P(W2), P(oY), None, P(b2), None, P(tile_e), P(nm), None, rows_cap, E, 0, d, h, st),
         "dgelu": lambda: C.call("moe_grouped_gemm", C.GEMM_DGELU, P(dY), P(W2t), P(odU), None, None, P(U), P(tile_e), P(nm), None, rows_cap, E, 0, h, d, st),
         "dgrad": lambda: C.call("moe_grouped_gemm", C.GEMM_DGRAD, P(dU), P(W1t), P(odX), None, None, None, P(tile_e), P(nm), None, rows_cap, E, 0, d, h, st),
-        "wgrad1": lambda: C.call("moe_grouped_gemm", C.GEMM_WGRAD, P(dU), P(X), P(dW1), None, None, None, None, None, P(seg), rows_cap, E, h, d, 0, st),
-        "wgrad2": lambda: C.call("moe_grouped_gemm", C.GEMM_WGRAD, P(dY), P(Hh), P(dW2), None, None, None, None, None, P(seg), rows_cap, E, d, h, 0, st),
+        "wgrad1": lambda: C.call("moe_grouped_gemm", C.GEMM_WGRAD, P(dU), P(X), P(dW1), None, None, P(FL), None, None, P(seg), rows_cap, E, h, d, 0, st),
+        "wgrad2": lambda: C.call("moe_grouped_gemm", C.GEMM_WGRAD_T, P(Hh), P(dY), P(dW2), None, None, P(FL), None, None, P(seg), rows_cap, E, h, d, 0, st),
+        "wgrad2_mn": lambda: C.call("moe_grouped_gemm", C.GEMM_WGRAD, P(dY), P(Hh), P(dW2), None, None, None, None, None, P(seg), rows_cap, E, d, h, 0, st),
     }
     Xe, He = X[: seg_len * E].view(E, seg_len, d), Hh[: seg_len * E].view(E, seg_len, h)
     cublas = {
@@ -92,7 +94,7 @@ def main():
         ms = timeit(ops[name])
         total += ms
         line = f"{name:7s} {ms * 1e3:8.1f} us  {flops / ms / 1e9:7.1f} TFLOP/s"
-        if not a.no_cublas:
+        if not a.no_cublas and name in cublas:
             cms = timeit(cublas[name])
             line += f"   | cuBLAS bmm (padded rows, no epilogue) {cms * 1e3:8.1f} us {2.0 * seg_len * E * d * h / cms / 1e9:7.1f} TFLOP/s"
         print(line, flush=True)

@@ -88,13 +88,19 @@ def main():
         A = rnd(rows_cap, M); B = rnd(rows_cap, N)
         lm = live_mask()
         A[~lm] = 0  # contract: pad rows are zero in at least one operand
-        o0 = torch.full((E, M, N), 7.0, device=dev)
-        C.call("moe_grouped_gemm", op, C.ptr(A), C.ptr(B), C.ptr(o0), None, None, None, None, None, C.ptr(seg_t),
-               rows_cap, E, M, N, 0, st)
+        tr = op == C.GEMM_WGRAD_T    # out [E, N, M] = (A_e^T B_e)^T
+        o0 = torch.full((E, N, M) if tr else (E, M, N), 7.0, device=dev)
+        fl = C.wgrad_flags(E, M, N, dev)
+        for _ in range(2):   # twice: the second launch finds the flags the first one left behind
+            C.call("moe_grouped_gemm", op, C.ptr(A), C.ptr(B), C.ptr(o0), None, None, C.ptr(fl), None, None, C.ptr(seg_t),
+                   rows_cap, E, M, N, 0, st)
         torch.cuda.synchronize()
+        print(f"      split-K flags left clear: {int(fl.abs().sum()) == 0}")
         ref = torch.zeros(E, M, N, device=dev)
         for e in range(E):
             ref[e] = A[seg[e]:seg[e + 1]].float().t() @ B[seg[e]:seg[e + 1]].float()
+        if tr:
+            o0 = o0.transpose(1, 2)
         err0 = (o0 - ref).abs().max().item()
         print(f"op={op} wgrad max_abs_err={err0:.4g} ref_max={ref.abs().max().item():.4g}")
         ok = err0 < 1e-3 * max(1.0, ref.abs().max().item())

@@ -39,8 +39,8 @@ ops = {
     "fc2": lambda: C.call("moe_grouped_gemm", C.GEMM_FC2, P(Hh), P(W2), P(oY), None, P(b2), None, P(tile_e), P(nm), None, rows_cap, E, 0, d, h, st),
     "dgelu": lambda: C.call("moe_grouped_gemm", C.GEMM_DGELU, P(dY), P(W2t), P(odU), None, None, P(U), P(tile_e), P(nm), None, rows_cap, E, 0, h, d, st),
     "dgrad": lambda: C.call("moe_grouped_gemm", C.GEMM_DGRAD, P(dU), P(W1t), P(odX), None, None, None, P(tile_e), P(nm), None, rows_cap, E, 0, d, h, st),
-    "wgrad1": lambda: C.call("moe_grouped_gemm", C.GEMM_WGRAD, P(dU), P(X), P(dW1), None, None, None, None, None, P(seg), rows_cap, E, h, d, 0, st),
-    "wgrad2": lambda: C.call("moe_grouped_gemm", C.GEMM_WGRAD, P(dY), P(Hh), P(dW2), None, None, None, None, None, P(seg), rows_cap, E, d, h, 0, st),
+    "wgrad1": lambda: C.call("moe_grouped_gemm", C.GEMM_WGRAD, P(dU), P(X), P(dW1), None, None, P(C.wgrad_flags(E, h, d, dev)), None, None, P(seg), rows_cap, E, h, d, 0, st),
+    "wgrad2": lambda: C.call("moe_grouped_gemm", C.GEMM_WGRAD_T, P(Hh), P(dY), P(dW2), None, None, P(C.wgrad_flags(E, h, d, dev)), None, None, P(seg), rows_cap, E, h, d, 0, st),
 }
 for _ in range(3):
     ops[a.op]()

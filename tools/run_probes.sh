@@ -20,3 +20,9 @@ run 4 4 300,5,0,129 192 768 0
 run 4 4 300,5,0,129 768 192 0
 run 4 2 1024 384 1536 0    # M = 384: second pair tile has an empty half
 run 4 2 1024 1536 384 0
+run 4 4 300,5,0,129 256 192 0      # BN = 192: B through 64-byte-swizzle atoms
+run 4 3 640,64,1 1536 384 0
+run 5 2 128 64 64 0        # wgrad, transposed store
+run 5 4 300,5,0,129 768 192 0
+run 5 2 1024 1536 384 0
+run 5 3 700,0,129 3072 768 0
