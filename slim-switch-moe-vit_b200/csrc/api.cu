@@ -232,7 +232,7 @@ int moe_colsum(const void* buf, int dtype, int64_t rows, int cols, void* workspa
 
 size_t moe_wgrad_flags_bytes(int E, int M, int N) {
     // one int per (tile, CTA rank, epilogue warp); tiles counted for the narrowest tile the launcher may pick (128)
-    return static_cast<size_t>(E) * ((M + 255) / 256) * ((N + 127) / 128) * 2 * 8 * sizeof(int32_t);
+    return static_cast<size_t>(E) * ((M + 255) / 256) * ((N + 127) / 128) * 2 * 16 * sizeof(int32_t);
 }
 
 int moe_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out1, const float* bias, const void* aux,

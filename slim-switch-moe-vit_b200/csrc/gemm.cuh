@@ -76,7 +76,8 @@ constexpr int kBK = 64;
 #ifndef MOE_FC1_EPI_WARPS
 #define MOE_FC1_EPI_WARPS 12
 #endif
-__host__ __device__ constexpr int epi_warps(int epi) { return epi == 0 /* EPI_BIAS_GELU_DUAL */ ? MOE_FC1_EPI_WARPS : 8; }
+// The fp32 (weight-gradient) epilogues also run 12 warps: their tile is up to 384 columns wide and not overlapped.
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == 0 /* EPI_BIAS_GELU_DUAL */ ? MOE_FC1_EPI_WARPS : epi >= 4 /* EPI_F32, EPI_F32_T */ ? 12 : 8; }
 constexpr int kSmemLimit = 232448;    // 227 KB
 
 template <int BN, int EPI>
@@ -432,9 +433,14 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         [[maybe_unused]] const int tl_role = warp == 2 ? 2 : 3;
         [[maybe_unused]] const bool tl_on = (warp == 2 || warp == 6) && lane == 0;
         if constexpr (Cfg::F32) {
-            uint8_t* const slab = staging + ew * Cfg::SLAB_BYTES;     // 32 rows x 128 B, 128-byte swizzle
-            uint8_t* const my_row = slab + lane * 128;
-            const int sw = lane & 7;
+            // Two half-slabs per warp (16 accumulator columns each, 2 KB), used alternately: the TMA store of one
+            // half reads its slab while the next half is loaded from TMEM and staged (one full slab per warp exposed the
+            // store's ~600-clock shared-memory read latency once per chunk — with a single 384-column accumulator the
+            // epilogue does not overlap the mainloop, so its length is paid in full).
+            //   EPI_F32  : slab = 32 rows (m) x 64 B, 64-byte swizzle (unit u of row r at u ^ ((r >> 1) & 3))
+            //   EPI_F32_T: slab = 16 rows (n) x 128 B, 128-byte swizzle (row j = accumulator column j, this lane = column)
+            uint8_t* const slab0 = staging + ew * Cfg::SLAB_BYTES;
+            uint32_t nhalf = 0;   // half-slabs filled so far (parity selects the slab)
             for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++ti) {
                 const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
                 const bool live = c.kb != 0;
@@ -465,42 +471,54 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
                 for (int ch = grp; ch < Cfg::NCHUNK; ch += Cfg::NGRP) {
                     const bool last_chunk = (ch + Cfg::NGRP >= Cfg::NCHUNK);
-                    uint32_t acc[32];
-                    if (live) {
-                        tmem_ld32(tmem_row + ch * 32, acc);
-                        tmem_ld_wait();
-                        if (last_chunk) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive_cluster(tempty_bar + as, 0);
-                            if (tl_on) MOE_TL(tl_role, ti, 2);
+                    uint32_t acc[2][16];
+                    if (live) tmem_ld16(tmem_row + ch * 32, acc[0]);
+#pragma unroll
+                    for (int hb = 0; hb < 2; ++hb) {   // 16 accumulator columns at a time
+                        if (live) {
+                            tmem_ld_wait();
+                            if (hb == 0) {
+                                tmem_ld16(tmem_row + ch * 32 + 16, acc[1]);
+                            } else if (last_chunk) {
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive_cluster(tempty_bar + as, 0);
+                                if (tl_on) MOE_TL(tl_role, ti, 2);
+                            }
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) asm volatile("" : "+r"(acc[hb][r]));
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) acc[hb][r] = 0u;
                         }
-                    } else {
+                        uint8_t* const slab = slab0 + (nhalf & 1) * 2048;
+                        ++nhalf;
+                        if (lane == 0) tma_store_wait_read<1>();   // the store issued two halves ago has left this slab
+                        __syncwarp();
+                        if constexpr (EPI == EPI_F32) {
+                            uint8_t* const my_row = slab + lane * 64;
+                            const int sw = (lane >> 1) & 3;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) acc[i] = 0u;
-                    }
-                    if (lane == 0) tma_store_wait_read<0>();   // this warp's previous store has left its slab
-                    __syncwarp();
-                    if constexpr (EPI == EPI_F32) {
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) =
+                                    make_uint4(acc[hb][4 * j], acc[hb][4 * j + 1], acc[hb][4 * j + 2], acc[hb][4 * j + 3]);
+                        } else {
+                            uint8_t* const my_col = slab + (lane & 3) * 4;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) =
-                                make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-                    } else {
-                        // transposed: slab row j = accumulator column j, this lane's accumulator row is slab column `lane`
-                        uint8_t* const my_col = slab + (lane & 3) * 4;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            *reinterpret_cast<uint32_t*>(my_col + j * 128 + (((lane >> 2) ^ (j & 7)) << 4)) = acc[j];
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0 && c.m0 + q * 32 < p.M && c.n0 + ch * 32 < p.N) {
-                        const int o_col = EPI == EPI_F32 ? c.n0 + ch * 32 : c.m0 + q * 32;
-                        const int o_row = EPI == EPI_F32 ? c.m0 + q * 32 : c.n0 + ch * 32;
-                        if (c.part == 0) tma_reduce_add_3d(&tmO0, slab, o_col, o_row, c.e);
-                        else tma_store_3d(&tmO0, slab, o_col, o_row, c.e);
-                        tma_store_commit();
+                            for (int j = 0; j < 16; ++j)
+                                *reinterpret_cast<uint32_t*>(my_col + j * 128 + (((lane >> 2) ^ (j & 7)) << 4)) = acc[hb][j];
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (c.m0 + q * 32 < p.M && c.n0 + ch * 32 + hb * 16 < p.N) {
+                                const int o_col = EPI == EPI_F32 ? c.n0 + ch * 32 + hb * 16 : c.m0 + q * 32;
+                                const int o_row = EPI == EPI_F32 ? c.m0 + q * 32 : c.n0 + ch * 32 + hb * 16;
+                                if (c.part == 0) tma_reduce_add_3d(&tmO0, slab, o_col, o_row, c.e);
+                                else tma_store_3d(&tmO0, slab, o_col, o_row, c.e);
+                            }
+                            tma_store_commit();   // one group per half even when it is empty: wait_group.read 1 counts groups
+                        }
                     }
                 }
                 if (c.part == 1) {   // early half: its stores are complete and visible before the flag goes up

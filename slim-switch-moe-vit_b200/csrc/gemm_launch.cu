@@ -42,8 +42,9 @@ bool encode_2d(CUtensorMap* m, CUtensorMapDataType dt, int esz, const void* base
     return true;
 }
 
-// 3-D tensor [d2, d1, d0] (d0 innermost), fp32, 128-byte swizzle
-bool encode_3d_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+// 3-D tensor [d2, d1, d0] (d0 innermost), fp32
+bool encode_3d_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                   CUtensorMapSwizzle swz) {
     auto fn = get_encode_fn();
     if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
     cuuint64_t dims[3] = {d0, d1, d2};
@@ -51,7 +52,7 @@ bool encode_3d_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, u
     cuuint32_t box[3] = {b0, b1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3d) failed: CUresult %d", (int)r); return false; }
     return true;
@@ -148,8 +149,9 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
         ok = ok && encode_2d(&tA, BF, 2, A, M, R, 64, 64);
         if ((bn / 2) % 64 == 0) ok = ok && encode_2d(&tB, BF, 2, B, N, R, 64, 64);
         else ok = ok && encode_2d(&tB, BF, 2, B, N, R, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B);
-        if (op == MOE_GEMM_WGRAD) ok = ok && encode_3d_f32(&tO0, out0, N, M, E, 32, 32);
-        else ok = ok && encode_3d_f32(&tO0, out0, M, N, E, 32, 32);
+        // half-slab boxes: 16 columns x 32 rows (64-byte rows, 64-byte swizzle) / transposed: 32 x 16 (128-byte rows)
+        if (op == MOE_GEMM_WGRAD) ok = ok && encode_3d_f32(&tO0, out0, N, M, E, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+        else ok = ok && encode_3d_f32(&tO0, out0, M, N, E, 32, 16, CU_TENSOR_MAP_SWIZZLE_128B);
         tO1 = tO0;
         tAux = tO0;
     }
