@@ -584,6 +584,69 @@ __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
     *reinterpret_cast<uint2*>(p) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
 }
 
+// Feature phase of the staged path for one (column group, token group) thread: n_it tokens, TG apart.
+//   rp: this thread's 4 features of the first token's staged rows; dr: its dlogits row; op: its output
+//   KT: compile-time k (0 = runtime k);  REGS: dense dlogits and E <= 16 -> the Wg slice lives in registers
+//   idx_t: sparse dlogits only (NaiveGate without aux loss): the token's selected experts
+template <typename OT, int KT, bool REGS>
+__device__ __forceinline__ void gdb_tokens(const __nv_bfloat16* rp, const float* dr, const float* __restrict__ Wg,
+                                           const int* idx_t, OT* op, int n_it, int TG, int d, int E, int k, int cg) {
+    float4 wg[16];
+    if constexpr (REGS) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+            wg[e] = e < E ? __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e) * d + cg * 4))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int kk = KT > 0 ? KT : k;
+    const size_t r_step = static_cast<size_t>(TG) * kk * d, o_step = static_cast<size_t>(TG) * d;
+    const int ne4 = (E + 3) >> 2;
+#pragma unroll 2
+    for (int it = 0; it < n_it; ++it, rp += r_step, dr += TG * E, op += o_step) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < (KT > 0 ? KT : 1); ++j) {
+            for (int jj = j; jj < kk; jj += (KT > 0 ? kk : 1)) {   // KT > 0: exactly one pass per j
+                const uint2 r = *reinterpret_cast<const uint2*>(rp + jj * d);
+                acc.x += __uint_as_float(r.x << 16); acc.y += __uint_as_float(r.x & 0xffff0000u);
+                acc.z += __uint_as_float(r.y << 16); acc.w += __uint_as_float(r.y & 0xffff0000u);
+            }
+        }
+        if constexpr (REGS) {
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+                // experts past E carry zero weights: re-reading an in-range (finite) quad keeps the products at zero
+                const float4 g4 = *reinterpret_cast<const float4*>(dr + (e4 < ne4 ? e4 * 4 : 0));
+                const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 w = wg[e4 * 4 + i];
+                    acc.x = fmaf(gg[i], w.x, acc.x); acc.y = fmaf(gg[i], w.y, acc.y);
+                    acc.z = fmaf(gg[i], w.z, acc.z); acc.w = fmaf(gg[i], w.w, acc.w);
+                }
+            }
+        } else if (idx_t == nullptr) {
+            for (int e = 0; e < E; ++e) {
+                const float g = dr[e];
+                const float4 w = __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e) * d + cg * 4));
+                acc.x = fmaf(g, w.x, acc.x); acc.y = fmaf(g, w.y, acc.y);
+                acc.z = fmaf(g, w.z, acc.z); acc.w = fmaf(g, w.w, acc.w);
+            }
+        } else {
+            const int* ip = idx_t + static_cast<size_t>(it) * TG * k;
+            for (int j = 0; j < k; ++j) {
+                const int e = __ldg(ip + j);
+                if (e < 0) continue;
+                const float g = dr[e];
+                const float4 w = __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e) * d + cg * 4));
+                acc.x = fmaf(g, w.x, acc.x); acc.y = fmaf(g, w.y, acc.y);
+                acc.z = fmaf(g, w.z, acc.z); acc.w = fmaf(g, w.w, acc.w);
+            }
+        }
+        st4(op, acc);
+    }
+}
+
 template <typename OT>
 __global__ void __launch_bounds__(256, 2)
 gate_dispatch_bwd_kernel(const __nv_bfloat16* __restrict__ dxbuf, const int* __restrict__ pos,
@@ -678,6 +741,7 @@ gate_dispatch_bwd_kernel(const __nv_bfloat16* __restrict__ dxbuf, const int* __r
     const int CG = d / 4;
     const int TG = CG >= 256 ? 1 : 256 / CG;
     if (staged) {
+        const bool regs = dense && E <= 16;
         for (int sub = 0; sub < n_tok; sub += ts) {
             if (sub > 0) {
                 __syncthreads();   // the previous sub-tile's rows have been consumed
@@ -690,56 +754,13 @@ gate_dispatch_bwd_kernel(const __nv_bfloat16* __restrict__ dxbuf, const int* __r
                 const int cg = CG >= 256 ? cgb + tid : tid % CG;
                 const int tg = CG >= 256 ? 0 : tid / CG;
                 if (cg >= CG || tg >= TG) continue;
-                const bool regs = dense && E <= 16;
-                float4 wg[16];
-                if (regs) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        wg[e] = e < E ? __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e) * d + cg * 4))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                for (int tl = sub + tg; tl < sub_end; tl += TG) {
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const __nv_bfloat16* rp = rows_s + static_cast<size_t>(tl - sub) * k * d + cg * 4;
-                    for (int j = 0; j < k; ++j) {
-                        const uint2 r = *reinterpret_cast<const uint2*>(rp + j * d);
-                        acc.x += __uint_as_float(r.x << 16); acc.y += __uint_as_float(r.x & 0xffff0000u);
-                        acc.z += __uint_as_float(r.y << 16); acc.w += __uint_as_float(r.y & 0xffff0000u);
-                    }
-                    const float* dr = dl_s + tl * E;
-                    if (regs) {
-#pragma unroll
-                        for (int e4 = 0; e4 < 4; ++e4) {
-                            const float4 g4 = *reinterpret_cast<const float4*>(dr + (e4 * 4 < E ? e4 * 4 : 0));   // E % 4 == 0 rows are 16-byte aligned
-                            const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float g = e4 * 4 + i < E ? gg[i] : 0.0f;
-                                const float4 w = wg[e4 * 4 + i];
-                                acc.x = fmaf(g, w.x, acc.x); acc.y = fmaf(g, w.y, acc.y);
-                                acc.z = fmaf(g, w.z, acc.z); acc.w = fmaf(g, w.w, acc.w);
-                            }
-                        }
-                    } else if (dense) {
-                        for (int e = 0; e < E; ++e) {
-                            const float g = dr[e];
-                            const float4 w = __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e) * d + cg * 4));
-                            acc.x = fmaf(g, w.x, acc.x); acc.y = fmaf(g, w.y, acc.y);
-                            acc.z = fmaf(g, w.z, acc.z); acc.w = fmaf(g, w.w, acc.w);
-                        }
-                    } else {
-                        const int64_t t = t_base + tl;
-                        for (int j = 0; j < k; ++j) {
-                            const int e = __ldg(idx + t * k + j);
-                            if (e < 0) continue;
-                            const float g = dr[e];
-                            const float4 w = __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e) * d + cg * 4));
-                            acc.x = fmaf(g, w.x, acc.x); acc.y = fmaf(g, w.y, acc.y);
-                            acc.z = fmaf(g, w.z, acc.z); acc.w = fmaf(g, w.w, acc.w);
-                        }
-                    }
-                    st4(dx + (t_base + tl) * d + cg * 4, acc);
-                }
+                const __nv_bfloat16* rp = rows_s + static_cast<size_t>(tg) * k * d + cg * 4;
+                const float* dr = dl_s + (sub + tg) * E;
+                OT* op = dx + (t_base + sub + tg) * d + cg * 4;
+                const int n_it = (sub_end - sub - tg + TG - 1) / TG;
+                if (regs && k == 1) gdb_tokens<OT, 1, true>(rp, dr, Wg, nullptr, op, n_it, TG, d, E, k, cg);
+                else if (regs && k == 2) gdb_tokens<OT, 2, true>(rp, dr, Wg, nullptr, op, n_it, TG, d, E, k, cg);
+                else gdb_tokens<OT, 0, false>(rp, dr, Wg, dense ? nullptr : idx + (t_base + sub + tg) * k, op, n_it, TG, d, E, k, cg);
             }
         }
         return;
