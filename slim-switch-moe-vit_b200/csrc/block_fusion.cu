@@ -89,7 +89,7 @@ addln_fwd_kernel(const float* __restrict__ x_in, const DT* __restrict__ delta, c
 
 // dx_in = (dx_out or 0) + LN'(dn);  d_delta (nullable) = dx_in in the delta dtype;  partial dgamma / dbeta per CTA.
 template <typename NT, typename DT, int NV>
-__global__ void __launch_bounds__(256, NV <= 3 ? 3 : (NV <= 6 ? 2 : 1))
+__global__ void __launch_bounds__(256, NV <= 6 ? 2 : 1)
 addln_bwd_kernel(const NT* __restrict__ dn, const float* __restrict__ dx_out, const float* __restrict__ x, const float* __restrict__ mean,
                  const float* __restrict__ rstd, const float* __restrict__ gamma, int64_t T, int d, float* __restrict__ dx_in,
                  DT* __restrict__ d_delta, float* __restrict__ part /* [grid][2][d] */) {
@@ -104,21 +104,37 @@ addln_bwd_kernel(const NT* __restrict__ dn, const float* __restrict__ dx_out, co
         gam[i] = (i * 32 + lane < nv) ? __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float inv_d = 1.0f / static_cast<float>(d);
-    for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < T; row += static_cast<int64_t>(gridDim.x) * 8) {
-        const float mu = mean[row], rs = rstd[row];
-        float4 xh[NV], g[NV];
-        float c1 = 0.0f, c2 = 0.0f;
+    // One row per warp at a time, the NEXT row's operands (x, dn, the incoming residual gradient and the row
+    // statistics) already in flight while this one is reduced and stored: every load of a row is issued at once,
+    // two rows deep (ping-pong register sets a / b, no copies).  With the loads in two dependent phases per row
+    // and a single row in flight the kernel ran at 3.6-3.9 TB/s (round 1c-1e).
+    struct RowRegs { float4 x[NV], g[NV], r[NV]; float mu, rs; };
+    auto load_row = [&](RowRegs& R, int64_t row) {
+        R.mu = mean[row]; R.rs = rstd[row];
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = (i * 32 + lane) * 4;
             if (i * 32 + lane < nv) {
-                const float4 xv = ld_f4(x + row * d + c), gv = ld_f4(dn + row * d + c);
-                xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-                dg[i].x += gv.x * xh[i].x; dg[i].y += gv.y * xh[i].y; dg[i].z += gv.z * xh[i].z; dg[i].w += gv.w * xh[i].w;
+                R.x[i] = ld_f4(x + row * d + c);
+                R.g[i] = ld_f4(dn + row * d + c);
+                if constexpr (NV <= 3) R.r[i] = dx_out != nullptr ? ld_f4(dx_out + row * d + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+    auto do_row = [&](RowRegs& R, int64_t row) {
+        const float mu = R.mu, rs = R.rs;
+        float c1 = 0.0f, c2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (i * 32 + lane < nv) {
+                const float4 xv = R.x[i], gv = R.g[i];
+                const float4 xh = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                dg[i].x += gv.x * xh.x; dg[i].y += gv.y * xh.y; dg[i].z += gv.z * xh.z; dg[i].w += gv.w * xh.w;
                 db[i].x += gv.x; db[i].y += gv.y; db[i].z += gv.z; db[i].w += gv.w;
-                g[i] = make_float4(gv.x * gam[i].x, gv.y * gam[i].y, gv.z * gam[i].z, gv.w * gam[i].w);
-                c1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-                c2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+                const float4 g = make_float4(gv.x * gam[i].x, gv.y * gam[i].y, gv.z * gam[i].z, gv.w * gam[i].w);
+                c1 += (g.x + g.y) + (g.z + g.w);
+                c2 += (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w);
+                R.x[i] = xh; R.g[i] = g;
             }
         }
         c1 = warp_sum(c1) * inv_d;
@@ -127,16 +143,38 @@ addln_bwd_kernel(const NT* __restrict__ dn, const float* __restrict__ dx_out, co
         for (int i = 0; i < NV; ++i) {
             const int c = (i * 32 + lane) * 4;
             if (i * 32 + lane < nv) {
+                const float4 xh = R.x[i], g = R.g[i];
+                float4 r;   // wide rows: no registers left to hold it across the reduction
+                if constexpr (NV <= 3) r = R.r[i];
+                else r = dx_out != nullptr ? ld_f4(dx_out + row * d + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                 float4 o;
-                o.x = rs * (g[i].x - c1 - xh[i].x * c2); o.y = rs * (g[i].y - c1 - xh[i].y * c2);
-                o.z = rs * (g[i].z - c1 - xh[i].z * c2); o.w = rs * (g[i].w - c1 - xh[i].w * c2);
-                if (dx_out != nullptr) {
-                    const float4 r = ld_f4(dx_out + row * d + c);
-                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                }
+                o.x = rs * (g.x - c1 - xh.x * c2); o.y = rs * (g.y - c1 - xh.y * c2);
+                o.z = rs * (g.z - c1 - xh.z * c2); o.w = rs * (g.w - c1 - xh.w * c2);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                 st_f4(dx_in + row * d + c, o);
                 if (d_delta != nullptr) st_f4(d_delta + row * d + c, o);
             }
+        }
+    };
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * 8;
+    int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+    if constexpr (NV <= 3) {
+        RowRegs a, b;
+        if (row < T) load_row(a, row);
+        while (row < T) {
+            if (row + stride < T) load_row(b, row + stride);
+            do_row(a, row);
+            row += stride;
+            if (row >= T) break;
+            if (row + stride < T) load_row(a, row + stride);
+            do_row(b, row);
+            row += stride;
+        }
+    } else {
+        RowRegs a;
+        for (; row < T; row += stride) {
+            load_row(a, row);
+            do_row(a, row);
         }
     }
     // combine the 8 warps of the CTA in warp order
@@ -242,7 +280,7 @@ cudaError_t launch_colsum(const void* buf, int dtype, int64_t rows, int cols, vo
 
 static int addln_bwd_blocks(int64_t T, int d) {
     const int64_t want = (T + 7) / 8;
-    const int per_sm = d <= 384 ? 3 : (d <= 768 ? 2 : 1);   // matches the kernels' __launch_bounds__ residency
+    const int per_sm = d <= 768 ? 2 : 1;   // matches the kernels' __launch_bounds__ residency
     const int64_t cap = static_cast<int64_t>(sm_count()) * per_sm;
     return static_cast<int>(want < cap ? want : cap);
 }

@@ -141,6 +141,7 @@ def stream_ptr() -> int:
 
 
 _WGRAD_FLAGS: dict = {}
+_WGRAD_FLAGS_RETIRED: list = []
 
 
 def wgrad_flags(E: int, M: int, N: int, dev) -> torch.Tensor:
@@ -150,10 +151,12 @@ def wgrad_flags(E: int, M: int, N: int, dev) -> torch.Tensor:
     key = (torch.device(dev).index, stream_ptr())
     t = _WGRAD_FLAGS.get(key)
     if t is None or t.numel() * 4 < nbytes:
-        t = torch.zeros(nbytes // 4, dtype=torch.int32, device=dev)
+        new = torch.zeros(nbytes // 4, dtype=torch.int32, device=dev)
         if torch.cuda.is_current_stream_capturing():
-            return t   # lives in the graph's pool (the fill is replayed with the graph): not cached
-        _WGRAD_FLAGS[key] = t
+            return new   # lives in the graph's pool (the fill is replayed with the graph): not cached
+        if t is not None:
+            _WGRAD_FLAGS_RETIRED.append(t)   # a captured graph may still point at it: never freed
+        _WGRAD_FLAGS[key] = t = new
     return t
 
 

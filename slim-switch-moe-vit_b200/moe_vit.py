@@ -17,7 +17,8 @@ The reference hard-codes E=8, k=2, every block (resMoE.py:194-207); `moe_stride`
 `top_k`, `gate` and `capacity_factor` are the north-star extensions.  The MoE module
 is injected through `moe_mlp` (default: the B200 `fmoe.FMoETransformerMLP`) so bench.py's CPU
 baseline can build the same model around the CPU restatement; nothing here imports `oracle/`.
-The dense parts (attention, LayerNorm, dense MLP) stay stock PyTorch and data-parallel.
+Attention and the dense MLP stay stock PyTorch and data-parallel; with the B200 layer the residual + LayerNorm
+pairs run on fmoe.AddLayerNorm (and, opt-in, the dense MLP on fmoe.DenseFFN).
 """
 from __future__ import annotations
 
@@ -154,7 +155,7 @@ def _b200_moe_mlp(cfg: MoEViTConfig, dim: int, hidden: int) -> nn.Module:
 
 
 class MoEViT(nn.Module):
-    def __init__(self, cfg: MoEViTConfig, moe_mlp=None, fused_norm: bool | None = None):
+    def __init__(self, cfg: MoEViTConfig, moe_mlp=None, fused_norm: bool | None = None, dense_ffn: bool = False):
         """`moe_mlp(dim, hidden)` builds the MoE module (default: the B200 layer).  `fused_norm` selects the
         fused residual-add + LayerNorm kernels around the sub-layers (default: on with the B200 layer, off
         otherwise — the CPU baseline runs the stock block)."""
@@ -164,15 +165,19 @@ class MoEViT(nn.Module):
         self.fused_norm = (moe_mlp is None) if fused_norm is None else fused_norm
         norm, linear = nn.LayerNorm, nn.Linear
         if self.fused_norm:
-            from fmoe import AddLayerNorm, Linear
+            from fmoe import AddLayerNorm, DenseFFN, Linear
             norm, linear = AddLayerNorm, Linear     # same parameters; fused residual+LN and the fast bias-gradient backward
         moe_mlp = moe_mlp or partial(_b200_moe_mlp, cfg)
+        # dense blocks: stock MLP by default.  `dense_ffn=True` runs them on the layer's grouped GEMM as a single expert
+        # (fmoe.DenseFFN, same fc1 / fc2 parameters): measured at config 2 it ties with cuBLAS + the two GELU passes
+        # (18.08 vs 17.90 ms per step, profiles/r01f_*), so it is off unless asked for.
+        dense_mlp = DenseFFN if (dense_ffn and self.fused_norm and dim % 64 == 0) else partial(Mlp, linear=linear)
         n_patches = (cfg.img_size // cfg.patch) ** 2
         self.patch_embed = nn.Conv2d(3, dim, kernel_size=cfg.patch, stride=cfg.patch)
         self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
         self.pos_embed = nn.Parameter(torch.zeros(1, n_patches + 1, dim))
         self.blocks = nn.ModuleList(
-            Block(dim, heads, moe_mlp(dim, 4 * dim) if cfg.is_moe_block(i) else Mlp(dim, 4 * dim, linear), norm, linear)
+            Block(dim, heads, moe_mlp(dim, 4 * dim) if cfg.is_moe_block(i) else dense_mlp(dim, 4 * dim), norm, linear)
             for i in range(depth))
         self.norm = nn.LayerNorm(dim, eps=1e-6)
         self.head = nn.Linear(dim, cfg.num_classes)

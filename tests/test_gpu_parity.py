@@ -498,3 +498,27 @@ def test_residual_moe_block_vs_reference_golden(name):
         else:
             got = torch.stack([p.grad[i].norm() for i in range(E)]).double()
             assert rel_err(got, torch.from_numpy(z["gradnorm.mlp." + pn])) <= IDEAL_REL, pn
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,d", [(394, 192), (512, 384), (1000, 64)])
+def test_dense_ffn_vs_torch_fp32(T, d):
+    """fmoe.DenseFFN (the block's dense MLP on the grouped GEMM, E = 1) against the same MLP in fp32 PyTorch.
+    Tolerance: relative Frobenius error <= 1e-2 (bf16 operands, fp32 accumulation) for the output and every gradient."""
+    fm, _, _ = _fm()
+    torch.manual_seed(0)
+    m = fm.DenseFFN(d, 4 * d).cuda()
+    x = torch.randn(T, d, device="cuda")
+    dy = torch.randn(T, d, device="cuda")
+    xb = x.to(torch.bfloat16).requires_grad_()
+    y = m(xb)
+    assert y.dtype == torch.bfloat16 and y.shape == (T, d)
+    y.backward(dy.to(torch.bfloat16))
+    got = [y.float(), xb.grad.float()] + [p.grad.clone() for p in m.parameters()]
+    m.zero_grad()
+    xr = xb.detach().float().requires_grad_()
+    yr = m(xr)                       # fp32 input -> the stock fp32 path of the same module
+    yr.backward(dy.to(torch.bfloat16).float())
+    want = [yr, xr.grad] + [p.grad for p in m.parameters()]
+    for name, a, b in zip(["y", "dx", "dW1", "db1", "dW2", "db2"], got, want):
+        assert rel_err(a, b) <= 1e-2, f"{name}: {rel_err(a, b)}"
