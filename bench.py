@@ -517,6 +517,15 @@ def main():
             actual_ms += ms_
         roofline["per_op"] = per_op
         roofline["frac_vs_per_op_roofline"] = round(ideal_ms / actual_ms, 4) if actual_ms > 0 else None
+        # DRAM bytes per launch from the committed `ncu --set full` capture of the same six launches at this layer shape
+        # (tools/gemm_traffic.py); the capture is of this shape only, so other configs report null
+        roofline["algorithmic_bytes"] = round(sum(op_bytes.get(t_, 0.0) for t_ in gemm_tags) / max(1, len(gemm_tags)))
+        tr_path = os.path.join(ROOT, "profiles", "gemm_dram_traffic.json")
+        if os.path.exists(tr_path) and d == 384 and cfg.num_experts == 16 and world == 1 and B == 256:
+            tr = json.load(open(tr_path))
+            roofline["traffic"] = tr["mean_dram_bytes_per_launch"]
+            roofline["traffic_per_op"] = {k_: v_["dram_bytes"] for k_, v_ in tr["per_op"].items()}
+            roofline["traffic_source"] = "profiles/gemm_dram_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, " + tr["source"] + ")"
         moe_ms = sum(n * m for n, m in kern.values())
         flops_img = inner.train_flops_per_image(kept_fraction=sum(kept) / max(1, n_moe) / (B * 197 * cfg.top_k))
         line = {

@@ -77,7 +77,12 @@ constexpr int kBK = 64;
 #define MOE_FC1_EPI_WARPS 12
 #endif
 // The fp32 (weight-gradient) epilogues also run 12 warps: their tile is up to 384 columns wide and not overlapped.
-__host__ __device__ constexpr int epi_warps(int epi) { return epi == 0 /* EPI_BIAS_GELU_DUAL */ ? MOE_FC1_EPI_WARPS : epi >= 4 /* EPI_F32, EPI_F32_T */ ? 12 : 8; }
+#ifndef MOE_WIDE_EPI_WARPS
+#define MOE_WIDE_EPI_WARPS 8
+#endif
+__host__ __device__ constexpr int epi_warps(int epi, int bn) {
+    return epi == 0 /* EPI_BIAS_GELU_DUAL */ ? MOE_FC1_EPI_WARPS : epi >= 4 /* EPI_F32, EPI_F32_T */ ? 12 : bn > 256 ? MOE_WIDE_EPI_WARPS : 8;
+}
 constexpr int kSmemLimit = 232448;    // 227 KB
 
 template <int BN, int EPI>
@@ -93,7 +98,7 @@ struct GemmCfg {
     static constexpr int B_BYTES = (BN / 2) * kBK * 2;  // this CTA's half of the B tile (one k-block)
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int NOUT = (EPI == EPI_BIAS_GELU_DUAL) ? 2 : 1;
-    static constexpr int EPI_WARPS = epi_warps(EPI);
+    static constexpr int EPI_WARPS = epi_warps(EPI, BN);
     static constexpr int NGRP = EPI_WARPS / 4;          // column groups: group g takes chunks g, g + NGRP, ...
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;  // warp 0 = TMA producer, warp 1 = TMEM owner / MMA issuer
     // The epilogue works in chunks of 32 accumulator columns.  Every epilogue warp owns one 32-row slab per output
