@@ -522,3 +522,85 @@ def test_dense_ffn_vs_torch_fp32(T, d):
     want = [yr, xr.grad] + [p.grad for p in m.parameters()]
     for name, a, b in zip(["y", "dx", "dW1", "db1", "dW2", "db2"], got, want):
         assert rel_err(a, b) <= 1e-2, f"{name}: {rel_err(a, b)}"
+
+
+def _gemm_setup(E, counts, dev="cuda"):
+    seg = [0]
+    for c in counts:
+        seg.append(seg[-1] + (c + 255) // 256 * 256)
+    rows = seg[-1]
+    rows_cap = rows + 256
+    tile_e = torch.full((rows_cap // 256,), -1, dtype=torch.int32)
+    live = torch.zeros(rows_cap, dtype=torch.bool)
+    for e in range(E):
+        tile_e[seg[e] // 256: seg[e + 1] // 256] = e
+        live[seg[e]: seg[e] + counts[e]] = True
+    return seg, rows, rows_cap, tile_e.to(dev), torch.tensor([rows // 256], dtype=torch.int32, device=dev), \
+        torch.tensor(seg, dtype=torch.int32, device=dev), live.to(dev)
+
+
+# (op, counts, M, N, K): every tile shape the launcher can pick — 64 / 128 / 192 / 256-wide double-buffered tiles, the
+# 384-wide single-accumulator tiles of fc2 / dgrad / wgrad, 64-byte-swizzle B atoms (wgrad N = 192), split-K with and
+# without empty / one-k-block experts, transposed weight-gradient stores
+GEMM_CASES = [
+    ("fc2", [128, 128], 0, 64, 64), ("fc2", [300, 5, 0, 129], 0, 192, 384), ("fc2", [700, 300, 5, 129], 0, 384, 1536),
+    ("fc2", [256, 256, 256], 0, 768, 768), ("fc1", [300, 5, 0, 129], 0, 256, 192), ("fc1", [512, 512], 0, 1536, 384),
+    ("dgrad", [300, 5, 0, 129], 0, 384, 1536), ("dgrad", [1024, 1024], 0, 768, 3072), ("dgelu", [600, 600], 0, 1536, 384),
+    ("wgrad", [100, 100, 100, 100], 256, 64, 0), ("wgrad", [640, 64, 1], 1536, 384, 0), ("wgrad", [300, 5, 0, 129], 768, 192, 0),
+    ("wgrad", [300, 5, 0, 129], 192, 768, 0), ("wgrad", [1024, 1024], 384, 1536, 0),
+    ("wgrad_t", [100, 100, 100, 100], 256, 64, 0), ("wgrad_t", [700, 0, 129], 3072, 768, 0), ("wgrad_t", [640, 64, 1], 1536, 384, 0),
+]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES, ids=lambda c: f"{c[0]}-E{len(c[1])}-M{c[2]}N{c[3]}K{c[4]}")
+def test_grouped_gemm_ops_vs_torch(case):
+    """Every grouped-GEMM op through the C ABI (moe_grouped_gemm) against fp32 torch.matmul on the same bf16 operands.
+    Tolerance: max abs error <= 2 % of the output range for bf16 outputs (one bf16 rounding of a K-term sum),
+    <= 1e-3 of the range for the fp32 weight gradients; rows beyond the live tiles must stay untouched."""
+    fm, C, _ = _fm()
+    name, counts, M, N, K = case
+    E = len(counts)
+    seg, rows, rows_cap, tile_e, nm, seg_t, live = _gemm_setup(E, counts)
+    torch.manual_seed(0)
+    bf, dev, st = torch.bfloat16, "cuda", C.stream_ptr()
+    rnd = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf)
+    if name in ("fc1", "fc2", "dgrad", "dgelu"):
+        op = {"fc1": C.GEMM_FC1, "fc2": C.GEMM_FC2, "dgrad": C.GEMM_DGRAD, "dgelu": C.GEMM_DGELU}[name]
+        A, B, aux = rnd(rows_cap, K), rnd(E, N, K), rnd(rows_cap, N)
+        bias = torch.randn(E, N, device=dev) if name in ("fc1", "fc2") else None
+        o0 = torch.zeros(rows_cap, N, dtype=bf, device=dev)
+        o1 = torch.zeros_like(o0)
+        C.call("moe_grouped_gemm", op, C.ptr(A), C.ptr(B), C.ptr(o0), C.ptr(o1) if name == "fc1" else None, C.ptr(bias),
+               C.ptr(aux) if name == "dgelu" else None, C.ptr(tile_e), C.ptr(nm), None, rows_cap, E, 0, N, K, st)
+        torch.cuda.synchronize()
+        ref = torch.zeros(rows_cap, N, device=dev)
+        for e in range(E):
+            ref[seg[e]:seg[e + 1]] = A[seg[e]:seg[e + 1]].float() @ B[e].float().t() + (bias[e] if bias is not None else 0.0)
+        if name == "dgelu":
+            ref = ref * aux.float()
+        want0 = ref
+        if name == "fc1":   # out0 = gelu'(U), out1 = gelu(U)
+            want0 = 0.5 * (1 + torch.erf(ref / 2 ** 0.5)) + ref * torch.exp(-0.5 * ref * ref) / (2 * 3.141592653589793) ** 0.5
+            g = torch.nn.functional.gelu(ref)
+            assert max_abs(o1[:rows].float(), g[:rows]) <= 0.02 * max(1.0, float(g.abs().max()))
+        assert max_abs(o0[:rows].float(), want0[:rows]) <= 0.02 * max(1.0, float(want0.abs().max()))
+        assert float(o0[rows:].float().abs().max()) == 0.0
+    else:
+        tr = name == "wgrad_t"
+        A, B = rnd(rows_cap, M), rnd(rows_cap, N)
+        A[~live] = 0   # layout contract: pad rows are zero in one operand
+        o0 = torch.full((E, N, M) if tr else (E, M, N), 7.0, device=dev)
+        fl = C.wgrad_flags(E, M, N, dev)
+        for _ in range(2):   # the second launch runs on the flags the first one left behind
+            C.call("moe_grouped_gemm", C.GEMM_WGRAD_T if tr else C.GEMM_WGRAD, C.ptr(A), C.ptr(B), C.ptr(o0), None, None,
+                   C.ptr(fl), None, None, C.ptr(seg_t), rows_cap, E, M, N, 0, st)
+        torch.cuda.synchronize()
+        assert int(fl.abs().sum()) == 0, "split-K flags must be left clear"
+        ref = torch.stack([A[seg[e]:seg[e + 1]].float().t() @ B[seg[e]:seg[e + 1]].float() for e in range(E)])
+        got = o0.transpose(1, 2) if tr else o0
+        assert max_abs(got, ref) <= 1e-3 * max(1.0, float(ref.abs().max()))
+        first = got.clone()
+        C.call("moe_grouped_gemm", C.GEMM_WGRAD_T if tr else C.GEMM_WGRAD, C.ptr(A), C.ptr(B), C.ptr(o0), None, None,
+               C.ptr(fl), None, None, C.ptr(seg_t), rows_cap, E, M, N, 0, st)
+        torch.cuda.synchronize()
+        assert torch.equal(o0.transpose(1, 2) if tr else o0, first), "split-K accumulation must be bit-reproducible"
