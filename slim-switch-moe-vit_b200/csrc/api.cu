@@ -264,19 +264,27 @@ int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* G, const
     rc = launch_grouped_gemm(MOE_GEMM_DGELU, dybuf, W2tb, dU, nullptr, nullptr, G, tile_expert, num_mtiles, nullptr,
                              rows_cap, E, 0, h, d, sms, st);
     if (rc) return rc;
+    // split-K flags of the two weight gradients: the head of the column-sum workspace, which is not in use until the
+    // GEMMs are done (cleared here; the kernels leave it clear)
+    if (colsum_ws == nullptr) { set_error("moe_expert_ffn_bwd: colsum workspace (moe_segment_colsum_workspace_bytes(rows_cap, h)) required"); return 1; }
+    void* flags = nullptr;
+    const size_t flag_bytes = moe_wgrad_flags_bytes(E, h, d);
+    if (flag_bytes <= segment_colsum_workspace_bytes(rows_cap, h)) {
+        if (check(cudaMemsetAsync(colsum_ws, 0, flag_bytes, st), "wgrad flags memset")) return 1;
+        flags = colsum_ws;
+    }
     // dW2[e] = dY_e^T H_e = (H_e^T dY_e)^T      [d, h]   computed with M = h, stored transposed
-    rc = launch_grouped_gemm(MOE_GEMM_WGRAD_T, H, dybuf, dW2, nullptr, nullptr, nullptr, nullptr, nullptr, seg_start,
+    rc = launch_grouped_gemm(MOE_GEMM_WGRAD_T, H, dybuf, dW2, nullptr, nullptr, flags, nullptr, nullptr, seg_start,
                              rows_cap, E, h, d, 0, sms, st);
     if (rc) return rc;
     // dW1[e] = dU_e^T X_e                          [h, d]
-    rc = launch_grouped_gemm(MOE_GEMM_WGRAD, dU, xbuf, dW1, nullptr, nullptr, nullptr, nullptr, nullptr, seg_start,
+    rc = launch_grouped_gemm(MOE_GEMM_WGRAD, dU, xbuf, dW1, nullptr, nullptr, flags, nullptr, nullptr, seg_start,
                              rows_cap, E, h, d, 0, sms, st);
     if (rc) return rc;
     // dX = dU W1                                   [rows, d]   K = h, B = W1^T [E, d, h] K-major
     rc = launch_grouped_gemm(MOE_GEMM_DGRAD, dU, W1tb, dxbuf, nullptr, nullptr, nullptr, tile_expert, num_mtiles, nullptr,
                              rows_cap, E, 0, d, h, sms, st);
     if (rc) return rc;
-    if (colsum_ws == nullptr) { set_error("moe_expert_ffn_bwd: colsum workspace (moe_segment_colsum_workspace_bytes(rows_cap, h)) required"); return 1; }
     if (check(launch_segment_colsum(dybuf, seg_start, rows_cap, E, d, colsum_ws, db2, st), "db2 colsum")) return 1;
     return check(launch_segment_colsum(dU, seg_start, rows_cap, E, h, colsum_ws, db1, st), "db1 colsum");
 }

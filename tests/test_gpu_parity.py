@@ -604,3 +604,48 @@ def test_grouped_gemm_ops_vs_torch(case):
                C.ptr(fl), None, None, C.ptr(seg_t), rows_cap, E, M, N, 0, st)
         torch.cuda.synchronize()
         assert torch.equal(o0.transpose(1, 2) if tr else o0, first), "split-K accumulation must be bit-reproducible"
+
+
+@pytest.mark.parametrize("counts,d", [([700, 300, 5, 129], 384), ([100, 0, 260], 64)])
+def test_bundled_ffn_entry_points_equal_the_op_sequence(counts, d):
+    """moe_expert_ffn_fwd / moe_expert_ffn_bwd (the two bundled C entry points a non-Python host would bind) produce
+    exactly the bits of the grouped-GEMM + column-sum calls the Python layer issues one by one."""
+    fm, C, _ = _fm()
+    E, h = len(counts), 4 * d
+    seg, rows, rows_cap, tile_e, nm, seg_t, live = _gemm_setup(E, counts)
+    torch.manual_seed(1)
+    bf, dev, st = torch.bfloat16, "cuda", C.stream_ptr()
+    rnd = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf)
+    X, dY = rnd(rows_cap, d), rnd(rows_cap, d)
+    X[~live] = 0
+    dY[~live] = 0
+    W1, W2, W1t, W2t = rnd(E, h, d), rnd(E, d, h), rnd(E, d, h), rnd(E, h, d)
+    b1, b2 = torch.randn(E, h, device=dev), torch.randn(E, d, device=dev)
+    P = C.ptr
+
+    def buffers():
+        z = lambda n: torch.zeros(rows_cap, n, dtype=bf, device=dev)
+        return dict(G=z(h), H=z(h), Y=z(d), dU=z(h), dX=z(d), dW1=torch.zeros(E, h, d, device=dev), db1=torch.zeros(E, h, device=dev),
+                    dW2=torch.zeros(E, d, h, device=dev), db2=torch.zeros(E, d, device=dev))
+
+    a, b = buffers(), buffers()
+    ws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, h), dtype=torch.uint8, device=dev)
+    C.call("moe_expert_ffn_fwd", P(X), P(W1), P(b1), P(W2), P(b2), P(tile_e), P(nm), rows_cap, d, h, E, P(a["G"]), P(a["H"]), P(a["Y"]), st)
+    C.call("moe_expert_ffn_bwd", P(dY), P(X), P(a["G"]), P(a["H"]), P(W1t), P(W2t), P(tile_e), P(nm), P(seg_t), rows_cap, d, h, E,
+           P(a["dU"]), P(a["dX"]), P(a["dW1"]), P(a["db1"]), P(a["dW2"]), P(a["db2"]), P(ws), st)
+    g = lambda op, *args: C.call("moe_grouped_gemm", op, *args)
+    g(C.GEMM_FC1, P(X), P(W1), P(b["G"]), P(b["H"]), P(b1), None, P(tile_e), P(nm), None, rows_cap, E, 0, h, d, st)
+    g(C.GEMM_FC2, P(b["H"]), P(W2), P(b["Y"]), None, P(b2), None, P(tile_e), P(nm), None, rows_cap, E, 0, d, h, st)
+    g(C.GEMM_DGELU, P(dY), P(W2t), P(b["dU"]), None, None, P(b["G"]), P(tile_e), P(nm), None, rows_cap, E, 0, h, d, st)
+    fl = C.wgrad_flags(E, h, d, dev)
+    g(C.GEMM_WGRAD_T, P(b["H"]), P(dY), P(b["dW2"]), None, None, P(fl), None, None, P(seg_t), rows_cap, E, h, d, 0, st)
+    g(C.GEMM_WGRAD, P(b["dU"]), P(X), P(b["dW1"]), None, None, P(fl), None, None, P(seg_t), rows_cap, E, h, d, 0, st)
+    g(C.GEMM_DGRAD, P(b["dU"]), P(W1t), P(b["dX"]), None, None, None, P(tile_e), P(nm), None, rows_cap, E, 0, d, h, st)
+    C.call("moe_segment_colsum", P(dY), P(seg_t), rows_cap, E, d, P(ws), P(b["db2"]), st)
+    C.call("moe_segment_colsum", P(b["dU"]), P(seg_t), rows_cap, E, h, P(ws), P(b["db1"]), st)
+    torch.cuda.synchronize()
+    for name in a:
+        assert torch.equal(a[name], b[name]), name
+    # and the weight gradients against fp32 matmul of the same bf16 operands
+    ref = torch.stack([dY[seg[e]:seg[e + 1]].float().t() @ a["H"][seg[e]:seg[e + 1]].float() for e in range(E)])
+    assert max_abs(a["dW2"], ref) <= 1e-3 * max(1.0, float(ref.abs().max()))
