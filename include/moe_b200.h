@@ -47,7 +47,7 @@ extern "C" {
 /* grouped GEMM ops (moe_grouped_gemm) */
 #define MOE_GEMM_FC1 0   /* U = A W^T + b: out0 = gelu_erf'(U), out1 = gelu_erf(U)   A[rows,K] B[E,N,K] */
 #define MOE_GEMM_FC2 1   /* out0 = A W^T + b                            A[rows,K] B[E,N,K]            */
-#define MOE_GEMM_DGELU 2 /* out0 = (A Wt^T) * aux  (aux = FC1's out0)       A[rows,K] B[E,N,K] aux[rows,N] */
+#define MOE_GEMM_DGELU 2 /* out0 = (A Wt^T) * aux  (aux = FC1's out0)       A[rows,K] B[E,N,K] aux[rows,N]; out1: optional slab column sums */
 #define MOE_GEMM_DGRAD 3 /* out0 = A Wt^T                               A[rows,K] B[E,N,K]            */
 #define MOE_GEMM_WGRAD 4 /* out0[e] (fp32 [E,M,N]) = A_e^T B_e          A[rows,M] B[rows,N]           */
 #define MOE_GEMM_WGRAD_T 5 /* out0[e] (fp32 [E,N,M]) = (A_e^T B_e)^T = B_e^T A_e, same tiles as WGRAD, transposed store:
@@ -187,6 +187,12 @@ int moe_segment_colsum(const void *buf, const int32_t *seg_start, int64_t rows_c
 
 /* ---- the grouped tcgen05 GEMM itself (building block of the two FFN entry points; exported so
  * each contraction can be tested and timed on its own).  See MOE_GEMM_* for operand shapes. */
+/* MOE_GEMM_DGELU only: when `out1` is not NULL it receives the column sums of every 32-row slab of out0
+ * ([rows_cap / 32, N] fp32, moe_slab_colsum_bytes(rows_cap, N) bytes; slabs of tiles that are not live are not written).
+ * moe_slab_colsum_final adds the slabs of each expert segment in row order: out[E, cols] = the bias gradient db1 of the
+ * first expert projection, without a second pass over dU (replaces fmoe_cuda's column_reduce for that tensor). */
+size_t moe_slab_colsum_bytes(int64_t rows_cap, int cols);
+int moe_slab_colsum_final(const float *part, const int32_t *seg_start, int E, int cols, float *out, void *stream);
 /* MOE_GEMM_WGRAD / MOE_GEMM_WGRAD_T only: bytes of the optional split-K flag workspace passed as `aux` (int32, zero-filled
  * once by the caller; every launch leaves it zero again; one workspace per stream).  With it each output tile's K range
  * is computed as two halves on two CTA pairs (second half stored, first half added: bit-reproducible). */

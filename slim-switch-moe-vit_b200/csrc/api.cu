@@ -230,6 +230,13 @@ int moe_colsum(const void* buf, int dtype, int64_t rows, int cols, void* workspa
     return check(launch_colsum(buf, dtype, rows, cols, workspace, out, static_cast<cudaStream_t>(stream)), "moe_colsum");
 }
 
+size_t moe_slab_colsum_bytes(int64_t rows_cap, int cols) { return static_cast<size_t>(rows_cap / 32) * cols * sizeof(float); }
+
+int moe_slab_colsum_final(const float* part, const int32_t* seg_start, int E, int cols, float* out, void* stream) {
+    if (part == nullptr || seg_start == nullptr || out == nullptr || E <= 0 || cols <= 0) { set_error("moe_slab_colsum_final: bad arguments"); return 1; }
+    return check(launch_slab_colsum_final(part, seg_start, E, cols, out, static_cast<cudaStream_t>(stream)), "moe_slab_colsum_final");
+}
+
 size_t moe_wgrad_flags_bytes(int E, int M, int N) {
     // one int per (tile, CTA rank, epilogue warp); tiles counted for the narrowest tile the launcher may pick (128)
     return static_cast<size_t>(E) * ((M + 255) / 256) * ((N + 127) / 128) * 2 * 16 * sizeof(int32_t);

@@ -59,6 +59,7 @@ struct GemmParams {
     const int* seg_start;    // WGRAD: first row of each expert segment      [E+1]
     const float* bias;       // [E, N] fp32 or nullptr
     const __nv_bfloat16* aux;  // EPI_DGELU: G = gelu'(U) [rows_cap, N] (read through its tensor map)
+    float* colsum;           // EPI_DGELU (optional): column sums of every 32-row output slab, [rows_cap / 32, N] fp32
     int* flags;              // WGRAD split-K: one int per (tile, CTA rank, epilogue warp), zero between launches
     int ksplit;              // WGRAD: 1, or 2 = every tile's K range is done in two halves by two work units
     int E;
@@ -80,8 +81,12 @@ constexpr int kBK = 64;
 #ifndef MOE_WIDE_EPI_WARPS
 #define MOE_WIDE_EPI_WARPS 8
 #endif
+#ifndef MOE_DGELU_EPI_WARPS
+#define MOE_DGELU_EPI_WARPS 8
+#endif
 __host__ __device__ constexpr int epi_warps(int epi, int bn) {
-    return epi == 0 /* EPI_BIAS_GELU_DUAL */ ? MOE_FC1_EPI_WARPS : epi >= 4 /* EPI_F32, EPI_F32_T */ ? 12 : bn > 256 ? MOE_WIDE_EPI_WARPS : 8;
+    return epi == 0 /* EPI_BIAS_GELU_DUAL */ ? MOE_FC1_EPI_WARPS : epi >= 4 /* EPI_F32, EPI_F32_T */ ? 12
+           : epi == 2 /* EPI_DGELU */ ? MOE_DGELU_EPI_WARPS : bn > 256 ? MOE_WIDE_EPI_WARPS : 8;
 }
 constexpr int kSmemLimit = 232448;    // 227 KB
 
@@ -636,6 +641,33 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         uint32_t o0[8];                       // 16 columns of output 0, packed bf16x2
                         [[maybe_unused]] uint32_t o1[8];      // 16 columns of output 1 (fc1: gelu)
                         epilogue_block16<EPI>(acc[blk], cbias + blk * 64, aux, o0, o1);
+                        if constexpr (EPI == EPI_DGELU) {
+                            // db1 on the way out: column sums of this warp's 32 rows x 16 columns of dU (the bf16 values
+                            // that are stored), by a transposing butterfly — lane l ends with column l >> 1 — written
+                            // per 32-row slab; moe_slab_colsum_final adds the slabs of an expert in row order.
+                            if (p.colsum != nullptr) {
+                                float v[16];
+#pragma unroll
+                                for (int r = 0; r < 8; ++r) {
+                                    v[2 * r] = __uint_as_float(o0[r] << 16);
+                                    v[2 * r + 1] = __uint_as_float(o0[r] & 0xffff0000u);
+                                }
+#pragma unroll
+                                for (int lvl = 0; lvl < 4; ++lvl) {
+                                    const int off = 16 >> lvl, n = 8 >> lvl;
+                                    const bool upper = (lane & off) != 0;
+#pragma unroll
+                                    for (int j = 0; j < n; ++j) {
+                                        const float send = upper ? v[j] : v[j + n];
+                                        const float keep = upper ? v[j + n] : v[j];
+                                        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                                    }
+                                }
+                                v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+                                if ((lane & 1) == 0)
+                                    p.colsum[static_cast<size_t>((c.m0 + q * 32) >> 5) * p.N + c.n0 + ch * 32 + blk * 16 + (lane >> 1)] = v[0];
+                            }
+                        }
                         if (EPI != EPI_DGELU && blk == 0) {
                             if (lane == 0) tma_store_wait_read<0>();   // this warp's previous store has left its slab(s)
                             __syncwarp();

@@ -125,6 +125,7 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
     // WGRAD: `aux` is the optional split-K flag workspace (moe_wgrad_flags_bytes(E, M, N) bytes, zero-filled once; the
     // kernel leaves it zero).  With it every tile's K range runs as two work units on two CTA pairs — 96 tiles of
     // 256 x 384 on 74 pairs would otherwise take two full rounds.
+    p.colsum = op == MOE_GEMM_DGELU ? static_cast<float*>(out1) : nullptr;   // DGELU: out1 = optional slab column sums
     p.flags = wgrad ? static_cast<int*>(const_cast<void*>(aux)) : nullptr;
     p.ksplit = (wgrad && aux != nullptr && getenv("MOE_WGRAD_NO_SPLIT") == nullptr) ? 2 : 1;
     p.E = E; p.M = M; p.N = N; p.K = K;

@@ -50,6 +50,8 @@ SIGNATURES = {
     "moe_colsum_workspace_bytes": (_sz, [_i64, _i]),
     "moe_colsum": (_i, [_p, _i, _i64, _i, _p, _p, _p]),
     "moe_wgrad_flags_bytes": (_sz, [_i, _i, _i]),
+    "moe_slab_colsum_bytes": (_sz, [_i64, _i]),
+    "moe_slab_colsum_final": (_i, [_p, _p, _i, _i, _p, _p]),
     "moe_grouped_gemm": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
 }
 
@@ -78,7 +80,7 @@ class MoeB200Error(RuntimeError):
 KERNELS_PER_CALL = {
     "moe_gate_fwd": 1, "moe_route_scan": 1, "moe_ep_tables": 1, "moe_ep_repack": 1, "moe_dispatch_fwd": 1, "moe_expert_ffn_fwd": 2, "moe_combine_fwd": 1,
     "moe_combine_bwd": 1, "moe_expert_ffn_bwd": 8, "moe_gate_bwd": 1, "moe_dispatch_bwd": 1, "moe_gate_dispatch_bwd": 1,
-    "moe_gate_wgrad": 2, "moe_addln_fwd": 1, "moe_addln_bwd": 2, "moe_colsum": 2, "moe_cast_bf16": 1, "moe_cast_bf16_transposed": 1, "moe_segment_colsum": 2, "moe_grouped_gemm": 1,
+    "moe_gate_wgrad": 2, "moe_addln_fwd": 1, "moe_addln_bwd": 2, "moe_colsum": 2, "moe_cast_bf16": 1, "moe_cast_bf16_transposed": 1, "moe_segment_colsum": 2, "moe_grouped_gemm": 1, "moe_slab_colsum_final": 1,
 }
 
 

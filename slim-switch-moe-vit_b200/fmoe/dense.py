@@ -86,7 +86,8 @@ class _DenseFFN(torch.autograd.Function):
         dW1, db1 = torch.empty((1, h, d), device=dev), torch.empty((1, h), device=dev)
         dW2, db2 = torch.empty((1, d, h), device=dev), torch.empty((1, d), device=dev)
         pte, pnm, psg = C.ptr(te), C.ptr(nm), C.ptr(sg)
-        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dyb), C.ptr(W2tb), C.ptr(dU), None, None, C.ptr(G),
+        slab_sums = torch.empty(C.lib.moe_slab_colsum_bytes(rows_cap, h) // 4, dtype=torch.float32, device=dev)
+        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dyb), C.ptr(W2tb), C.ptr(dU), C.ptr(slab_sums), None, C.ptr(G),
                pte, pnm, None, rows_cap, 1, 0, h, d, st, tag="dense_dgelu")
         wfl = C.ptr(C.wgrad_flags(1, h, d, dev))
         C.call("moe_grouped_gemm", C.GEMM_WGRAD_T, C.ptr(H), C.ptr(dyb), C.ptr(dW2), None, None, wfl,
@@ -95,9 +96,9 @@ class _DenseFFN(torch.autograd.Function):
                None, None, psg, rows_cap, 1, h, d, 0, st, tag="dense_wgrad1")
         C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1tb), C.ptr(dxb), None, None, None,
                pte, pnm, None, rows_cap, 1, 0, d, h, st, tag="dense_dgrad")
-        cws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, h), dtype=torch.uint8, device=dev)
+        cws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, d), dtype=torch.uint8, device=dev)
         C.call("moe_segment_colsum", C.ptr(dyb), psg, rows_cap, 1, d, C.ptr(cws), C.ptr(db2), st, tag="dense_db2")
-        C.call("moe_segment_colsum", C.ptr(dU), psg, rows_cap, 1, h, C.ptr(cws), C.ptr(db1), st, tag="dense_db1")
+        C.call("moe_slab_colsum_final", C.ptr(slab_sums), psg, 1, h, C.ptr(db1), st, tag="dense_db1")
         dx = dxb[:T].view(shape)
         if x_dtype != bf:
             dx = dx.to(x_dtype)

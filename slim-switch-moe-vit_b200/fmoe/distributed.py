@@ -218,7 +218,8 @@ class EPMoEFunction(torch.autograd.Function):
         dW1, db1 = _f32((El, h, d), dev), _f32((El, h), dev)
         dW2, db2 = _f32((El, d, h), dev), _f32((El, d), dev)
         te, nm, sg = C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_loc)
-        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), None, None, C.ptr(G),
+        slab_sums = torch.empty(C.lib.moe_slab_colsum_bytes(rows_cap, h) // 4, dtype=torch.float32, device=dev)
+        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), C.ptr(slab_sums), None, C.ptr(G),
                te, nm, None, rows_cap, El, 0, h, d, st, tag="gemm_dgelu")
         C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1tb), C.ptr(dxbuf), None, None, None,
                te, nm, None, rows_cap, El, 0, d, h, st, tag="gemm_dgrad")
@@ -237,7 +238,7 @@ class EPMoEFunction(torch.autograd.Function):
                None, None, sg, rows_cap, El, h, d, 0, st, tag="gemm_wgrad1")
         cws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, h), dtype=torch.uint8, device=dev)
         C.call("moe_segment_colsum", C.ptr(dybuf), sg, rows_cap, El, d, C.ptr(cws), C.ptr(db2), st, tag="colsum_db2")
-        C.call("moe_segment_colsum", C.ptr(dU), sg, rows_cap, El, h, C.ptr(cws), C.ptr(db1), st, tag="colsum_db1")
+        C.call("moe_slab_colsum_final", C.ptr(slab_sums), sg, El, h, C.ptr(db1), st, tag="colsum_db1")
         work.wait()
         dx_slabs = dx_recv.view(E * slab, d)
 

@@ -11,7 +11,11 @@ from dataclasses import dataclass
 
 import torch
 
+import os
+
 from . import _cabi as C
+
+_DB1_SEPARATE = bool(os.environ.get("MOE_DB1_SEPARATE"))   # experiment hook: db1 by a separate pass over dU
 
 
 @dataclass(frozen=True)
@@ -190,7 +194,9 @@ class MoEFunction(torch.autograd.Function):
         dW2, db2 = _f32((E, d, h), dev), _f32((E, d), dev)
         # same kernel sequence as the bundled moe_expert_ffn_bwd entry point
         te, nm, sg = C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_start)
-        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), None, None, C.ptr(G),
+        # db1 = column sums of dU per expert: the dgelu epilogue leaves the sums of every 32-row slab behind
+        slab_sums = None if _DB1_SEPARATE else torch.empty(C.lib.moe_slab_colsum_bytes(rows_cap, h) // 4, dtype=torch.float32, device=dev)
+        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), C.ptr(slab_sums), None, C.ptr(G),
                te, nm, None, rows_cap, E, 0, h, d, st, tag="gemm_dgelu")
         # dW2 = (H^T dY)^T: the wide dimension h is M (256-row tiles), the store is transposed
         wfl = C.ptr(C.wgrad_flags(E, h, d, dev))   # split-K flags: each tile's K range runs as two halves
@@ -202,7 +208,10 @@ class MoEFunction(torch.autograd.Function):
                te, nm, None, rows_cap, E, 0, d, h, st, tag="gemm_dgrad")
         cws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, h), dtype=torch.uint8, device=dev)
         C.call("moe_segment_colsum", C.ptr(dybuf), sg, rows_cap, E, d, C.ptr(cws), C.ptr(db2), st, tag="colsum_db2")
-        C.call("moe_segment_colsum", C.ptr(dU), sg, rows_cap, E, h, C.ptr(cws), C.ptr(db1), st, tag="colsum_db1")
+        if slab_sums is None:
+            C.call("moe_segment_colsum", C.ptr(dU), sg, rows_cap, E, h, C.ptr(cws), C.ptr(db1), st, tag="colsum_db1")
+        else:
+            C.call("moe_slab_colsum_final", C.ptr(slab_sums), sg, E, h, C.ptr(db1), st, tag="colsum_db1")
         # gate backward (dlogits) + un-permute of dX + dlogits Wg in one pass
         dlogits = _f32((T, E), dev)
         dx = torch.empty_like(x)

@@ -649,3 +649,29 @@ def test_bundled_ffn_entry_points_equal_the_op_sequence(counts, d):
     # and the weight gradients against fp32 matmul of the same bf16 operands
     ref = torch.stack([dY[seg[e]:seg[e + 1]].float().t() @ a["H"][seg[e]:seg[e + 1]].float() for e in range(E)])
     assert max_abs(a["dW2"], ref) <= 1e-3 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("counts,N,K", [([600, 600], 1536, 384), ([300, 5, 0, 129], 256, 192), ([100, 100, 100], 64, 64)])
+def test_dgelu_slab_column_sums(counts, N, K):
+    """db1 out of the dgelu epilogue: slab sums + moe_slab_colsum_final == per-expert column sums of the stored bf16 dU
+    (fp32, <= 1e-4 of the range: only the order of the additions differs), and the dU bits do not depend on the option."""
+    fm, C, _ = _fm()
+    E = len(counts)
+    seg, rows, rows_cap, tile_e, nm, seg_t, live = _gemm_setup(E, counts)
+    torch.manual_seed(2)
+    bf, dev, st = torch.bfloat16, "cuda", C.stream_ptr()
+    rnd = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf)
+    A, B, aux = rnd(rows_cap, K), rnd(E, N, K), rnd(rows_cap, N)
+    A[~live] = 0
+    o_plain = torch.zeros(rows_cap, N, dtype=bf, device=dev)
+    o_sum = torch.zeros_like(o_plain)
+    part = torch.full((C.lib.moe_slab_colsum_bytes(rows_cap, N) // 4,), float("nan"), device=dev)
+    db = torch.empty(E, N, device=dev)
+    for o, p_ in ((o_plain, None), (o_sum, part)):
+        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(A), C.ptr(B), C.ptr(o), C.ptr(p_), None, C.ptr(aux), C.ptr(tile_e), C.ptr(nm),
+               None, rows_cap, E, 0, N, K, st)
+    C.call("moe_slab_colsum_final", C.ptr(part), C.ptr(seg_t), E, N, C.ptr(db), st)
+    torch.cuda.synchronize()
+    assert torch.equal(o_plain, o_sum)
+    ref = torch.stack([o_sum[seg[e]:seg[e + 1]].float().sum(0) for e in range(E)])
+    assert max_abs(db, ref) <= 1e-4 * max(1.0, float(ref.abs().max()))
