@@ -1196,26 +1196,29 @@ segment_colsum_partial_kernel(const __nv_bfloat16* __restrict__ buf, const int* 
 }
 
 // part holds one row of column sums per `rows_per_part` packed rows (128: segment_colsum_partial_kernel; 32: the
-// slab sums the dgelu epilogue of the grouped GEMM leaves behind)
+// slab sums the dgelu epilogue of the grouped GEMM leaves behind).  CTA = 64 columns x 4 slices of the expert's parts
+// (slice s takes parts b0 + s, b0 + s + 4, ...), four independent chains per thread, slices combined in a fixed order:
+// one dependent chain per column took 25 us for the 104 slabs per expert of config 2.
 __global__ void __launch_bounds__(256)
 segment_colsum_final_kernel(const float* __restrict__ part, const int* __restrict__ seg_start, int cols,
                             float* __restrict__ out, int rows_per_part) {
+    __shared__ float red[4][64];
     const int e = blockIdx.y;
-    const int c = blockIdx.x * 256 + threadIdx.x;
-    if (c >= cols) return;
+    const int cl = threadIdx.x & 63, slice = threadIdx.x >> 6;
+    const int c = blockIdx.x * 64 + cl;
     const int b0 = __ldg(seg_start + e) / rows_per_part, b1 = __ldg(seg_start + e + 1) / rows_per_part;
-    // eight independent chains (part b goes to chain (b - b0) % 8), combined in a fixed tree: the loads of a step are all
-    // in flight together (one dependent chain took 25 us for 104 slabs per expert)
-    float acc[8];
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (c < cols) {
+        int b = b0 + slice;
+        for (; b + 12 < b1; b += 16) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-    int b = b0;
-    for (; b + 8 <= b1; b += 8) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += part[static_cast<size_t>(b + i) * cols + c];
+            for (int i = 0; i < 4; ++i) acc[i] += part[static_cast<size_t>(b + 4 * i) * cols + c];
+        }
+        for (int i = 0; b < b1; b += 4, ++i) acc[i] += part[static_cast<size_t>(b) * cols + c];
     }
-    for (int i = 0; b + i < b1; ++i) acc[i] += part[static_cast<size_t>(b + i) * cols + c];
-    out[static_cast<size_t>(e) * cols + c] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    red[slice][cl] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    __syncthreads();
+    if (slice == 0 && c < cols) out[static_cast<size_t>(e) * cols + c] = (red[0][cl] + red[1][cl]) + (red[2][cl] + red[3][cl]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1517,13 +1520,13 @@ cudaError_t launch_segment_colsum(const void* buf, const int* seg_start, int64_t
     segment_colsum_partial_kernel<<<g1, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(buf), seg_start, E, cols, part);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    dim3 g2((cols + 255) / 256, E);
+    dim3 g2((cols + 63) / 64, E);
     segment_colsum_final_kernel<<<g2, 256, 0, st>>>(part, seg_start, cols, out, 128);
     return cudaGetLastError();
 }
 
 cudaError_t launch_slab_colsum_final(const float* part, const int* seg_start, int E, int cols, float* out, cudaStream_t st) {
-    dim3 g2((cols + 255) / 256, E);
+    dim3 g2((cols + 63) / 64, E);
     segment_colsum_final_kernel<<<g2, 256, 0, st>>>(part, seg_start, cols, out, 32);
     return cudaGetLastError();
 }
