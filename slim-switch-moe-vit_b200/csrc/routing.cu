@@ -601,6 +601,51 @@ __device__ __forceinline__ void gdb_tokens(const __nv_bfloat16* rp, const float*
     const int kk = KT > 0 ? KT : k;
     const size_t r_step = static_cast<size_t>(TG) * kk * d, o_step = static_cast<size_t>(TG) * d;
     const int ne4 = (E + 3) >> 2;
+    if constexpr (!REGS) {
+        if (idx_t == nullptr) {
+            // dense dlogits, E > 16: four tokens per pass over the experts, 16 experts of Wg in registers at a time
+            // (256 FMAs per 16 L1-resident loads instead of one load per expert and token)
+            constexpr int TB = 4;
+            for (int it0 = 0; it0 < n_it; it0 += TB) {
+                float4 acc[TB];
+#pragma unroll
+                for (int u = 0; u < TB; ++u) {
+                    acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const __nv_bfloat16* ru = rp + static_cast<size_t>(min(it0 + u, n_it - 1)) * r_step;
+                    for (int j = 0; j < kk; ++j) {
+                        const uint2 r = *reinterpret_cast<const uint2*>(ru + j * d);
+                        acc[u].x += __uint_as_float(r.x << 16); acc[u].y += __uint_as_float(r.x & 0xffff0000u);
+                        acc[u].z += __uint_as_float(r.y << 16); acc[u].w += __uint_as_float(r.y & 0xffff0000u);
+                    }
+                }
+                for (int e0 = 0; e0 < E; e0 += 16) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        wg[e] = e0 + e < E ? __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e0 + e) * d + cg * 4))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < TB; ++u) {
+                        const float* du = dr + static_cast<size_t>(min(it0 + u, n_it - 1)) * TG * E + e0;
+#pragma unroll
+                        for (int e4 = 0; e4 < 4; ++e4) {
+                            const float4 g4 = *reinterpret_cast<const float4*>(du + (e0 + e4 * 4 < E ? e4 * 4 : 0));   // past E: zero weights
+                            const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 w = wg[e4 * 4 + i];
+                                acc[u].x = fmaf(gg[i], w.x, acc[u].x); acc[u].y = fmaf(gg[i], w.y, acc[u].y);
+                                acc[u].z = fmaf(gg[i], w.z, acc[u].z); acc[u].w = fmaf(gg[i], w.w, acc[u].w);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < TB; ++u)
+                    if (it0 + u < n_it) st4(op + static_cast<size_t>(it0 + u) * o_step, acc[u]);
+            }
+            return;
+        }
+    }
 #pragma unroll 2
     for (int it = 0; it < n_it; ++it, rp += r_step, dr += TG * E, op += o_step) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -625,14 +670,7 @@ __device__ __forceinline__ void gdb_tokens(const __nv_bfloat16* rp, const float*
                     acc.z = fmaf(gg[i], w.z, acc.z); acc.w = fmaf(gg[i], w.w, acc.w);
                 }
             }
-        } else if (idx_t == nullptr) {
-            for (int e = 0; e < E; ++e) {
-                const float g = dr[e];
-                const float4 w = __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e) * d + cg * 4));
-                acc.x = fmaf(g, w.x, acc.x); acc.y = fmaf(g, w.y, acc.y);
-                acc.z = fmaf(g, w.z, acc.z); acc.w = fmaf(g, w.w, acc.w);
-            }
-        } else {
+        } else {   // sparse dlogits (NaiveGate without an aux loss): only the selected experts
             const int* ip = idx_t + static_cast<size_t>(it) * TG * k;
             for (int j = 0; j < k; ++j) {
                 const int e = __ldg(ip + j);
