@@ -34,6 +34,20 @@ def test_library_exports_every_declared_symbol():
     assert C.lib.moe_rows_cap(1000, 1, 8, 100) == 1024 + 2048    # min(T*k, E*C) rounded up to 256, + 256 per expert
 
 
+def test_op_codes_and_workspace_sizes_match_the_header():
+    """The ctypes side mirrors the header's op codes; the size functions are pure host arithmetic (no GPU needed)."""
+    from fmoe import _cabi as C
+    src = open(HEADER).read()
+    for name in ("FC1", "FC2", "DGELU", "DGRAD", "WGRAD", "WGRAD_T"):
+        m = re.search(rf"#define MOE_GEMM_{name} (\d+)", src)
+        assert m and int(m.group(1)) == getattr(C, f"GEMM_{name}"), name
+    # split-K flags: one int per (tile, CTA of the pair, epilogue warp), tiles counted for 128-wide tiles
+    assert C.lib.moe_wgrad_flags_bytes(16, 1536, 384) == 16 * 6 * 3 * 2 * 16 * 4
+    # slab column sums of the dgelu epilogue: one fp32 row per 32 packed rows
+    assert C.lib.moe_slab_colsum_bytes(53504, 1536) == 53504 // 32 * 1536 * 4
+    assert C.lib.moe_segment_colsum_workspace_bytes(53504, 1536) == 53504 // 128 * 1536 * 4
+
+
 def test_library_is_sm100a_tcgen05_code():
     """The shipped kernels are Blackwell-native: tcgen05.mma (UTCHMMA), TMA (UTMALDG/UTMASTG), TMEM loads (LDTM)."""
     from fmoe import _cabi as C
@@ -41,7 +55,7 @@ def test_library_is_sm100a_tcgen05_code():
     if sass.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in sass.stdout
-    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"):
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "UTMAREDG", "LDTM"):
         assert mnemonic in sass.stdout, mnemonic
 
 
