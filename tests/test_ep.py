@@ -1,4 +1,4 @@
-"""Expert parallelism: host-side logic on CPU (gloo, world_size 2) and the 2-GPU parity run (NCCL)."""
+"""Expert parallelism: host-side logic on CPU (gloo, world_size 2 and 4) and the 2-GPU parity run (NCCL)."""
 import os
 import subprocess
 import sys
@@ -21,16 +21,16 @@ def _cpu_worker(rank, world, port, q):
         from moe_vit import MoEViT, MoEViTConfig
 
         # 1. slab exchange: chunk j of rank r lands as chunk r of rank j
-        El, slab, d = 3, 4, 2
-        send = torch.zeros(world, El * slab * d)
+        El0, slab, d = 3, 4, 2
+        send = torch.zeros(world, El0 * slab * d)
         for j in range(world):
-            send[j] = 1000 * rank + 10 * j + torch.arange(El * slab * d) * 0.001
+            send[j] = 1000 * rank + 10 * j + torch.arange(El0 * slab * d) * 0.001
         recv = D.all_to_all_slabs(send)
         for s in range(world):
-            assert torch.equal(recv[s], 1000 * s + 10 * rank + torch.arange(El * slab * d) * 0.001)
-        kept = torch.arange(world * El, dtype=torch.int32).view(world, El) + 100 * rank
+            assert torch.equal(recv[s], 1000 * s + 10 * rank + torch.arange(El0 * slab * d) * 0.001)
+        kept = torch.arange(world * El0, dtype=torch.int32).view(world, El0) + 100 * rank
         kr = D.all_to_all_slabs(kept)
-        assert kr.tolist() == [[100 * s + rank * El + e for e in range(El)] for s in range(world)]
+        assert kr.tolist() == [[100 * s + rank * El0 + e for e in range(El0)] for s in range(world)]
         assert D.slab_rows_for(3940) == 4096 and D.slab_rows_for(256) == 256 and D.slab_rows_for(1) == 256
 
         # 2. a model with sharded experts: expert parameters are kept out of DDP and carry the 1/W hook
@@ -38,7 +38,8 @@ def _cpu_worker(rank, world, port, q):
         torch.manual_seed(0)
         model = MoEViT(cfg)
         layer = model.moe_layers[0]
-        assert layer.num_expert == 4 and layer.world_size == world and layer.gate.gate.out_features == 8
+        El = 8 // world
+        assert layer.num_expert == El and layer.world_size == world and layer.gate.gate.out_features == 8
         names = D.mark_expert_parallel(model)
         assert len(names) == 4 * len(model.moe_layers) and all(".experts." in n for n in names)
         ddp = torch.nn.parallel.DistributedDataParallel(model)
@@ -53,13 +54,13 @@ def _cpu_worker(rank, world, port, q):
         # 2b. EP-aware checkpointing: the gathered state dict has global expert shapes and round-trips
         full = D.full_state_dict(model)
         w_name = "blocks.1.mlp.experts.htoh4.weight"
-        assert full[w_name].shape[0] == 8 and torch.equal(full[w_name][rank * 4:(rank + 1) * 4], layer.experts.htoh4.weight)
+        assert full[w_name].shape[0] == 8 and torch.equal(full[w_name][rank * El:(rank + 1) * El], layer.experts.htoh4.weight)
         single = MoEViT(MoEViTConfig(size="tiny", num_experts=8, top_k=1, capacity_factor=1.25, moe_stride=2, world_size=1))
         single.load_state_dict(full)            # what rank 0 saves loads into a single-process model unchanged
         with torch.no_grad():
             layer.experts.htoh4.weight.zero_()
         D.load_full_state_dict(model, full)
-        assert torch.equal(layer.experts.htoh4.weight, full[w_name][rank * 4:(rank + 1) * 4])
+        assert torch.equal(layer.experts.htoh4.weight, full[w_name][rank * El:(rank + 1) * El])
 
         # 3. gates without a capacity are refused under expert parallelism, before any kernel is touched
         naive = fmoe.FMoETransformerMLP(2, 64, 256, torch.nn.GELU(), top_k=2, world_size=world)
@@ -76,11 +77,12 @@ def _cpu_worker(rank, world, port, q):
         q.put((rank, traceback.format_exc()))
 
 
-def test_ep_host_logic_gloo_world2():
+@pytest.mark.parametrize("world", [2, 4])
+def test_ep_host_logic_gloo(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_cpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7 * world) % 2000
+    procs = [ctx.Process(target=_cpu_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in procs]
