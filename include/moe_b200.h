@@ -129,11 +129,17 @@ int moe_combine_bwd(const void *dy, int dy_dtype, const void *ybuf, const int32_
  * (moe_cast_bf16_transposed), so that every row-mode contraction reads K-major operands.
  * dU[rows_cap,h] and dxbuf[rows_cap,d] are bf16 outputs (dU doubles as workspace);
  * dW1[E,h,d], db1[E,h], dW2[E,d,h], db2[E,d] are fp32 and are overwritten. */
+size_t moe_expert_ffn_bwd_workspace_bytes(int64_t rows_cap, int d, int h, int E);
 int moe_expert_ffn_bwd(const void *dybuf, const void *xbuf, const void *G, const void *H, const void *W1tb,
                        const void *W2tb, const int32_t *tile_expert, const int32_t *num_mtiles,
                        const int32_t *seg_start, int64_t rows_cap, int d, int h, int E, void *dU, void *dxbuf,
                        float *dW1, float *db1, float *dW2, float *db2,
-                       void *colsum_ws /* moe_segment_colsum_workspace_bytes(rows_cap, h) bytes */, void *stream);
+                       void *workspace /* moe_expert_ffn_bwd_workspace_bytes(rows_cap, d, h, E) bytes */, void *stream);
+
+/* One scratch size that covers every `workspace` argument of one layer's forward + backward (the expert-FFN backward
+ * and the gate weight gradient never hold theirs at the same time): max over moe_expert_ffn_bwd_workspace_bytes and
+ * moe_gate_wgrad_workspace_bytes at rows_cap = moe_rows_cap(T, k, E, capacity). */
+size_t moe_workspace_bytes(int64_t T, int d, int h, int E, int k, int64_t capacity);
 
 /* ---- gate backward: dlogits[T,E] from dscore[T,k] and (nullable) dpsum[E]. */
 int moe_gate_bwd(const float *logits, const int32_t *idx, const float *score, const float *dscore, const float *dpsum,

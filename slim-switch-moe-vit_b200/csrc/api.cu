@@ -260,26 +260,42 @@ int moe_expert_ffn_fwd(const void* xbuf, const void* W1b, const float* b1, const
                                E, 0, d, h, sm_count(), st);
 }
 
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+size_t moe_expert_ffn_bwd_workspace_bytes(int64_t rows_cap, int d, int h, int E) {
+    // [slab column sums of dU (db1)] [row-block column sums of dY (db2)] [split-K flags of the two weight gradients]
+    return align256(moe_slab_colsum_bytes(rows_cap, h)) + align256(segment_colsum_workspace_bytes(rows_cap, d)) +
+           align256(moe_wgrad_flags_bytes(E, h, d));
+}
+
+size_t moe_workspace_bytes(int64_t T, int d, int h, int E, int k, int64_t capacity) {
+    // one scratch buffer that covers every workspace argument of one layer's forward + backward (they are never live
+    // at the same time: the expert-FFN backward finishes before the gate weight gradient starts)
+    const int64_t rows_cap = moe_rows_cap(T, k, E, capacity);
+    const size_t a = moe_expert_ffn_bwd_workspace_bytes(rows_cap, d, h, E);
+    const size_t b = gate_wgrad_workspace_bytes(T, d, E);
+    return a > b ? a : b;
+}
+
 int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* G, const void* H, const void* W1tb,
                        const void* W2tb, const int32_t* tile_expert, const int32_t* num_mtiles,
                        const int32_t* seg_start, int64_t rows_cap, int d, int h, int E, void* dU, void* dxbuf,
-                       float* dW1, float* db1, float* dW2, float* db2, void* colsum_ws, void* stream) {
+                       float* dW1, float* db1, float* dW2, float* db2, void* workspace, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int sms = sm_count();
     int rc;
+    if (workspace == nullptr) { set_error("moe_expert_ffn_bwd: workspace (moe_expert_ffn_bwd_workspace_bytes(rows_cap, d, h, E)) required"); return 1; }
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    float* slab_sums = reinterpret_cast<float*>(ws);
+    void* colsum_ws = ws + align256(moe_slab_colsum_bytes(rows_cap, h));
+    void* flags = static_cast<uint8_t*>(colsum_ws) + align256(segment_colsum_workspace_bytes(rows_cap, d));
     // dU = (dY W2) * G, G = gelu'(U)                   [rows, h]   K = d, B = W2^T [E, h, d] K-major
-    rc = launch_grouped_gemm(MOE_GEMM_DGELU, dybuf, W2tb, dU, nullptr, nullptr, G, tile_expert, num_mtiles, nullptr,
+    // (the epilogue leaves the column sums of every 32-row slab of dU behind: db1 without a second pass over dU)
+    rc = launch_grouped_gemm(MOE_GEMM_DGELU, dybuf, W2tb, dU, slab_sums, nullptr, G, tile_expert, num_mtiles, nullptr,
                              rows_cap, E, 0, h, d, sms, st);
     if (rc) return rc;
-    // split-K flags of the two weight gradients: the head of the column-sum workspace, which is not in use until the
-    // GEMMs are done (cleared here; the kernels leave it clear)
-    if (colsum_ws == nullptr) { set_error("moe_expert_ffn_bwd: colsum workspace (moe_segment_colsum_workspace_bytes(rows_cap, h)) required"); return 1; }
-    void* flags = nullptr;
-    const size_t flag_bytes = moe_wgrad_flags_bytes(E, h, d);
-    if (flag_bytes <= segment_colsum_workspace_bytes(rows_cap, h)) {
-        if (check(cudaMemsetAsync(colsum_ws, 0, flag_bytes, st), "wgrad flags memset")) return 1;
-        flags = colsum_ws;
-    }
+    // split-K flags of the two weight gradients (cleared here; the kernels leave them clear)
+    if (check(cudaMemsetAsync(flags, 0, moe_wgrad_flags_bytes(E, h, d), st), "wgrad flags memset")) return 1;
     // dW2[e] = dY_e^T H_e = (H_e^T dY_e)^T      [d, h]   computed with M = h, stored transposed
     rc = launch_grouped_gemm(MOE_GEMM_WGRAD_T, H, dybuf, dW2, nullptr, nullptr, flags, nullptr, nullptr, seg_start,
                              rows_cap, E, h, d, 0, sms, st);
@@ -293,7 +309,7 @@ int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* G, const
                              rows_cap, E, 0, d, h, sms, st);
     if (rc) return rc;
     if (check(launch_segment_colsum(dybuf, seg_start, rows_cap, E, d, colsum_ws, db2, st), "db2 colsum")) return 1;
-    return check(launch_segment_colsum(dU, seg_start, rows_cap, E, h, colsum_ws, db1, st), "db1 colsum");
+    return check(launch_slab_colsum_final(slab_sums, seg_start, E, h, db1, st), "db1 slab sums");
 }
 
 }  // extern "C"

@@ -79,7 +79,9 @@ int launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& 
 // ROWS mode: N must be tiled exactly (the outputs are dense row buffers).  fc2 / dgrad (`wide_ok`) take 384-wide
 // single-accumulator tiles when N allows it and K is long enough to amortise the un-overlapped epilogue.
 int pick_bn_rows(int N, int K, bool wide_ok) {
-    if (wide_ok && getenv("MOE_ROWS_BN")) return atoi(getenv("MOE_ROWS_BN"));   // experiment hook
+#ifdef MOE_EXPERIMENT_HOOKS   // tools/build_variant.sh only: the shipped library never reads the environment
+    if (wide_ok && getenv("MOE_ROWS_BN")) return atoi(getenv("MOE_ROWS_BN"));
+#endif
     if (wide_ok && N % 384 == 0 && N % 256 != 0 && K >= 768) return 384;
     if (N % 256 == 0) return 256;
     if (N % 192 == 0) return 192;
@@ -92,7 +94,9 @@ int pick_bn_rows(int N, int K, bool wide_ok) {
 // when part of the last tile is padding (N = 384: measured 75 us vs 86 us with three 128-wide tiles): the A tile
 // is re-read once per N tile, and operand feed is the limit.
 int pick_bn_wgrad(int N) {
-    if (getenv("MOE_WGRAD_BN")) return atoi(getenv("MOE_WGRAD_BN"));   // experiment hook
+#ifdef MOE_EXPERIMENT_HOOKS
+    if (getenv("MOE_WGRAD_BN")) return atoi(getenv("MOE_WGRAD_BN"));
+#endif
     if (N % 384 == 0 && N % 256 != 0) return 384;   // one 384-column accumulator: A is read once per 384 columns
     if (N % 256 == 0) return 256;
     if (N % 192 == 0) return 192;
@@ -127,7 +131,10 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
     // 256 x 384 on 74 pairs would otherwise take two full rounds.
     p.colsum = op == MOE_GEMM_DGELU ? static_cast<float*>(out1) : nullptr;   // DGELU: out1 = optional slab column sums
     p.flags = wgrad ? static_cast<int*>(const_cast<void*>(aux)) : nullptr;
-    p.ksplit = (wgrad && aux != nullptr && getenv("MOE_WGRAD_NO_SPLIT") == nullptr) ? 2 : 1;
+    p.ksplit = (wgrad && aux != nullptr) ? 2 : 1;
+#ifdef MOE_EXPERIMENT_HOOKS
+    if (getenv("MOE_WGRAD_NO_SPLIT") != nullptr) p.ksplit = 1;
+#endif
     p.E = E; p.M = M; p.N = N; p.K = K;
 
     CUtensorMap tA, tB, tO0, tO1, tAux;

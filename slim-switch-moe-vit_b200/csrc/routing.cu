@@ -1467,7 +1467,7 @@ cudaError_t launch_gate_dispatch_bwd(const void* dxbuf, const int* pos, const fl
     const int ntiles = static_cast<int>((T + kTokTile - 1) / kTokTile);
     // staged gather: the largest sub-tile (tokens) whose k rows each fit 64 KB, so that 2-3 CTAs stay resident per SM
     int ts = 0;
-    if (dxbuf != nullptr && d % 8 == 0 && E % 4 == 0 && getenv("MOE_GDB_NO_STAGE") == nullptr) {
+    if (dxbuf != nullptr && d % 8 == 0 && E % 4 == 0) {
         ts = kTokTile;
         while (ts > 4 && static_cast<size_t>(ts) * k * d * 2 > 65536) ts >>= 1;
         if (static_cast<size_t>(ts) * k * d * 2 > 98304) ts = 0;
@@ -1515,11 +1515,6 @@ cudaError_t launch_gate_wgrad(const float* dlogits, const void* x, int x_dtype, 
         err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
         kfn<<<nb, 256, smem, st>>>(dlogits, static_cast<const float*>(x), T, d, E, ntiles, part_w, part_b);
-    } else if (getenv("MOE_GATE_WGRAD_SIMT") != nullptr) {   // experiment hook: the CUDA-core kernel on bf16 activations
-        auto kfn = gate_wgrad_partial_kernel<__nv_bfloat16>;
-        err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        kfn<<<nb, 256, smem, st>>>(dlogits, static_cast<const __nv_bfloat16*>(x), T, d, E, ntiles, part_w, part_b);
     } else {
         const size_t smem_mma = 2 * static_cast<size_t>(kWgSub) * (d + 8) * 2 + 2 * static_cast<size_t>(kWgSub) * kWgLdl * 4;
         auto kfn = gate_wgrad_partial_mma_kernel;

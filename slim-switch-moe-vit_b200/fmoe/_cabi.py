@@ -35,6 +35,8 @@ SIGNATURES = {
     "moe_combine_fwd": (_i, [_p, _p, _p, _i64, _i, _i, _p, _i, _p]),
     "moe_combine_bwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p]),
     "moe_expert_ffn_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "moe_expert_ffn_bwd_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
+    "moe_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i, _i64]),
     "moe_gate_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p]),
     "moe_dispatch_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _i, _p]),
     "moe_gate_wgrad_workspace_bytes": (_sz, [_i64, _i, _i]),

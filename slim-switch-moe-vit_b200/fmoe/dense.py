@@ -60,7 +60,7 @@ class _DenseFFN(torch.autograd.Function):
                 raise C.MoeB200Error("DenseFFN parameters must be fp32 (master weights)")
         xb = _rows(x2, rows_cap)
         te, nm, sg = _tables(rows_cap, dev)
-        W1b, W2b, W1tb, W2tb = cache.get(W1.detach().view(1, h, d), W2.detach().view(1, d, h))
+        W1b, W2b, W1tb, W2tb = cache.get(W1.detach().view(1, h, d), W2.detach().view(1, d, h), fresh=True)
         G = torch.empty((rows_cap, h), dtype=bf, device=dev)
         H = torch.empty((rows_cap, h), dtype=bf, device=dev)
         Y = torch.empty((rows_cap, d), dtype=bf, device=dev)

@@ -55,6 +55,20 @@ def expert_parameters(model: torch.nn.Module):
     return out
 
 
+def _check_group(layer) -> None:
+    """Experts are sharded over the layer's `moe_group`, and their gradients are scaled by 1 / (global world size)
+    without any all-reduce: that is only right when the expert-parallel group IS the whole world.  A strict
+    subgroup (experts replicated across data-parallel groups, FastMoE's `expert_dp_comm='dp'`) would leave the
+    replicas unsynchronised — refuse it instead of diverging silently."""
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("expert parallelism (world_size > 1) needs an initialised torch.distributed process group")
+    g, w = dist.get_world_size(layer.moe_group), dist.get_world_size()
+    if not (g == layer.world_size == w):
+        raise NotImplementedError(
+            f"expert-parallel group of {g} ranks, layer.world_size={layer.world_size}, global world size {w}: the B200 layer "
+            "shards experts over the whole world only (no expert replicas across data-parallel groups)")
+
+
 def mark_expert_parallel(model: torch.nn.Module, world_size: int | None = None) -> list[str]:
     """Prepares `model` for `torch.nn.parallel.DistributedDataParallel` (reference main.py:610-612):
     expert parameters are sharded, not replicated, so they are excluded from DDP's all-reduce
@@ -62,6 +76,10 @@ def mark_expert_parallel(model: torch.nn.Module, world_size: int | None = None) 
     every rank's tokens after the backward all-to-all — are divided by W, the same 1/W DDP applies to
     the replicated parameters (so the optimised objective is the mean of the ranks' losses everywhere).
     Returns the ignored parameter names."""
+    from .layers import FMoE
+    for mod in model.modules():
+        if isinstance(mod, FMoE) and mod.world_size > 1:
+            _check_group(mod)
     names = []
     for name, p in expert_parameters(model):
         names.append(name)
@@ -126,7 +144,8 @@ class EPMoEFunction(torch.autograd.Function):
     """y, aux_loss, count, kept = expert-parallel MoE(x; Wg, bg, local W1, b1, W2, b2)."""
 
     @staticmethod
-    def forward(ctx, x, Wg, bg, W1, b1, W2, b2, spec: RouteSpec, cache: Bf16WeightCache, noise, group, world):
+    def forward(ctx, x, Wg, bg, W1, b1, W2, b2, spec: RouteSpec, cache: Bf16WeightCache, noise, group, world,
+                fresh: bool = True):
         x = _as_kernel_input(x)
         T, d = x.shape
         El, h = W1.shape[0], W1.shape[1]
@@ -143,7 +162,7 @@ class EPMoEFunction(torch.autograd.Function):
         recv_x = torch.empty((W, El * slab * d), dtype=torch.bfloat16, device=dev)
         w1 = dist.all_to_all_single(kept_recv, r["kept"].view(W, El), group=group, async_op=True)     # [W(src), El]
         w2 = dist.all_to_all_single(recv_x, r["xbuf"].view(W, El * slab * d), group=group, async_op=True)  # [W(src), El, slab, d]
-        W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c)
+        W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c, fresh)
         w1.wait()
         w2.wait()
 
@@ -236,7 +255,7 @@ class EPMoEFunction(torch.autograd.Function):
                None, None, sg, rows_cap, El, h, d, 0, st, tag="gemm_wgrad2")
         C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dU), C.ptr(xbuf), C.ptr(dW1), None, None, wfl,
                None, None, sg, rows_cap, El, h, d, 0, st, tag="gemm_wgrad1")
-        cws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, h), dtype=torch.uint8, device=dev)
+        cws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, d), dtype=torch.uint8, device=dev)
         C.call("moe_segment_colsum", C.ptr(dybuf), sg, rows_cap, El, d, C.ptr(cws), C.ptr(db2), st, tag="colsum_db2")
         C.call("moe_slab_colsum_final", C.ptr(slab_sums), sg, El, h, C.ptr(db1), st, tag="colsum_db1")
         work.wait()
@@ -250,7 +269,7 @@ class EPMoEFunction(torch.autograd.Function):
         dWg = _f32((E, d), dev)
         dbg = _f32(E, dev) if ctx.has_bg else None
         C.call("moe_gate_wgrad", C.ptr(dlogits), C.ptr(x), C.dtype_code(x), T, d, E, C.ptr(ws), C.ptr(dWg), C.ptr(dbg), st)
-        return dx, dWg, dbg, dW1, db1, dW2, db2, None, None, None, None, None
+        return dx, dWg, dbg, dW1, db1, dW2, db2, None, None, None, None, None, None
 
 
 def ep_forward(layer, moe_inp: torch.Tensor) -> torch.Tensor:
@@ -262,9 +281,13 @@ def ep_forward(layer, moe_inp: torch.Tensor) -> torch.Tensor:
         raise NotImplementedError(
             f"{type(gate).__name__} has no per-expert capacity: expert parallelism exchanges fixed-size slabs and needs a "
             "capacity-limited gate (SwitchGate / GShardGate)")
+    if not getattr(layer, "_ep_group_checked", False):
+        _check_group(layer)
+        layer._ep_group_checked = True
     W1, b1, W2, b2 = layer._expert_params()
+    fresh = torch.is_grad_enabled() and (W1.requires_grad or W2.requires_grad)
     y, aux, count, kept = EPMoEFunction.apply(moe_inp, gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec,
-                                              layer._bf16_cache, gate.make_noise(moe_inp), layer.moe_group, layer.world_size)
+                                              layer._bf16_cache, gate.make_noise(moe_inp), layer.moe_group, layer.world_size, fresh)
     gate.finish(aux)
     layer.last_count, layer.last_kept = count, kept
     return y

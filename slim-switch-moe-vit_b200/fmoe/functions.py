@@ -11,11 +11,7 @@ from dataclasses import dataclass
 
 import torch
 
-import os
-
 from . import _cabi as C
-
-_DB1_SEPARATE = bool(os.environ.get("MOE_DB1_SEPARATE"))   # experiment hook: db1 by a separate pass over dU
 
 
 @dataclass(frozen=True)
@@ -33,16 +29,27 @@ class RouteSpec:
 
 class Bf16WeightCache:
     """bf16 operand copies of the fp32 expert weights — W1b [E,h,d], W2b [E,d,h] and their per-expert
-    transposes W1tb [E,d,h], W2tb [E,h,d] (so that dgrad / dgelu read K-major operands too) — refreshed
-    only when a parameter changed (optimizer step, load_state_dict, .to()).  Keyed on (data_ptr, _version)."""
+    transposes W1tb [E,d,h], W2tb [E,h,d] (so that dgrad / dgelu read K-major operands too).
+
+    A training forward (`fresh=True`: autograd is recording and the weights require grad) ALWAYS re-casts: the
+    weights move once per optimizer step anyway, and neither `p.data.add_` (many timm / apex optimizers) nor a CUDA-graph
+    replay of the optimizer bumps `p._version`, so no host-side key can be trusted there.  Inference forwards
+    (`torch.no_grad()`, frozen weights) reuse the copies keyed on (data_ptr, _version); `invalidate()` drops them
+    (call it after writing weights through `.data` outside of training)."""
 
     def __init__(self):
         self._key = None
         self._val = None
+        self._graph_seen = False   # a CUDA graph that updates the weights may be replayed behind Python's back: never trust the key again
 
-    def get(self, W1: torch.Tensor, W2: torch.Tensor):
+    def invalidate(self):
+        self._key, self._val = None, None
+
+    def get(self, W1: torch.Tensor, W2: torch.Tensor, fresh: bool = False):
         key = (W1.data_ptr(), W1._version, W2.data_ptr(), W2._version, W1.device)
-        if key != self._key:
+        capturing = torch.cuda.is_current_stream_capturing()
+        self._graph_seen = self._graph_seen or capturing
+        if fresh or self._graph_seen or key != self._key:
             bf = torch.bfloat16
             E, h, d = W1.shape
             W1b, W2b = torch.empty((E, h, d), dtype=bf, device=W1.device), torch.empty((E, d, h), dtype=bf, device=W1.device)
@@ -50,6 +57,8 @@ class Bf16WeightCache:
             st = C.stream_ptr()
             C.call("moe_cast_bf16_transposed", C.ptr(W1.detach()), C.ptr(W1b), C.ptr(W1tb), E, h, d, st)
             C.call("moe_cast_bf16_transposed", C.ptr(W2.detach()), C.ptr(W2b), C.ptr(W2tb), E, d, h, st)
+            if capturing:
+                return W1b, W2b, W1tb, W2tb      # copies live in the graph's pool and are refreshed by every replay: not cached
             self._key, self._val = key, (W1b, W2b, W1tb, W2tb)
         return self._val
 
@@ -121,7 +130,8 @@ class MoEFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, Wg, bg, W1, b1, W2, b2, spec: RouteSpec, cache: Bf16WeightCache, noise, token_mask=None):
+    def forward(ctx, x, Wg, bg, W1, b1, W2, b2, spec: RouteSpec, cache: Bf16WeightCache, noise, token_mask=None,
+                fresh: bool = True):
         x = _as_kernel_input(x)
         T, d = x.shape
         E, h = W1.shape[0], W1.shape[1]
@@ -135,7 +145,7 @@ class MoEFunction(torch.autograd.Function):
         bg_c = None if bg is None else bg.detach().contiguous()
         r = route(x, Wg_c, bg_c, spec, noise, token_mask=token_mask)
         rows_cap = r["rows_cap"]
-        W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c)
+        W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c, fresh)
         G = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
         H = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
         Y = torch.empty((rows_cap, d), dtype=torch.bfloat16, device=dev)
@@ -195,7 +205,7 @@ class MoEFunction(torch.autograd.Function):
         # same kernel sequence as the bundled moe_expert_ffn_bwd entry point
         te, nm, sg = C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_start)
         # db1 = column sums of dU per expert: the dgelu epilogue leaves the sums of every 32-row slab behind
-        slab_sums = None if _DB1_SEPARATE else torch.empty(C.lib.moe_slab_colsum_bytes(rows_cap, h) // 4, dtype=torch.float32, device=dev)
+        slab_sums = torch.empty(C.lib.moe_slab_colsum_bytes(rows_cap, h) // 4, dtype=torch.float32, device=dev)
         C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), C.ptr(slab_sums), None, C.ptr(G),
                te, nm, None, rows_cap, E, 0, h, d, st, tag="gemm_dgelu")
         # dW2 = (H^T dY)^T: the wide dimension h is M (256-row tiles), the store is transposed
@@ -206,12 +216,9 @@ class MoEFunction(torch.autograd.Function):
                None, None, sg, rows_cap, E, h, d, 0, st, tag="gemm_wgrad1")
         C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1tb), C.ptr(dxbuf), None, None, None,
                te, nm, None, rows_cap, E, 0, d, h, st, tag="gemm_dgrad")
-        cws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, h), dtype=torch.uint8, device=dev)
+        cws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, d), dtype=torch.uint8, device=dev)
         C.call("moe_segment_colsum", C.ptr(dybuf), sg, rows_cap, E, d, C.ptr(cws), C.ptr(db2), st, tag="colsum_db2")
-        if slab_sums is None:
-            C.call("moe_segment_colsum", C.ptr(dU), sg, rows_cap, E, h, C.ptr(cws), C.ptr(db1), st, tag="colsum_db1")
-        else:
-            C.call("moe_slab_colsum_final", C.ptr(slab_sums), sg, E, h, C.ptr(db1), st, tag="colsum_db1")
+        C.call("moe_slab_colsum_final", C.ptr(slab_sums), sg, E, h, C.ptr(db1), st, tag="colsum_db1")
         # gate backward (dlogits) + un-permute of dX + dlogits Wg in one pass
         dlogits = _f32((T, E), dev)
         dx = torch.empty_like(x)
@@ -222,7 +229,7 @@ class MoEFunction(torch.autograd.Function):
         dbg = _f32(E, dev) if ctx.has_bg else None
         C.call("moe_gate_wgrad", C.ptr(dlogits), C.ptr(x), C.dtype_code(x), T, d, E, C.ptr(ws), C.ptr(dWg),
                C.ptr(dbg), st)
-        return dx, dWg, dbg, dW1, db1, dW2, db2, None, None, None, None
+        return dx, dWg, dbg, dW1, db1, dW2, db2, None, None, None, None, None
 
 
 class SkipFill(torch.autograd.Function):

@@ -40,10 +40,11 @@ class FMoE(nn.Module):
         self.slice_rank = 0
         self.top_k = top_k
         self.moe_group = moe_group
-        if isinstance(gate, type) and issubclass(gate, BaseGate):
-            self.gate = gate(d_model, num_expert, world_size, top_k)
-        else:
-            raise NotImplementedError("gate must be one of the fmoe.gates classes (NaiveGate, SwitchGate, GShardGate)")
+        # a gate CLASS as upstream, or any callable with the same (d_model, num_expert, world_size, top_k) signature
+        # (e.g. functools.partial(SwitchGate, capacity=(1.25, 1.25)), see fmoe.integration.make_gate)
+        self.gate = gate(d_model, num_expert, world_size, top_k) if callable(gate) else None
+        if not isinstance(self.gate, BaseGate):
+            raise NotImplementedError("gate must build one of the fmoe.gates classes (NaiveGate, SwitchGate, GShardGate)")
         if self.gate.top_k != top_k:
             raise ValueError(f"gate {type(self.gate).__name__} fixes top_k={self.gate.top_k}, layer was given top_k={top_k}")
         self.experts = None            # set by the subclass (FMoETransformerMLP)
@@ -57,6 +58,11 @@ class FMoE(nn.Module):
 
     def _expert_params(self):
         raise NotImplementedError
+
+    def invalidate_weight_cache(self):
+        """Drop the cached bf16 copies of the expert weights (only inference forwards reuse them; call this after
+        writing weights through `.data` or by any other route that does not bump the tensor version)."""
+        self._bf16_cache.invalidate()
 
     def forward(self, moe_inp: torch.Tensor, token_mask: torch.Tensor | None = None) -> torch.Tensor:
         """moe_inp [T, d_model] -> [T, d_model]; sets `self.gate`'s aux loss as a side effect.
@@ -83,8 +89,10 @@ class FMoE(nn.Module):
             if token_mask.numel() != T:
                 raise ValueError(f"token_mask has {token_mask.numel()} entries for {T} tokens")
             keep = (token_mask.reshape(T) != 0).to(torch.uint8)
+        # a forward that autograd records re-casts the bf16 weight copies (see Bf16WeightCache); inference reuses them
+        fresh = torch.is_grad_enabled() and (W1.requires_grad or W2.requires_grad)
         y, aux, count, kept = MoEFunction.apply(moe_inp, gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec,
-                                                self._bf16_cache, gate.make_noise(moe_inp), keep)
+                                                self._bf16_cache, gate.make_noise(moe_inp), keep, fresh)
         if keep is not None:
             c, J0 = zero_token_path(gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec.top_k, spec.score_mode)
             y = SkipFill.apply(y, moe_inp, keep, c, J0)

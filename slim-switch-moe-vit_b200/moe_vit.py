@@ -134,24 +134,9 @@ class Block(nn.Module):
 
 
 def _b200_moe_mlp(cfg: MoEViTConfig, dim: int, hidden: int) -> nn.Module:
-    import fmoe  # the B200 drop-in (fails loudly without libmoe_b200.so)
-
-    cf = cfg.capacity_factor
-
-    class _Switch(fmoe.SwitchGate):
-        def __init__(self, d_model, num_expert, world_size, top_k):
-            super().__init__(d_model, num_expert, world_size, topk=top_k, switch_eps=0.0, capacity=(cf, cf))
-
-    class _GShard(fmoe.GShardGate):
-        def __init__(self, d_model, num_expert, world_size, top_k):
-            super().__init__(d_model, num_expert, world_size, topk=top_k, capacity=(cf, cf))
-
-    gate = {"switch": _Switch, "naive": fmoe.NaiveGate, "gshard": _GShard}[cfg.gate]
-    act = nn.Sequential(nn.GELU(), nn.Dropout(p=0.0))      # reference models/resMoE.py:25
-    if cfg.num_experts % cfg.world_size:
-        raise ValueError("num_experts must be divisible by the expert-parallel world size")
-    return fmoe.FMoETransformerMLP(cfg.num_experts // cfg.world_size, dim, hidden, act, top_k=cfg.top_k, gate=gate,
-                                   world_size=cfg.world_size)
+    from fmoe.integration import build_moe_mlp  # the B200 drop-in (fails loudly without libmoe_b200.so)
+    return build_moe_mlp(dim, hidden, num_experts=cfg.num_experts, top_k=cfg.top_k, gate=cfg.gate,
+                         capacity_factor=cfg.capacity_factor, world_size=cfg.world_size)
 
 
 class MoEViT(nn.Module):

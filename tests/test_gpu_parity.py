@@ -629,20 +629,22 @@ def test_bundled_ffn_entry_points_equal_the_op_sequence(counts, d):
                     dW2=torch.zeros(E, d, h, device=dev), db2=torch.zeros(E, d, device=dev))
 
     a, b = buffers(), buffers()
-    ws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, h), dtype=torch.uint8, device=dev)
+    ws = torch.empty(C.lib.moe_expert_ffn_bwd_workspace_bytes(rows_cap, d, h, E), dtype=torch.uint8, device=dev)
     C.call("moe_expert_ffn_fwd", P(X), P(W1), P(b1), P(W2), P(b2), P(tile_e), P(nm), rows_cap, d, h, E, P(a["G"]), P(a["H"]), P(a["Y"]), st)
     C.call("moe_expert_ffn_bwd", P(dY), P(X), P(a["G"]), P(a["H"]), P(W1t), P(W2t), P(tile_e), P(nm), P(seg_t), rows_cap, d, h, E,
            P(a["dU"]), P(a["dX"]), P(a["dW1"]), P(a["db1"]), P(a["dW2"]), P(a["db2"]), P(ws), st)
     g = lambda op, *args: C.call("moe_grouped_gemm", op, *args)
     g(C.GEMM_FC1, P(X), P(W1), P(b["G"]), P(b["H"]), P(b1), None, P(tile_e), P(nm), None, rows_cap, E, 0, h, d, st)
     g(C.GEMM_FC2, P(b["H"]), P(W2), P(b["Y"]), None, P(b2), None, P(tile_e), P(nm), None, rows_cap, E, 0, d, h, st)
-    g(C.GEMM_DGELU, P(dY), P(W2t), P(b["dU"]), None, None, P(b["G"]), P(tile_e), P(nm), None, rows_cap, E, 0, h, d, st)
+    slab = torch.empty(C.lib.moe_slab_colsum_bytes(rows_cap, h) // 4, dtype=torch.float32, device=dev)
+    g(C.GEMM_DGELU, P(dY), P(W2t), P(b["dU"]), P(slab), None, P(b["G"]), P(tile_e), P(nm), None, rows_cap, E, 0, h, d, st)
     fl = C.wgrad_flags(E, h, d, dev)
     g(C.GEMM_WGRAD_T, P(b["H"]), P(dY), P(b["dW2"]), None, None, P(fl), None, None, P(seg_t), rows_cap, E, h, d, 0, st)
     g(C.GEMM_WGRAD, P(b["dU"]), P(X), P(b["dW1"]), None, None, P(fl), None, None, P(seg_t), rows_cap, E, h, d, 0, st)
     g(C.GEMM_DGRAD, P(b["dU"]), P(W1t), P(b["dX"]), None, None, None, P(tile_e), P(nm), None, rows_cap, E, 0, d, h, st)
-    C.call("moe_segment_colsum", P(dY), P(seg_t), rows_cap, E, d, P(ws), P(b["db2"]), st)
-    C.call("moe_segment_colsum", P(b["dU"]), P(seg_t), rows_cap, E, h, P(ws), P(b["db1"]), st)
+    ws2 = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, max(d, h)), dtype=torch.uint8, device=dev)
+    C.call("moe_segment_colsum", P(dY), P(seg_t), rows_cap, E, d, P(ws2), P(b["db2"]), st)
+    C.call("moe_slab_colsum_final", P(slab), P(seg_t), E, h, P(b["db1"]), st)
     torch.cuda.synchronize()
     for name in a:
         assert torch.equal(a[name], b[name]), name

@@ -152,3 +152,81 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "moe_oracle" not in text, f
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not mounted (GPU box)")
+def test_north_star_factories_register_and_build_on_the_reference_backbones():
+    """switch_moe_models.py: the four BASELINE configs as timm-registered factories over the reference's own dense
+    backbones (pattern of /root/reference/models/resMoE.py:190-209), selected exactly as main.py:520-530 does.
+    Tiny / Small are built for real; the MoE layers of Base / Large on the meta device (their expert weights are GBs)."""
+    code = r"""
+import sys
+sys.path[:0] = [%r, %r, '/root/reference']
+import torch, fmoe, models, switch_moe_models as Z
+from timm.models import create_model
+kw = dict(num_classes=10, drop_rate=0., drop_path_rate=0., drop_block_rate=None, img_size=224, starting_threshold=1., target_threshold=.9)
+want = {'switch_moe_tiny_patch16_224_e8_top1': (192, 12, 6, 8, 1, fmoe.SwitchGate),
+        'switch_moe_small_patch16_224_e16_top1': (384, 12, 6, 16, 1, fmoe.SwitchGate),
+        'gshard_moe_base_patch16_224_e32_top2': (768, 12, 6, 32, 2, fmoe.GShardGate),
+        'switch_moe_large_patch16_224_e64_top1': (1024, 24, 12, 64, 1, fmoe.SwitchGate)}
+import fmoe.integration as I
+_real = I.build_moe_mlp
+def _on_meta(dim, hidden, **k):      # Base / Large expert weights are GBs: build those layers on the meta device
+    with torch.device('meta' if dim >= 768 else 'cpu'):
+        return _real(dim, hidden, **k)
+I.build_moe_mlp = _on_meta
+for name, (d, depth, n_moe, E, k, gate_cls) in want.items():
+    big = d >= 768
+    m = create_model(name, **kw)
+    blocks = [b for b in m.modules() if type(b).__name__ == 'Block']
+    moe = [b.mlp for b in blocks if isinstance(b.mlp, fmoe.FMoETransformerMLP)]
+    assert len(blocks) == depth and len(moe) == n_moe, (name, len(blocks), len(moe))
+    assert [isinstance(b.mlp, fmoe.FMoETransformerMLP) for b in blocks[:4]] == [False, True, False, True]   # every other block
+    l = moe[0]
+    assert (l.d_model, l.d_hidden, l.num_expert, l.top_k, l.world_size) == (d, 4 * d, E, k, 1)
+    assert isinstance(l.gate, gate_cls) and l.gate.capacity == (1.25, 1.25) and l.gate.gate.out_features == E
+    assert not getattr(m, '_ddp_params_and_buffers_to_ignore', [])
+    # the optimizer grouping of main.py:619-631 keeps every MoE parameter in the base group
+    assert all('moe_gate' not in n and 'dense_gate' not in n for n, _ in m.named_parameters())
+    if not big:
+        import copy; copy.deepcopy(m)               # ModelEma (main.py:602-607)
+        crit = fmoe.MoEAuxCriterion(lambda s, o, t: o.sum() * 0, m, 0.01)
+        assert len(crit._layers) == n_moe
+print('OK')
+""" % (os.path.join(ROOT, "oracle", "stubs"), os.path.join(ROOT, "slim-switch-moe-vit_b200"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-3000:]
+
+
+def test_aux_criterion_and_load_balance_logging_host_logic():
+    """MoEAuxCriterion adds coef * sum(gate losses) and clears them; log_load_balance feeds a MetricLogger-like object
+    (reference utils.py:118-211) and a TensorboardXTracker-like writer (utils.py:299-319).  Pure host logic: the gate
+    losses / counts are planted by hand (no kernels run on CPU)."""
+    import fmoe
+    act = torch.nn.Sequential(torch.nn.GELU(), torch.nn.Dropout(p=0.0))
+    model = torch.nn.ModuleList([fmoe.FMoETransformerMLP(4, 64, 256, act, top_k=1, gate=fmoe.make_gate("switch", 1.25)) for _ in range(2)])
+    for i, l in enumerate(model):
+        l.gate.set_loss(torch.tensor(1.5 + i, requires_grad=True))
+        l.last_count = torch.tensor([10, 30, 0, 40], dtype=torch.int32)
+        l.last_kept = torch.tensor([10, 25, 0, 25], dtype=torch.int32)
+    crit = fmoe.MoEAuxCriterion(lambda s, o, t: o.sum(), model, coef=0.1)
+    out = torch.ones(3, requires_grad=True)
+    loss = crit(None, out, None)
+    assert abs(float(loss) - (3.0 + 0.1 * (1.5 + 2.5))) < 1e-6 and abs(float(crit.last_aux) - 4.0) < 1e-6
+    assert not any(l.gate.has_loss for l in model), "gate losses are consumed"
+    assert float(crit(None, out, None)) == 3.0          # nothing pending: plain criterion
+
+    class Logger:
+        def __init__(self): self.kw = {}
+        def update(self, **kw): self.kw.update(kw)
+
+    class Writer:
+        def __init__(self): self.rows = []
+        def log_scalar(self, name, value, step): self.rows.append((name, value, step))
+
+    lg, wr = Logger(), Writer()
+    scalars = fmoe.log_load_balance(model, lg, wr, step=7)
+    assert abs(scalars["moe_drop_rate"] - 0.25) < 1e-12 and abs(scalars["moe_max_load"] - 2.0) < 1e-12
+    assert lg.kw == scalars and len(wr.rows) == 4 and wr.rows[0] == ("moe/0/drop_rate", 0.25, 7)
+    st = fmoe.load_balance_stats(model)["1"]
+    assert st["routed_pairs"] == 80 and st["kept_pairs"] == 60 and st["count"] == [10, 30, 0, 40]
