@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — the driver's measurement contract for the B200 Switch-MoE layer and the MoE-ViT built on it.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c2|c3|c4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One JSON line on stdout (rank 0).  A *step* is one full training step (forward, loss + Switch aux
@@ -49,11 +49,29 @@ def emit(line: dict) -> None:
 import torch  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
-METRIC = "MoE-ViT training throughput (ViT-S/16 Switch-MoE E16 top-1 cf1.25, bf16, 224px, batch 256/GPU)"
 UNIT = "images/s"
-PER_GPU_BATCH = 256
 CPU_SAMPLE_BATCH = 8
 AUX_COEF = 0.01
+# BASELINE.json configs[1..3] (SURVEY.md §8 cfg table).  c2 is the default: the configuration the metric is quoted on
+# that fits one GPU; c3 / c4 are the expert-parallel configurations (run them under torchrun with --gpus 2/4/8).
+CONFIGS = {
+    "c1": dict(size="tiny", num_experts=8, top_k=1, gate="switch", batch=8,
+               metric="MoE-ViT training throughput (ViT-Ti/16 Switch-MoE E8 top-1 cf1.25, fp32, 224px, batch 8, CPU)"),
+    "c2": dict(size="small", num_experts=16, top_k=1, gate="switch", batch=256,
+               metric="MoE-ViT training throughput (ViT-S/16 Switch-MoE E16 top-1 cf1.25, bf16, 224px, batch 256/GPU)"),
+    "c3": dict(size="base", num_experts=32, top_k=2, gate="gshard", batch=128,
+               metric="MoE-ViT training throughput (ViT-B/16 GShard-MoE E32 top-2 cf1.25, bf16, 224px, batch 128/GPU, expert parallel)"),
+    "c4": dict(size="large", num_experts=64, top_k=1, gate="switch", batch=128,
+               metric="MoE-ViT training throughput (ViT-L/16 Switch-MoE E64 top-1 cf1.25, bf16, 224px, batch 128/GPU = 1024 on 8 GPUs, expert parallel)"),
+}
+CONFIG = "c2"       # set by --config
+METRIC = CONFIGS["c2"]["metric"]
+PER_GPU_BATCH = CONFIGS["c2"]["batch"]
+
+
+def select_config(name: str) -> None:
+    global CONFIG, METRIC, PER_GPU_BATCH
+    CONFIG, METRIC, PER_GPU_BATCH = name, CONFIGS[name]["metric"], CONFIGS[name]["batch"]
 
 
 def load_peaks():
@@ -112,10 +130,11 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # the workload
 # ------------------------------------------------------------------------------------------------
-def make_cfg(world_size: int):
+def make_cfg(world_size: int, name: str | None = None):
     from moe_vit import MoEViTConfig
-    return MoEViTConfig(size="small", num_experts=16, top_k=1, capacity_factor=1.25, moe_stride=2, gate="switch",
-                        num_classes=1000, world_size=world_size)
+    c = CONFIGS[name or CONFIG]
+    return MoEViTConfig(size=c["size"], num_experts=c["num_experts"], top_k=c["top_k"], capacity_factor=1.25, moe_stride=2,
+                        gate=c["gate"], num_classes=1000, world_size=world_size)
 
 
 def synthetic_batch(batch: int, seed: int, pin: bool):
@@ -148,18 +167,21 @@ def train_step(model, opt, img, lab, autocast_dtype, zero_grad=True):
 # ------------------------------------------------------------------------------------------------
 # CPU arm (reported baseline): same host model around the CPU restatement of the reference's layer
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps: int, warmup: int, budget_s: float | None):
+def cpu_reference_run(steps: int, warmup: int, budget_s: float | None, name: str | None = None):
     """Times `steps` training steps (after `warmup`) of the config on the host cores at batch
-    CPU_SAMPLE_BATCH, fp32.  With `budget_s` the step count is cut so the leg stays inside the budget."""
+    CPU_SAMPLE_BATCH, fp32.  With `budget_s` the step count is cut so the leg stays inside the budget.
+    All host cores are used (torchrun exports OMP_NUM_THREADS=1, which would leave this arm on one thread)."""
     from moe_vit import MoEViT
     from oracle import fmoe_cpu, moe_oracle as O
 
-    cfg = make_cfg(1)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    cfg = make_cfg(1, name)
     act = torch.nn.Sequential(torch.nn.GELU(), torch.nn.Dropout(p=0.0))
+    score_mode = O.SCORE_FULL_SOFTMAX if cfg.gate == "switch" else O.SCORE_TOPK_SOFTMAX
 
     def moe_mlp(dim, hidden):
         return fmoe_cpu.FMoETransformerMLP(cfg.num_experts, dim, hidden, act, top_k=cfg.top_k,
-                                           score_mode=O.SCORE_FULL_SOFTMAX, capacity_factor=cfg.capacity_factor)
+                                           score_mode=score_mode, capacity_factor=cfg.capacity_factor)
 
     torch.manual_seed(0)
     model = MoEViT(cfg, moe_mlp=moe_mlp)
@@ -187,7 +209,9 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, args.warmup, budget_s=150.0)
+    r = cpu_reference_run(args.steps, args.warmup, budget_s=120.0)
+    # BASELINE.md §3's CPU-runnable case (configs[0]: ViT-Ti/16, E = 8, top-1, MoE every other block, batch 8), reported beside it
+    r1 = cpu_reference_run(10, 3, budget_s=30.0, name="c1")
     cfg = make_cfg(1)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["images_per_s"], "unit": UNIT, "n_gpus": args.gpus,
@@ -198,6 +222,8 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": r["images_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["images_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "config1_cpu": {"value": r1["images_per_s"], "unit": UNIT, "ms_per_step": r1["ms_per_step"], "cores": r1["cores"],
+                        "moe_layer_tokens_per_s": r1["images_per_s"] * 197, "sample": r1["sample"]},
     }
     emit(line)
 
@@ -212,7 +238,7 @@ PHASE_BYTES = {
     "moe_combine_fwd": lambda T, d, h, E, k, R: R * d * 2 + R * 4 + T * d * 2,
     "moe_combine_bwd": lambda T, d, h, E, k, R: T * d * 2 + 2 * R * d * 2 + 2 * R * 4,
     "moe_gate_dispatch_bwd": lambda T, d, h, E, k, R: R * d * 2 + T * d * 2 + 2 * T * E * 4 + T * k * 12,
-    "colsum_db1": lambda T, d, h, E, k, R: R * h * 2,
+    "colsum_db1": lambda T, d, h, E, k, R: (R // 32 + E) * h * 4,   # reads the dgelu epilogue's slab sums, not dU
     "colsum_db2": lambda T, d, h, E, k, R: R * d * 2,
     "moe_gate_wgrad": lambda T, d, h, E, k, R: T * d * 2 + T * E * 4,
 }
@@ -223,18 +249,15 @@ GEMM_FLOPS = {
 }
 
 
-def layer_bench(peaks, iters=20, warmup=5, T=PER_GPU_BATCH * 197, d=384, E=16, k=1, cf=1.25):
+def layer_bench(peaks, iters=20, warmup=5, T=None, d=384, E=16, k=1, cf=1.25, gate="switch"):
     import fmoe
     from fmoe import _cabi as C
 
-    class Gate(fmoe.SwitchGate):
-        def __init__(self, d_model, num_expert, world_size, top_k):
-            super().__init__(d_model, num_expert, world_size, topk=top_k, switch_eps=0.0, capacity=(cf, cf))
-
+    T = PER_GPU_BATCH * 197 if T is None else T
     torch.manual_seed(0)
     h = 4 * d
     layer = fmoe.FMoETransformerMLP(E, d, h, torch.nn.Sequential(torch.nn.GELU(), torch.nn.Dropout(p=0.0)), top_k=k,
-                                    gate=Gate).cuda()
+                                    gate=fmoe.make_gate(gate, cf)).cuda()
     x = torch.randn(T, d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
     dy = torch.randn(T, d, device="cuda", dtype=torch.bfloat16)
 
@@ -297,7 +320,7 @@ def layer_bench(peaks, iters=20, warmup=5, T=PER_GPU_BATCH * 197, d=384, E=16, k
     gemm_ms = sum(v["ms"] for t, v in phases.items() if t in GEMM_FLOPS)
     flops = 12.0 * R * d * h
     return {
-        "shape": {"T": T, "d": d, "h": h, "E": E, "k": k, "capacity_factor": cf, "kept_pairs": R},
+        "shape": {"T": T, "d": d, "h": h, "E": E, "k": k, "gate": gate, "capacity_factor": cf, "kept_pairs": R},
         "tokens_per_s_fwd_bwd": T / (ms * 1e-3), "ms_fwd_bwd": round(ms, 4), "host_enqueue_ms_fwd_bwd_eager": round(host_ms, 4),
         "timing": "CUDA-graph replay of fwd+bwd (total); CUDA events per launch, eager (kernels)",
         "ffn_tflops_fwd_bwd": round(flops / (gemm_ms * 1e-3) / 1e12, 1),
@@ -305,6 +328,44 @@ def layer_bench(peaks, iters=20, warmup=5, T=PER_GPU_BATCH * 197, d=384, E=16, k
         "layer_tflops": round(flops / (ms * 1e-3) / 1e12, 1),
         "kernels": phases,
     }
+
+
+def routing_self_check(inner, B: int, rank: int, world: int):
+    """Bit-exactness of the routing integers on every rank at the benchmark's own shape (T = B * 197 tokens per rank):
+    expert indices, per-expert counts / kept counts, the rank of every pair inside its expert and the drop mask, against
+    oracle/gate_ref.c run on the same seeded shard with the first MoE layer's gate parameters."""
+    import torch.distributed as dist
+    from fmoe import functions as Fn
+    from fmoe.distributed import slab_rows_for
+    from oracle import moe_oracle as O
+
+    layer = inner.moe_layers[0]
+    T, d = B * 197, layer.d_model
+    g = torch.Generator().manual_seed(4242 + rank)
+    x = torch.randn(T, d, generator=g).to(torch.bfloat16)
+    Wg = layer.gate.gate.weight.detach().float().cpu()
+    bg = layer.gate.gate.bias.detach().float().cpu()
+    spec = layer.gate.route_spec(T)
+    slab = slab_rows_for(spec.capacity) if world > 1 else 0
+    r = Fn.route(x.cuda(), Wg.cuda(), bg.cuda(), spec, slab_rows=slab)
+    torch.cuda.synchronize()
+    logits = O.gate_logits(x, Wg, bg)
+    ref = O.route(logits, spec.top_k, spec.score_mode, spec.capacity)
+    idx, pos, seg = r["idx"].cpu(), r["pos"].cpu(), r["seg_start"].cpu()
+    live, live_ref = pos >= 0, ref.pos >= 0
+    ok = torch.equal(idx, ref.idx) and torch.equal(r["count"].cpu(), ref.count) and torch.equal(r["kept"].cpu(), ref.kept)
+    ok = ok and torch.equal(live, live_ref)
+    if ok:   # rank of every kept pair inside its expert (the packed and the slab layouts differ only in the segment starts)
+        e = idx[live].long()
+        ok = torch.equal(pos[live] - seg[e], ref.pos[live_ref] - ref.seg_start[e])
+    mine = torch.tensor([1.0 if ok else 0.0, float((~live).sum()), float((r["logits"].cpu() - logits).abs().max())],
+                        device="cuda", dtype=torch.float64)
+    rows = [mine.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(rows, mine)
+    return {"what": "idx / count / kept / rank-in-expert / drop mask of a seeded [T, d] bf16 shard per rank vs oracle/gate_ref.c",
+            "tokens_per_rank": T, "bit_exact": all(bool(t[0] == 1.0) for t in rows), "ranks_ok": [bool(t[0] == 1.0) for t in rows],
+            "dropped_pairs_per_rank": [int(t[1]) for t in rows], "logits_max_abs_err_per_rank": [float(t[2]) for t in rows]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -316,12 +377,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4"],
+                    help="BASELINE.json configs[1..3]; c2 (default) is the single-GPU configuration the metric is quoted on")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the per-rank routing self-check against the C oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-layer", action="store_true", help="skip the isolated-layer breakdown (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of replaying the captured training step")
     ap.add_argument("--profile-window", action="store_true",
                     help="cudaProfilerStart/Stop around the device-resident timed region (ncu --profile-from-start off)")
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)
@@ -390,6 +455,15 @@ def main():
     launches_per_step = C.PROF.launches // prof_steps
     kern = C.PROF.summary_ms()
     kept = [int(m.last_kept.sum()) for m in inner.moe_layers]
+    # load-balance statistics of the last step (what /root/reference/main.py:945-951 would log)
+    import fmoe
+    lb_full = fmoe.load_balance_stats(inner)
+    lb = {"drop_rate_mean": round(sum(v["drop_rate"] for v in lb_full.values()) / max(1, len(lb_full)), 5),
+          "max_over_mean_load": round(max(v["max_over_mean_load"] for v in lb_full.values()), 3),
+          "per_layer_drop_rate": {k_: round(v["drop_rate"], 5) for k_, v in lb_full.items()}}
+    # parity evidence that travels with the number: every rank routes a seeded token shard of the benchmark's shape through
+    # the CUDA gate / scan / dispatch and compares every routing integer with the C oracle (the checker, never the thing timed)
+    parity = None if args.no_parity_check else routing_self_check(inner, B, rank, world)
 
     # ---- the whole training step as ONE CUDA graph (single GPU): the layer never synchronises the host and all
     # its buffers are static functions of the shapes, so forward + backward + fused AdamW capture as they are.
@@ -521,7 +595,7 @@ def main():
         # (tools/gemm_traffic.py); the capture is of this shape only, so other configs report null
         roofline["algorithmic_bytes"] = round(sum(op_bytes.get(t_, 0.0) for t_ in gemm_tags) / max(1, len(gemm_tags)))
         tr_path = os.path.join(ROOT, "profiles", "gemm_dram_traffic.json")
-        if os.path.exists(tr_path) and d == 384 and cfg.num_experts == 16 and world == 1 and B == 256:
+        if os.path.exists(tr_path) and CONFIG == "c2" and world == 1:
             tr = json.load(open(tr_path))
             roofline["traffic"] = tr["mean_dram_bytes_per_launch"]
             roofline["traffic_per_op"] = {k_: v_["dram_bytes"] for k_, v_ in tr["per_op"].items()}
@@ -555,8 +629,12 @@ def main():
                 "calls_per_step": {t_: kern[t_][0] // prof_steps for t_ in sorted(ep_tags)},
                 "ms_per_step": round(sum(kern[t_][0] * kern[t_][1] for t_ in ep_tags) / prof_steps, 3),
                 "note": "NCCL all_to_all_single on fixed slabs [W, E_local, slab_rows, d] bf16; not overlapped with the expert GEMMs yet"}
+        line["config"]["name"] = CONFIG
+        line["load_balance"] = lb
+        if parity is not None:
+            line["parity_check"] = parity
         if not args.no_layer:
-            line["moe_layer"] = layer_bench(peaks)
+            line["moe_layer"] = layer_bench(peaks, d=d, E=cfg.num_experts, k=cfg.top_k, gate=cfg.gate)
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(steps=1000, warmup=1, budget_s=20.0)
             line["cpu_baseline"] = {"value": r["images_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",

@@ -60,9 +60,17 @@ int moe_version(void);
 int64_t moe_rows_cap(int64_t T, int k, int E, int64_t capacity);
 
 /* ---- gate: replaces NaiveGate's nn.Linear + torch.topk + F.softmax and fmoe_cuda.expert_count.
- * logits[T,E] fp32 (LOGIT ORDER v1, bit-identical to oracle/gate_ref.c), idx[T,k] i32,
- * score[T,k] fp32, tile_hist[E,ntiles] i32, tile_psum[E,ntiles] fp32 (only if want_psum);
- * ntiles = ceil(T / MOE_TOKEN_TILE).
+ * logits[T,E] fp32, idx[T,k] i32, score[T,k] fp32, tile_hist[E,ntiles] i32, tile_psum[E,ntiles] fp32 (only if
+ * want_psum); ntiles = ceil(T / MOE_TOKEN_TILE).
+ * Two arithmetic paths, both with routing integers (idx and everything derived from it) bit-identical to
+ * oracle/gate_ref.c:
+ *   workspace == NULL (or fp32 activations, or E > 64): fp32 FMA chains on the CUDA cores in LOGIT ORDER v1 — the
+ *     logits themselves are bit-identical to the oracle's;
+ *   workspace != NULL (moe_gate_fwd_workspace_bytes(d, E) bytes), bf16 activations, E <= 64: the projection runs on
+ *     the tensor cores (mma.sync, Wg split into two bf16 planes); a token whose top-(k+1) logits are further apart
+ *     than a rigorous bound on the difference to the oracle's logits keeps the tensor-core logits (certified: the
+ *     oracle cannot route it differently), every other token is recomputed in LOGIT ORDER v1.  Emitted logits are
+ *     within kappa(d) * ||x_t|| * max_e ||Wg_e|| of the oracle's (kappa(384) = 1.6e-5), exact for recomputed tokens.
  * token_mask (nullable, uint8 [T]): the token-skip mask of the residual-MoE block
  * (/root/reference/models/resMoE.py:126-145, `tk = x * mask[:, :, 1]`).  A token with mask 0 is not routed at
  * all: idx = -1 and score = 0 in every slot, no histogram entry (it takes no capacity), no share in psum; every
@@ -71,7 +79,8 @@ int moe_gate_fwd(const void *x, int x_dtype, const float *Wg, const float *bg /*
                  const float *noise /* nullable [T,E], added to the logits (SwitchGate jitter) */,
                  const uint8_t *token_mask /* nullable [T] */, int64_t T, int d, int E,
                  int k, int score_mode, int want_psum, float *logits, int32_t *idx, float *score, int32_t *tile_hist,
-                 float *tile_psum, void *stream);
+                 float *tile_psum, void *workspace /* nullable, see above */, void *stream);
+size_t moe_gate_fwd_workspace_bytes(int d, int E);
 
 /* ---- scan: replaces torch.cumsum + .item() + limit_by_capacity (no host sync).
  * tile_base[E,ntiles], count[E], kept[E] = min(count, capacity), seg_start[E+1],

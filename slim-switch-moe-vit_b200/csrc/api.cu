@@ -60,12 +60,19 @@ int64_t moe_rows_cap(int64_t T, int k, int E, int64_t capacity) {
     return (pairs + MOE_ROW_ALIGN - 1) / MOE_ROW_ALIGN * MOE_ROW_ALIGN + static_cast<int64_t>(MOE_ROW_ALIGN) * E;
 }
 
+size_t moe_gate_fwd_workspace_bytes(int d, int E) { return gate_fwd_workspace_bytes(d, E); }
+
 int moe_gate_fwd(const void* x, int x_dtype, const float* Wg, const float* bg, const float* noise, const uint8_t* token_mask, int64_t T, int d, int E, int k,
                  int score_mode, int want_psum, float* logits, int32_t* idx, float* score, int32_t* tile_hist,
-                 float* tile_psum, void* stream) {
+                 float* tile_psum, void* workspace, void* stream) {
     if (!dims_ok("moe_gate_fwd", T, d, E, k) || !dtype_ok("moe_gate_fwd", x_dtype)) return 1;
     if (score_mode != MOE_SCORE_TOPK_SOFTMAX && score_mode != MOE_SCORE_FULL_SOFTMAX) { set_error("moe_gate_fwd: bad score_mode %d", score_mode); return 1; }
     if (want_psum && tile_psum == nullptr) { set_error("moe_gate_fwd: want_psum needs tile_psum"); return 1; }
+    // tensor-core path (certified routing) when the caller provides its workspace and the shape allows it; otherwise the
+    // CUDA-core kernel, whose logits are bit-identical to the oracle's (LOGIT ORDER v1)
+    if (workspace != nullptr && gate_mma_supported(x_dtype, d, E))
+        return launch_gate_fwd_mma(x, Wg, bg, noise, token_mask, T, d, E, k, score_mode, want_psum, logits, idx, score, tile_hist,
+                                   tile_psum, workspace, static_cast<cudaStream_t>(stream));
     return check(launch_gate_fwd(x, x_dtype, Wg, bg, noise, token_mask, T, d, E, k, score_mode, want_psum, logits, idx, score, tile_hist,
                                  tile_psum, static_cast<cudaStream_t>(stream)),
                  "moe_gate_fwd");

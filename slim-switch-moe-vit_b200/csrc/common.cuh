@@ -1,5 +1,6 @@
 // common.cuh — declarations shared by the translation units of libmoe_b200.so
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -57,6 +58,16 @@ cudaError_t launch_addln_bwd(const void* dn, int n_dtype, const float* dx_out, c
 
 size_t colsum_workspace_bytes(int64_t rows, int cols);
 cudaError_t launch_colsum(const void* buf, int dtype, int64_t rows, int cols, void* workspace, float* out, cudaStream_t st);
+
+// gate_mma.cu — tensor-core gate with certified routing (bf16 activations, E <= 64); returns 0 on success
+bool gate_mma_supported(int x_dtype, int d, int E);
+size_t gate_fwd_workspace_bytes(int d, int E);
+int launch_gate_fwd_mma(const void* x, const float* Wg, const float* bg, const float* noise, const uint8_t* token_mask,
+                        int64_t T, int d, int E, int k, int score_mode, int want_psum, float* logits, int* idx, float* score,
+                        int* tile_hist, float* tile_psum, void* workspace, cudaStream_t st);
+
+// gemm_launch.cu — TMA descriptor of a [outer, inner] bf16 row-major tensor, 128-byte swizzle (false + set_error on failure)
+bool encode_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer);
 
 // gemm_launch.cu — returns 0 on success, otherwise sets the error string via set_error()
 int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* out1, const float* bias, const void* aux,

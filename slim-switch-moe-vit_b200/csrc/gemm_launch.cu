@@ -58,6 +58,15 @@ bool encode_3d_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, u
     return true;
 }
 
+}  // namespace
+
+// shared with the other translation units (gate_mma.cu): [outer, inner] bf16 row-major, 128-byte swizzle
+bool encode_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+    return encode_2d(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, inner, outer, box_inner, box_outer);
+}
+
+namespace {
+
 template <int BN, int EPI, bool WGRAD>
 int launch_one(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tO0, const CUtensorMap& tO1,
                const CUtensorMap& tAux, const GemmParams& p, int grid, cudaStream_t st) {

@@ -74,6 +74,18 @@ def _as_kernel_input(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+# Gate arithmetic: False (default) = tensor-core projection with certified routing wherever the kernel supports it (bf16
+# activations, E <= 64); True = always the CUDA-core kernel whose logits are bit-identical to the CPU oracle's (LOGIT
+# ORDER v1).  The routing integers are bit-identical to the oracle's either way.
+GATE_EXACT_LOGITS = False
+
+
+def _gate_workspace(x, E):
+    if GATE_EXACT_LOGITS or x.dtype != torch.bfloat16 or E > 64:
+        return None
+    return torch.empty(int(C.lib.moe_gate_fwd_workspace_bytes(x.shape[1], E)), dtype=torch.uint8, device=x.device)
+
+
 def _i32(n, dev):
     return torch.empty(n, dtype=torch.int32, device=dev)
 
@@ -107,9 +119,10 @@ def route(x, Wg, bg, spec: RouteSpec, noise=None, slab_rows: int = 0, token_mask
     r["psum"] = _f32(E, dev) if spec.want_psum else None
     r["aux_loss"] = _f32(1, dev) if spec.want_psum else None
     r["aux_coef"] = _f32(E, dev) if spec.want_psum else None
+    gws = _gate_workspace(x, E)
     C.call("moe_gate_fwd", C.ptr(x), C.dtype_code(x), C.ptr(Wg), C.ptr(bg), C.ptr(noise), C.ptr(token_mask), T, d, E, k,
            spec.score_mode, int(spec.want_psum), C.ptr(r["logits"]), C.ptr(r["idx"]), C.ptr(r["score"]),
-           C.ptr(r["tile_hist"]), C.ptr(tile_psum), st)
+           C.ptr(r["tile_hist"]), C.ptr(tile_psum), C.ptr(gws), st)
     C.call("moe_route_scan", C.ptr(r["tile_hist"]), C.ptr(tile_psum), ntiles, E, spec.capacity,
            C.ptr(r["tile_base"]), C.ptr(r["count"]), C.ptr(r["kept"]), C.ptr(r["seg_start"]),
            C.ptr(r["tile_expert"]), C.ptr(r["num_mtiles"]), max_mtiles, C.ptr(r["psum"]), int(spec.aux_mode), T, k,
@@ -302,9 +315,10 @@ class GateFunction(torch.autograd.Function):
         tile_psum = _f32((E, ntiles), dev) if spec.want_psum else None
         Wg_c = Wg.detach().contiguous()
         bg_c = None if bg is None else bg.detach().contiguous()
+        gws = _gate_workspace(x, E)
         C.call("moe_gate_fwd", C.ptr(x), C.dtype_code(x), C.ptr(Wg_c), C.ptr(bg_c), C.ptr(noise), None, T, d, E,
                spec.top_k, spec.score_mode, int(spec.want_psum), C.ptr(logits), C.ptr(idx), C.ptr(score),
-               C.ptr(tile_hist), C.ptr(tile_psum), st)
+               C.ptr(tile_hist), C.ptr(tile_psum), C.ptr(gws), st)
         ctx.spec, ctx.has_bg = spec, bg is not None
         ctx.save_for_backward(x, Wg_c, logits, idx, score)
         idx64 = idx.long()

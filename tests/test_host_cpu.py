@@ -64,7 +64,7 @@ def test_argument_validation_without_gpu():
     with pytest.raises(C.MoeB200Error, match="multiple of 8"):
         C.call("moe_cast_bf16", None, None, 12, None)
     with pytest.raises(C.MoeB200Error, match="unsupported shape"):
-        C.call("moe_gate_fwd", None, 0, None, None, None, None, 10, 100, 4, 1, 0, 0, None, None, None, None, None, None)
+        C.call("moe_gate_fwd", None, 0, None, None, None, None, 10, 100, 4, 1, 0, 0, None, None, None, None, None, None, None)
     with pytest.raises(C.MoeB200Error, match="multiple of 64"):
         C.call("moe_grouped_gemm", C.GEMM_FC2, None, None, None, None, None, None, None, None, None, 256, 2, 0, 100, 64, None)
 
