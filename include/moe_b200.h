@@ -109,6 +109,49 @@ int moe_ep_tables(const int32_t *kept_recv, int W, int E_local, int32_t *slab_ds
 int moe_ep_repack(const void *src, void *dst, const int32_t *kept_recv, const int32_t *slab_dst, const int32_t *seg_start,
                   const int32_t *kept_local, int W, int E_local, int64_t slab_rows, int d, int to_packed, void *stream);
 
+/* ---- expert parallelism over NVLink / NVSwitch peer memory: replaces fmoe_cuda.expert_exchange + global_scatter /
+ * global_gather (NCCL grouped send/recv around a host round trip for the counts) AND the NCCL all_to_all_single +
+ * moe_ep_repack path above.  One process per GPU, all ranks of the expert-parallel group on one NVLink domain (W <= 8).
+ * Every rank allocates one symmetric heap (moe_ep_heap_alloc: cudaMalloc, zero-filled, + a 64-byte CUDA IPC handle that
+ * the host exchanges by any means, e.g. torch.distributed.all_gather_object), opens its peers' heaps
+ * (moe_ep_heap_open) and carves the same regions out of each: flags int32[W], kept_all int32[W][E], and the packed row
+ * buffers xbuf / ybuf / dybuf / dxbuf [rows_per_rank, d] bf16 of its LOCAL experts.  `void *const *x_peers` arguments
+ * are HOST arrays of W device pointers, entry r = that region in rank r's heap (entry `rank` = the local one).
+ * "Global rows": row index g = owner_rank * rows_per_rank + row inside the owner's buffer; `pos` holds global rows.
+ *   moe_ep_exchange_counts  writes this rank's kept[E] (moe_route_scan) into every rank's kept_all, meets the other ranks
+ *                           (device-side barrier through `flags`, epoch counter in `epoch`, both graph-replay safe), and
+ *                           lays out the packed buffers: dst_row[E] = global row of this rank's first pair of each expert
+ *                           (inside an expert segment the sources follow each other in rank order), and for the local
+ *                           experts kept_local[E_local], seg_start[E_local + 1], tile_expert[max_mtiles], num_mtiles[1]
+ *                           exactly as moe_route_scan produces them on one GPU.
+ *   moe_dispatch_fwd_peer   moe_dispatch_fwd with the kept rows written straight into the owners' packed segments
+ *                           (seg_start := dst_row); zeroes the pad rows of the local xbuf.
+ *   moe_ep_barrier          all ranks' previous writes to this rank's heap are complete and visible afterwards.
+ *   moe_combine_fwd_peer / moe_combine_bwd_peer / moe_gate_dispatch_bwd_peer   the single-GPU kernels reading Y / dX rows
+ *                           from, and writing dY rows to, the owners' buffers in place.
+ * status[1] (device int32, caller-zeroed): set to 1 if a barrier spin exceeded its bound (a rank is missing), 2 if a
+ * packed layout does not fit rows_per_rank; never hangs the GPU. */
+#define MOE_IPC_HANDLE_BYTES 64
+int moe_ep_heap_alloc(size_t bytes, void **ptr, void *handle_out /* host, MOE_IPC_HANDLE_BYTES */);
+int moe_ep_heap_open(const void *handle /* host, MOE_IPC_HANDLE_BYTES */, void **ptr);
+int moe_ep_heap_close(void *ptr);
+int moe_ep_heap_free(void *ptr);
+int moe_ep_barrier(void *const *flags, int32_t *epoch, int rank, int W, int32_t *status, void *stream);
+int moe_ep_exchange_counts(const int32_t *kept, void *const *kept_all, void *const *flags, int32_t *epoch, int rank, int W,
+                           int E_local, int64_t rows_per_rank, int32_t *dst_row, int32_t *kept_local, int32_t *seg_start,
+                           int32_t *tile_expert, int32_t *num_mtiles, int max_mtiles, int32_t *status, void *stream);
+int moe_dispatch_fwd_peer(const void *x, int x_dtype, const int32_t *idx, const int32_t *tile_base, const int32_t *dst_row, int64_t T,
+                          int d, int E, int k, int64_t capacity, void *const *xbuf_peers, int rank, int W, int64_t rows_per_rank,
+                          const int32_t *seg_start_local, const int32_t *kept_local, int32_t *pos, void *stream);
+int moe_combine_fwd_peer(void *const *ybuf_peers, int rank, int W, int64_t rows_per_rank, const int32_t *pos, const float *score,
+                         int64_t T, int d, int k, void *out, int out_dtype, void *stream);
+int moe_combine_bwd_peer(const void *dy, int dy_dtype, void *const *ybuf_peers, void *const *dybuf_peers, int rank, int W,
+                         int64_t rows_per_rank, const int32_t *pos, const float *score, const int32_t *seg_start_local,
+                         const int32_t *kept_local, int E_local, int64_t T, int d, int k, float *dscore, void *stream);
+int moe_gate_dispatch_bwd_peer(void *const *dxbuf_peers, int rank, int W, int64_t rows_per_rank, const int32_t *pos, const float *logits,
+                               const int32_t *idx, const float *score, const float *dscore, const float *dpsum, const float *Wg,
+                               int64_t T, int d, int E, int k, int score_mode, float *dlogits, void *dx, int dx_dtype, void *stream);
+
 /* ---- dispatch: replaces fmoe_cuda.assign_pos + MOEScatter (deterministic, token order).
  * pos[T,k] row of each (token,slot) or -1 if dropped; row_src[rows_cap] flattened pair index of
  * each row (-1 on padding); xbuf[rows_cap,d] bf16 with padding rows zeroed. */

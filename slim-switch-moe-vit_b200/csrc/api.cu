@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -99,6 +100,113 @@ int moe_route_scan(const int32_t* tile_hist, const float* tile_psum, int ntiles,
                                    tile_expert, num_mtiles, max_mtiles, psum, aux_mode, T, k, aux_loss, aux_coef, slab_rows,
                                    static_cast<cudaStream_t>(stream)),
                  "moe_route_scan");
+}
+
+// ---- expert parallelism over peer memory (csrc/ep_peer.cu)
+static bool peers_ok(const char* fn, void* const* ptrs, int W, int rank, PeerRows* out, int rows_per_rank) {
+    if (W < 1 || W > kMaxPeers || rank < 0 || rank >= W || ptrs == nullptr) {
+        set_error("%s: expert-parallel group of %d ranks (rank %d): 1..%d ranks of one NVLink domain are supported", fn, W, rank, kMaxPeers);
+        return false;
+    }
+    *out = PeerRows{};
+    for (int i = 0; i < W; ++i) {
+        if (ptrs[i] == nullptr) { set_error("%s: peer pointer %d is NULL", fn, i); return false; }
+        out->base[i] = ptrs[i];
+    }
+    out->rows_per_rank = rows_per_rank;
+    out->n = W;
+    return true;
+}
+
+int moe_ep_heap_alloc(size_t bytes, void** ptr, void* handle_out) {
+    if (bytes == 0 || ptr == nullptr || handle_out == nullptr) { set_error("moe_ep_heap_alloc: bad arguments"); return 1; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == MOE_IPC_HANDLE_BYTES, "IPC handle size");
+    if (check(cudaMalloc(ptr, bytes), "moe_ep_heap_alloc: cudaMalloc")) return 1;
+    if (check(cudaMemset(*ptr, 0, bytes), "moe_ep_heap_alloc: cudaMemset") ||
+        check(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle_out), *ptr), "moe_ep_heap_alloc: cudaIpcGetMemHandle") ||
+        check(cudaDeviceSynchronize(), "moe_ep_heap_alloc: sync")) {
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        return 1;
+    }
+    return 0;
+}
+int moe_ep_heap_open(const void* handle, void** ptr) {
+    if (handle == nullptr || ptr == nullptr) { set_error("moe_ep_heap_open: bad arguments"); return 1; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    return check(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess), "moe_ep_heap_open: cudaIpcOpenMemHandle");
+}
+int moe_ep_heap_close(void* ptr) { return check(cudaIpcCloseMemHandle(ptr), "moe_ep_heap_close"); }
+int moe_ep_heap_free(void* ptr) { return check(cudaFree(ptr), "moe_ep_heap_free"); }
+
+int moe_ep_barrier(void* const* flags, int32_t* epoch, int rank, int W, int32_t* status, void* stream) {
+    PeerRows fl;
+    if (!peers_ok("moe_ep_barrier", flags, W, rank, &fl, 0)) return 1;
+    return check(launch_ep_barrier(fl, epoch, rank, W, status, static_cast<cudaStream_t>(stream)), "moe_ep_barrier");
+}
+
+int moe_ep_exchange_counts(const int32_t* kept, void* const* kept_all, void* const* flags, int32_t* epoch, int rank, int W,
+                           int E_local, int64_t rows_per_rank, int32_t* dst_row, int32_t* kept_local, int32_t* seg_start,
+                           int32_t* tile_expert, int32_t* num_mtiles, int max_mtiles, int32_t* status, void* stream) {
+    PeerRows ka, fl;
+    if (!peers_ok("moe_ep_exchange_counts", kept_all, W, rank, &ka, 0) || !peers_ok("moe_ep_exchange_counts", flags, W, rank, &fl, 0)) return 1;
+    if (E_local < 1 || W * E_local > 1024 || rows_per_rank <= 0 || rows_per_rank % MOE_ROW_ALIGN != 0 ||
+        rows_per_rank * W > 0x7fffffffLL || max_mtiles < 1) {
+        set_error("moe_ep_exchange_counts: bad arguments E_local=%d rows_per_rank=%lld", E_local, (long long)rows_per_rank);
+        return 1;
+    }
+    return check(launch_ep_exchange_counts(kept, ka, fl, epoch, rank, W, E_local, static_cast<int>(rows_per_rank), dst_row, kept_local,
+                                           seg_start, tile_expert, num_mtiles, max_mtiles, status, static_cast<cudaStream_t>(stream)),
+                 "moe_ep_exchange_counts");
+}
+
+int moe_dispatch_fwd_peer(const void* x, int x_dtype, const int32_t* idx, const int32_t* tile_base, const int32_t* dst_row, int64_t T,
+                          int d, int E, int k, int64_t capacity, void* const* xbuf_peers, int rank, int W, int64_t rows_per_rank,
+                          const int32_t* seg_start_local, const int32_t* kept_local, int32_t* pos, void* stream) {
+    PeerRows xr;
+    if (!dims_ok("moe_dispatch_fwd_peer", T, d, E, k) || !dtype_ok("moe_dispatch_fwd_peer", x_dtype) ||
+        !peers_ok("moe_dispatch_fwd_peer", xbuf_peers, W, rank, &xr, static_cast<int>(rows_per_rank))) return 1;
+    if (E % W != 0) { set_error("moe_dispatch_fwd_peer: E=%d is not a multiple of the group size %d", E, W); return 1; }
+    return check(launch_dispatch_fwd_rows(x, x_dtype, idx, tile_base, dst_row, T, d, E, k, capacity, pos, nullptr, xr, xbuf_peers[rank],
+                                          seg_start_local, kept_local, E / W, static_cast<cudaStream_t>(stream)),
+                 "moe_dispatch_fwd_peer");
+}
+
+int moe_combine_fwd_peer(void* const* ybuf_peers, int rank, int W, int64_t rows_per_rank, const int32_t* pos, const float* score,
+                         int64_t T, int d, int k, void* out, int out_dtype, void* stream) {
+    PeerRows yr;
+    if (!dims_ok("moe_combine_fwd_peer", T, d, k, k) || !dtype_ok("moe_combine_fwd_peer", out_dtype) ||
+        !peers_ok("moe_combine_fwd_peer", ybuf_peers, W, rank, &yr, static_cast<int>(rows_per_rank))) return 1;
+    return check(launch_combine_fwd_rows(yr, pos, score, T, d, k, out, out_dtype, sm_count(), static_cast<cudaStream_t>(stream)),
+                 "moe_combine_fwd_peer");
+}
+
+int moe_combine_bwd_peer(const void* dy, int dy_dtype, void* const* ybuf_peers, void* const* dybuf_peers, int rank, int W,
+                         int64_t rows_per_rank, const int32_t* pos, const float* score, const int32_t* seg_start_local,
+                         const int32_t* kept_local, int E_local, int64_t T, int d, int k, float* dscore, void* stream) {
+    PeerRows yr, dr;
+    if (!dims_ok("moe_combine_bwd_peer", T, d, k, k) || !dtype_ok("moe_combine_bwd_peer", dy_dtype) ||
+        !peers_ok("moe_combine_bwd_peer", ybuf_peers, W, rank, &yr, static_cast<int>(rows_per_rank)) ||
+        !peers_ok("moe_combine_bwd_peer", dybuf_peers, W, rank, &dr, static_cast<int>(rows_per_rank))) return 1;
+    return check(launch_combine_bwd_rows(dy, dy_dtype, yr, pos, score, seg_start_local, kept_local, E_local, T, d, k, dr, dybuf_peers[rank],
+                                         dscore, static_cast<cudaStream_t>(stream)),
+                 "moe_combine_bwd_peer");
+}
+
+int moe_gate_dispatch_bwd_peer(void* const* dxbuf_peers, int rank, int W, int64_t rows_per_rank, const int32_t* pos, const float* logits,
+                               const int32_t* idx, const float* score, const float* dscore, const float* dpsum, const float* Wg,
+                               int64_t T, int d, int E, int k, int score_mode, float* dlogits, void* dx, int dx_dtype, void* stream) {
+    PeerRows xr;
+    if (!dims_ok("moe_gate_dispatch_bwd_peer", T, d, E, k) || !dtype_ok("moe_gate_dispatch_bwd_peer", dx_dtype) ||
+        !peers_ok("moe_gate_dispatch_bwd_peer", dxbuf_peers, W, rank, &xr, static_cast<int>(rows_per_rank))) return 1;
+    if (!gate_dispatch_bwd_mma_supported(d, E, k)) {
+        set_error("moe_gate_dispatch_bwd_peer: shape d=%d E=%d k=%d is outside the peer-memory kernel (E <= 64, staged rows must fit shared memory)", d, E, k);
+        return 1;
+    }
+    return check(launch_gate_dispatch_bwd_mma(xr, pos, logits, idx, score, dscore, dpsum, Wg, T, d, E, k, score_mode, dlogits, dx, dx_dtype,
+                                              static_cast<cudaStream_t>(stream)),
+                 "moe_gate_dispatch_bwd_peer");
 }
 
 int moe_ep_tables(const int32_t* kept_recv, int W, int E_local, int32_t* slab_dst, int32_t* kept_local, int32_t* seg_start,

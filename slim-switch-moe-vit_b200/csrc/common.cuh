@@ -9,6 +9,35 @@
 
 namespace moe {
 
+// A packed row buffer addressed through `pos` / row indices that may be spread over the GPUs of an expert-parallel
+// group (NVLink peer memory, csrc/ep_peer.cu): global row r is row r % rows_per_rank of rank r / rows_per_rank.
+// A local buffer is the n == 1 case (base[0], rows_per_rank = INT_MAX).  base[0] == nullptr: no buffer.
+constexpr int kMaxPeers = 8;
+struct PeerRows {
+    void* base[kMaxPeers];
+    int rows_per_rank;
+    int n;
+};
+inline PeerRows local_rows(const void* p) {
+    PeerRows r{};
+    r.base[0] = const_cast<void*>(p);
+    r.rows_per_rank = 0x7fffffff;
+    r.n = 1;
+    return r;
+}
+#ifdef __CUDACC__
+template <typename T>
+__device__ __forceinline__ T* peer_row(const PeerRows& pr, int row, int d) {
+    if (pr.n == 1) return static_cast<T*>(pr.base[0]) + static_cast<size_t>(row) * d;
+    const int rk = row / pr.rows_per_rank;
+    void* b = pr.base[0];   // select chain: a dynamic index would make the compiler copy the parameter struct to local memory
+#pragma unroll
+    for (int i = 1; i < kMaxPeers; ++i)
+        if (rk == i) b = pr.base[i];
+    return static_cast<T*>(b) + static_cast<size_t>(row - rk * pr.rows_per_rank) * d;
+}
+#endif
+
 // routing.cu
 cudaError_t launch_gate_fwd(const void* x, int x_dtype, const float* Wg, const float* bg, const float* noise, const uint8_t* token_mask, int64_t T, int d, int E, int k,
                             int score_mode, int want_psum, float* logits, int* idx, float* score, int* tile_hist,
@@ -47,6 +76,31 @@ cudaError_t launch_segment_colsum(const void* buf, const int* seg_start, int64_t
 cudaError_t launch_gate_dispatch_bwd(const void* dxbuf, const int* pos, const float* logits, const int* idx, const float* score,
                                      const float* dscore, const float* dpsum, const float* Wg, int64_t T, int d, int E, int k,
                                      int score_mode, float* dlogits, void* dx, int dx_dtype, cudaStream_t st);
+
+// the same three with the packed rows addressed through PeerRows (expert parallelism over peer memory); pad rows are
+// zeroed in the LOCAL buffer (xpad / dypad) for the n_pad segments of pad_seg / pad_kept
+cudaError_t launch_dispatch_fwd_rows(const void* x, int x_dtype, const int* idx, const int* tile_base, const int* seg_start,
+                                     int64_t T, int d, int E, int k, long long capacity, int* pos, int* row_src,
+                                     const PeerRows& xrows, void* xpad, const int* pad_seg, const int* pad_kept, int n_pad,
+                                     cudaStream_t st);
+cudaError_t launch_combine_fwd_rows(const PeerRows& yrows, const int* pos, const float* score, int64_t T, int d, int k, void* out,
+                                    int out_dtype, int sm_count, cudaStream_t st);
+cudaError_t launch_combine_bwd_rows(const void* dy, int dy_dtype, const PeerRows& yrows, const int* pos, const float* score,
+                                    const int* pad_seg, const int* pad_kept, int n_pad, int64_t T, int d, int k,
+                                    const PeerRows& dyrows, void* dypad, float* dscore, cudaStream_t st);
+
+// ep_peer.cu — expert parallelism over NVLink peer memory: counts exchange + packed layout, device barrier
+cudaError_t launch_ep_exchange_counts(const int* kept, const PeerRows& kept_all, const PeerRows& flags, int* epoch, int rank, int W,
+                                      int El, int rows_per_rank, int* dst_row, int* kept_local, int* seg_start, int* tile_expert,
+                                      int* num_mtiles, int max_mtiles, int* status, cudaStream_t st);
+cudaError_t launch_ep_barrier(const PeerRows& flags, int* epoch, int rank, int W, int* status, cudaStream_t st);
+
+// gate_bwd_mma.cu — the same pass with dlogits Wg on the tensor cores (tf32 mma.sync); dXbuf rows may live on peer GPUs
+bool gate_dispatch_bwd_mma_supported(int d, int E, int k);
+cudaError_t launch_gate_dispatch_bwd_mma(const PeerRows& rows, const int* pos, const float* logits, const int* idx,
+                                         const float* score, const float* dscore, const float* dpsum, const float* Wg, int64_t T,
+                                         int d, int E, int k, int score_mode, float* dlogits, void* dx, int dx_dtype,
+                                         cudaStream_t st);
 
 // block_fusion.cu
 size_t addln_bwd_workspace_bytes(int64_t T, int d);

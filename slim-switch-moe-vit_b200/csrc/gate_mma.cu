@@ -1,28 +1,33 @@
-// gate_mma.cu — the gate projection on the tensor cores, with CERTIFIED routing (sm_100a).
+// gate_mma.cu — the gate projection on the 5th-generation tensor cores (tcgen05 / TMEM), with CERTIFIED routing (sm_100a).
 //
 // The gate of the MoE layer (FastMoE NaiveGate / SwitchGate / GShardGate: nn.Linear(d, E) + top-k + softmax, reached
 // from /root/reference/models/resMoE.py:27-29; attribute path pinned by models/resmoe_flop_hook.py:7) is a skinny
-// contraction logits[T, E] = x[T, d] Wg[E, d]^T with E = 8..64.  On the CUDA cores it costs T d E fp32 FMAs — 4x the
-// time at E = 64 of what it costs at E = 16, and far above the HBM time of reading x once (round 1: 48 us at the
-// config-2 shape against a 6 us HBM floor).  Here it runs on mma.sync m16n8k16 (bf16 x bf16 -> fp32):
+// contraction logits[T, E] = x[T, d] Wg[E, d]^T with E = 8..64.  On the CUDA cores it costs T d E fp32 FMAs (round 1:
+// 48 us at the config-2 shape against a 6 us HBM floor, and 4x that at E = 64); a first mma.sync version was bound by
+// the per-CTA latency chain (31 us) and, at E = 64, by mma.sync's own rate.  This version is a persistent,
+// warp-specialised pipeline — one CTA per SM, token tiles of 128:
+//
+//   warp 0      TMA producer: 64-feature chunks of x (128 tokens) and of the two weight planes stream through a ring
+//               of shared-memory stages (128-byte swizzle), running ahead across tile boundaries;
+//   warp 1      one thread issues tcgen05.mma (cta_group::1, M = 128 tokens, N = 2 E_PAD, K = 16) straight from shared
+//               memory into a double-buffered TMEM accumulator: columns [0, E_PAD) = x w0^T, [E_PAD, 2 E_PAD) = x w1^T;
+//   warps 2-5   one thread per token row: ||x_t||^2 from the staged chunks (needed by the certification bound);
+//   warps 6-9   epilogue, one thread per token (its TMEM lane): logits, certification, top-k, scores, per-tile
+//               histogram and probability sums — while the other warps are already on the next tile.
 //
 //   * x is bf16 (exact operand).  Wg (fp32) is split once per forward into two bf16 planes w0 = bf16(w),
-//     w1 = bf16(w - w0) (|w - w0 - w1| <= 2^-18 |w|); products are exact in fp32, the planes go to two accumulators
-//     (hi, lo) that are added once at the end.
+//     w1 = bf16(w - w0) (|w - w0 - w1| <= 2^-18 |w|); products are exact in fp32, the planes accumulate separately
+//     and are added once at the end.
 //   * The routing INTEGERS must stay bit-identical to the CPU oracle, whose logits are fp32 FMA chains in a fixed
 //     order (LOGIT ORDER v1, oracle/gate_ref.c).  The tensor-core logits differ from those by rounding only, and the
 //     difference is bounded per token:  |v_e - L_e| <= B_t = kappa * ||x_t||_2 * max_e ||w_e||_2  (Cauchy-Schwarz on
 //     sum_i |x_i w_ei|; kappa covers the accumulation error of both sides and the split residual, see gate_kappa()).
 //     A token whose k + 1 largest logits are pairwise further apart than 2 B_t + 16 u max|v| cannot be routed
-//     differently by the oracle: its top-k selection AND order are certified.  Every other token (a fraction of a
-//     percent, and every exact tie) is recomputed by its warp in LOGIT ORDER v1 — bit-exact logits — before top-k.
-//     So idx / counts / positions are bit-exact against the oracle for every token, and the emitted logits are
-//     either bit-exact (recomputed tokens) or within B_t of the oracle's (certified tokens).
-//   * top-k runs on 4 lanes per token (the quad that holds the token's accumulator row), scores / softmax sums in
-//     registers; per-64-token-tile histograms and probability sums leave through shared memory in a fixed order.
-//
-// Pipeline: one producer warp streams 64-feature chunks of x (128 tokens) and of the two weight planes through a
-// ring of shared-memory stages with TMA (128-byte swizzle, read back with ldmatrix), 8 MMA warps of 16 tokens each.
+//     differently by the oracle: its top-k selection AND order are certified.  For every other token (a fraction of a
+//     percent, and every exact tie) the experts that can still reach the oracle's top-k — those within the margin of
+//     the k-th largest logit — are recomputed by the token's warp in LOGIT ORDER v1 (bit-exact) before the selection
+//     is redone.  So idx / counts / positions are bit-exact against the oracle for every token, and every emitted
+//     logit is either bit-exact (recomputed candidates) or within B_t of the oracle's.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -35,7 +40,8 @@ namespace moe {
 
 constexpr int kGmTok = 128;       // tokens per CTA = two 64-token routing tiles
 constexpr int kGmKC = 64;         // features per pipeline stage (one 128-byte swizzle row)
-constexpr int kGmThreads = 288;   // 8 MMA warps + 1 producer warp
+constexpr int kGmThreads = 320;   // producer, MMA issuer, 4 row-norm warps, 4 epilogue warps
+constexpr int kGmMaxStages = 8;
 constexpr int kGmMaxK = 8;
 
 // kappa of the certification bound (see the header): accumulation error of the tensor-core path (d / 16 dependent
@@ -74,331 +80,408 @@ gate_split_kernel(const float* __restrict__ Wg, int E, int E_pad, int d, __nv_bf
     }
 }
 
-__device__ __forceinline__ void ldsm_x4(uint32_t saddr, uint32_t (&r)[4]) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
-}
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
-// top-`npick` of one token's logits held by a quad (lane t of the quad owns experts 8j + 2t + c): descending value,
-// ties -> lowest expert index.  v is not modified; `pv` / `pi` are returned in every lane of the quad.
-template <int NT>
-__device__ __forceinline__ void quad_topk(const float (&v)[NT][2], int t, int E, int npick, float (&pv)[kGmMaxK + 1],
-                                          int (&pi)[kGmMaxK + 1]) {
-    uint32_t used = 0;
-    for (int p = 0; p < npick; ++p) {
+// Up to four logits of one token in LOGIT ORDER v1 (bit-exact with oracle/gate_ref.c), computed by a whole warp: feature i
+// belongs to lane (i / 4) % 32, ascending-i FMA chains from +0, xor butterfly 16..1 (the caller adds bias and noise last).
+// Out of line on purpose: it runs for a fraction of a percent of the tokens and must not cost the main path registers or
+// code size.  Experts e[j] < 0 are skipped.  The loads of four iterations are independent and issued together.
+__device__ __noinline__ float4 gate_exact_dots(const __nv_bfloat16* __restrict__ xr, const float* __restrict__ Wg, int d,
+                                               int e0, int e1, int e2, int e3, int lane) {
+    const float* w0 = Wg + static_cast<size_t>(max(e0, 0)) * d;
+    const float* w1 = Wg + static_cast<size_t>(max(e1, 0)) * d;
+    const float* w2 = Wg + static_cast<size_t>(max(e2, 0)) * d;
+    const float* w3 = Wg + static_cast<size_t>(max(e3, 0)) * d;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll 4
+    for (int c4 = lane; c4 < d / 4; c4 += 32) {
+        const uint2 xb = __ldg(reinterpret_cast<const uint2*>(xr + c4 * 4));
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(w0 + c4 * 4));
+        const float4 q1 = __ldg(reinterpret_cast<const float4*>(w1 + c4 * 4));
+        const float4 q2 = __ldg(reinterpret_cast<const float4*>(w2 + c4 * 4));
+        const float4 q3 = __ldg(reinterpret_cast<const float4*>(w3 + c4 * 4));
+        const float x0 = bf_lo(xb.x), x1 = bf_hi(xb.x), x2 = bf_lo(xb.y), x3 = bf_hi(xb.y);
+        a0 = fmaf(x0, q0.x, a0); a0 = fmaf(x1, q0.y, a0); a0 = fmaf(x2, q0.z, a0); a0 = fmaf(x3, q0.w, a0);
+        a1 = fmaf(x0, q1.x, a1); a1 = fmaf(x1, q1.y, a1); a1 = fmaf(x2, q1.z, a1); a1 = fmaf(x3, q1.w, a1);
+        a2 = fmaf(x0, q2.x, a2); a2 = fmaf(x1, q2.y, a2); a2 = fmaf(x2, q2.z, a2); a2 = fmaf(x3, q2.w, a2);
+        a3 = fmaf(x0, q3.x, a3); a3 = fmaf(x1, q3.y, a3); a3 = fmaf(x2, q3.z, a3); a3 = fmaf(x3, q3.w, a3);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        a0 = a0 + __shfl_xor_sync(0xffffffffu, a0, off);
+        a1 = a1 + __shfl_xor_sync(0xffffffffu, a1, off);
+        a2 = a2 + __shfl_xor_sync(0xffffffffu, a2, off);
+        a3 = a3 + __shfl_xor_sync(0xffffffffu, a3, off);
+    }
+    return make_float4(a0, a1, a2, a3);
+}
+
+// top-NP of one token's logits held by ONE thread: descending value, ties -> lowest expert index.  Everything is
+// compile-time indexed so that v / pv / pi stay in registers.
+template <int EP, int NP>
+__device__ __forceinline__ void thread_topk(const float (&v)[EP], int E, int npick, float (&pv)[NP], int (&pi)[NP]) {
+    uint64_t used = 0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
         float bv = -INFINITY;
         int be = 0x7fffffff;
+        if (p < npick) {
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int e = 8 * j + 2 * t + c;
-                const bool ok = e < E && !((used >> (2 * j + c)) & 1u);
-                if (ok && (be == 0x7fffffff || v[j][c] > bv)) { bv = v[j][c]; be = e; }
+            for (int e = 0; e < EP; ++e) {
+                const bool ok = e < E && !((used >> e) & 1ull);
+                if (ok && (be == 0x7fffffff || v[e] > bv)) { bv = v[e]; be = e; }
             }
-        }
-#pragma unroll
-        for (int off = 1; off <= 2; off <<= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-            const int oe = __shfl_xor_sync(0xffffffffu, be, off);
-            if (oe != 0x7fffffff && (be == 0x7fffffff || ov > bv || (ov == bv && oe < be))) { bv = ov; be = oe; }
+            if (be != 0x7fffffff) used |= 1ull << be;
         }
         pv[p] = bv;
         pi[p] = be;
-        if (be != 0x7fffffff && ((be & 7) >> 1) == t) used |= 1u << (2 * (be >> 3) + (be & 1));
     }
 }
 
-template <int NT>
-__global__ void __launch_bounds__(kGmThreads, 2)
-gate_fwd_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                    const __nv_bfloat16* __restrict__ x, const float* __restrict__ Wg, const float* __restrict__ bg,
-                    const float* __restrict__ noise, const uint8_t* __restrict__ token_mask, const float* __restrict__ wnorm,
-                    float kappa, int64_t T, int d, int E, int k, int score_mode, int want_psum, int ntiles, int nstages,
-                    float* __restrict__ logits, int* __restrict__ idx, float* __restrict__ score, int* __restrict__ tile_hist,
-                    float* __restrict__ tile_psum) {
-    constexpr int E_PAD = NT * 8;
-    constexpr int X_BYTES = kGmTok * 128;            // 128 token rows x 64 bf16
-    constexpr int W_BYTES = 2 * E_PAD * 128;         // both planes, E_PAD rows each
+// lane l returns sum over the warp's lanes of their v[l] (fixed xor-butterfly order); v is destroyed
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int lvl = 0; lvl < 5; ++lvl) {
+        const int off = 16 >> lvl;
+        const int n = 16 >> lvl;
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            const float send = upper ? v[j] : v[j + n];
+            const float keep = upper ? v[j + n] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+template <int EP, int NP>   // EP: padded expert count (16 / 32 / 64); NP: picks held in registers (>= min(k + 1, E))
+__global__ void __launch_bounds__(kGmThreads, 1)
+gate_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                     const __nv_bfloat16* __restrict__ x, const float* __restrict__ Wg, const float* __restrict__ bg,
+                     const float* __restrict__ noise, const uint8_t* __restrict__ token_mask, const float* __restrict__ wnorm,
+                     float kappa, int64_t T, int d, int E, int k, int score_mode, int want_psum, int ntiles, int nstages,
+                     float* __restrict__ logits, int* __restrict__ idx, float* __restrict__ score, int* __restrict__ tile_hist,
+                     float* __restrict__ tile_psum) {
+    constexpr int NCOL = 2 * EP;                      // accumulator columns: both planes
+    constexpr int X_BYTES = kGmTok * 128;             // 128 token rows x 64 bf16
+    constexpr int W_BYTES = NCOL * 128;               // both planes, EP rows each
     constexpr int STAGE_BYTES = X_BYTES + W_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * NCOL < 32 ? 32 : 2 * NCOL;   // two accumulator stages (a power of two: 64 / 128 / 256)
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* tail = smem + nstages * STAGE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);        // [nstages]
-    uint64_t* empty_bar = full_bar + 8;                            // [nstages]
-    int* hist_s = reinterpret_cast<int*>(tail + 128);              // [2][E_PAD]
-    float* psum_s = reinterpret_cast<float*>(hist_s + 2 * E_PAD);  // [8 warps][E_PAD]
-    float* exact_s = psum_s + 8 * E_PAD;                           // [8 warps][E_PAD]
-    float* wmax_s = exact_s + 8 * E_PAD;                           // [1]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);              // [8]
+    uint64_t* empty_bar = full_bar + kGmMaxStages;                       // [8]
+    uint64_t* tfull_bar = empty_bar + kGmMaxStages;                      // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                                // [2]
+    uint64_t* ssfull_bar = tempty_bar + 2;                               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ssfull_bar + 2);   // [1] (+ pad)
+    float* ss_s = reinterpret_cast<float*>(tail + 256);                  // [2][128] squared row norms per accumulator stage
+    float* bias_s = ss_s + 2 * kGmTok;                                   // [EP]
+    int* hist_s = reinterpret_cast<int*>(bias_s + EP);                   // [2 parities][2 halves][EP]
+    float* psum_s = reinterpret_cast<float*>(hist_s + 4 * EP);           // [2 parities][4 quarters][EP]
+    float* exact_s = psum_s + 8 * EP;                                    // [4 warps][EP]
+    float* wmax_s = exact_s + 4 * EP;                                    // [1]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t t_base = static_cast<int64_t>(blockIdx.x) * kGmTok;
     const int nk = d / kGmKC;
+    const int ntiles128 = (ntiles + 1) >> 1;
 
     if (tid == 0) {
         for (int s = 0; s < nstages; ++s) {
-            mbar_init(full_bar + s, 1);
-            mbar_init(empty_bar + s, 8);
+            mbar_init(full_bar + s, 1);       // producer's arrive.expect_tx
+            mbar_init(empty_bar + s, 5);      // tcgen05.commit + the four row-norm warps
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar + a, 1);      // tcgen05.commit
+            mbar_init(tempty_bar + a, 4);     // the four epilogue warps
+            mbar_init(ssfull_bar + a, 4);     // the four row-norm warps
         }
         fence_mbar_init();
     }
-    for (int i = tid; i < 2 * E_PAD; i += kGmThreads) hist_s[i] = 0;
-    if (warp == 0) {
+    for (int i = tid; i < 4 * EP; i += kGmThreads) hist_s[i] = 0;
+    for (int i = tid; i < EP; i += kGmThreads) bias_s[i] = (bg != nullptr && i < E) ? __ldg(bg + i) : 0.0f;
+    if (warp == 2) {
         float m = 0.0f;
         for (int e = lane; e < E; e += 32) m = fmaxf(m, __ldg(wnorm + e));
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
         if (lane == 0) *wmax_s = m;
     }
+    if (warp == 1) {
+        tmem_alloc1(tmem_slot, TMEM_COLS);
+        tmem_relinquish1();
+    }
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
-        // ================================ producer: TMA, one elected lane ==========================
+    if (warp == 0) {
+        // ================================ TMA producer ===========================================
         if (lane == 0) {
             tma_prefetch_desc(&tmX);
             tma_prefetch_desc(&tmW);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < ntiles128; tile += gridDim.x) {
+                for (int kc = 0; kc < nk; ++kc) {
+                    mbar_wait(empty_bar + s, ph ^ 1);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    mbar_arrive_expect_tx(full_bar + s, STAGE_BYTES);
+                    tma_load_2d(st, &tmX, full_bar + s, kc * kGmKC, tile * kGmTok);   // rows past T: zero-filled
+                    tma_load_2d(st + X_BYTES, &tmW, full_bar + s, kc * kGmKC, 0);
+                    if (++s == nstages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (one thread) ================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kGmTok, NCOL, false, false);
+            int s = 0, as = 0;
+            uint32_t ph = 0, aph = 0;
+            for (int tile = blockIdx.x; tile < ntiles128; tile += gridDim.x) {
+                mbar_wait(tempty_bar + as, aph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * NCOL;
+                for (int kc = 0; kc < nk; ++kc) {
+                    mbar_wait(full_bar + s, ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + X_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < kGmKC / 16; ++k4)
+                        umma_bf16_1(tmem_d, umma_smem_desc(a_addr + k4 * 32, 16, 1024), umma_smem_desc(b_addr + k4 * 32, 16, 1024),
+                                    idesc, (kc | k4) != 0);
+                    umma_commit1(empty_bar + s);
+                    if (++s == nstages) { s = 0; ph ^= 1; }
+                }
+                umma_commit1(tfull_bar + as);
+                if (++as == 2) { as = 0; aph ^= 1; }
+            }
+        }
+    } else if (warp < 6) {
+        // ================================ row norms: one thread per token row =====================
+        const int r = (warp - 2) * 32 + lane;
+        int s = 0, as = 0;
+        uint32_t ph = 0, aph = 0;
+        for (int tile = blockIdx.x; tile < ntiles128; tile += gridDim.x) {
+            float ss = 0.0f;
             for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % nstages;
-                if (kc >= nstages) mbar_wait(empty_bar + s, ((kc / nstages) - 1) & 1);
-                uint8_t* st = smem + s * STAGE_BYTES;
-                mbar_arrive_expect_tx(full_bar + s, STAGE_BYTES);
-                tma_load_2d(st, &tmX, full_bar + s, kc * kGmKC, static_cast<int>(t_base));   // rows past T: zero-filled
-                tma_load_2d(st + X_BYTES, &tmW, full_bar + s, kc * kGmKC, 0);
+                mbar_wait(full_bar + s, ph);
+                const uint8_t* xr = smem + s * STAGE_BYTES + r * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {   // 128-byte swizzle: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
+                    const uint4 q = *reinterpret_cast<const uint4*>(xr + ((c ^ (r & 7)) << 4));
+                    ss = fmaf(bf_lo(q.x), bf_lo(q.x), ss); ss = fmaf(bf_hi(q.x), bf_hi(q.x), ss);
+                    ss = fmaf(bf_lo(q.y), bf_lo(q.y), ss); ss = fmaf(bf_hi(q.y), bf_hi(q.y), ss);
+                    ss = fmaf(bf_lo(q.z), bf_lo(q.z), ss); ss = fmaf(bf_hi(q.z), bf_hi(q.z), ss);
+                    ss = fmaf(bf_lo(q.w), bf_lo(q.w), ss); ss = fmaf(bf_hi(q.w), bf_hi(q.w), ss);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_bar + s);
+                if (++s == nstages) { s = 0; ph ^= 1; }
             }
+            mbar_wait(tempty_bar + as, aph ^ 1);     // the epilogue has read this stage's norms of two tiles ago
+            ss_s[as * kGmTok + r] = ss;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ssfull_bar + as);
+            if (++as == 2) { as = 0; aph ^= 1; }
         }
-        return;
-    }
-
-    // ==================================== 8 MMA warps, 16 tokens each ==============================
-    const int g = lane >> 2, t = lane & 3;
-    float hi[NT][4], lo[NT][4];
+    } else {
+        // ================================ epilogue: one thread per token (TMEM lane) ==============
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;                  // token row inside the tile
+        const int et = tid - 6 * 32;                  // 0..127 among the epilogue threads
+        const float wmax = *wmax_s;
+        const int npick = min(k + 1, E);
+        const bool need_p = (score_mode == 1) || want_psum;
+        int as = 0, it = 0;
+        uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < ntiles128; tile += gridDim.x, ++it) {
+            const int par = it & 1;
+            const int64_t tok = static_cast<int64_t>(tile) * kGmTok + r;
+            const bool in_range = tok < T;
+            const bool masked = in_range && token_mask != nullptr && token_mask[tok] == 0;
+            mbar_wait(tfull_bar + as, aph);
+            mbar_wait(ssfull_bar + as, aph);
+            tc_fence_after();
+            float v[EP];
+            const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * NCOL;
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
+            for (int c = 0; c < EP / 16; ++c) {
+                uint32_t hi[16], lo[16];
+                tmem_ld16(trow + c * 16, hi);
+                tmem_ld16(trow + EP + c * 16, lo);
+                tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { hi[j][c] = 0.0f; lo[j][c] = 0.0f; }
-    }
-    float ss0 = 0.0f, ss1 = 0.0f;   // partial sum of squares of token rows g and g + 8 (this lane's k columns)
-    // ldmatrix lane addresses (128-byte swizzle: 16-byte chunk c of row r lives at chunk c ^ (r & 7))
-    const int a_row = warp * 16 + (lane & 15);            // A: lanes 0-15 rows 0-15 at k-chunk 2 ks, lanes 16-31 at 2 ks + 1
-    const int a_kc = lane >> 4;
-    const int b_row = ((lane >> 4) << 3) + (lane & 7);    // B: matrices (n 0-7, k lo), (n 0-7, k hi), (n 8-15, k lo), (n 8-15, k hi)
-    const int b_kc = (lane >> 3) & 1;
-    for (int kc = 0; kc < nk; ++kc) {
-        const int s = kc % nstages;
-        mbar_wait(full_bar + s, (kc / nstages) & 1);
-        const uint32_t xs = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t ws = xs + X_BYTES;
-#pragma unroll
-        for (int ks = 0; ks < kGmKC / 16; ++ks) {
-            uint32_t a[4];
-            ldsm_x4(xs + a_row * 128 + (((2 * ks + a_kc) ^ (a_row & 7)) << 4), a);
-            ss0 = fmaf(bf_lo(a[0]), bf_lo(a[0]), ss0); ss0 = fmaf(bf_hi(a[0]), bf_hi(a[0]), ss0);
-            ss0 = fmaf(bf_lo(a[2]), bf_lo(a[2]), ss0); ss0 = fmaf(bf_hi(a[2]), bf_hi(a[2]), ss0);
-            ss1 = fmaf(bf_lo(a[1]), bf_lo(a[1]), ss1); ss1 = fmaf(bf_hi(a[1]), bf_hi(a[1]), ss1);
-            ss1 = fmaf(bf_lo(a[3]), bf_lo(a[3]), ss1); ss1 = fmaf(bf_hi(a[3]), bf_hi(a[3]), ss1);
-#pragma unroll
-            for (int jp = 0; jp < NT / 2; ++jp) {
-                const int r0 = jp * 16 + b_row;             // plane 0 row
-                const int r1 = E_PAD + r0;                  // plane 1 row
-                uint32_t b[4];
-                ldsm_x4(ws + r0 * 128 + (((2 * ks + b_kc) ^ (r0 & 7)) << 4), b);
-                mma_bf16_16816(hi[2 * jp], a, b[0], b[1]);
-                mma_bf16_16816(hi[2 * jp + 1], a, b[2], b[3]);
-                ldsm_x4(ws + r1 * 128 + (((2 * ks + b_kc) ^ (r1 & 7)) << 4), b);
-                mma_bf16_16816(lo[2 * jp], a, b[0], b[1]);
-                mma_bf16_16816(lo[2 * jp + 1], a, b[2], b[3]);
+                for (int i = 0; i < 16; ++i) v[c * 16 + i] = __uint_as_float(hi[i]) + __uint_as_float(lo[i]);
             }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar + s);
-    }
+            const float ss = ss_s[as * kGmTok + r];
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar + as);   // accumulator stage and its norms are free again
+            if (++as == 2) { as = 0; aph ^= 1; }
 
-    // ---- epilogue: everything stays in the quad that owns the token row
-    ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1); ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
-    ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1); ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
-    const float wmax = *wmax_s;
-    const int npick = min(k + 1, E);
-    float v[2][NT][2];
-    float pv[2][kGmMaxK + 1];
-    int pi[2][kGmMaxK + 1];
-    bool amb[2];
-    int64_t tok[2];
-    bool in_range[2], masked[2];
+            float vmax = 0.0f;
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        tok[rr] = t_base + warp * 16 + g + rr * 8;
-        in_range[rr] = tok[rr] < T;
-        masked[rr] = in_range[rr] && token_mask != nullptr && token_mask[tok[rr]] == 0;
-        float vmax = 0.0f;
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int e = 8 * j + 2 * t + c;
-                float val = hi[j][rr * 2 + c] + lo[j][rr * 2 + c];
+            for (int e = 0; e < EP; ++e) {
                 if (e < E) {
-                    if (bg != nullptr) val += __ldg(bg + e);
-                    if (noise != nullptr && in_range[rr]) val += __ldg(noise + tok[rr] * E + e);
+                    float val = v[e] + bias_s[e];
+                    if (noise != nullptr && in_range) val += __ldg(noise + tok * E + e);
+                    v[e] = val;
                     vmax = fmaxf(vmax, fabsf(val));
                 }
-                v[rr][j][c] = val;
             }
-        }
-        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 1));
-        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 2));
-        quad_topk<NT>(v[rr], t, E, npick, pv[rr], pi[rr]);
-        const float margin = 2.0f * kappa * sqrtf(rr == 0 ? ss0 : ss1) * wmax + 9.5367431640625e-07f * vmax;   // 16 u max|v|
-        bool a = false;
-        for (int p = 0; p + 1 < npick; ++p) a = a || !(pv[rr][p] - pv[rr][p + 1] > margin);
-        amb[rr] = a && in_range[rr] && !masked[rr];
-    }
+            float pv[NP];
+            int pi[NP];
+            thread_topk<EP, NP>(v, E, npick, pv, pi);
+            const float margin = 2.0f * kappa * sqrtf(ss) * wmax + 9.5367431640625e-07f * vmax;   // 16 u max|v|
+            bool amb = false;
+#pragma unroll
+            for (int p = 0; p + 1 < NP; ++p)
+                if (p + 1 < npick) amb = amb || !(pv[p] - pv[p + 1] > margin);
+            amb = amb && in_range && !masked;
 
-    // ---- uncertified tokens: the warp recomputes the token's logits in LOGIT ORDER v1 (bit-exact with the oracle)
+            // ---- uncertified tokens.  The oracle's top-k can only contain experts whose tensor-core logit lies within
+            // `margin` (> 2 B_t) of the k-th largest one: every other expert is provably below k exact values.  Only those
+            // candidates (typically k + 1 of them) are recomputed — by the whole warp, in LOGIT ORDER v1, bit-exact with the
+            // oracle — and the selection is redone on the corrected values.
+            uint64_t cand = 0;
+            if (amb) {
+                float kth = pv[0];
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        unsigned flagged = __ballot_sync(0xffffffffu, amb[rr] && t == 0);   // one bit per ambiguous row (lane 4 g)
-        while (flagged) {
-            const int src = __ffs(flagged) - 1;
-            flagged &= flagged - 1;
-            const int64_t tk = t_base + warp * 16 + (src >> 2) + rr * 8;
-            const __nv_bfloat16* xr = x + tk * d;
-            float* ex = exact_s + warp * E_PAD;
-            for (int e0 = 0; e0 < E; e0 += 16) {
-                float acc[16];
+                for (int p = 1; p < NP; ++p)
+                    if (p < k) kth = pv[p];
+                const float lim = kth - margin;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
-                for (int c4 = lane; c4 < d / 4; c4 += 32) {   // feature i belongs to lane (i / 4) % 32, ascending i
-                    const uint2 xb = __ldg(reinterpret_cast<const uint2*>(xr + c4 * 4));
-                    const float x0 = bf_lo(xb.x), x1 = bf_hi(xb.x), x2 = bf_lo(xb.y), x3 = bf_hi(xb.y);
+                for (int e = 0; e < EP; ++e)
+                    if (e < E && v[e] >= lim) cand |= 1ull << e;
+            }
+            unsigned flagged = __ballot_sync(0xffffffffu, amb);
+            if (flagged) {
+                float* ex = exact_s + q * EP;
+                while (flagged) {
+                    const int src = __ffs(flagged) - 1;
+                    flagged &= flagged - 1;
+                    const int64_t tk = static_cast<int64_t>(tile) * kGmTok + q * 32 + src;
+                    uint32_t c_lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(cand), src);
+                    uint32_t c_hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(cand >> 32), src);
+                    uint64_t cm = (static_cast<uint64_t>(c_hi) << 32) | c_lo;
+                    while (cm) {
+                        int e4[4];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (e0 + i < E) {
-                            const float4 w = __ldg(reinterpret_cast<const float4*>(Wg + static_cast<size_t>(e0 + i) * d + c4 * 4));
-                            float a_ = acc[i];
-                            a_ = fmaf(x0, w.x, a_); a_ = fmaf(x1, w.y, a_); a_ = fmaf(x2, w.z, a_); a_ = fmaf(x3, w.w, a_);
-                            acc[i] = a_;
+                        for (int j = 0; j < 4; ++j) {
+                            e4[j] = cm ? __ffsll(static_cast<long long>(cm)) - 1 : -1;
+                            if (cm) cm &= cm - 1;
+                        }
+                        const float4 dots = gate_exact_dots(x + tk * d, Wg, d, e4[0], e4[1], e4[2], e4[3], lane);
+                        if (lane == 0) {
+                            const float dv[4] = {dots.x, dots.y, dots.z, dots.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (e4[j] >= 0) {
+                                    float val = dv[j] + (bg != nullptr ? __ldg(bg + e4[j]) : 0.0f);
+                                    if (noise != nullptr) val += __ldg(noise + tk * E + e4[j]);
+                                    ex[e4[j]] = val;
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == src) {
+#pragma unroll
+                        for (int e = 0; e < EP; ++e)
+                            if ((cand >> e) & 1ull) v[e] = ex[e];
+                    }
+                    __syncwarp();
+                }
+                if (amb) thread_topk<EP, NP>(v, E, npick, pv, pi);
+            }
+
+            // ---- outputs: logits, idx, score, per-tile histogram, per-tile probability sums
+            if (in_range) {
+                float* lrow = logits + tok * E;
+                if ((E & 3) == 0) {
+#pragma unroll
+                    for (int e = 0; e < EP; e += 4)
+                        if (e < E) *reinterpret_cast<float4*>(lrow + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < EP; ++e)
+                        if (e < E) lrow[e] = v[e];
+                }
+            }
+            const bool live = in_range && !masked;
+            const float m = pv[0];
+            float rz = 0.0f;
+            if (need_p) {
+                float z = 0.0f;
+#pragma unroll
+                for (int e = 0; e < EP; ++e) {
+                    v[e] = e < E ? expf(v[e] - m) : 0.0f;      // v now holds the un-normalised probabilities
+                    z += v[e];
+                }
+                rz = 1.0f / z;
+                if (want_psum) {
+#pragma unroll
+                    for (int g0 = 0; g0 < EP; g0 += 32) {
+                        float grp[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) grp[i] = (g0 + i < EP && live) ? v[g0 + i < EP ? g0 + i : 0] / z : 0.0f;
+                        const float colsum = warp_transpose_sum32(grp, lane);
+                        if (g0 + lane < EP) psum_s[(par * 4 + q) * EP + g0 + lane] = colsum;
+                    }
+                }
+            }
+            if (in_range) {
+                int* irow = idx + tok * k;
+                float* srow = score + tok * k;
+                if (masked) {
+                    for (int p = 0; p < k; ++p) { irow[p] = -1; srow[p] = 0.0f; }
+                } else {
+                    float ssum = 0.0f;
+                    if (score_mode == 0) {
+#pragma unroll
+                        for (int p = 0; p < NP; ++p)
+                            if (p < k) ssum += expf(pv[p] - m);
+                    }
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        if (p < k) {
+                            const float w = expf(pv[p] - m);
+                            irow[p] = pi[p];
+                            srow[p] = score_mode == 0 ? w / ssum : w * rz;
+                            atomicAdd(hist_s + (par * 2 + (q >> 1)) * EP + pi[p], 1);
                         }
                     }
                 }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float p = acc[i];
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) p = p + __shfl_xor_sync(0xffffffffu, p, off);
-                    if (lane == 0 && e0 + i < E) {
-                        float val = p + (bg != nullptr ? __ldg(bg + e0 + i) : 0.0f);
-                        if (noise != nullptr) val += __ldg(noise + tk * E + e0 + i);
-                        ex[e0 + i] = val;
-                    }
-                }
             }
-            __syncwarp();
-            if ((lane >> 2) == (src >> 2)) {   // the quad that owns the row takes the exact values
-#pragma unroll
-                for (int j = 0; j < NT; ++j) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int e = 8 * j + 2 * t + c;
-                        if (e < E) v[rr][j][c] = ex[e];
-                    }
+            named_bar_sync(2, 128);   // the four epilogue warps: this tile's histogram and column sums are complete
+            for (int i = et; i < 2 * EP; i += 128) {
+                const int hf = i / EP, e = i - hf * EP;
+                const int rt = tile * 2 + hf;             // 64-token routing tile
+                if (e < E && rt < ntiles) {
+                    tile_hist[static_cast<size_t>(e) * ntiles + rt] = hist_s[par * 2 * EP + i];
+                    if (want_psum)
+                        tile_psum[static_cast<size_t>(e) * ntiles + rt] =
+                            psum_s[(par * 4 + 2 * hf) * EP + e] + psum_s[(par * 4 + 2 * hf + 1) * EP + e];
                 }
-            }
-            __syncwarp();
-        }
-        if (__any_sync(0xffffffffu, amb[rr])) quad_topk<NT>(v[rr], t, E, npick, pv[rr], pi[rr]);   // warp-uniform branch
-    }
-
-    // ---- outputs: logits, idx, score, per-tile histogram, per-tile probability sums
-    const int half = warp >> 2;                       // routing tile of this warp inside the CTA
-    const bool need_p = (score_mode == 1) || want_psum;
-    float pcol[NT][2];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) { pcol[j][0] = 0.0f; pcol[j][1] = 0.0f; }
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        if (in_range[rr]) {
-            float* lrow = logits + tok[rr] * E;
-            if ((E & 1) == 0) {
-#pragma unroll
-                for (int j = 0; j < NT; ++j)
-                    if (8 * j + 2 * t < E) *reinterpret_cast<float2*>(lrow + 8 * j + 2 * t) = make_float2(v[rr][j][0], v[rr][j][1]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    if (8 * j + 2 * t < E) lrow[8 * j + 2 * t] = v[rr][j][0];
-                    if (8 * j + 2 * t + 1 < E) lrow[8 * j + 2 * t + 1] = v[rr][j][1];
-                }
-            }
-        }
-        const bool live = in_range[rr] && !masked[rr];
-        const float m = pv[rr][0];
-        float z = 0.0f, rz = 0.0f;
-        if (need_p) {
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-                    if (8 * j + 2 * t + c < E) z += expf(v[rr][j][c] - m);
-            }
-            z += __shfl_xor_sync(0xffffffffu, z, 1);
-            z += __shfl_xor_sync(0xffffffffu, z, 2);
-            rz = 1.0f / z;
-            if (want_psum && live) {
-#pragma unroll
-                for (int j = 0; j < NT; ++j) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-                        if (8 * j + 2 * t + c < E) pcol[j][c] += expf(v[rr][j][c] - m) / z;
-                }
-            }
-        }
-        if (t == 0 && in_range[rr]) {
-            if (masked[rr]) {
-                for (int p = 0; p < k; ++p) { idx[tok[rr] * k + p] = -1; score[tok[rr] * k + p] = 0.0f; }
-            } else {
-                float w[kGmMaxK], ssum = 0.0f;
-                if (score_mode == 0)
-                    for (int p = 0; p < k; ++p) { w[p] = expf(pv[rr][p] - m); ssum += w[p]; }
-                for (int p = 0; p < k; ++p) {
-                    idx[tok[rr] * k + p] = pi[rr][p];
-                    score[tok[rr] * k + p] = score_mode == 0 ? w[p] / ssum : expf(pv[rr][p] - m) * rz;
-                    atomicAdd(hist_s + half * E_PAD + pi[rr][p], 1);
-                }
+                hist_s[par * 2 * EP + i] = 0;             // reused two tiles later, behind the next tile's barrier
             }
         }
     }
-    if (want_psum) {   // column sums over the warp's 16 tokens: lanes with the same t, fixed xor order
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                float p = pcol[j][c];
-                p += __shfl_xor_sync(0xffffffffu, p, 4);
-                p += __shfl_xor_sync(0xffffffffu, p, 8);
-                p += __shfl_xor_sync(0xffffffffu, p, 16);
-                if (g == 0) psum_s[warp * E_PAD + 8 * j + 2 * t + c] = p;
-            }
-        }
-    }
-    named_bar_sync(1, 256);   // the 8 MMA warps (the producer warp has left)
-    for (int i = tid; i < 2 * E_PAD; i += 256) {
-        const int hf = i / E_PAD, e = i - hf * E_PAD;
-        const int tile = blockIdx.x * 2 + hf;
-        if (e < E && tile < ntiles) {
-            tile_hist[static_cast<size_t>(e) * ntiles + tile] = hist_s[i];
-            if (want_psum) {
-                const float* ps = psum_s + (hf * 4) * E_PAD + e;
-                tile_psum[static_cast<size_t>(e) * ntiles + tile] = ((ps[0] + ps[E_PAD]) + ps[2 * E_PAD]) + ps[3 * E_PAD];
-            }
-        }
+
+    // teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc1(tmem_base, TMEM_COLS);
     }
 }
 
@@ -415,28 +498,25 @@ size_t gate_fwd_workspace_bytes(int d, int E) {
     return (2 * ep * d * 2 + ep * 4 + 255) / 256 * 256;
 }
 
-template <int NT>
+template <int EP, int NP>
 static int launch_gate_mma_t(const CUtensorMap& tX, const CUtensorMap& tW, const __nv_bfloat16* x, const float* Wg, const float* bg,
                              const float* noise, const uint8_t* token_mask, const float* wnorm, int64_t T, int d, int E, int k,
                              int score_mode, int want_psum, float* logits, int* idx, float* score, int* tile_hist,
                              float* tile_psum, cudaStream_t st) {
-    constexpr int E_PAD = NT * 8;
-    constexpr int STAGE = kGmTok * 128 + 2 * E_PAD * 128;
+    constexpr int STAGE = kGmTok * 128 + 2 * EP * 128;
     const int ntiles = static_cast<int>((T + MOE_TOKEN_TILE - 1) / MOE_TOKEN_TILE);
-    const int nk = d / kGmKC;
-    int nstages = (110 * 1024) / STAGE;   // two CTAs per SM: one's epilogue overlaps the other's loads
-    if (nstages > 6) nstages = 6;
-    if (nstages > nk) nstages = nk;
-    if (nstages < 2) nstages = nk < 2 ? 1 : 2;
-    const size_t smem = 1024 + static_cast<size_t>(nstages) * STAGE + 128 + (2 * E_PAD + 16 * E_PAD + 4) * 4;
-    auto kfn = gate_fwd_mma_kernel<NT>;
+    const int ntiles128 = (ntiles + 1) / 2;
+    int nstages = (196 * 1024) / STAGE;   // one CTA per SM: the ring runs ahead across tile boundaries
+    if (nstages > kGmMaxStages) nstages = kGmMaxStages;
+    const size_t smem = 1024 + static_cast<size_t>(nstages) * STAGE + 256 + (2 * kGmTok + EP + 4 * EP + 8 * EP + 4 * EP + 4) * 4;
+    auto kfn = gate_fwd_umma_kernel<EP, NP>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) { set_error("gate_fwd_mma: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
         configured = true;
     }
-    const int grid = (ntiles + 1) / 2;
+    const int grid = ntiles128 < sm_count() ? ntiles128 : sm_count();
     kfn<<<grid, kGmThreads, smem, st>>>(tX, tW, x, Wg, bg, noise, token_mask, wnorm, gate_kappa(d), T, d, E, k, score_mode,
                                         want_psum, ntiles, nstages, logits, idx, score, tile_hist, tile_psum);
     cudaError_t e = cudaGetLastError();
@@ -457,11 +537,16 @@ int launch_gate_fwd_mma(const void* x, const float* Wg, const float* bg, const f
     if (!encode_tmap_2d_bf16(&tX, x, static_cast<uint64_t>(d), static_cast<uint64_t>(T), 64, kGmTok)) return 1;
     if (!encode_tmap_2d_bf16(&tW, planes, static_cast<uint64_t>(d), static_cast<uint64_t>(2 * ep), 64, static_cast<uint32_t>(2 * ep))) return 1;
     auto xb = static_cast<const __nv_bfloat16*>(x);
-    switch (ep) {
-        case 16: return launch_gate_mma_t<2>(tX, tW, xb, Wg, bg, noise, token_mask, wnorm, T, d, E, k, score_mode, want_psum, logits, idx, score, tile_hist, tile_psum, st);
-        case 32: return launch_gate_mma_t<4>(tX, tW, xb, Wg, bg, noise, token_mask, wnorm, T, d, E, k, score_mode, want_psum, logits, idx, score, tile_hist, tile_psum, st);
-        default: return launch_gate_mma_t<8>(tX, tW, xb, Wg, bg, noise, token_mask, wnorm, T, d, E, k, score_mode, want_psum, logits, idx, score, tile_hist, tile_psum, st);
-    }
+    // picks kept in registers: top-(k + 1); the common gates (k = 1, 2) get their own instantiation
+#define MOE_GATE_LAUNCH(EP_, NP_) \
+    return launch_gate_mma_t<EP_, NP_>(tX, tW, xb, Wg, bg, noise, token_mask, wnorm, T, d, E, k, score_mode, want_psum, logits, idx, score, tile_hist, tile_psum, st)
+    const int np = k + 1 <= 2 ? 2 : k + 1 <= 3 ? 3 : kGmMaxK + 1;
+    if (ep == 16) { if (np == 2) MOE_GATE_LAUNCH(16, 2); if (np == 3) MOE_GATE_LAUNCH(16, 3); MOE_GATE_LAUNCH(16, kGmMaxK + 1); }
+    if (ep == 32) { if (np == 2) MOE_GATE_LAUNCH(32, 2); if (np == 3) MOE_GATE_LAUNCH(32, 3); MOE_GATE_LAUNCH(32, kGmMaxK + 1); }
+    if (np == 2) MOE_GATE_LAUNCH(64, 2);
+    if (np == 3) MOE_GATE_LAUNCH(64, 3);
+    MOE_GATE_LAUNCH(64, kGmMaxK + 1);
+#undef MOE_GATE_LAUNCH
 }
 
 }  // namespace moe

@@ -342,14 +342,19 @@ __device__ __forceinline__ void zero_pad_rows(__nv_bfloat16* buf, int d, const i
 // ------------------------------------------------------------------------------------------------
 // K3: dispatch forward — positions + packed bf16 copy
 // ------------------------------------------------------------------------------------------------
+// `seg_start[e]` is the (global) row of expert e's first pair of THIS token set: the packed segment start on one GPU, or —
+// under expert parallelism over peer memory — owner_rank * rows_per_rank + the row inside the owner's packed buffer
+// where this source rank's share of expert e begins (moe_ep_exchange_counts).  Rows are written through `xrows`.
+// Blocks >= ntiles zero the pad rows of the LOCAL buffer `xpad` (segments pad_seg / pad_kept).
 template <typename XT>
 __global__ void __launch_bounds__(256)
 dispatch_fwd_kernel(const XT* __restrict__ x, const int* __restrict__ idx, const int* __restrict__ tile_base,
-                    const int* __restrict__ seg_start, const int* __restrict__ kept, int64_t T, int d, int E, int k,
+                    const int* __restrict__ seg_start, int64_t T, int d, int E, int k,
                     long long capacity, int ntiles, int* __restrict__ pos, int* __restrict__ row_src,
-                    __nv_bfloat16* __restrict__ xbuf) {
+                    PeerRows xrows, __nv_bfloat16* __restrict__ xpad, const int* __restrict__ pad_seg,
+                    const int* __restrict__ pad_kept) {
     if (static_cast<int>(blockIdx.x) >= ntiles) {
-        zero_pad_rows(xbuf, d, seg_start, kept, blockIdx.x - ntiles, row_src);
+        zero_pad_rows(xpad, d, pad_seg, pad_kept, blockIdx.x - ntiles, row_src);
         return;
     }
     extern __shared__ int smem_i[];
@@ -394,7 +399,7 @@ dispatch_fwd_kernel(const XT* __restrict__ x, const int* __restrict__ idx, const
         const long long rank = e >= 0 ? static_cast<long long>(chunk_cnt[(il >> 5) * E + e]) + ent_row[il] : capacity;
         const int row = rank < capacity ? seg_start[e] + static_cast<int>(rank) : -1;
         pos[i_base + il] = row;
-        if (row >= 0) row_src[row] = static_cast<int>(i_base + il);
+        if (row >= 0 && row_src != nullptr) row_src[row] = static_cast<int>(i_base + il);
         ent_row[il] = row;
     }
     __syncthreads();
@@ -407,7 +412,7 @@ dispatch_fwd_kernel(const XT* __restrict__ x, const int* __restrict__ idx, const
         if (row < 0) continue;
         float v[8];
         load8(x + (t_base + il / k) * d + c, v);
-        store8(xbuf + static_cast<size_t>(row) * d + c, v);
+        store8(peer_row<__nv_bfloat16>(xrows, row, d) + c, v);
     }
 }
 
@@ -416,7 +421,7 @@ dispatch_fwd_kernel(const XT* __restrict__ x, const int* __restrict__ idx, const
 // ------------------------------------------------------------------------------------------------
 template <typename OT>
 __global__ void __launch_bounds__(256)
-combine_fwd_kernel(const __nv_bfloat16* __restrict__ ybuf, const int* __restrict__ pos, const float* __restrict__ score,
+combine_fwd_kernel(PeerRows yrows, const int* __restrict__ pos, const float* __restrict__ score,
                    int64_t T, int d, int k, OT* __restrict__ out) {
     const int per_row = d / 8;
     const int64_t items = T * per_row;
@@ -432,7 +437,7 @@ combine_fwd_kernel(const __nv_bfloat16* __restrict__ ybuf, const int* __restrict
             if (row < 0) continue;
             const float s = __ldg(score + t * k + j);
             float y[8];
-            load8(ybuf + static_cast<size_t>(row) * d + c, y);
+            load8(peer_row<const __nv_bfloat16>(yrows, row, d) + c, y);
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = fmaf(s, y[i], acc[i]);
         }
@@ -445,12 +450,12 @@ combine_fwd_kernel(const __nv_bfloat16* __restrict__ ybuf, const int* __restrict
 // ------------------------------------------------------------------------------------------------
 template <typename GT>
 __global__ void __launch_bounds__(256)
-combine_bwd_kernel(const GT* __restrict__ dy, const __nv_bfloat16* __restrict__ ybuf, const int* __restrict__ pos,
-                   const float* __restrict__ score, const int* __restrict__ seg_start, const int* __restrict__ kept,
-                   int64_t T, int d, int k, int E, int n_tok_blocks, __nv_bfloat16* __restrict__ dybuf,
+combine_bwd_kernel(const GT* __restrict__ dy, PeerRows yrows, const int* __restrict__ pos,
+                   const float* __restrict__ score, const int* __restrict__ pad_seg, const int* __restrict__ pad_kept,
+                   int64_t T, int d, int k, int n_tok_blocks, PeerRows dyrows, __nv_bfloat16* __restrict__ dypad,
                    float* __restrict__ dscore) {
-    if (static_cast<int>(blockIdx.x) >= n_tok_blocks) {
-        zero_pad_rows(dybuf, d, seg_start, kept, blockIdx.x - n_tok_blocks, nullptr);
+    if (static_cast<int>(blockIdx.x) >= n_tok_blocks) {   // pad rows of the LOCAL buffer
+        zero_pad_rows(dypad, d, pad_seg, pad_kept, blockIdx.x - n_tok_blocks, nullptr);
         return;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -461,13 +466,15 @@ combine_bwd_kernel(const GT* __restrict__ dy, const __nv_bfloat16* __restrict__ 
         float dot = 0.0f;
         if (row >= 0) {
             const float s = __ldg(score + t * k + j);
+            const __nv_bfloat16* yr = peer_row<const __nv_bfloat16>(yrows, row, d);
+            __nv_bfloat16* dyr = peer_row<__nv_bfloat16>(dyrows, row, d);
             for (int c = lane * 8; c < d; c += 256) {
                 float g[8], y[8], o[8];
                 load8(dy + t * d + c, g);
-                load8(ybuf + static_cast<size_t>(row) * d + c, y);
+                load8(yr + c, y);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { dot = fmaf(g[i], y[i], dot); o[i] = s * g[i]; }
-                store8(dybuf + static_cast<size_t>(row) * d + c, o);
+                store8(dyr + c, o);
             }
             dot = warp_sum_xor(dot);
         }
@@ -1018,8 +1025,6 @@ gate_wgrad_partial_kernel(const float* __restrict__ dlogits, const XT* __restric
 // group (cp.async, double-buffered 32-token sub-tiles).  Same block -> tile assignment and partial layout as the SIMT
 // kernel, so the result stays reproducible bit for bit.
 constexpr int kWgSub = 32;     // tokens per staged sub-tile
-constexpr int kWgLdl = 24;     // floats per staged dlogits row (16 experts + 8: conflict-free A-fragment reads)
-constexpr int kWgMaxNT = 16;   // 8-column n-tiles per warp at d = 1024
 
 __device__ __forceinline__ uint32_t to_tf32(float v) {
     uint32_t r;
@@ -1032,27 +1037,36 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// MT: 16-expert m-tiles held in registers (ALL experts in one pass over x: E <= 16 MT).  gridDim.y feature slices: slice s
+// owns features [s d / S, (s + 1) d / S) — it stages only that part of every x row — so that MT x (n-tiles per warp) stays
+// within 16 accumulator tiles whatever E and d are (round 1 re-read x once per 16 experts: 4 passes at E = 64).
+template <int MT>
 __global__ void __launch_bounds__(256)
 gate_wgrad_partial_mma_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x, int64_t T, int d, int E,
                               int ntiles, float* __restrict__ part_w, float* __restrict__ part_b) {
+    constexpr int EG = 16 * MT;            // experts per pass
+    constexpr int LDL = EG + 8;            // floats per staged dlogits row (+8: conflict-free A-fragment reads)
+    constexpr int MAXT = 16;               // accumulator tiles per thread (MT x n-tiles per warp)
     extern __shared__ __align__(16) uint8_t smem_wg[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int ldx = d + 8;                                   // staged x row, in bf16 (16-byte multiple, bank-skewed)
+    const int ds = d / gridDim.y;                            // features of this slice
+    const int f0 = blockIdx.y * ds;
+    const int ldx = ds + 8;                                  // staged x row, in bf16 (16-byte multiple, bank-skewed)
     const size_t xbytes = static_cast<size_t>(kWgSub) * ldx * 2;
     auto xs = [&](int buf) { return reinterpret_cast<uint16_t*>(smem_wg + buf * xbytes); };
-    auto dls = [&](int buf) { return reinterpret_cast<float*>(smem_wg + 2 * xbytes) + buf * (kWgSub * kWgLdl); };
-    const int fw = d / 8;                                    // features per warp
-    const int nt = fw / 8;                                   // n-tiles per warp
-    const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    auto dls = [&](int buf) { return reinterpret_cast<float*>(smem_wg + 2 * xbytes) + buf * (kWgSub * LDL); };
+    const int fw = ds / 8;                                   // features per warp
+    const int nt = fw / 8;                                   // n-tiles per warp (MT * nt <= MAXT, checked at launch)
+    const int my_tiles = static_cast<int>(blockIdx.x) < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     const int steps = my_tiles * (kWgTile / kWgSub);
     float* pw = part_w + static_cast<size_t>(blockIdx.x) * E * d;
-    const int chunks_per_row = d / 8;                        // 16-byte pieces of one x row
+    const int chunks_per_row = ds / 8;                       // 16-byte pieces of one staged x row
 
-    for (int g0 = 0; g0 < E; g0 += 16) {
-        float acc[kWgMaxNT][4];
+    for (int g0 = 0; g0 < E; g0 += EG) {                     // one pass unless E > 16 MT
+        float acc[MAXT][4];
 #pragma unroll
-        for (int j = 0; j < kWgMaxNT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
+        for (int j = 0; j < MAXT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
         float bsum = 0.0f;
         auto tok_base = [&](int st) {   // first token of step st
             const int tile = blockIdx.x + (st / (kWgTile / kWgSub)) * gridDim.x;
@@ -1062,26 +1076,26 @@ gate_wgrad_partial_mma_kernel(const float* __restrict__ dlogits, const __nv_bflo
             const int64_t t0 = tok_base(st);
             for (int c = tid; c < kWgSub * chunks_per_row; c += 256) {
                 const int r = c / chunks_per_row, cc = c - r * chunks_per_row;
-                const __nv_bfloat16* src = x + min(t0 + r, T - 1) * d + cc * 8;
+                const __nv_bfloat16* src = x + min(t0 + r, T - 1) * d + f0 + cc * 8;
                 const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(xs(buf) + static_cast<size_t>(r) * ldx + cc * 8));
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        float dreg[2];
-        auto fetch_dl = [&](int st) {   // 32 tokens x 16 experts = 512 values, two per thread
+        float dreg[2 * MT];
+        auto fetch_dl = [&](int st) {   // 32 tokens x EG experts, 2 MT values per thread
             const int64_t t0 = tok_base(st);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int idx = tid + i * 256, r = idx >> 4, e = g0 + (idx & 15);
+            for (int i = 0; i < 2 * MT; ++i) {
+                const int ix = tid + i * 256, r = ix / EG, e = g0 + (ix % EG);
                 dreg[i] = (t0 + r < T && e < E) ? __ldg(dlogits + (t0 + r) * E + e) : 0.0f;
             }
         };
         auto store_dl = [&](int buf) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int idx = tid + i * 256;
-                dls(buf)[(idx >> 4) * kWgLdl + (idx & 15)] = dreg[i];
+            for (int i = 0; i < 2 * MT; ++i) {
+                const int ix = tid + i * 256;
+                dls(buf)[(ix / EG) * LDL + (ix % EG)] = dreg[i];
             }
         };
         if (steps > 0) {
@@ -1104,35 +1118,46 @@ gate_wgrad_partial_mma_kernel(const float* __restrict__ dlogits, const __nv_bflo
 #pragma unroll
             for (int ks = 0; ks < kWgSub / 8; ++ks) {
                 const int k0 = ks * 8;
-                uint32_t a[4];
-                a[0] = to_tf32(db[(k0 + t) * kWgLdl + g]);
-                a[1] = to_tf32(db[(k0 + t) * kWgLdl + g + 8]);
-                a[2] = to_tf32(db[(k0 + t + 4) * kWgLdl + g]);
-                a[3] = to_tf32(db[(k0 + t + 4) * kWgLdl + g + 8]);
+                uint32_t a[MT][4];
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    a[m][0] = to_tf32(db[(k0 + t) * LDL + 16 * m + g]);
+                    a[m][1] = to_tf32(db[(k0 + t) * LDL + 16 * m + g + 8]);
+                    a[m][2] = to_tf32(db[(k0 + t + 4) * LDL + 16 * m + g]);
+                    a[m][3] = to_tf32(db[(k0 + t + 4) * LDL + 16 * m + g + 8]);
+                }
                 const uint16_t* r0 = xb + static_cast<size_t>(k0 + t) * ldx + warp * fw + g;
                 const uint16_t* r1 = r0 + 4 * static_cast<size_t>(ldx);
 #pragma unroll
-                for (int j = 0; j < kWgMaxNT; ++j) {
-                    if (j < nt) mma_tf32_16x8x8(acc[j], a, static_cast<uint32_t>(r0[j * 8]) << 16, static_cast<uint32_t>(r1[j * 8]) << 16);
+                for (int j = 0; j < MAXT / MT; ++j) {
+                    if (j < nt) {
+                        const uint32_t b0 = static_cast<uint32_t>(r0[j * 8]) << 16, b1 = static_cast<uint32_t>(r1[j * 8]) << 16;
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) mma_tf32_16x8x8(acc[j * MT + m], a[m], b0, b1);
+                    }
                 }
             }
-            if (tid < 16) {
+            if (blockIdx.y == 0 && tid < EG) {
 #pragma unroll 8
-                for (int r = 0; r < kWgSub; ++r) bsum += db[r * kWgLdl + tid];
+                for (int r = 0; r < kWgSub; ++r) bsum += db[r * LDL + tid];
             }
             if (st + 1 < steps) store_dl(buf ^ 1);
             __syncthreads();                // readers of buffer `buf` are done before step st + 2 overwrites it
         }
         // C fragment: rows g, g + 8 = experts, columns 2t, 2t + 1 of each n-tile = features
 #pragma unroll
-        for (int j = 0; j < kWgMaxNT; ++j) {
+        for (int j = 0; j < MAXT / MT; ++j) {
             if (j < nt) {
-                const int col = warp * fw + j * 8 + 2 * t;
-                if (g0 + g < E) *reinterpret_cast<float2*>(pw + static_cast<size_t>(g0 + g) * d + col) = make_float2(acc[j][0], acc[j][1]);
-                if (g0 + g + 8 < E) *reinterpret_cast<float2*>(pw + static_cast<size_t>(g0 + g + 8) * d + col) = make_float2(acc[j][2], acc[j][3]);
+                const int col = f0 + warp * fw + j * 8 + 2 * t;
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    const int e = g0 + 16 * m + g;
+                    if (e < E) *reinterpret_cast<float2*>(pw + static_cast<size_t>(e) * d + col) = make_float2(acc[j * MT + m][0], acc[j * MT + m][1]);
+                    if (e + 8 < E) *reinterpret_cast<float2*>(pw + static_cast<size_t>(e + 8) * d + col) = make_float2(acc[j * MT + m][2], acc[j * MT + m][3]);
+                }
             }
         }
-        if (tid < 16 && g0 + tid < E) part_b[static_cast<size_t>(blockIdx.x) * E + g0 + tid] = bsum;
+        if (blockIdx.y == 0 && tid < EG && g0 + tid < E) part_b[static_cast<size_t>(blockIdx.x) * E + g0 + tid] = bsum;
         __syncthreads();
     }
 }
@@ -1382,27 +1407,35 @@ cudaError_t launch_route_scan(const int* tile_hist, const float* tile_psum, int 
     return cudaGetLastError();
 }
 
-cudaError_t launch_dispatch_fwd(const void* x, int x_dtype, const int* idx, const int* tile_base, const int* seg_start,
-                                const int* kept, int64_t T, int d, int E, int k, long long capacity, int* pos,
-                                int* row_src, void* xbuf, cudaStream_t st) {
+cudaError_t launch_dispatch_fwd_rows(const void* x, int x_dtype, const int* idx, const int* tile_base, const int* seg_start,
+                                     int64_t T, int d, int E, int k, long long capacity, int* pos, int* row_src,
+                                     const PeerRows& xrows, void* xpad, const int* pad_seg, const int* pad_kept, int n_pad,
+                                     cudaStream_t st) {
     const int ntiles = static_cast<int>((T + kTokTile - 1) / kTokTile);
     const size_t smem = (static_cast<size_t>(kTokTile * k / 32) * E + static_cast<size_t>(kTokTile) * k) * 4;
-    auto xb = static_cast<__nv_bfloat16*>(xbuf);
+    auto xp = static_cast<__nv_bfloat16*>(xpad);
     cudaError_t err;
     if (x_dtype == MOE_DTYPE_F32) {
         auto kfn = dispatch_fwd_kernel<float>;
         err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        kfn<<<ntiles + E, 256, smem, st>>>(static_cast<const float*>(x), idx, tile_base, seg_start, kept, T, d, E, k,
-                                           capacity, ntiles, pos, row_src, xb);
+        kfn<<<ntiles + n_pad, 256, smem, st>>>(static_cast<const float*>(x), idx, tile_base, seg_start, T, d, E, k,
+                                               capacity, ntiles, pos, row_src, xrows, xp, pad_seg, pad_kept);
     } else {
         auto kfn = dispatch_fwd_kernel<__nv_bfloat16>;
         err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        kfn<<<ntiles + E, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(x), idx, tile_base, seg_start, kept, T, d,
-                                           E, k, capacity, ntiles, pos, row_src, xb);
+        kfn<<<ntiles + n_pad, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(x), idx, tile_base, seg_start, T, d,
+                                               E, k, capacity, ntiles, pos, row_src, xrows, xp, pad_seg, pad_kept);
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_dispatch_fwd(const void* x, int x_dtype, const int* idx, const int* tile_base, const int* seg_start,
+                                const int* kept, int64_t T, int d, int E, int k, long long capacity, int* pos,
+                                int* row_src, void* xbuf, cudaStream_t st) {
+    return launch_dispatch_fwd_rows(x, x_dtype, idx, tile_base, seg_start, T, d, E, k, capacity, pos, row_src, local_rows(xbuf),
+                                    xbuf, seg_start, kept, E, st);
 }
 
 static int grid_for(int64_t items, int sm_count) {
@@ -1413,30 +1446,40 @@ static int grid_for(int64_t items, int sm_count) {
     return static_cast<int>(blocks);
 }
 
+cudaError_t launch_combine_fwd_rows(const PeerRows& yrows, const int* pos, const float* score, int64_t T, int d, int k, void* out,
+                                    int out_dtype, int sm_count, cudaStream_t st) {
+    const int grid = grid_for(T * (d / 8), sm_count);
+    if (out_dtype == MOE_DTYPE_F32)
+        combine_fwd_kernel<float><<<grid, 256, 0, st>>>(yrows, pos, score, T, d, k, static_cast<float*>(out));
+    else
+        combine_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(yrows, pos, score, T, d, k, static_cast<__nv_bfloat16*>(out));
+    return cudaGetLastError();
+}
+
 cudaError_t launch_combine_fwd(const void* ybuf, const int* pos, const float* score, int64_t T, int d, int k, void* out,
                                int out_dtype, int sm_count, cudaStream_t st) {
-    const int grid = grid_for(T * (d / 8), sm_count);
-    auto yb = static_cast<const __nv_bfloat16*>(ybuf);
-    if (out_dtype == MOE_DTYPE_F32)
-        combine_fwd_kernel<float><<<grid, 256, 0, st>>>(yb, pos, score, T, d, k, static_cast<float*>(out));
+    return launch_combine_fwd_rows(local_rows(ybuf), pos, score, T, d, k, out, out_dtype, sm_count, st);
+}
+
+cudaError_t launch_combine_bwd_rows(const void* dy, int dy_dtype, const PeerRows& yrows, const int* pos, const float* score,
+                                    const int* pad_seg, const int* pad_kept, int n_pad, int64_t T, int d, int k,
+                                    const PeerRows& dyrows, void* dypad, float* dscore, cudaStream_t st) {
+    const int nb = static_cast<int>((T + 7) / 8);
+    auto db = static_cast<__nv_bfloat16*>(dypad);
+    if (dy_dtype == MOE_DTYPE_F32)
+        combine_bwd_kernel<float><<<nb + n_pad, 256, 0, st>>>(static_cast<const float*>(dy), yrows, pos, score, pad_seg, pad_kept,
+                                                              T, d, k, nb, dyrows, db, dscore);
     else
-        combine_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(yb, pos, score, T, d, k, static_cast<__nv_bfloat16*>(out));
+        combine_bwd_kernel<__nv_bfloat16><<<nb + n_pad, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), yrows, pos, score,
+                                                                      pad_seg, pad_kept, T, d, k, nb, dyrows, db, dscore);
     return cudaGetLastError();
 }
 
 cudaError_t launch_combine_bwd(const void* dy, int dy_dtype, const void* ybuf, const int* pos, const float* score,
                                const int* seg_start, const int* kept, int64_t T, int d, int k, int E, void* dybuf,
                                float* dscore, cudaStream_t st) {
-    const int nb = static_cast<int>((T + 7) / 8);
-    auto yb = static_cast<const __nv_bfloat16*>(ybuf);
-    auto db = static_cast<__nv_bfloat16*>(dybuf);
-    if (dy_dtype == MOE_DTYPE_F32)
-        combine_bwd_kernel<float><<<nb + E, 256, 0, st>>>(static_cast<const float*>(dy), yb, pos, score, seg_start, kept,
-                                                          T, d, k, E, nb, db, dscore);
-    else
-        combine_bwd_kernel<__nv_bfloat16><<<nb + E, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), yb, pos, score,
-                                                                  seg_start, kept, T, d, k, E, nb, db, dscore);
-    return cudaGetLastError();
+    return launch_combine_bwd_rows(dy, dy_dtype, local_rows(ybuf), pos, score, seg_start, kept, E, T, d, k, local_rows(dybuf), dybuf,
+                                   dscore, st);
 }
 
 cudaError_t launch_gate_bwd(const float* logits, const int* idx, const float* score, const float* dscore,
@@ -1464,6 +1507,9 @@ cudaError_t launch_dispatch_bwd(const void* dxbuf, const int* pos, const float* 
 cudaError_t launch_gate_dispatch_bwd(const void* dxbuf, const int* pos, const float* logits, const int* idx, const float* score,
                                      const float* dscore, const float* dpsum, const float* Wg, int64_t T, int d, int E, int k,
                                      int score_mode, float* dlogits, void* dx, int dx_dtype, cudaStream_t st) {
+    if (gate_dispatch_bwd_mma_supported(d, E, k))   // E <= 64: dlogits Wg on the tensor cores (csrc/gate_bwd_mma.cu)
+        return launch_gate_dispatch_bwd_mma(local_rows(dxbuf), pos, logits, idx, score, dscore, dpsum, Wg, T, d, E, k, score_mode,
+                                            dlogits, dx, dx_dtype, st);
     const int ntiles = static_cast<int>((T + kTokTile - 1) / kTokTile);
     // staged gather: the largest sub-tile (tokens) whose k rows each fit 64 KB, so that 2-3 CTAs stay resident per SM
     int ts = 0;
@@ -1501,28 +1547,51 @@ size_t gate_wgrad_workspace_bytes(int64_t T, int d, int E) {
     return nb * (static_cast<size_t>(E) * d + E) * 4;
 }
 
+template <int MT>
+static cudaError_t launch_gate_wgrad_mma(const float* dlogits, const __nv_bfloat16* x, int64_t T, int d, int E, int ntiles, int nb,
+                                         int slices, float* part_w, float* part_b, cudaStream_t st) {
+    const int ds = d / slices;
+    const size_t smem = 2 * static_cast<size_t>(kWgSub) * (ds + 8) * 2 + 2 * static_cast<size_t>(kWgSub) * (16 * MT + 8) * 4;
+    auto kfn = gate_wgrad_partial_mma_kernel<MT>;
+    cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    kfn<<<dim3(nb, slices), 256, smem, st>>>(dlogits, x, T, d, E, ntiles, part_w, part_b);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gate_wgrad(const float* dlogits, const void* x, int x_dtype, int64_t T, int d, int E, void* workspace,
                               float* dWg, float* dbg, cudaStream_t st) {
     const int ntiles = static_cast<int>((T + kWgTile - 1) / kWgTile);
-    const int nb = gate_wgrad_blocks(T, sm_count());
+    int nb = gate_wgrad_blocks(T, sm_count());
     float* part_w = static_cast<float*>(workspace);
-    float* part_b = part_w + static_cast<size_t>(nb) * E * d;
-    const int CG = d / 4, TG = CG + 1 > 256 ? 1 : 256 / (CG + 1);
-    const size_t smem = (static_cast<size_t>(kWgTile) * E + (TG > 1 ? static_cast<size_t>(TG) * kWgEG * (d + 4) : 0)) * 4;
     cudaError_t err;
     if (x_dtype == MOE_DTYPE_F32) {
+        float* part_b = part_w + static_cast<size_t>(nb) * E * d;
+        const int CG = d / 4, TG = CG + 1 > 256 ? 1 : 256 / (CG + 1);
+        const size_t smem = (static_cast<size_t>(kWgTile) * E + (TG > 1 ? static_cast<size_t>(TG) * kWgEG * (d + 4) : 0)) * 4;
         auto kfn = gate_wgrad_partial_kernel<float>;
         err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
         kfn<<<nb, 256, smem, st>>>(dlogits, static_cast<const float*>(x), T, d, E, ntiles, part_w, part_b);
-    } else {
-        const size_t smem_mma = 2 * static_cast<size_t>(kWgSub) * (d + 8) * 2 + 2 * static_cast<size_t>(kWgSub) * kWgLdl * 4;
-        auto kfn = gate_wgrad_partial_mma_kernel;
-        err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+        err = cudaGetLastError();
         if (err != cudaSuccess) return err;
-        kfn<<<nb, 256, smem_mma, st>>>(dlogits, static_cast<const __nv_bfloat16*>(x), T, d, E, ntiles, part_w, part_b);
+        const int n = E * d + E;
+        gate_wgrad_reduce_kernel<<<(n + 7) / 8, 256, 0, st>>>(part_w, part_b, nb, d, E, dWg, dbg);
+        return cudaGetLastError();
     }
-    err = cudaGetLastError();
+    // bf16 activations: tensor cores, every expert in one pass over x.  MT 16-expert m-tiles x (d / 64 / slices) n-tiles per
+    // warp must fit 16 accumulator tiles: wide layers are cut into feature slices (grid.y), and the token blocks shrink by
+    // the same factor so that the grid stays at two CTAs per SM and the partials to reduce get fewer.
+    const int mt = E <= 16 ? 1 : E <= 32 ? 2 : 4;
+    const int nt_full = d / 64;
+    int slices = 1;
+    while (slices < nt_full && (nt_full % slices != 0 || mt * (nt_full / slices) > 16)) ++slices;
+    nb = nb / slices > 0 ? nb / slices : 1;
+    float* part_b = part_w + static_cast<size_t>(nb) * E * d;
+    auto xb = static_cast<const __nv_bfloat16*>(x);
+    err = mt == 1 ? launch_gate_wgrad_mma<1>(dlogits, xb, T, d, E, ntiles, nb, slices, part_w, part_b, st)
+        : mt == 2 ? launch_gate_wgrad_mma<2>(dlogits, xb, T, d, E, ntiles, nb, slices, part_w, part_b, st)
+                  : launch_gate_wgrad_mma<4>(dlogits, xb, T, d, E, ntiles, nb, slices, part_w, part_b, st);
     if (err != cudaSuccess) return err;
     const int n = E * d + E;
     gate_wgrad_reduce_kernel<<<(n + 7) / 8, 256, 0, st>>>(part_w, part_b, nb, d, E, dWg, dbg);

@@ -6,7 +6,7 @@ from .dense import DenseFFN  # noqa: F401
 from .distributed import DistributedGroupedDataParallel  # noqa: F401
 from .fused import AddLayerNorm, Linear, add_layer_norm, fast_linear  # noqa: F401
 from .gates import BaseGate, GShardGate, NaiveGate, SwitchGate  # noqa: F401
-from .integration import MoEAuxCriterion, install_switch_moe, load_balance_stats, log_load_balance, make_gate  # noqa: F401
+from .integration import MoEAuxCriterion, build_moe_mlp, install_switch_moe, load_balance_stats, log_load_balance, make_gate  # noqa: F401
 from .layers import FMoE  # noqa: F401
 from .linear import FMoELinear  # noqa: F401
 from .transformer import FMoETransformerMLP  # noqa: F401

@@ -31,6 +31,16 @@ SIGNATURES = {
     "moe_route_scan": (_i, [_p, _p, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _i, _p, _i, _i64, _i, _p, _p, _i64, _p]),
     "moe_ep_tables": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "moe_ep_repack": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _i, _i, _p]),
+    "moe_ep_heap_alloc": (_i, [_sz, ctypes.POINTER(_p), _p]),
+    "moe_ep_heap_open": (_i, [_p, ctypes.POINTER(_p)]),
+    "moe_ep_heap_close": (_i, [_p]),
+    "moe_ep_heap_free": (_i, [_p]),
+    "moe_ep_barrier": (_i, [_p, _p, _i, _i, _p, _p]),
+    "moe_ep_exchange_counts": (_i, [_p, _p, _p, _p, _i, _i, _i, _i64, _p, _p, _p, _p, _p, _i, _p, _p]),
+    "moe_dispatch_fwd_peer": (_i, [_p, _i, _p, _p, _p, _i64, _i, _i, _i, _i64, _p, _i, _i, _i64, _p, _p, _p, _p]),
+    "moe_combine_fwd_peer": (_i, [_p, _i, _i, _i64, _p, _p, _i64, _i, _i, _p, _i, _p]),
+    "moe_combine_bwd_peer": (_i, [_p, _i, _p, _p, _i, _i, _i64, _p, _p, _p, _p, _i, _i64, _i, _i, _p, _p]),
+    "moe_gate_dispatch_bwd_peer": (_i, [_p, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _i, _p]),
     "moe_dispatch_fwd": (_i, [_p, _i, _p, _p, _p, _p, _i64, _i, _i, _i, _i64, _p, _p, _p, _p]),
     "moe_expert_ffn_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p, _p]),
     "moe_combine_fwd": (_i, [_p, _p, _p, _i64, _i, _i, _p, _i, _p]),
@@ -81,6 +91,8 @@ class MoeB200Error(RuntimeError):
 
 # kernels launched by each entry point (for the launch count the bench reports)
 KERNELS_PER_CALL = {
+    "moe_ep_barrier": 1, "moe_ep_exchange_counts": 1, "moe_dispatch_fwd_peer": 1, "moe_combine_fwd_peer": 1, "moe_combine_bwd_peer": 1,
+    "moe_gate_dispatch_bwd_peer": 1,
     "moe_gate_fwd": 2, "moe_route_scan": 1, "moe_ep_tables": 1, "moe_ep_repack": 1, "moe_dispatch_fwd": 1, "moe_expert_ffn_fwd": 2, "moe_combine_fwd": 1,
     "moe_combine_bwd": 1, "moe_expert_ffn_bwd": 8, "moe_gate_bwd": 1, "moe_dispatch_bwd": 1, "moe_gate_dispatch_bwd": 1,
     "moe_gate_wgrad": 2, "moe_addln_fwd": 1, "moe_addln_bwd": 2, "moe_colsum": 2, "moe_cast_bf16": 1, "moe_cast_bf16_transposed": 1, "moe_segment_colsum": 2, "moe_grouped_gemm": 1, "moe_slab_colsum_final": 1,

@@ -272,6 +272,23 @@ class EPMoEFunction(torch.autograd.Function):
         return dx, dWg, dbg, dW1, db1, dW2, db2, None, None, None, None, None, None
 
 
+# How the rows travel between the ranks: "peer" = NVLink / NVSwitch peer memory, kernels write and read the owners'
+# packed buffers in place (fmoe/peer.py); "nccl" = all_to_all_single on fixed slabs (this file); "auto" = peer when every
+# rank sits on this node with peer access and the shape fits its kernels (E <= 64), else nccl.
+TRANSPORT = "auto"
+
+
+def _pick_transport(layer, x: torch.Tensor, spec: RouteSpec) -> str:
+    if TRANSPORT in ("peer", "nccl"):
+        return TRANSPORT
+    if not x.is_cuda:
+        return "nccl"
+    from .peer import peer_transport_available
+    E, d, k = layer.num_expert * layer.world_size, layer.d_model, spec.top_k
+    fits = E <= 64 and 16 * k * (2 * d + 16) + 64 * (E + 12) * 4 <= 100 * 1024     # gate/dispatch backward stages k rows per token
+    return "peer" if (fits and peer_transport_available(layer.moe_group)) else "nccl"
+
+
 def ep_forward(layer, moe_inp: torch.Tensor) -> torch.Tensor:
     """`FMoE.forward` for world_size > 1."""
     gate = layer.gate
@@ -279,15 +296,25 @@ def ep_forward(layer, moe_inp: torch.Tensor) -> torch.Tensor:
     spec = gate.route_spec(T)
     if spec.capacity >= T * spec.top_k:
         raise NotImplementedError(
-            f"{type(gate).__name__} has no per-expert capacity: expert parallelism exchanges fixed-size slabs and needs a "
-            "capacity-limited gate (SwitchGate / GShardGate)")
+            f"{type(gate).__name__} has no per-expert capacity: expert parallelism exchanges rows into statically sized buffers and "
+            "needs a capacity-limited gate (SwitchGate / GShardGate)")
     if not getattr(layer, "_ep_group_checked", False):
         _check_group(layer)
         layer._ep_group_checked = True
     W1, b1, W2, b2 = layer._expert_params()
     fresh = torch.is_grad_enabled() and (W1.requires_grad or W2.requires_grad)
-    y, aux, count, kept = EPMoEFunction.apply(moe_inp, gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec,
-                                              layer._bf16_cache, gate.make_noise(moe_inp), layer.moe_group, layer.world_size, fresh)
+    transport = getattr(layer, "_ep_transport", None)
+    if transport is None or TRANSPORT != "auto":
+        transport = layer._ep_transport = _pick_transport(layer, moe_inp, spec)
+    if transport == "peer":
+        from .peer import EPPeerMoEFunction, peer_buffers
+        pb = peer_buffers(layer, T, layer.d_model, layer.num_expert * layer.world_size, layer.num_expert, spec.top_k, spec.capacity,
+                          moe_inp.device)
+        y, aux, count, kept = EPPeerMoEFunction.apply(moe_inp, gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec,
+                                                      layer._bf16_cache, gate.make_noise(moe_inp), pb, fresh)
+    else:
+        y, aux, count, kept = EPMoEFunction.apply(moe_inp, gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec,
+                                                  layer._bf16_cache, gate.make_noise(moe_inp), layer.moe_group, layer.world_size, fresh)
     gate.finish(aux)
     layer.last_count, layer.last_kept = count, kept
     return y

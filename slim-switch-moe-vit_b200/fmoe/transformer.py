@@ -67,4 +67,6 @@ class FMoETransformerMLP(FMoE):
         original_shape = inp.shape
         inp = inp.reshape(-1, self.d_model)
         output = super().forward(inp, None if token_mask is None else token_mask.reshape(-1))
+        if output.dtype != inp.dtype:   # fp16 activations are widened to fp32 inside the layer; the caller gets its dtype back
+            output = output.to(inp.dtype)
         return output.reshape(original_shape)

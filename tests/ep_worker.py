@@ -1,7 +1,8 @@
 """Expert-parallel parity worker: run under torch.distributed.run with W ranks (one GPU each, NCCL).
 Every rank checks its own outputs / gradients against the single-process CPU oracle evaluated with
 ALL experts on that rank's token shard (per-source-rank capacity keeps the routing identical).
-Prints `EP_OK rank=<r>` on success."""
+usage: ep_worker.py [peer|nccl]  — how the rows travel: NVLink peer memory (fmoe/peer.py, default) or NCCL all-to-all on
+slabs (fmoe/distributed.py).  Prints `EP_OK rank=<r>` on success."""
 import os
 import sys
 
@@ -21,6 +22,10 @@ def main():
     from fmoe import _cabi as C
     from fmoe import functions as Fn
     from fmoe.distributed import EPMoEFunction
+    from fmoe.peer import EPPeerMoEFunction, PeerBuffers, peer_transport_available
+    transport = sys.argv[1] if len(sys.argv) > 1 else "peer"
+    if transport == "peer":
+        assert peer_transport_available(None), "peer transport needs all ranks on one NVLink node"
 
     for (T, d, h, E, k, mode, cf, aux_mode) in [(1000, 128, 256, 8, 1, 1, 1.25, C.AUX_SWITCH),
                                                 (777, 192, 768, 4 * W, 2, 0, 1.0, C.AUX_GSHARD),
@@ -38,10 +43,24 @@ def main():
         sl = slice(rank * El, (rank + 1) * El)
         dev = [t.cuda().requires_grad_() for t in (xs[rank], Wg, bg, W1[sl].contiguous(), b1[sl].contiguous(),
                                                    W2[sl].contiguous(), b2[sl].contiguous())]
-        y, aux, count, kept = EPMoEFunction.apply(*dev, spec, Fn.Bf16WeightCache(), None, None, W)
+        if transport == "peer":
+            pb = PeerBuffers(T, d, E, El, k, cap, None, torch.device("cuda", torch.cuda.current_device()))
+            y, aux, count, kept = EPPeerMoEFunction.apply(*dev, spec, Fn.Bf16WeightCache(), None, pb)
+        else:
+            y, aux, count, kept = EPMoEFunction.apply(*dev, spec, Fn.Bf16WeightCache(), None, None, W)
         aux_w = 0.37
         ((y * dys[rank].cuda()).sum() + aux_w * aux).backward()
         torch.cuda.synchronize()
+        if transport == "peer":
+            pb.check()          # no barrier timed out, every packed layout fitted
+            # a second forward + backward on the same buffers (epochs keep counting; what a training loop / graph replay does)
+            for t_ in dev:
+                t_.grad = None
+            y2, aux2, _, _ = EPPeerMoEFunction.apply(*dev, spec, Fn.Bf16WeightCache(), None, pb)
+            ((y2 * dys[rank].cuda()).sum() + aux_w * aux2).backward()
+            torch.cuda.synchronize()
+            pb.check()
+            assert torch.equal(y2, y), "second pass over the same peer buffers must reproduce the first bit for bit"
 
         exp = {}
         for r in range(W):   # oracle of every rank's shard (expert gradients sum over the source ranks)
@@ -62,7 +81,10 @@ def main():
             assert e <= 6e-3, f"{name}: {e} (T={T} E={E} k={k})"
         dropped = int((mine_sv.r.pos < 0).sum())
         if rank == 0:
-            print(f"case T={T} d={d} E={E} k={k}: ok (dropped pairs on rank 0: {dropped})", flush=True)
+            print(f"case T={T} d={d} E={E} k={k} transport={transport} W={W}: ok (dropped pairs on rank 0: {dropped})", flush=True)
+        if transport == "peer":
+            dist.barrier()
+            pb.heap.close()
     dist.barrier()
     print(f"EP_OK rank={rank}", flush=True)
     dist.destroy_process_group()

@@ -92,10 +92,15 @@ def test_ep_host_logic_gloo(world):
 
 
 @pytest.mark.gpu
-def test_ep_parity_two_gpus():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29631", os.path.join(ROOT, "tests", "ep_worker.py")]
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_ep_parity_multi_gpu(transport):
+    """Expert-parallel layer on every visible GPU (2, 4 or 8; `gpurun --gpus N`) against the single-process oracle of each
+    rank's token shard — rows exchanged through NVLink peer memory (fmoe/peer.py) and through NCCL slabs."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2|4|8)")
+    W = 8 if n >= 8 else 4 if n >= 4 else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={W}", "--master-addr", "127.0.0.1",
+           "--master-port", "29631" if transport == "peer" else "29633", os.path.join(ROOT, "tests", "ep_worker.py"), transport]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0 and out.stdout.count("EP_OK") == 2, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.returncode == 0 and out.stdout.count("EP_OK") == W, out.stdout[-3000:] + out.stderr[-3000:]
