@@ -382,6 +382,8 @@ def main():
     ap.add_argument("--no-parity-check", action="store_true", help="skip the per-rank routing self-check against the C oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-layer", action="store_true", help="skip the isolated-layer breakdown (profiling runs)")
+    ap.add_argument("--ep-transport", choices=["auto", "peer", "nccl"], default="auto",
+                    help="expert-parallel row exchange: NVLink peer memory (fmoe/peer.py) or NCCL all-to-all on slabs (fmoe/distributed.py)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of replaying the captured training step")
     ap.add_argument("--profile-window", action="store_true",
                     help="cudaProfilerStart/Stop around the device-resident timed region (ncu --profile-from-start off)")
@@ -407,8 +409,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from fmoe import _cabi as C
+    from fmoe import distributed as fmoe_dist
     from moe_vit import MoEViT
 
+    fmoe_dist.TRANSPORT = args.ep_transport
     peaks = load_peaks()
     cfg = make_cfg(world)
     torch.manual_seed(0)           # same dense/gate init on every rank; experts differ per rank below
@@ -622,13 +626,21 @@ def main():
                                "moe_kernels_share_of_step": round(moe_ms / prof_steps / (ms_total / args.steps), 4)},
         }
         if world > 1:   # expert-parallel exchange: per-call CUDA-event times of the eager profiling pass (rank 0)
-            ep_tags = [t_ for t_ in kern if t_.startswith("a2a_") or t_ == "moe_ep_repack" or t_ == "moe_ep_tables"]
-            slab_mb = None
+            transport = getattr(inner.moe_layers[0], "_ep_transport", "nccl")
+            peer_tags = ("moe_ep_exchange_counts", "moe_ep_barrier", "moe_dispatch_fwd_peer", "moe_combine_fwd_peer", "moe_combine_bwd_peer",
+                         "moe_gate_dispatch_bwd_peer")
+            ep_tags = [t_ for t_ in kern if t_.startswith("a2a_") or t_ in ("moe_ep_repack", "moe_ep_tables") or t_ in peer_tags]
+            sync_tags = [t_ for t_ in ep_tags if t_ in ("moe_ep_exchange_counts", "moe_ep_barrier") or t_.startswith("a2a_")]
             line["expert_parallel"] = {
+                "transport": transport,
                 "per_call_ms": {t_: round(kern[t_][1], 4) for t_ in sorted(ep_tags)},
                 "calls_per_step": {t_: kern[t_][0] // prof_steps for t_ in sorted(ep_tags)},
                 "ms_per_step": round(sum(kern[t_][0] * kern[t_][1] for t_ in ep_tags) / prof_steps, 3),
-                "note": "NCCL all_to_all_single on fixed slabs [W, E_local, slab_rows, d] bf16; not overlapped with the expert GEMMs yet"}
+                "sync_ms_per_step": round(sum(kern[t_][0] * kern[t_][1] for t_ in sync_tags) / prof_steps, 3),
+                "note": ("NVLink peer memory: dispatch / combine kernels write and read the owners' packed buffers in place, device-side "
+                         "barriers (eager-mode times include the inter-rank skew they absorb); the peer kernels' times include their local work"
+                         if transport == "peer" else
+                         "NCCL all_to_all_single on fixed slabs [W, E_local, slab_rows, d] bf16 + repack passes")}
         line["config"]["name"] = CONFIG
         line["load_balance"] = lb
         if parity is not None:

@@ -53,6 +53,9 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t saddr, uint32_t (&r)[4]) 
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
 }
+__device__ __forceinline__ void stsm_x2(uint32_t saddr, uint32_t r0, uint32_t r1) {   // row addresses from lanes 0-15
+    asm volatile("stmatrix.sync.aligned.m8n8.x2.shared.b16 [%0], {%1, %2};" ::"r"(saddr), "r"(r0), "r"(r1) : "memory");
+}
 __device__ __forceinline__ void stsm_x4(uint32_t saddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
     asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
@@ -63,7 +66,7 @@ __device__ __forceinline__ void stsm_x4(uint32_t saddr, uint32_t r0, uint32_t r1
 // fragment), so  acc = dlogits Wg (tf32)  +  I rows_slot0 (+ I rows_slot1 ...)  exactly, in fp32, with two shared-memory
 // instructions per 16 x 16 block instead of a load / unpack / add per element pair.
 template <typename OT, int NKB, int KT>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (NKB <= 2 ? 4 : NKB == 4 ? 3 : 2))   // resident CTAs hide each other's phase latencies
 gate_dispatch_bwd_mma_kernel(PeerRows dxrows, const int* __restrict__ pos, const float* __restrict__ logits,
                              const int* __restrict__ idx, const float* __restrict__ score, const float* __restrict__ dscore,
                              const float* __restrict__ dpsum, const float* __restrict__ Wg, int64_t T, int d, int E, int k_rt,
@@ -198,7 +201,7 @@ gate_dispatch_bwd_mma_kernel(PeerRows dxrows, const int* __restrict__ pos, const
         __syncthreads();
         const int n_mt = (min(ts, n_tok - sub) + 15) >> 4;
         for (int c0 = 0; c0 < NTW; c0 += NC) {
-            const int nc = min(NC, NTW - c0);   // even: d % 128 == 0 ... or 2 / 6 n-tiles per warp: always a multiple of 2? (checked at launch)
+            const int nc = min(NC, NTW - c0);
             uint32_t bf[NKB][NC][2];
 #pragma unroll
             for (int ks = 0; ks < NKB; ++ks) {
@@ -231,15 +234,19 @@ gate_dispatch_bwd_mma_kernel(PeerRows dxrows, const int* __restrict__ pos, const
 #pragma unroll
                 for (int np = 0; np < NC / 2; ++np) {
                     if (2 * np < nc) {
+                        const bool pair = 2 * np + 1 < nc;   // an odd tail (d / 64 odd) reads its neighbour's 8 columns (or the row pad) and drops them
                         for (int j = 0; j < k; ++j) {
                             uint32_t b[4];
                             ldsm_x4_trans(blk + j * RS + np * 32, b);
                             mma_bf16(acc[2 * np], ident, 0u, 0u, ident, b[0], b[1]);
-                            mma_bf16(acc[2 * np + 1], ident, 0u, 0u, ident, b[2], b[3]);
+                            if (pair) mma_bf16(acc[2 * np + 1], ident, 0u, 0u, ident, b[2], b[3]);
                         }
                         if constexpr (sizeof(OT) == 2) {   // slot j = 0 of the block now holds dx (bf16), row-major again
-                            stsm_x4(blk + np * 32, pack_bf162(acc[2 * np][0], acc[2 * np][1]), pack_bf162(acc[2 * np][2], acc[2 * np][3]),
-                                    pack_bf162(acc[2 * np + 1][0], acc[2 * np + 1][1]), pack_bf162(acc[2 * np + 1][2], acc[2 * np + 1][3]));
+                            if (pair)
+                                stsm_x4(blk + np * 32, pack_bf162(acc[2 * np][0], acc[2 * np][1]), pack_bf162(acc[2 * np][2], acc[2 * np][3]),
+                                        pack_bf162(acc[2 * np + 1][0], acc[2 * np + 1][1]), pack_bf162(acc[2 * np + 1][2], acc[2 * np + 1][3]));
+                            else
+                                stsm_x2(blk + np * 32, pack_bf162(acc[2 * np][0], acc[2 * np][1]), pack_bf162(acc[2 * np][2], acc[2 * np][3]));
                         }
                     }
                 }
@@ -295,14 +302,18 @@ cudaError_t launch_k(const PeerRows& rows, const int* pos, const float* logits, 
 }  // namespace
 
 // sub-tile (tokens per staged gather) of the tensor-core kernel, 0 = shape not supported (the CUDA-core kernel runs)
+static size_t gdb_fixed_smem(int nkb, int k) { return static_cast<size_t>(kTile) * (8 * nkb + 4) * 4 + ((kTile * k + 3) & ~3) * 4; }
+
 static int gdb_mma_subtile(int d, int E, int k) {
-    if (E > 64 || d % 128 != 0 || k > kMaxPick) return 0;   // d / 8 columns per warp in pairs of 8-column n-tiles
+    if (E > 64 || d % 64 != 0 || k > kMaxPick) return 0;
     const size_t rs = static_cast<size_t>(d) * 2 + 16;
-    int ts = kTile;
-    while (ts > 16 && static_cast<size_t>(ts) * k * rs > 66 * 1024) ts >>= 1;
     const int nkb = E <= 8 ? 1 : E <= 16 ? 2 : E <= 32 ? 4 : 8;
-    const size_t fixed = static_cast<size_t>(kTile) * (8 * nkb + 4) * 4 + ((kTile * k + 3) & ~3) * 4;
-    return fixed + static_cast<size_t>(ts) * k * rs <= 100 * 1024 ? ts : 0;
+    const int ctas = nkb <= 2 ? 4 : nkb == 4 ? 3 : 2;       // the kernel's launch bounds
+    const size_t budget = (226 * 1024) / ctas - 1024 - gdb_fixed_smem(nkb, k);
+    int ts = kTile;
+    while (ts > 16 && static_cast<size_t>(ts) * k * rs > budget) ts >>= 1;
+    if (static_cast<size_t>(ts) * k * rs <= budget) return ts;
+    return gdb_fixed_smem(nkb, k) + static_cast<size_t>(ts) * k * rs <= 100 * 1024 ? ts : 0;   // fewer resident CTAs, still one kernel
 }
 
 bool gate_dispatch_bwd_mma_supported(int d, int E, int k) { return gdb_mma_subtile(d, E, k) > 0; }
@@ -313,7 +324,7 @@ cudaError_t launch_gate_dispatch_bwd_mma(const PeerRows& rows, const int* pos, c
                                          cudaStream_t st) {
     const int ts = gdb_mma_subtile(d, E, k);
     const int nkb = E <= 8 ? 1 : E <= 16 ? 2 : E <= 32 ? 4 : 8;
-    const size_t smem = static_cast<size_t>(kTile) * (8 * nkb + 4) * 4 + ((kTile * k + 3) & ~3) * 4 + static_cast<size_t>(ts) * k * (d * 2 + 16);
+    const size_t smem = gdb_fixed_smem(nkb, k) + static_cast<size_t>(ts) * k * (d * 2 + 16);
 #define MOE_GDB_LAUNCH(OT_, NKB_) \
     return launch_k<OT_, NKB_>(rows, pos, logits, idx, score, dscore, dpsum, Wg, T, d, E, k, score_mode, dlogits, dx, ts, smem, st)
     if (dx_dtype == MOE_DTYPE_F32) {

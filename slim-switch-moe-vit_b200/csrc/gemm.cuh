@@ -51,7 +51,8 @@
 
 namespace moe {
 
-enum : int { EPI_BIAS_GELU_DUAL = 0, EPI_BIAS = 1, EPI_DGELU = 2, EPI_PLAIN = 3, EPI_F32 = 4, EPI_F32_T = 5 };
+enum : int { EPI_BIAS_GELU_DUAL = 0, EPI_BIAS = 1, EPI_DGELU = 2, EPI_PLAIN = 3, EPI_F32 = 4, EPI_F32_T = 5,
+              EPI_BIAS_GELU = 6 /* fc1 without gelu': forward-only (evaluation) passes */ };
 
 struct GemmParams {
     const int* tile_expert;  // ROWS: expert of each 256-row pair tile       [max_mtiles]
@@ -61,7 +62,7 @@ struct GemmParams {
     const __nv_bfloat16* aux;  // EPI_DGELU: G = gelu'(U) [rows_cap, N] (read through its tensor map)
     float* colsum;           // EPI_DGELU (optional): column sums of every 32-row output slab, [rows_cap / 32, N] fp32
     int* flags;              // WGRAD split-K: one int per (tile, CTA rank, epilogue warp), zero between launches
-    int ksplit;              // WGRAD: 1, or 2 = every tile's K range is done in two halves by two work units
+    int ksplit;              // WGRAD: S >= 2 = every tile's K range is done in S parts by S work units (chained through the flags)
     int E;
     int M;  // WGRAD: output rows per expert
     int N;  // output columns (per expert)
@@ -85,7 +86,7 @@ constexpr int kBK = 64;
 #define MOE_DGELU_EPI_WARPS 8
 #endif
 __host__ __device__ constexpr int epi_warps(int epi, int bn) {
-    return epi == 0 /* EPI_BIAS_GELU_DUAL */ ? MOE_FC1_EPI_WARPS : epi >= 4 /* EPI_F32, EPI_F32_T */ ? 12
+    return epi == 0 /* EPI_BIAS_GELU_DUAL */ ? MOE_FC1_EPI_WARPS : (epi == 4 || epi == 5) /* EPI_F32, EPI_F32_T */ ? 12
            : epi == 2 /* EPI_DGELU */ ? MOE_DGELU_EPI_WARPS : bn > 256 ? MOE_WIDE_EPI_WARPS : 8;
 }
 constexpr int kSmemLimit = 232448;    // 227 KB
@@ -163,7 +164,7 @@ __device__ __forceinline__ void epilogue_block16(const uint32_t* acc, uint32_t b
     float2 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-    if constexpr (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS) {
+    if constexpr (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
         float2 b[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -210,6 +211,26 @@ __device__ __forceinline__ void epilogue_block16(const uint32_t* acc, uint32_t b
             const float2 om = __ffma2_rn(m, splat2(-1.0f), splat2(1.0f));
             o0[i] = pack_bf16x2(make_float2(v[i].x < 0.0f ? m.x : om.x, v[i].y < 0.0f ? m.y : om.y));
         }
+    } else if constexpr (EPI == EPI_BIAS_GELU) {   // same arithmetic as the gelu half of the dual epilogue (bit-identical H)
+        float2 a[8], g[8], w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = make_float2(fminf(fabsf(v[i].x), kGeluAMax), fminf(fabsf(v[i].y), kGeluAMax));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = __fmul2_rn(__fmul2_rn(a[i], splat2(kNegHalfLog2e)), a[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = make_float2(ex2_approx(g[i].x), ex2_approx(g[i].y));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = __ffma2_rn(splat2(kGeluW[7]), a[i], splat2(kGeluW[6]));
+#pragma unroll
+        for (int k = 5; k >= 0; --k) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = __ffma2_rn(w[i], a[i], splat2(kGeluW[k]));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 q = __fmul2_rn(g[i], w[i]);                                                   // Phi(-a)
+            o0[i] = pack_bf16x2(__ffma2_rn(make_float2(-a[i].x, -a[i].y), q, make_float2(fmaxf(v[i].x, 0.0f), fmaxf(v[i].y, 0.0f))));
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) o0[i] = pack_bf16x2(v[i]);
@@ -235,7 +256,7 @@ struct TileCoord {
     int row0;   // WGRAD: first packed row of the expert segment
     int kb;     // number of 64-deep k-blocks
     int kb0;    // WGRAD: first k-block of this work unit inside the expert segment
-    int part;   // WGRAD split-K: 1 = early half (plain store, then raises the flags), 0 = late half (waits, reduce-adds); -1 = unsplit
+    int part;   // WGRAD split-K: part s of S: 0 = plain store, s > 0 waits for part s - 1 and reduce-adds (fixed order); -1 = unsplit
     int tile;   // WGRAD: output tile index (flags)
 };
 // first B column (inside the pair tile) of this CTA's i-th 64-column block: BN <= 256: this CTA's half;
@@ -261,10 +282,10 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
         int m_tiles = (p.M + kPairM - 1) / kPairM;
         int per_e = m_tiles * n_ntiles;
         c.part = -1;
-        if (p.ksplit == 2) {   // units [0, tiles) are the early halves, [tiles, 2 tiles) the late ones
+        if (p.ksplit >= 2) {   // units [s tiles, (s + 1) tiles) are part s of every tile: a part only ever waits on a lower unit index
             const int ntile = p.E * per_e;
-            c.part = tile < ntile ? 1 : 0;
-            if (tile >= ntile) tile -= ntile;
+            c.part = tile / ntile;
+            tile -= c.part * ntile;
         }
         c.tile = tile;
         c.e = tile / per_e;
@@ -275,10 +296,11 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
         c.row0 = __ldg(p.seg_start + c.e);
         c.kb = (__ldg(p.seg_start + c.e + 1) - c.row0) / kBK;
         c.kb0 = 0;
-        if (c.part >= 0) {
-            const int h0 = c.kb / 2;   // late half: [0, h0); early half: [h0, kb) — never smaller than the late one
-            if (c.part == 0) c.kb = h0;
-            else { c.kb0 = h0; c.kb -= h0; }
+        if (c.part >= 0) {     // part s covers k-blocks [kb s / S, kb (s + 1) / S)
+            const int b0 = static_cast<int>(static_cast<long long>(c.kb) * c.part / p.ksplit);
+            const int b1 = static_cast<int>(static_cast<long long>(c.kb) * (c.part + 1) / p.ksplit);
+            c.kb0 = b0;
+            c.kb = b1 - b0;
         }
     }
     return c;
@@ -455,22 +477,23 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
                 const bool live = c.kb != 0;
                 if (tl_on) MOE_TL(tl_role, ti, 0);
-                // split-K: this warp's slabs of the tile are also written by the same warp of the pair that runs the
-                // other half.  The early half stores and then raises its flag; the late half waits for it and
-                // reduce-adds (a + b in one fixed order: bit-reproducible), and leaves the flag cleared.
+                // split-K: this warp's slabs of the tile are also written by the same warp of the pairs that run the other
+                // parts.  Part 0 stores and sets the flag to 1; part s waits for the flag to read s, reduce-adds and passes
+                // s + 1 on (the last part leaves 0): one store, then the adds in one fixed order — bit-reproducible.
                 int* const my_flag = c.part >= 0 ? p.flags + (static_cast<size_t>(c.tile) * 2 + rank) * Cfg::EPI_WARPS + ew : nullptr;
-                if (c.part == 0) {
+                const int pass_on = c.part + 1 == p.ksplit ? 0 : c.part + 1;
+                if (c.part > 0) {
                     if (lane == 0) {
                         uint32_t spins = 0;
-                        while (ld_acquire_gpu(my_flag) == 0) {
+                        while (ld_acquire_gpu(my_flag) != c.part) {
                             __nanosleep(64);
                             if (++spins > (1u << 27)) __trap();
                         }
-                        *reinterpret_cast<volatile int*>(my_flag) = 0;
                         fence_proxy_async_all();
+                        if (!live) st_release_gpu(my_flag, pass_on);   // nothing to add: hand the tile on
                     }
                     __syncwarp();
-                    if (!live) continue;   // nothing to add
+                    if (!live) continue;
                 }
                 if (live) {
                     mbar_wait(tfull_bar + as, aph);
@@ -524,18 +547,18 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             if (c.m0 + q * 32 < p.M && c.n0 + ch * 32 + hb * 16 < p.N) {
                                 const int o_col = EPI == EPI_F32 ? c.n0 + ch * 32 + hb * 16 : c.m0 + q * 32;
                                 const int o_row = EPI == EPI_F32 ? c.m0 + q * 32 : c.n0 + ch * 32 + hb * 16;
-                                if (c.part == 0) tma_reduce_add_3d(&tmO0, slab, o_col, o_row, c.e);
+                                if (c.part > 0) tma_reduce_add_3d(&tmO0, slab, o_col, o_row, c.e);
                                 else tma_store_3d(&tmO0, slab, o_col, o_row, c.e);
                             }
                             tma_store_commit();   // one group per half even when it is empty: wait_group.read 1 counts groups
                         }
                     }
                 }
-                if (c.part == 1) {   // early half: its stores are complete and visible before the flag goes up
+                if (c.part >= 0) {   // this part's stores / adds are complete and visible before the next part is let in
                     if (lane == 0) {
                         tma_store_wait_all<0>();
                         __threadfence();
-                        st_release_gpu(my_flag, 1);
+                        st_release_gpu(my_flag, pass_on);
                     }
                     __syncwarp();
                 }
@@ -565,7 +588,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
                 const bool live = c.kb != 0;
                 if (tl_on) MOE_TL(tl_role, ti, 0);
-                if constexpr (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS) {
+                if constexpr (EPI == EPI_BIAS_GELU_DUAL || EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
                     // lane l fetches 4 consecutive bias values of the group's chunks, four chunks per pass
                     __syncwarp();                                // previous tile's reads of wbias are done
 #pragma unroll

@@ -126,6 +126,7 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
     if ((op == MOE_GEMM_FC1 || op == MOE_GEMM_FC2) && bias == nullptr) { set_error("grouped gemm: fc1 / fc2 need a bias vector"); return 1; }
     if (op == MOE_GEMM_DGELU && aux == nullptr) { set_error("grouped gemm: dgelu needs the pre-activation (aux)"); return 1; }
     const bool wide_ok = op == MOE_GEMM_FC2 || op == MOE_GEMM_DGRAD;
+    const bool infer_fc1 = op == MOE_GEMM_FC1 && out0 == nullptr && out1 != nullptr;
     const int bn = wgrad ? pick_bn_wgrad(N) : pick_bn_rows(N, K, wide_ok);
     if (!wgrad && (bn <= 0 || N % bn != 0 || (bn == 384 && !wide_ok))) { set_error("grouped gemm: BN=%d does not tile N=%d for op %d", bn, N, op); return 1; }
 
@@ -156,6 +157,8 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
         ok = ok && encode_2d(&tB, BF, 2, B, K, static_cast<uint64_t>(E) * N, 64, bn <= 256 ? bn / 2 : 64);
         // each epilogue warp stores (and, for dgelu, loads its rows of the pre-activation as) 32-row x 32-column slabs
         const auto S64 = CU_TENSOR_MAP_SWIZZLE_64B;
+        // fc1 without out0 (G = gelu'): forward-only pass, the single output H goes through the first descriptor
+        if (infer_fc1) out0 = out1;
         ok = ok && encode_2d(&tO0, BF, 2, out0, N, R, 32, 32, S64);
         ok = ok && encode_2d(&tO1, BF, 2, op == MOE_GEMM_FC1 ? out1 : out0, N, R, 32, 32, S64);
         ok = ok && encode_2d(&tAux, BF, 2, op == MOE_GEMM_DGELU ? aux : out0, N, R, 32, 32, S64);
@@ -174,9 +177,20 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
     }
     if (!ok) return 1;
     const int grid = (sm_count / 2) * 2;
-    if (wgrad && p.ksplit == 2) {   // with three or more full rounds of tiles the split buys no balance, only epilogue work
+    if (wgrad && p.ksplit >= 2) {
+        // How many parts per tile: with three or more full rounds of tiles a split buys no balance, only epilogue work; with
+        // fewer tiles than CTA pairs (few local experts under expert parallelism: 12 tiles for 74 pairs at E_local = 2)
+        // every tile is cut into pairs / tiles parts, as long as a part keeps ~16 k-blocks to amortise its epilogue.
+        const int pairs = grid / 2;
         const int64_t ntile = static_cast<int64_t>(E) * ((M + 255) / 256) * ((N + bn - 1) / bn);
-        if (ntile >= 3LL * (grid / 2)) p.ksplit = 1;
+        const int64_t avg_kb = rows_cap / (64LL * (E > 0 ? E : 1));
+        int S = ntile >= 3LL * pairs ? 1 : 2;
+        if (ntile * 2 <= pairs) {
+            S = static_cast<int>(pairs / ntile);
+            if (S > 8) S = 8;
+            while (S > 2 && avg_kb / S < 16) --S;
+        }
+        p.ksplit = S;
     }
 
 #define MOE_BN_ROWS_WIDE(EPI)                                                             \
@@ -190,7 +204,9 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
         default: return launch_one<64, EPI, false>(tA, tB, tO0, tO1, tAux, p, grid, st);        \
     }
     switch (op) {
-        case MOE_GEMM_FC1: MOE_BN_ROWS(EPI_BIAS_GELU_DUAL)
+        case MOE_GEMM_FC1:
+            if (infer_fc1) { MOE_BN_ROWS(EPI_BIAS_GELU) }
+            MOE_BN_ROWS(EPI_BIAS_GELU_DUAL)
         case MOE_GEMM_FC2: MOE_BN_ROWS_WIDE(EPI_BIAS)
         case MOE_GEMM_DGELU: MOE_BN_ROWS(EPI_DGELU)
         case MOE_GEMM_DGRAD: MOE_BN_ROWS_WIDE(EPI_PLAIN)

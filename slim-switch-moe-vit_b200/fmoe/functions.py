@@ -144,7 +144,9 @@ class MoEFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, Wg, bg, W1, b1, W2, b2, spec: RouteSpec, cache: Bf16WeightCache, noise, token_mask=None,
-                fresh: bool = True):
+                fresh: bool = True, infer: bool = False):
+        """infer=True: forward-only pass (torch.no_grad(): the reference's `evaluate`, /root/reference/engine.py:88-121) —
+        fc1 runs its single-output epilogue and G = gelu'(U), which only backward reads, is neither computed nor written."""
         x = _as_kernel_input(x)
         T, d = x.shape
         E, h = W1.shape[0], W1.shape[1]
@@ -159,7 +161,7 @@ class MoEFunction(torch.autograd.Function):
         r = route(x, Wg_c, bg_c, spec, noise, token_mask=token_mask)
         rows_cap = r["rows_cap"]
         W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c, fresh)
-        G = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
+        G = None if infer else torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
         H = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
         Y = torch.empty((rows_cap, d), dtype=torch.bfloat16, device=dev)
         # the two forward GEMMs (same kernels as the bundled moe_expert_ffn_fwd entry point)
@@ -177,6 +179,10 @@ class MoEFunction(torch.autograd.Function):
         ctx.has_bg = bg is not None
         ctx.rows_cap = rows_cap
         coef = r["aux_coef"] if spec.want_psum else torch.empty(0, dtype=torch.float32, device=dev)
+        if infer:
+            aux = r["aux_loss"].reshape(()) if spec.want_psum else torch.empty(0, dtype=torch.float32, device=dev)
+            ctx.mark_non_differentiable(y, aux, r["count"], r["kept"])
+            return y, aux, r["count"], r["kept"]
         ctx.save_for_backward(x, Wg_c, r["logits"], r["idx"], r["score"], r["pos"], r["seg_start"], r["kept"],
                               r["tile_expert"], r["num_mtiles"], r["xbuf"], G, H, Y, W1tb, W2tb, coef)
         ctx.set_materialize_grads(False)
@@ -242,7 +248,7 @@ class MoEFunction(torch.autograd.Function):
         dbg = _f32(E, dev) if ctx.has_bg else None
         C.call("moe_gate_wgrad", C.ptr(dlogits), C.ptr(x), C.dtype_code(x), T, d, E, C.ptr(ws), C.ptr(dWg),
                C.ptr(dbg), st)
-        return dx, dWg, dbg, dW1, db1, dW2, db2, None, None, None, None, None
+        return dx, dWg, dbg, dW1, db1, dW2, db2, None, None, None, None, None, None
 
 
 class SkipFill(torch.autograd.Function):

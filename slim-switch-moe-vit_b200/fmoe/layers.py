@@ -91,8 +91,9 @@ class FMoE(nn.Module):
             keep = (token_mask.reshape(T) != 0).to(torch.uint8)
         # a forward that autograd records re-casts the bf16 weight copies (see Bf16WeightCache); inference reuses them
         fresh = torch.is_grad_enabled() and (W1.requires_grad or W2.requires_grad)
+        infer = not torch.is_grad_enabled()      # evaluate() / no_grad: nothing is kept for a backward pass
         y, aux, count, kept = MoEFunction.apply(moe_inp, gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec,
-                                                self._bf16_cache, gate.make_noise(moe_inp), keep, fresh)
+                                                self._bf16_cache, gate.make_noise(moe_inp), keep, fresh, infer)
         if keep is not None:
             c, J0 = zero_token_path(gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec.top_k, spec.score_mode)
             y = SkipFill.apply(y, moe_inp, keep, c, J0)

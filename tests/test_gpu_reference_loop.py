@@ -144,10 +144,10 @@ def test_fp16_input_is_widened_and_returned_in_fp16():
     torch.manual_seed(0)
     layer = fmoe.FMoETransformerMLP(8, 192, 768, _act(), top_k=2).cuda()
     x = torch.randn(2, 197, 192, device="cuda")
-    y32 = layer(x)
-    y16 = layer(x.half())
+    y32 = layer(x.half().float() * 64.0)          # same values; x64 keeps the outputs clear of fp16's subnormal range
+    y16 = layer(x.half() * 64.0)
     assert y16.dtype == torch.float16 and y16.shape == x.shape
-    assert rel_err(y16, y32) <= 2e-3
+    assert rel_err(y16, y32) <= 2e-3                # fp16 rounding of the returned tensor only (2^-11)
 
 
 def test_full_size_config2_forward_backward_vs_model():
