@@ -64,6 +64,8 @@ CONFIGS = {
     "c4": dict(size="large", num_experts=64, top_k=1, gate="switch", batch=128,
                metric="MoE-ViT training throughput (ViT-L/16 Switch-MoE E64 top-1 cf1.25, bf16, 224px, batch 128/GPU = 1024 on 8 GPUs, expert parallel)"),
 }
+BACKLOG_CYCLES_STEP = int(60e-3 * 1.9e9)    # torch.cuda._sleep spin before each profiled training step (~60 ms)
+BACKLOG_CYCLES_LAYER = int(4e-3 * 1.9e9)    # ... before each profiled isolated-layer iteration (~4 ms)
 CONFIG = "c2"       # set by --config
 METRIC = CONFIGS["c2"]["metric"]
 PER_GPU_BATCH = CONFIGS["c2"]["batch"]
@@ -276,6 +278,7 @@ def layer_bench(peaks, iters=20, warmup=5, T=None, d=384, E=16, k=1, cf=1.25, ga
     C.PROF.reset()
     C.PROF.enabled = True
     for _ in range(iters):
+        torch.cuda._sleep(BACKLOG_CYCLES_LAYER)   # the device starts behind the host: event pairs bracket kernels, not launch gaps
         it()
     torch.cuda.synchronize()
     C.PROF.enabled = False
@@ -453,6 +456,9 @@ def main():
     C.PROF.reset()
     C.PROF.enabled = True
     for _ in range(prof_steps):
+        # eager launches are host-bound (the host needs longer to enqueue a step than the device to run it), so an event pair
+        # around a launch would also time the idle gap before it; a spin kernel first puts the device ~60 ms behind the host
+        torch.cuda._sleep(BACKLOG_CYCLES_STEP)
         train_step(model, opt, img_d, lab_d, bf16)
     barrier()
     C.PROF.enabled = False
@@ -571,7 +577,7 @@ def main():
                     "achieved": round(achieved, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                     "frac": round(achieved / peaks["tf_sustained"], 4), "traffic": None,
                     "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                    "timing": f"CUDA events around each launch in {prof_steps} eager steps of the same loop directly before the timed region",
+                    "timing": f"CUDA events around each launch in {prof_steps} eager steps of the same loop directly before the timed region, device kept backlogged behind the host by a spin kernel (no launch gaps inside the event pairs)",
                     "launches_timed": gemm_calls, "avg_launch_ms": round(gemm_ms / max(1, gemm_calls), 4),
                     "flops_per_launch": flops_per_launch,
                     "share_of_step": round(gemm_ms / prof_steps / (ms_total / args.steps), 4),

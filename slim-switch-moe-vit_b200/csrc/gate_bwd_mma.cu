@@ -176,13 +176,10 @@ gate_dispatch_bwd_mma_kernel(PeerRows dxrows, const int* __restrict__ pos, const
                 if (dpsum != nullptr) v += pe[i] * (dpsum[e] - pdot);
             }
             dl[e] = v;   // rows past the end of the batch and expert columns past E are zero: they feed the MMA
+            if (live && e < E) dlogits[t * E + e] = v;   // the quad of a token covers 4 consecutive experts: 16-byte segments
         }
     }
     __syncthreads();
-    for (int i = tid; i < n_tok * E; i += 256) {
-        const int r = i / E, e = i - r * E;
-        dlogits[t_base * E + i] = dl_s[r * DLS + e];
-    }
 
     const int CW = d >> 3;          // output columns of this warp
     const int NTW = CW >> 3;        // its 8-column n-tiles
@@ -207,10 +204,12 @@ gate_dispatch_bwd_mma_kernel(PeerRows dxrows, const int* __restrict__ pos, const
             for (int ks = 0; ks < NKB; ++ks) {
 #pragma unroll
                 for (int n = 0; n < NC; ++n) {
-                    const int col = warp * CW + (c0 + n) * 8 + g;
-                    const int e0 = ks * 8 + t4, e1 = e0 + 4;
-                    bf[ks][n][0] = (n < nc && e0 < E) ? f2tf32(__ldg(Wg + static_cast<size_t>(e0) * d + col)) : 0u;
-                    bf[ks][n][1] = (n < nc && e1 < E) ? f2tf32(__ldg(Wg + static_cast<size_t>(e1) * d + col)) : 0u;
+                    // expert rows past E are clamped (their dlogits columns are zero), n-tiles past the warp's range re-read
+                    // its last one (their MMAs are skipped): no predicates on the loads
+                    const int col = warp * CW + (c0 + min(n, nc - 1)) * 8 + g;
+                    const int e0 = min(ks * 8 + t4, E - 1), e1 = min(ks * 8 + t4 + 4, E - 1);
+                    bf[ks][n][0] = f2tf32(__ldg(Wg + static_cast<size_t>(e0) * d + col));
+                    bf[ks][n][1] = f2tf32(__ldg(Wg + static_cast<size_t>(e1) * d + col));
                 }
             }
             for (int mt = 0; mt < n_mt; ++mt) {
@@ -221,10 +220,12 @@ gate_dispatch_bwd_mma_kernel(PeerRows dxrows, const int* __restrict__ pos, const
 #pragma unroll
                 for (int ks = 0; ks < NKB; ++ks) {
                     uint32_t a[4];
-                    a[0] = f2tf32(a0p[ks * 8]);
-                    a[1] = f2tf32(a0p[ks * 8 + 8 * DLS]);
-                    a[2] = f2tf32(a0p[ks * 8 + 4]);
-                    a[3] = f2tf32(a0p[ks * 8 + 8 * DLS + 4]);
+                    // raw fp32 bits: the tensor core reads the tf32 part (truncation, 2^-10 relative — the tolerance of this
+                    // term is the bf16 one; cvt.rna costs three instructions per element here, once per m-tile and chunk)
+                    a[0] = __float_as_uint(a0p[ks * 8]);
+                    a[1] = __float_as_uint(a0p[ks * 8 + 8 * DLS]);
+                    a[2] = __float_as_uint(a0p[ks * 8 + 4]);
+                    a[3] = __float_as_uint(a0p[ks * 8 + 8 * DLS + 4]);
 #pragma unroll
                     for (int n = 0; n < NC; ++n)
                         if (n < nc) mma_tf32(acc[n], a, bf[ks][n][0], bf[ks][n][1]);

@@ -11,9 +11,11 @@
 //               of shared-memory stages (128-byte swizzle), running ahead across tile boundaries;
 //   warp 1      one thread issues tcgen05.mma (cta_group::1, M = 128 tokens, N = 2 E_PAD, K = 16) straight from shared
 //               memory into a double-buffered TMEM accumulator: columns [0, E_PAD) = x w0^T, [E_PAD, 2 E_PAD) = x w1^T;
-//   warps 2-5   one thread per token row: ||x_t||^2 from the staged chunks (needed by the certification bound);
-//   warps 6-9   epilogue, one thread per token (its TMEM lane): logits, certification, top-k, scores, per-tile
-//               histogram and probability sums — while the other warps are already on the next tile.
+//   warps 2-3   two token rows per thread: ||x_t||^2 from the staged chunks (needed by the certification bound);
+//   warps 4-11  two epilogue groups of four warps, alternating tiles (each owns one accumulator stage), one thread per
+//               token (its TMEM lane): logits, certification, top-k, scores, per-tile histogram and probability sums —
+//               while the other warps are already two tiles ahead.  (ncu, round 2: with one group the kernel was bound
+//               by the epilogue's instruction issue — four warps, one per scheduler, with dependent chains.)
 //
 //   * x is bf16 (exact operand).  Wg (fp32) is split once per forward into two bf16 planes w0 = bf16(w),
 //     w1 = bf16(w - w0) (|w - w0 - w1| <= 2^-18 |w|); products are exact in fp32, the planes accumulate separately
@@ -40,7 +42,7 @@ namespace moe {
 
 constexpr int kGmTok = 128;       // tokens per CTA = two 64-token routing tiles
 constexpr int kGmKC = 64;         // features per pipeline stage (one 128-byte swizzle row)
-constexpr int kGmThreads = 320;   // producer, MMA issuer, 4 row-norm warps, 4 epilogue warps
+constexpr int kGmThreads = 384;   // producer, MMA issuer, 2 row-norm warps, 2 x 4 epilogue warps
 constexpr int kGmMaxStages = 8;
 constexpr int kGmMaxK = 8;
 
@@ -118,9 +120,34 @@ __device__ __noinline__ float4 gate_exact_dots(const __nv_bfloat16* __restrict__
 }
 
 // top-NP of one token's logits held by ONE thread: descending value, ties -> lowest expert index.  Everything is
-// compile-time indexed so that v / pv / pi stay in registers.
+// compile-time indexed so that v / pv / pi stay in registers.  NP = 2 and 3 (top-1 and top-2 gates: k + 1 picks) are a
+// single insertion pass over the experts; larger NP selects pick by pick.
 template <int EP, int NP>
 __device__ __forceinline__ void thread_topk(const float (&v)[EP], int E, int npick, float (&pv)[NP], int (&pi)[NP]) {
+    if constexpr (NP <= 3) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) { pv[p] = -INFINITY; pi[p] = 0x7fffffff; }
+#pragma unroll
+        for (int e = 0; e < EP; ++e) {
+            if (e < E) {   // ascending e + strict comparisons: equal values keep the lower index in front
+                const float x = v[e];
+                if (pi[0] == 0x7fffffff || x > pv[0]) {
+                    if constexpr (NP == 3) { pv[2] = pv[1]; pi[2] = pi[1]; }
+                    pv[1] = pv[0]; pi[1] = pi[0];
+                    pv[0] = x; pi[0] = e;
+                } else if (pi[1] == 0x7fffffff || x > pv[1]) {
+                    if constexpr (NP == 3) { pv[2] = pv[1]; pi[2] = pi[1]; }
+                    pv[1] = x; pi[1] = e;
+                } else if constexpr (NP == 3) {
+                    if (pi[2] == 0x7fffffff || x > pv[2]) { pv[2] = x; pi[2] = e; }
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+            if (p >= npick) { pv[p] = -INFINITY; pi[p] = 0x7fffffff; }
+        return;
+    }
     uint64_t used = 0;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
@@ -181,10 +208,10 @@ gate_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ssfull_bar + 2);   // [1] (+ pad)
     float* ss_s = reinterpret_cast<float*>(tail + 256);                  // [2][128] squared row norms per accumulator stage
     float* bias_s = ss_s + 2 * kGmTok;                                   // [EP]
-    int* hist_s = reinterpret_cast<int*>(bias_s + EP);                   // [2 parities][2 halves][EP]
-    float* psum_s = reinterpret_cast<float*>(hist_s + 4 * EP);           // [2 parities][4 quarters][EP]
-    float* exact_s = psum_s + 8 * EP;                                    // [4 warps][EP]
-    float* wmax_s = exact_s + 4 * EP;                                    // [1]
+    int* hist_s = reinterpret_cast<int*>(bias_s + EP);                   // [2 groups][2 parities][2 halves][EP]
+    float* psum_s = reinterpret_cast<float*>(hist_s + 8 * EP);           // [2 groups][2 parities][4 quarters][EP]
+    float* exact_s = psum_s + 16 * EP;                                   // [8 warps][EP]
+    float* wmax_s = exact_s + 8 * EP;                                    // [1]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nk = d / kGmKC;
@@ -193,16 +220,16 @@ gate_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (tid == 0) {
         for (int s = 0; s < nstages; ++s) {
             mbar_init(full_bar + s, 1);       // producer's arrive.expect_tx
-            mbar_init(empty_bar + s, 5);      // tcgen05.commit + the four row-norm warps
+            mbar_init(empty_bar + s, 3);      // tcgen05.commit + the two row-norm warps
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar + a, 1);      // tcgen05.commit
-            mbar_init(tempty_bar + a, 4);     // the four epilogue warps
-            mbar_init(ssfull_bar + a, 4);     // the four row-norm warps
+            mbar_init(tempty_bar + a, 4);     // the four warps of the epilogue group that owns the stage
+            mbar_init(ssfull_bar + a, 2);     // the two row-norm warps
         }
         fence_mbar_init();
     }
-    for (int i = tid; i < 4 * EP; i += kGmThreads) hist_s[i] = 0;
+    for (int i = tid; i < 8 * EP; i += kGmThreads) hist_s[i] = 0;
     for (int i = tid; i < EP; i += kGmThreads) bias_s[i] = (bg != nullptr && i < E) ? __ldg(bg + i) : 0.0f;
     if (warp == 2) {
         float m = 0.0f;
@@ -264,30 +291,37 @@ gate_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
         }
-    } else if (warp < 6) {
-        // ================================ row norms: one thread per token row =====================
-        const int r = (warp - 2) * 32 + lane;
+    } else if (warp < 4) {
+        // ================================ row norms: two token rows per thread =====================
+        const int r0 = (warp - 2) * 64 + lane, r1 = r0 + 32;
         int s = 0, as = 0;
         uint32_t ph = 0, aph = 0;
         for (int tile = blockIdx.x; tile < ntiles128; tile += gridDim.x) {
-            float ss = 0.0f;
+            float sa = 0.0f, sb = 0.0f;
             for (int kc = 0; kc < nk; ++kc) {
                 mbar_wait(full_bar + s, ph);
-                const uint8_t* xr = smem + s * STAGE_BYTES + r * 128;
+                const uint8_t* xa = smem + s * STAGE_BYTES + r0 * 128;
+                const uint8_t* xb = smem + s * STAGE_BYTES + r1 * 128;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {   // 128-byte swizzle: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
-                    const uint4 q = *reinterpret_cast<const uint4*>(xr + ((c ^ (r & 7)) << 4));
-                    ss = fmaf(bf_lo(q.x), bf_lo(q.x), ss); ss = fmaf(bf_hi(q.x), bf_hi(q.x), ss);
-                    ss = fmaf(bf_lo(q.y), bf_lo(q.y), ss); ss = fmaf(bf_hi(q.y), bf_hi(q.y), ss);
-                    ss = fmaf(bf_lo(q.z), bf_lo(q.z), ss); ss = fmaf(bf_hi(q.z), bf_hi(q.z), ss);
-                    ss = fmaf(bf_lo(q.w), bf_lo(q.w), ss); ss = fmaf(bf_hi(q.w), bf_hi(q.w), ss);
+                for (int c = 0; c < 8; ++c) {   // 128-byte swizzle: 16-byte chunk c of row r lives at chunk c ^ (r & 7); r1 & 7 == r0 & 7
+                    const uint4 q = *reinterpret_cast<const uint4*>(xa + ((c ^ (r0 & 7)) << 4));
+                    const uint4 u = *reinterpret_cast<const uint4*>(xb + ((c ^ (r0 & 7)) << 4));
+                    sa = fmaf(bf_lo(q.x), bf_lo(q.x), sa); sa = fmaf(bf_hi(q.x), bf_hi(q.x), sa);
+                    sb = fmaf(bf_lo(u.x), bf_lo(u.x), sb); sb = fmaf(bf_hi(u.x), bf_hi(u.x), sb);
+                    sa = fmaf(bf_lo(q.y), bf_lo(q.y), sa); sa = fmaf(bf_hi(q.y), bf_hi(q.y), sa);
+                    sb = fmaf(bf_lo(u.y), bf_lo(u.y), sb); sb = fmaf(bf_hi(u.y), bf_hi(u.y), sb);
+                    sa = fmaf(bf_lo(q.z), bf_lo(q.z), sa); sa = fmaf(bf_hi(q.z), bf_hi(q.z), sa);
+                    sb = fmaf(bf_lo(u.z), bf_lo(u.z), sb); sb = fmaf(bf_hi(u.z), bf_hi(u.z), sb);
+                    sa = fmaf(bf_lo(q.w), bf_lo(q.w), sa); sa = fmaf(bf_hi(q.w), bf_hi(q.w), sa);
+                    sb = fmaf(bf_lo(u.w), bf_lo(u.w), sb); sb = fmaf(bf_hi(u.w), bf_hi(u.w), sb);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty_bar + s);
                 if (++s == nstages) { s = 0; ph ^= 1; }
             }
             mbar_wait(tempty_bar + as, aph ^ 1);     // the epilogue has read this stage's norms of two tiles ago
-            ss_s[as * kGmTok + r] = ss;
+            ss_s[as * kGmTok + r0] = sa;
+            ss_s[as * kGmTok + r1] = sb;
             __syncwarp();
             if (lane == 0) mbar_arrive(ssfull_bar + as);
             if (++as == 2) { as = 0; aph ^= 1; }
@@ -295,14 +329,18 @@ gate_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     } else {
         // ================================ epilogue: one thread per token (TMEM lane) ==============
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int grp = (warp - 4) >> 2;              // epilogue group: tiles it = grp, grp + 2, ... of this CTA; accumulator stage grp
         const int r = q * 32 + lane;                  // token row inside the tile
-        const int et = tid - 6 * 32;                  // 0..127 among the epilogue threads
+        const int et = tid - (4 + 4 * grp) * 32;      // 0..127 inside the group
         const float wmax = *wmax_s;
         const int npick = min(k + 1, E);
         const bool need_p = (score_mode == 1) || want_psum;
-        int as = 0, it = 0;
+        const int as = grp;
+        int it = 0;
         uint32_t aph = 0;
-        for (int tile = blockIdx.x; tile < ntiles128; tile += gridDim.x, ++it) {
+        int* const hist_g = hist_s + grp * 4 * EP;
+        float* const psum_g = psum_s + grp * 8 * EP;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles128; tile += 2 * gridDim.x, ++it) {
             const int par = it & 1;
             const int64_t tok = static_cast<int64_t>(tile) * kGmTok + r;
             const bool in_range = tok < T;
@@ -325,7 +363,7 @@ gate_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar + as);   // accumulator stage and its norms are free again
-            if (++as == 2) { as = 0; aph ^= 1; }
+            aph ^= 1;
 
             float vmax = 0.0f;
 #pragma unroll
@@ -364,7 +402,7 @@ gate_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             }
             unsigned flagged = __ballot_sync(0xffffffffu, amb);
             if (flagged) {
-                float* ex = exact_s + q * EP;
+                float* ex = exact_s + (warp - 4) * EP;
                 while (flagged) {
                     const int src = __ffs(flagged) - 1;
                     flagged &= flagged - 1;
@@ -430,11 +468,11 @@ gate_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 if (want_psum) {
 #pragma unroll
                     for (int g0 = 0; g0 < EP; g0 += 32) {
-                        float grp[32];
+                        float cols[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) grp[i] = (g0 + i < EP && live) ? v[g0 + i < EP ? g0 + i : 0] / z : 0.0f;
-                        const float colsum = warp_transpose_sum32(grp, lane);
-                        if (g0 + lane < EP) psum_s[(par * 4 + q) * EP + g0 + lane] = colsum;
+                        for (int i = 0; i < 32; ++i) cols[i] = (g0 + i < EP && live) ? v[g0 + i < EP ? g0 + i : 0] * rz : 0.0f;
+                        const float colsum = warp_transpose_sum32(cols, lane);
+                        if (g0 + lane < EP) psum_g[(par * 4 + q) * EP + g0 + lane] = colsum;
                     }
                 }
             }
@@ -456,22 +494,22 @@ gate_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                             const float w = expf(pv[p] - m);
                             irow[p] = pi[p];
                             srow[p] = score_mode == 0 ? w / ssum : w * rz;
-                            atomicAdd(hist_s + (par * 2 + (q >> 1)) * EP + pi[p], 1);
+                            atomicAdd(hist_g + (par * 2 + (q >> 1)) * EP + pi[p], 1);
                         }
                     }
                 }
             }
-            named_bar_sync(2, 128);   // the four epilogue warps: this tile's histogram and column sums are complete
+            named_bar_sync(2 + grp, 128);   // the group's four warps: this tile's histogram and column sums are complete
             for (int i = et; i < 2 * EP; i += 128) {
                 const int hf = i / EP, e = i - hf * EP;
                 const int rt = tile * 2 + hf;             // 64-token routing tile
                 if (e < E && rt < ntiles) {
-                    tile_hist[static_cast<size_t>(e) * ntiles + rt] = hist_s[par * 2 * EP + i];
+                    tile_hist[static_cast<size_t>(e) * ntiles + rt] = hist_g[par * 2 * EP + i];
                     if (want_psum)
                         tile_psum[static_cast<size_t>(e) * ntiles + rt] =
-                            psum_s[(par * 4 + 2 * hf) * EP + e] + psum_s[(par * 4 + 2 * hf + 1) * EP + e];
+                            psum_g[(par * 4 + 2 * hf) * EP + e] + psum_g[(par * 4 + 2 * hf + 1) * EP + e];
                 }
-                hist_s[par * 2 * EP + i] = 0;             // reused two tiles later, behind the next tile's barrier
+                hist_g[par * 2 * EP + i] = 0;             // reused two of the group's tiles later, behind its next barrier
             }
         }
     }
@@ -506,9 +544,9 @@ static int launch_gate_mma_t(const CUtensorMap& tX, const CUtensorMap& tW, const
     constexpr int STAGE = kGmTok * 128 + 2 * EP * 128;
     const int ntiles = static_cast<int>((T + MOE_TOKEN_TILE - 1) / MOE_TOKEN_TILE);
     const int ntiles128 = (ntiles + 1) / 2;
-    int nstages = (196 * 1024) / STAGE;   // one CTA per SM: the ring runs ahead across tile boundaries
+    int nstages = (190 * 1024) / STAGE;   // one CTA per SM: the ring runs ahead across tile boundaries
     if (nstages > kGmMaxStages) nstages = kGmMaxStages;
-    const size_t smem = 1024 + static_cast<size_t>(nstages) * STAGE + 256 + (2 * kGmTok + EP + 4 * EP + 8 * EP + 4 * EP + 4) * 4;
+    const size_t smem = 1024 + static_cast<size_t>(nstages) * STAGE + 256 + (2 * kGmTok + EP + 8 * EP + 16 * EP + 8 * EP + 4) * 4;
     auto kfn = gate_fwd_umma_kernel<EP, NP>;
     static bool configured = false;
     if (!configured) {

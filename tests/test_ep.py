@@ -103,4 +103,8 @@ def test_ep_parity_multi_gpu(transport):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={W}", "--master-addr", "127.0.0.1",
            "--master-port", "29631" if transport == "peer" else "29633", os.path.join(ROOT, "tests", "ep_worker.py"), transport]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    log_dir = os.path.join(ROOT, "gpurun_out")      # the workers' per-case lines, kept as evidence next to the pytest log
+    if os.path.isdir(log_dir):
+        with open(os.path.join(log_dir, f"ep_worker_{transport}_w{W}.log"), "w") as f:
+            f.write(out.stdout)
     assert out.returncode == 0 and out.stdout.count("EP_OK") == W, out.stdout[-3000:] + out.stderr[-3000:]
