@@ -356,6 +356,11 @@ gate_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 tmem_ld16(trow + c * 16, hi);
                 tmem_ld16(trow + EP + c * 16, lo);
                 tmem_ld_wait();
+                // tcgen05.ld is asynchronous: its destination registers are valid only after the wait.  Without this pin the
+                // compiler may read them — or hand them to something else — before the data lands (seen as an illegal address
+                // at E = 64 once the surrounding code changed the register allocation)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(hi[i]), "+r"(lo[i]));
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[c * 16 + i] = __uint_as_float(hi[i]) + __uint_as_float(lo[i]);
             }
@@ -461,7 +466,9 @@ gate_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 float z = 0.0f;
 #pragma unroll
                 for (int e = 0; e < EP; ++e) {
-                    v[e] = e < E ? expf(v[e] - m) : 0.0f;      // v now holds the un-normalised probabilities
+                    // v now holds the un-normalised probabilities.  ex2.approx (2^-22 relative) is enough for the column sums and
+                    // the normaliser; the k selected scores below use expf
+                    v[e] = e < E ? ex2_approx((v[e] - m) * 1.4426950408889634f) : 0.0f;
                     z += v[e];
                 }
                 rz = 1.0f / z;

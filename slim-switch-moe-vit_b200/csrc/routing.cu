@@ -226,54 +226,79 @@ gate_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ Wg, const fl
 // ------------------------------------------------------------------------------------------------
 // K2: scan of the per-tile histograms -> tile bases, counts, capacity-clamped segments, GEMM tile table
 // ------------------------------------------------------------------------------------------------
+// K2a: one CTA per expert — exclusive prefix sum of its row of per-tile histograms (tile_base), its total (count) and the
+// sum of its row of per-tile probability sums (psum), all in a fixed order.  (Round 1 ran the whole scan in one CTA: 72 us
+// at E = 64, T = 262144 — one SM pulling every row through its L2 port.)
+__global__ void __launch_bounds__(256)
+route_scan_rows_kernel(const int* __restrict__ tile_hist, const float* __restrict__ tile_psum, int ntiles,
+                       int* __restrict__ tile_base, int* __restrict__ count, float* __restrict__ psum) {
+    __shared__ int wtot[8];
+    __shared__ float wps[8];
+    __shared__ int carry_s;
+    const int e = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int* hrow = tile_hist + static_cast<size_t>(e) * ntiles;
+    int* brow = tile_base + static_cast<size_t>(e) * ntiles;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int g0 = 0; g0 < ntiles; g0 += 256 * 8) {      // 8 consecutive tiles per thread
+        int v[8], tot = 0;
+        const int b0 = g0 + tid * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[i] = b0 + i < ntiles ? hrow[b0 + i] : 0;
+            tot += v[i];
+        }
+        int incl = tot;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += o;
+        }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        int base = carry_s;
+        for (int w = 0; w < warp; ++w) base += wtot[w];
+        int run = base + incl - tot;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (b0 + i < ntiles) brow[b0 + i] = run;
+            run += v[i];
+        }
+        __syncthreads();
+        if (tid == 255) carry_s = run;                   // thread 255 holds the running total of the whole chunk
+        __syncthreads();
+    }
+    if (tid == 0) count[e] = carry_s;
+    if (tile_psum != nullptr && psum != nullptr) {       // fixed order: thread-strided partial sums, xor butterfly, warps in order
+        const float* prow = tile_psum + static_cast<size_t>(e) * ntiles;
+        float part = 0.0f;
+#pragma unroll 4
+        for (int b = tid; b < ntiles; b += 256) part += prow[b];
+        part = warp_sum_xor(part);
+        if (lane == 0) wps[warp] = part;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.0f;
+            for (int w = 0; w < 8; ++w) t += wps[w];
+            psum[e] = t;
+        }
+    }
+}
+
+// K2b: one CTA — capacity-clamped segments, GEMM tile table, load-balancing loss from the per-expert totals
 __global__ void __launch_bounds__(1024)
-route_scan_kernel(const int* __restrict__ tile_hist, const float* __restrict__ tile_psum, int ntiles, int E,
-                  long long capacity, int* __restrict__ tile_base, int* __restrict__ count, int* __restrict__ kept,
+route_scan_kernel(int E, long long capacity, int* __restrict__ count, int* __restrict__ kept,
                   int* __restrict__ seg_start, int* __restrict__ tile_expert, int* __restrict__ num_mtiles,
-                  int max_mtiles, float* __restrict__ psum, int aux_mode, long long tokens, int k, float* __restrict__ aux_loss,
+                  int max_mtiles, const float* __restrict__ psum, int aux_mode, long long tokens, int k, float* __restrict__ aux_loss,
                   float* __restrict__ aux_coef, long long slab_rows) {
     extern __shared__ int smem_i[];
     int* cnt_s = smem_i;          // [E]
     int* seg_s = smem_i + E;      // [E+1]
     float* ps_s = reinterpret_cast<float*>(smem_i + 2 * E + 1);  // [E]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    // tile_hist / tile_base / tile_psum are [E, ntiles]: warp e walks row e 1024 tiles at a time with coalesced,
-    // fully unrolled loads (tile = g0 + i*32 + lane), then one warp scan per i turns them into exclusive prefixes.
-    for (int e = warp; e < E; e += 32) {
-        const int* hrow = tile_hist + static_cast<size_t>(e) * ntiles;
-        int* brow = tile_base + static_cast<size_t>(e) * ntiles;
-        int carried = 0;
-        for (int g0 = 0; g0 < ntiles; g0 += 1024) {
-            int v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int b = g0 + i * 32 + lane;
-                v[i] = b < ntiles ? hrow[b] : 0;
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                int incl = v[i];
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const int o = __shfl_up_sync(0xffffffffu, incl, off);
-                    if (lane >= off) incl += o;
-                }
-                const int b = g0 + i * 32 + lane;
-                if (b < ntiles) brow[b] = carried + incl - v[i];
-                carried += __shfl_sync(0xffffffffu, incl, 31);
-            }
-        }
-        if (lane == 0) cnt_s[e] = carried;
-        if (tile_psum != nullptr && psum != nullptr) {
-            // fixed order: lane-strided partial sums, then the xor butterfly
-            const float* prow = tile_psum + static_cast<size_t>(e) * ntiles;
-            float part = 0.0f;
-#pragma unroll 8
-            for (int b = lane; b < ntiles; b += 32) part += prow[b];
-            part = warp_sum_xor(part);
-            if (lane == 0) { psum[e] = part; ps_s[e] = part; }
-        }
+    const int tid = threadIdx.x;
+    for (int e = tid; e < E; e += 1024) {
+        cnt_s[e] = count[e];
+        ps_s[e] = (aux_mode != 0 && psum != nullptr) ? psum[e] : 0.0f;
     }
     __syncthreads();
     if (tid == 0) {
@@ -281,7 +306,6 @@ route_scan_kernel(const int* __restrict__ tile_hist, const float* __restrict__ t
         for (int e = 0; e < E; ++e) {
             const int c = cnt_s[e];
             const int kp = static_cast<long long>(c) < capacity ? c : static_cast<int>(capacity);
-            count[e] = c;
             kept[e] = kp;
             seg_s[e] = start;
             seg_start[e] = start;
@@ -423,25 +447,48 @@ template <typename OT>
 __global__ void __launch_bounds__(256)
 combine_fwd_kernel(PeerRows yrows, const int* __restrict__ pos, const float* __restrict__ score,
                    int64_t T, int d, int k, OT* __restrict__ out) {
+    // U items (token, 8-column chunk) per thread and pass: the U row gathers — possibly from a peer GPU, several
+    // microseconds away — are all in flight before the first one is used
+    constexpr int U = 4;
     const int per_row = d / 8;
-    const int64_t items = T * per_row;
-    for (int64_t it = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; it < items;
-         it += static_cast<int64_t>(gridDim.x) * 256) {
-        const int64_t t = it / per_row;
-        const int c = static_cast<int>(it - t * per_row) * 8;
-        float acc[8];
+    const int items = static_cast<int>(T) * per_row;     // < 2^31 (checked by the launcher): 32-bit index arithmetic
+    const int stride = static_cast<int>(gridDim.x) * 256;
+    for (int it0 = static_cast<int>(blockIdx.x) * 256 + threadIdx.x; it0 < items; it0 += U * stride) {
+        float acc[U][8];
+        int tok[U], col[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-        for (int j = 0; j < k; ++j) {
-            const int row = __ldg(pos + t * k + j);
-            if (row < 0) continue;
-            const float s = __ldg(score + t * k + j);
-            float y[8];
-            load8(peer_row<const __nv_bfloat16>(yrows, row, d) + c, y);
+        for (int u = 0; u < U; ++u) {
+            const int it = min(it0 + u * stride, items - 1);
+            tok[u] = it / per_row;
+            col[u] = (it - tok[u] * per_row) * 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaf(s, y[i], acc[i]);
+            for (int i = 0; i < 8; ++i) acc[u][i] = 0.0f;
         }
-        store8(out + t * d + c, acc);
+        for (int j = 0; j < k; ++j) {
+            int row[U];
+            float sc[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                row[u] = __ldg(pos + static_cast<int64_t>(tok[u]) * k + j);
+                sc[u] = __ldg(score + static_cast<int64_t>(tok[u]) * k + j);
+            }
+            uint4 raw[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                raw[u] = row[u] >= 0 ? __ldg(reinterpret_cast<const uint4*>(peer_row<const __nv_bfloat16>(yrows, row[u], d) + col[u])) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[u][2 * i] = fmaf(sc[u], __low2float(h2[i]), acc[u][2 * i]);
+                    acc[u][2 * i + 1] = fmaf(sc[u], __high2float(h2[i]), acc[u][2 * i + 1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (it0 + u * stride < items) store8(out + static_cast<int64_t>(tok[u]) * d + col[u], acc[u]);
     }
 }
 
@@ -1400,10 +1447,12 @@ cudaError_t launch_route_scan(const int* tile_hist, const float* tile_psum, int 
                               int* tile_base, int* count, int* kept, int* seg_start, int* tile_expert, int* num_mtiles,
                               int max_mtiles, float* psum, int aux_mode, long long tokens, int k, float* aux_loss,
                               float* aux_coef, long long slab_rows, cudaStream_t st) {
+    route_scan_rows_kernel<<<E, 256, 0, st>>>(tile_hist, tile_psum, ntiles, tile_base, count, psum);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
     const size_t smem = (3 * static_cast<size_t>(E) + 1) * 4;
-    route_scan_kernel<<<1, 1024, smem, st>>>(tile_hist, tile_psum, ntiles, E, capacity, tile_base, count, kept,
-                                             seg_start, tile_expert, num_mtiles, max_mtiles, psum, aux_mode, tokens, k,
-                                             aux_loss, aux_coef, slab_rows);
+    route_scan_kernel<<<1, 1024, smem, st>>>(E, capacity, count, kept, seg_start, tile_expert, num_mtiles, max_mtiles, psum,
+                                             aux_mode, tokens, k, aux_loss, aux_coef, slab_rows);
     return cudaGetLastError();
 }
 
@@ -1448,7 +1497,8 @@ static int grid_for(int64_t items, int sm_count) {
 
 cudaError_t launch_combine_fwd_rows(const PeerRows& yrows, const int* pos, const float* score, int64_t T, int d, int k, void* out,
                                     int out_dtype, int sm_count, cudaStream_t st) {
-    const int grid = grid_for(T * (d / 8), sm_count);
+    if (T * (d / 8) >= (1LL << 31) - 4LL * 256 * 8 * sm_count) return cudaErrorInvalidValue;   // 32-bit item index in the kernel
+    const int grid = grid_for((T * (d / 8) + 3) / 4, sm_count);
     if (out_dtype == MOE_DTYPE_F32)
         combine_fwd_kernel<float><<<grid, 256, 0, st>>>(yrows, pos, score, T, d, k, static_cast<float*>(out));
     else

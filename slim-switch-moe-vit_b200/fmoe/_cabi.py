@@ -93,7 +93,7 @@ class MoeB200Error(RuntimeError):
 KERNELS_PER_CALL = {
     "moe_ep_barrier": 1, "moe_ep_exchange_counts": 1, "moe_dispatch_fwd_peer": 1, "moe_combine_fwd_peer": 1, "moe_combine_bwd_peer": 1,
     "moe_gate_dispatch_bwd_peer": 1,
-    "moe_gate_fwd": 2, "moe_route_scan": 1, "moe_ep_tables": 1, "moe_ep_repack": 1, "moe_dispatch_fwd": 1, "moe_expert_ffn_fwd": 2, "moe_combine_fwd": 1,
+    "moe_gate_fwd": 2, "moe_route_scan": 2, "moe_ep_tables": 1, "moe_ep_repack": 1, "moe_dispatch_fwd": 1, "moe_expert_ffn_fwd": 2, "moe_combine_fwd": 1,
     "moe_combine_bwd": 1, "moe_expert_ffn_bwd": 8, "moe_gate_bwd": 1, "moe_dispatch_bwd": 1, "moe_gate_dispatch_bwd": 1,
     "moe_gate_wgrad": 2, "moe_addln_fwd": 1, "moe_addln_bwd": 2, "moe_colsum": 2, "moe_cast_bf16": 1, "moe_cast_bf16_transposed": 1, "moe_segment_colsum": 2, "moe_grouped_gemm": 1, "moe_slab_colsum_final": 1,
 }

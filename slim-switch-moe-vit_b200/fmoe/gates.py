@@ -91,7 +91,12 @@ def _capacity(cf: float, num_tokens: int, top_k: int, tot_expert: int) -> int:
 class SwitchGate(NaiveGate):
     """Top-1 Switch-Transformer gate: softmax over all experts, score = probability of the chosen
     expert, tokens beyond the per-expert capacity are dropped (zero layer output), aux loss
-    E * sum_e f_e P_e with f_e = fraction of kept tokens on e and P_e = mean softmax prob of e."""
+    E * sum_e f_e P_e with f_e = fraction of kept tokens on e and P_e = mean softmax prob of e.
+
+    Deliberate differences from upstream FastMoE's SwitchGate (SURVEY.md §8a defines the north-star semantics; tuned
+    aux-loss coefficients do not carry over unchanged): capacity is ceil(cf * T * k / E) per expert (upstream: ceil(cf * T),
+    which never binds on one worker); P_e averages the softmax probability over ALL T tokens (upstream: over the kept
+    tokens only); dropped tokens are the LAST ones of an expert in token order (upstream: whichever lose an atomics race)."""
 
     def __init__(self, d_model, num_expert, world_size, topk=1, switch_eps=0.1, capacity=(1.2, 2.4), gate_bias=True):
         assert topk == 1, "topk should be 1 in switch"
@@ -124,7 +129,11 @@ class SwitchGate(NaiveGate):
 class GShardGate(NaiveGate):
     """Top-2 GShard gate: NaiveGate scores, per-expert capacity, aux loss mean(c_e * m_e) * E^2 with
     c_e = fraction of pairs routed to e (before capacity) and m_e = mean softmax prob of e.
-    Upstream's `random_routing` of the second expert is not implemented (raises if requested)."""
+    Upstream's `random_routing` of the second expert is not implemented (raises if requested).
+
+    Deliberate differences from upstream FastMoE's GShardGate: c_e counts all k picks of a token divided by T * k (upstream:
+    the top-1 pick only, divided by T) and the scale is (global expert count)^2 (upstream: the local `num_expert`^2), so
+    the loss magnitude differs by a constant factor on one worker; capacity as in SwitchGate above."""
 
     def __init__(self, d_model, num_expert, world_size, topk=2, capacity=(1.2, 2.4), random_routing=False,
                  gate_bias=True):
