@@ -447,48 +447,25 @@ template <typename OT>
 __global__ void __launch_bounds__(256)
 combine_fwd_kernel(PeerRows yrows, const int* __restrict__ pos, const float* __restrict__ score,
                    int64_t T, int d, int k, OT* __restrict__ out) {
-    // U items (token, 8-column chunk) per thread and pass: the U row gathers — possibly from a peer GPU, several
-    // microseconds away — are all in flight before the first one is used
-    constexpr int U = 4;
     const int per_row = d / 8;
-    const int items = static_cast<int>(T) * per_row;     // < 2^31 (checked by the launcher): 32-bit index arithmetic
-    const int stride = static_cast<int>(gridDim.x) * 256;
-    for (int it0 = static_cast<int>(blockIdx.x) * 256 + threadIdx.x; it0 < items; it0 += U * stride) {
-        float acc[U][8];
-        int tok[U], col[U];
+    const int64_t items = T * per_row;
+    for (int64_t it = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; it < items;
+         it += static_cast<int64_t>(gridDim.x) * 256) {
+        const int64_t t = it / per_row;
+        const int c = static_cast<int>(it - t * per_row) * 8;
+        float acc[8];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int it = min(it0 + u * stride, items - 1);
-            tok[u] = it / per_row;
-            col[u] = (it - tok[u] * per_row) * 8;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[u][i] = 0.0f;
-        }
+        for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
         for (int j = 0; j < k; ++j) {
-            int row[U];
-            float sc[U];
+            const int row = __ldg(pos + t * k + j);
+            if (row < 0) continue;
+            const float s = __ldg(score + t * k + j);
+            float y[8];
+            load8(peer_row<const __nv_bfloat16>(yrows, row, d) + c, y);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                row[u] = __ldg(pos + static_cast<int64_t>(tok[u]) * k + j);
-                sc[u] = __ldg(score + static_cast<int64_t>(tok[u]) * k + j);
-            }
-            uint4 raw[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                raw[u] = row[u] >= 0 ? __ldg(reinterpret_cast<const uint4*>(peer_row<const __nv_bfloat16>(yrows, row[u], d) + col[u])) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    acc[u][2 * i] = fmaf(sc[u], __low2float(h2[i]), acc[u][2 * i]);
-                    acc[u][2 * i + 1] = fmaf(sc[u], __high2float(h2[i]), acc[u][2 * i + 1]);
-                }
-            }
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(s, y[i], acc[i]);
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (it0 + u * stride < items) store8(out + static_cast<int64_t>(tok[u]) * d + col[u], acc[u]);
+        store8(out + t * d + c, acc);
     }
 }
 
@@ -1497,8 +1474,7 @@ static int grid_for(int64_t items, int sm_count) {
 
 cudaError_t launch_combine_fwd_rows(const PeerRows& yrows, const int* pos, const float* score, int64_t T, int d, int k, void* out,
                                     int out_dtype, int sm_count, cudaStream_t st) {
-    if (T * (d / 8) >= (1LL << 31) - 4LL * 256 * 8 * sm_count) return cudaErrorInvalidValue;   // 32-bit item index in the kernel
-    const int grid = grid_for((T * (d / 8) + 3) / 4, sm_count);
+    const int grid = grid_for(T * (d / 8), sm_count);
     if (out_dtype == MOE_DTYPE_F32)
         combine_fwd_kernel<float><<<grid, 256, 0, st>>>(yrows, pos, score, T, d, k, static_cast<float*>(out));
     else
