@@ -5,7 +5,7 @@
     (tests/golden/ref_wrapper_*.npz, written by tests/golden/make_golden.py with the reference imported unmodified);
   * the layer inside `torch.cuda.amp.autocast()` (fp16) with a `GradScaler`-scaled backward, exactly what
     /root/reference/engine.py:52-54,68-74 does (timm's `NativeScaler` = scale -> backward -> unscale_ -> clip -> step);
-  * the full BASELINE configs[1] layer shape, forward AND backward, against the oracle's arithmetic model;
+  * the full per-GPU MoE-layer shapes of BASELINE configs[1..3], forward AND backward, against the oracle's arithmetic model;
   * a restated `train_one_epoch` body (engine.py:36-80) + `ModelEma` deepcopy (main.py:602-607) driving the CUDA layer.
 
 Tolerances are written at each assertion: integers bit-exact; fp32 logits bit-exact; bf16-operand tensors vs the fp32
@@ -150,25 +150,36 @@ def test_fp16_input_is_widened_and_returned_in_fp16():
     assert rel_err(y16, y32) <= 2e-3                # fp16 rounding of the returned tensor only (2^-11)
 
 
-def test_full_size_config2_forward_backward_vs_model():
-    """BASELINE configs[1] layer shape (T = 256 x 197, d = 384, h = 1536, E = 16, top-1, cf 1.25, bf16 activations):
-    every output and every gradient of the CUDA layer against the oracle's arithmetic model at full size (the model is
-    fp32 BLAS on the host: a few seconds), with real drops (skewed gate bias)."""
+FULL_SIZE = {
+    # name: (T, d, E, k, score mode, aux mode name)  — the per-GPU MoE-layer shapes of BASELINE configs[1..3]
+    "c2": (256 * 197, 384, 16, 1, 1, "switch"),      # ViT-S, Switch top-1
+    "c3": (128 * 197, 768, 32, 2, 0, "gshard"),      # ViT-B, GShard top-2
+    "c4": (128 * 197, 1024, 64, 1, 1, "switch"),     # ViT-L, Switch top-1, E = 64
+}
+
+
+@pytest.mark.parametrize("name", sorted(FULL_SIZE))
+def test_full_size_forward_backward_vs_model(name):
+    """The MoE-layer shapes of BASELINE configs[1..3] at FULL size (bf16 activations, cf 1.25, skewed gate bias -> real
+    drops): every output and every gradient of the CUDA layer against the oracle's arithmetic model (fp32 BLAS on the
+    host: seconds), routing counts bit-exact."""
     from fmoe import _cabi as C
     from fmoe import functions as Fn
-    T, d, h, E, k = 256 * 197, 384, 1536, 16, 1
+    T, d, E, k, mode, aux_name = FULL_SIZE[name]
+    h = 4 * d
+    aux_mode = C.AUX_SWITCH if aux_name == "switch" else C.AUX_GSHARD
     x, Wg, bg, W1, b1, W2, b2 = make_problem(T, d, h, E, seed=9, skew=0.5, x_dtype=torch.bfloat16)
     cap = O.capacity_from_factor(1.25, T, k, E)
-    spec = Fn.RouteSpec(k, 1, cap, C.AUX_SWITCH)
+    spec = Fn.RouteSpec(k, mode, cap, aux_mode)
     dev = [t.cuda().requires_grad_() for t in (x, Wg, bg, W1, b1, W2, b2)]
     dy = torch.randn(T, d, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
     y, aux, count, kept = Fn.MoEFunction.apply(*dev, spec, Fn.Bf16WeightCache(), None)
     torch.autograd.backward([y, aux], [dy.cuda(), torch.tensor(0.01, device="cuda")])
     torch.cuda.synchronize()
-    ym, sv = O.forward_model(x, Wg, bg, W1, b1, W2, b2, k, 1, cap)
+    ym, sv = O.forward_model(x, Wg, bg, W1, b1, W2, b2, k, mode, cap)
     assert torch.equal(count.cpu(), sv.r.count) and torch.equal(kept.cpu(), sv.r.kept)
     assert int(sv.r.count.sum() - sv.r.kept.sum()) > 0
-    dpsum = O.aux_coef(sv.r, T, C.AUX_SWITCH) * 0.01
+    dpsum = O.aux_coef(sv.r, T, aux_mode) * 0.01
     gm = O.backward_model(sv, dy, Wg, dpsum=dpsum)
     assert rel_err(y, ym.float()) <= 3e-3
     got = dict(zip(("dx", "dWg", "dbg", "dW1", "db1", "dW2", "db2"), (t.grad for t in dev)))
