@@ -308,10 +308,19 @@ def ep_forward(layer, moe_inp: torch.Tensor) -> torch.Tensor:
         transport = layer._ep_transport = _pick_transport(layer, moe_inp, spec)
     if transport == "peer":
         from .peer import EPPeerMoEFunction, peer_buffers
-        pb = peer_buffers(layer, T, layer.d_model, layer.num_expert * layer.world_size, layer.num_expert, spec.top_k, spec.capacity,
-                          moe_inp.device)
+        try:
+            pb = peer_buffers(layer, T, layer.d_model, layer.num_expert * layer.world_size, layer.num_expert, spec.top_k, spec.capacity,
+                              moe_inp.device)
+        except C.MoeB200Error as e:
+            if TRANSPORT != "auto":
+                raise
+            # the heap set-up fails on every rank together (fmoe/peer.py): all of them fall back to the NCCL exchange
+            import warnings
+            warnings.warn(f"fmoe: NVLink peer-memory exchange unavailable ({e}); expert parallelism falls back to NCCL all-to-all")
+            transport = layer._ep_transport = "nccl"
+    if transport == "peer":
         y, aux, count, kept = EPPeerMoEFunction.apply(moe_inp, gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec,
-                                                      layer._bf16_cache, gate.make_noise(moe_inp), pb, fresh)
+                                                      layer._bf16_cache, gate.make_noise(moe_inp), pb, fresh, not torch.is_grad_enabled())
     else:
         y, aux, count, kept = EPMoEFunction.apply(moe_inp, gate.gate.weight, gate.gate.bias, W1, b1, W2, b2, spec,
                                                   layer._bf16_cache, gate.make_noise(moe_inp), layer.moe_group, layer.world_size, fresh)

@@ -43,21 +43,38 @@ class PeerHeap:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.nbytes = int(nbytes)
-        base = ctypes.c_void_p()
-        handle = ctypes.create_string_buffer(IPC_BYTES)
-        C.call("moe_ep_heap_alloc", self.nbytes, ctypes.byref(base), handle)
-        self.local = int(base.value)
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle.raw), group=group)
-        self.bases = []
-        for r, h in enumerate(handles):
+        self.local, self.bases = 0, []
+        # every step is followed by an agreement round, so that a failure on ONE rank (no IPC permission, out of memory,
+        # no peer access) raises on EVERY rank instead of leaving the others inside a collective
+        base, handle, err = ctypes.c_void_p(), ctypes.create_string_buffer(IPC_BYTES), None
+        try:
+            C.call("moe_ep_heap_alloc", self.nbytes, ctypes.byref(base), handle)
+            self.local = int(base.value)
+        except C.MoeB200Error as e:
+            err = str(e)
+        got = [None] * self.world
+        dist.all_gather_object(got, (err, bytes(handle.raw)), group=group)
+        if any(g[0] for g in got):
+            self.close()
+            raise C.MoeB200Error("peer heap allocation failed on rank(s) " + ", ".join(f"{r}: {g[0]}" for r, g in enumerate(got) if g[0]))
+        bases, err = [], None
+        for r, (_, h) in enumerate(got):
             if r == self.rank:
-                self.bases.append(self.local)
-            else:
-                p = ctypes.c_void_p()
+                bases.append(self.local)
+                continue
+            p = ctypes.c_void_p()
+            try:
                 C.call("moe_ep_heap_open", ctypes.create_string_buffer(h, IPC_BYTES), ctypes.byref(p))
-                self.bases.append(int(p.value))
-        dist.barrier(group=group)   # nobody touches a peer's heap before every mapping exists
+                bases.append(int(p.value))
+            except C.MoeB200Error as e:
+                err = str(e)
+                bases.append(0)
+        self.bases = bases
+        got = [None] * self.world
+        dist.all_gather_object(got, err, group=group)   # doubles as the barrier: nobody touches a peer's heap before every mapping exists
+        if any(got):
+            self.close()
+            raise C.MoeB200Error("peer heap mapping failed on rank(s) " + ", ".join(f"{r}: {g}" for r, g in enumerate(got) if g))
 
     def region(self, offset: int):
         """HOST array of W device pointers: the same region in every rank's heap (entry `rank` is the local one)."""
@@ -139,7 +156,8 @@ class EPPeerMoEFunction(torch.autograd.Function):
     """y, aux_loss, count, kept = expert-parallel MoE(x; Wg, bg, local W1, b1, W2, b2), rows exchanged through peer memory."""
 
     @staticmethod
-    def forward(ctx, x, Wg, bg, W1, b1, W2, b2, spec: RouteSpec, cache: Bf16WeightCache, noise, pb: PeerBuffers, fresh: bool = True):
+    def forward(ctx, x, Wg, bg, W1, b1, W2, b2, spec: RouteSpec, cache: Bf16WeightCache, noise, pb: PeerBuffers, fresh: bool = True,
+                infer: bool = False):
         x = _as_kernel_input(x)
         T, d = x.shape
         El, h = W1.shape[0], W1.shape[1]
@@ -179,7 +197,7 @@ class EPPeerMoEFunction(torch.autograd.Function):
         W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c, fresh)      # the weight casts overlap the peers' pushes
         pb.barrier(st)                                           # every source's rows have landed in my xbuf
 
-        G = torch.empty((rpr, h), dtype=bf, device=dev)
+        G = None if infer else torch.empty((rpr, h), dtype=bf, device=dev)   # forward-only pass: fc1 writes no gelu'
         H = torch.empty((rpr, h), dtype=bf, device=dev)
         b1_c, b2_c = b1.detach().contiguous(), b2.detach().contiguous()
         te, nm = C.ptr(tile_expert), C.ptr(num_mtiles)
@@ -194,6 +212,10 @@ class EPPeerMoEFunction(torch.autograd.Function):
 
         ctx.spec, ctx.has_bg, ctx.pb = spec, bg is not None, pb
         coef = aux_coef if spec.want_psum else torch.empty(0, dtype=torch.float32, device=dev)
+        if infer:
+            aux = aux_loss.reshape(()) if spec.want_psum else torch.empty(0, dtype=torch.float32, device=dev)
+            ctx.mark_non_differentiable(y, aux, count, kept)
+            return y, aux, count, kept
         ctx.save_for_backward(x, Wg_c, logits, idx, score, pos, seg_loc, kept_loc, tile_expert, num_mtiles, G, H, W1tb, W2tb, coef)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(count, kept)
@@ -253,7 +275,7 @@ class EPPeerMoEFunction(torch.autograd.Function):
         dWg = _f32((E, d), dev)
         dbg = _f32(E, dev) if ctx.has_bg else None
         C.call("moe_gate_wgrad", C.ptr(dlogits), C.ptr(x), C.dtype_code(x), T, d, E, C.ptr(ws), C.ptr(dWg), C.ptr(dbg), st)
-        return dx, dWg, dbg, dW1, db1, dW2, db2, None, None, None, None, None
+        return dx, dWg, dbg, dW1, db1, dW2, db2, None, None, None, None, None, None
 
 
 def peer_transport_available(group=None) -> bool:

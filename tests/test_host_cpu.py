@@ -69,6 +69,52 @@ def test_argument_validation_without_gpu():
         C.call("moe_grouped_gemm", C.GEMM_FC2, None, None, None, None, None, None, None, None, None, 256, 2, 0, 100, 64, None)
 
 
+def test_gate_kernels_are_tensor_core_code():
+    """The gate forward runs on tcgen05 in its own single-CTA flavour (UTCHMMA without .2CTA next to the GEMM's .2CTA), the
+    gate / dispatch backward on mma.sync with ldmatrix.trans / stmatrix (HMMA, LDSM, STSM)."""
+    from fmoe import _cabi as C
+    sass = subprocess.run(["cuobjdump", "-sass", C.LIB_PATH], capture_output=True, text=True)
+    if sass.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    funcs = sass.stdout.split("Function : ")
+    gate = [f for f in funcs if f.startswith("_ZN3moe20gate_fwd_umma_kernel")]
+    gdb = [f for f in funcs if "gate_dispatch_bwd_mma_kernel" in f.split("\n", 1)[0]]
+    assert len(gate) >= 9 and len(gdb) >= 12
+    assert all("UTCHMMA" in f and "UTMALDG" in f and "LDTM" in f for f in gate)
+    assert all("HMMA.1688.F32.TF32" in f and "HMMA.16816.F32.BF16" in f and "LDSM" in f for f in gdb)
+    assert any("STSM" in f for f in gdb)
+
+
+def test_peer_entry_points_validate_their_arguments_without_gpu():
+    """Expert parallelism over peer memory: group size, rank and pointer-table checks happen before anything touches a GPU."""
+    import ctypes
+    from fmoe import _cabi as C
+    arr = (ctypes.c_void_p * 2)(None, None)
+    with pytest.raises(C.MoeB200Error, match="ranks"):
+        C.call("moe_ep_barrier", arr, None, 0, 9, None, None)            # more ranks than one NVLink node holds
+    with pytest.raises(C.MoeB200Error, match="rank"):
+        C.call("moe_ep_barrier", arr, None, 2, 2, None, None)            # rank outside the group
+    with pytest.raises(C.MoeB200Error, match="NULL"):
+        C.call("moe_ep_barrier", arr, None, 0, 2, None, None)            # unmapped peer
+    with pytest.raises(C.MoeB200Error, match="bad arguments"):
+        C.call("moe_ep_heap_alloc", 0, None, None)
+
+
+def test_expert_parallel_transport_selection():
+    from fmoe import distributed as D
+    from fmoe.functions import RouteSpec
+    lyr = _layer(top_k=2)
+    lyr.world_size, lyr.moe_group = 2, None
+    spec = RouteSpec(2, 0, 100, 0)
+    x = torch.zeros(4, 192)
+    assert D.TRANSPORT == "auto" and D._pick_transport(lyr, x, spec) == "nccl"     # CPU tensors (gloo tests): never the peer path
+    D.TRANSPORT = "peer"
+    try:
+        assert D._pick_transport(lyr, x, spec) == "peer"                            # an explicit choice is honoured (and fails loudly later)
+    finally:
+        D.TRANSPORT = "auto"
+
+
 def _layer(**kw):
     import fmoe
     act = torch.nn.Sequential(torch.nn.GELU(), torch.nn.Dropout(p=0.0))
