@@ -9,6 +9,6 @@ make -s -C $src > /dev/null
 mkdir -p tools/variants
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr "$@" \
      -c $src/gemm_launch.cu -o tools/variants/gemm_$name.o
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o tools/variants/libmoe_$name.so $bld/api.o $bld/routing.o $bld/block_fusion.o tools/variants/gemm_$name.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o tools/variants/libmoe_$name.so $bld/api.o $bld/routing.o $bld/gate_mma.o $bld/gate_bwd_mma.o $bld/ep_peer.o $bld/block_fusion.o tools/variants/gemm_$name.o
 rm tools/variants/gemm_$name.o
 echo built tools/variants/libmoe_$name.so
