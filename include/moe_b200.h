@@ -251,11 +251,14 @@ int moe_segment_colsum(const void *buf, const int32_t *seg_start, int64_t rows_c
  * first expert projection, without a second pass over dU (replaces fmoe_cuda's column_reduce for that tensor). */
 size_t moe_slab_colsum_bytes(int64_t rows_cap, int cols);
 int moe_slab_colsum_final(const float *part, const int32_t *seg_start, int E, int cols, float *out, void *stream);
-/* MOE_GEMM_WGRAD / MOE_GEMM_WGRAD_T only: bytes of the optional split-K flag workspace passed as `aux` (int32, zero-filled
- * once by the caller; every launch leaves it zero again; one workspace per stream).  With it each output tile's K range
- * is computed in S parts on S CTA pairs (S = 2 when the tiles fill fewer than three rounds of the grid, up to 8 when there
- * are fewer tiles than CTA pairs — few local experts under expert parallelism); part 0 stores, parts 1..S-1 are added in
- * order, chained through the flags: bit-reproducible. */
+/* MOE_GEMM_WGRAD / MOE_GEMM_WGRAD_T only: bytes of the optional flag workspace passed as `aux` (int32, zero-filled once by
+ * the caller; every launch leaves it zero again; one workspace per stream).  With it the K range of an output tile may be
+ * computed in several pieces on several CTA pairs whenever whole tiles would not fill the grid evenly: stream-K (every
+ * pair takes an equal share of the linearised (tile, k-block) space; config 2: 96 tiles on 74 pairs) or S equal parts per
+ * tile (S = 2, or pairs / tiles when there are fewer tiles than half the pairs — few local experts under expert
+ * parallelism).  The piece that starts a tile's K range stores, the others are added in order, chained through the flags:
+ * bit-reproducible.  All CTAs of the launch must be resident at once (one per SM): do not run it next to another kernel
+ * that occupies whole SMs for its entire duration. */
 size_t moe_wgrad_flags_bytes(int E, int M, int N);
 int moe_grouped_gemm(int op, const void *A, const void *B, void *out0, void *out1, const float *bias, const void *aux,
                      const int32_t *tile_expert, const int32_t *num_mtiles, const int32_t *seg_start, int64_t rows_cap,

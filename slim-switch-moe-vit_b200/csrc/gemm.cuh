@@ -61,8 +61,9 @@ struct GemmParams {
     const float* bias;       // [E, N] fp32 or nullptr
     const __nv_bfloat16* aux;  // EPI_DGELU: G = gelu'(U) [rows_cap, N] (read through its tensor map)
     float* colsum;           // EPI_DGELU (optional): column sums of every 32-row output slab, [rows_cap / 32, N] fp32
-    int* flags;              // WGRAD split-K: one int per (tile, CTA rank, epilogue warp), zero between launches
-    int ksplit;              // WGRAD: S >= 2 = every tile's K range is done in S parts by S work units (chained through the flags)
+    int* flags;              // WGRAD stream-K: one int per (tile, CTA rank, epilogue warp), zero between launches
+    int streamk;             // WGRAD: 1 = every CTA pair takes an equal share of the linearised (tile, k-block) space (StreamK below)
+    int ksplit;              // WGRAD, !streamk: S >= 2 = every tile's K range is cut in S equal parts = S work units (round-robin)
     int E;
     int M;  // WGRAD: output rows per expert
     int N;  // output columns (per expert)
@@ -256,7 +257,9 @@ struct TileCoord {
     int row0;   // WGRAD: first packed row of the expert segment
     int kb;     // number of 64-deep k-blocks
     int kb0;    // WGRAD: first k-block of this work unit inside the expert segment
-    int part;   // WGRAD split-K: part s of S: 0 = plain store, s > 0 waits for part s - 1 and reduce-adds (fixed order); -1 = unsplit
+    int part;   // WGRAD stream-K: this fragment is the part-th piece of its tile's K range: 0 = plain store, s > 0 waits for
+                //   part s - 1 and reduce-adds (fixed order); -1 = the whole tile (no flags)
+    bool last;  // WGRAD stream-K: the fragment that ends the tile's K range (leaves the flag at zero)
     int tile;   // WGRAD: output tile index (flags)
 };
 // first B column (inside the pair tile) of this CTA's i-th 64-column block: BN <= 256: this CTA's half;
@@ -301,10 +304,142 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
             const int b1 = static_cast<int>(static_cast<long long>(c.kb) * (c.part + 1) / p.ksplit);
             c.kb0 = b0;
             c.kb = b1 - b0;
+            c.last = c.part + 1 == p.ksplit;
+            return c;
         }
     }
+    c.last = true;
     return c;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Stream-K schedule of the weight gradients (WGRAD, p.streamk).
+//
+// 96 tiles of 256 x 384 (config 2) on 74 CTA pairs are 1.3 rounds; cutting every tile's K range in two equal work units
+// (round 2a) made that 2.6 -> 3 rounds of half length.  Here the (tile, k-block) space is laid out on one line — the tiles
+// in (expert, m, n) order, each as long as its expert's k-blocks plus kEpiKb units that stand for its epilogue — and pair p
+// takes the p-th of `pairs` equal spans of that line.  A span boundary that would leave fewer than kSkMinKb k-blocks of
+// a tile on one side (or that falls into the epilogue units) moves to the tile boundary.  A pair walks its span BACKWARDS:
+// the piece of a tile that starts the tile's K range (part 0, a plain store) is then the first thing its pair runs, and the
+// piece that continues a tile begun by the previous pair (part s > 0: waits for part s - 1 through the per-warp flag, then
+// reduce-adds) is the last thing its pair runs — by then the store it waits for is long done, and every wait points at a
+// fragment that is first on a lower-numbered pair: no circular wait as long as all pairs are resident (one CTA per SM).
+// One store then the adds in one fixed order: bit-reproducible.  The tables are rebuilt by every CTA from seg_start
+// (device data: ragged and empty experts need no host involvement).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSkMaxE = 128;       // experts per launch the tables hold (more experts => more tiles than 3 rounds: no stream-K)
+constexpr int kSkMaxPairs = 128;
+constexpr int kSkMinKb = 4;        // no fragment shorter than this many k-blocks
+constexpr int kSkMinSpan = 24;     // no span shorter than this many units of the line
+struct SkTab {
+    int off[kSkMaxE + 1];    // position of each expert's first tile on the line
+    int kb[kSkMaxE];         // k-blocks of each expert segment
+    int cut[kSkMaxPairs + 1];   // span boundaries: pair p owns [cut[p], cut[p + 1])
+};
+
+// one full warp, before the prologue's cluster barrier
+template <int EPI_KB>
+__device__ __forceinline__ void sk_build(SkTab* t, const GemmParams& p, int per_e, int pairs, int lane) {
+    for (int e = lane; e < p.E; e += 32) t->kb[e] = (__ldg(p.seg_start + e + 1) - __ldg(p.seg_start + e)) / kBK;
+    __syncwarp();
+    const int chunk = (p.E + 31) / 32;   // experts per lane (contiguous)
+    int s = 0;
+    for (int i = 0; i < chunk; ++i) {
+        const int e = lane * chunk + i;
+        if (e < p.E) s += per_e * (t->kb[e] + EPI_KB);
+    }
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    int run = incl - s;
+    for (int i = 0; i < chunk; ++i) {
+        const int e = lane * chunk + i;
+        if (e < p.E) { t->off[e] = run; run += per_e * (t->kb[e] + EPI_KB); }
+    }
+    const int L = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0) t->off[p.E] = L;
+    __syncwarp();
+    // small problems: a span shorter than kSkMinSpan units is mostly epilogue — use fewer pairs (the rest get empty spans)
+    const int act = max(1, min(pairs, L / kSkMinSpan));
+    for (int q = lane; q <= pairs; q += 32) {
+        int c = q >= act ? L : static_cast<int>(static_cast<long long>(L) * q / act);
+        if (q > 0 && q < act) {
+            int lo = 0, hi = p.E - 1;   // expert holding c: the largest e with off[e] <= c
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (t->off[mid] <= c) lo = mid; else hi = mid - 1;
+            }
+            const int kb = t->kb[lo], len = kb + EPI_KB;
+            const int within = c - t->off[lo];
+            const int ti = within / len, o = within - ti * len;
+            const int o_t = t->off[lo] + ti * len;
+            if (o == 0) c = o_t;
+            else if (o >= kb - kSkMinKb) c = o_t + len;   // too close to the end of the K range, or inside the epilogue units
+            else if (o < kSkMinKb) c = o_t;
+        }
+        t->cut[q] = c;
+    }
+    __syncwarp();
+}
+
+// The work units of one CTA pair, in the order the pair runs them: whole tiles p, p + pairs, ... — or the stream-K walk.
+template <int BN, bool WGRAD, int EPI_KB>
+struct WorkIter {
+    const GemmParams& p;
+    const SkTab* sk;
+    int n_ntiles, rank, tile, total, stride;
+    int cur, c0, e, per_e;
+    __device__ __forceinline__ WorkIter(const GemmParams& p_, const SkTab* sk_, int n_ntiles_, int rank_, int total_)
+        : p(p_), sk(sk_), n_ntiles(n_ntiles_), rank(rank_), tile(blockIdx.x >> 1), total(total_), stride(gridDim.x >> 1) {
+        if constexpr (WGRAD) {
+            if (p.streamk) {
+                c0 = sk->cut[tile];
+                cur = sk->cut[tile + 1];
+                e = p.E - 1;
+                per_e = ((p.M + kPairM - 1) / kPairM) * n_ntiles;
+            }
+        }
+    }
+    __device__ __forceinline__ bool next(TileCoord& c) {
+        if constexpr (WGRAD) {
+            if (p.streamk) {
+                if (cur <= c0) return false;
+                const int pos = cur - 1;
+                while (sk->off[e] > pos) --e;
+                const int kbe = sk->kb[e], len = kbe + EPI_KB;
+                const int ti = (pos - sk->off[e]) / len;
+                const int o_t = sk->off[e] + ti * len;
+                const int kend = min(cur - o_t, kbe);
+                const int kstart = max(c0 - o_t, 0);
+                const int mt = ti / n_ntiles;
+                c.e = e;
+                c.m0 = mt * kPairM + rank * kBM;
+                c.n0 = (ti - mt * n_ntiles) * BN;
+                c.row0 = __ldg(p.seg_start + e);
+                c.kb0 = kstart;
+                c.kb = kend - kstart;
+                c.tile = e * per_e + ti;
+                c.last = kend == kbe;
+                if (kstart == 0) {
+                    c.part = c.last ? -1 : 0;
+                } else {   // parts before this one: the non-empty spans of lower pairs that reach into this tile
+                    int part = 0;
+                    for (int q = tile - 1; q >= 0 && sk->cut[q + 1] > o_t; --q) part += sk->cut[q] < sk->cut[q + 1] ? 1 : 0;
+                    c.part = part;
+                }
+                cur = o_t;
+                return true;
+            }
+        }
+        if (tile >= total) return false;
+        c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
+        tile += stride;
+        return true;
+    }
+};
 
 template <int BN, int EPI, bool WGRAD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((GemmCfg<BN, EPI>::THREADS), 1)
@@ -355,17 +490,26 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
+    const int n_ntiles = (p.N + BN - 1) / BN;
+    // WGRAD has no bias: the stream-K tables live in the bias area
+    constexpr int kEpiKb = Cfg::ACC_STAGES == 1 ? 6 : 2;   // epilogue of one work unit, in k-blocks of mainloop time
+    static_assert(sizeof(SkTab) <= Cfg::EPI_WARPS * Cfg::BIAS_FLOATS * 4, "stream-K tables do not fit the bias area");
+    const SkTab* const sk = reinterpret_cast<const SkTab*>(bias_s);
+    if constexpr (WGRAD) {
+        if (p.streamk && warp == 2)
+            sk_build<kEpiKb>(reinterpret_cast<SkTab*>(bias_s), p, ((p.M + kPairM - 1) / kPairM) * n_ntiles, gridDim.x >> 1, lane);
+    }
     tc_fence_before();
-    cluster_sync_all();  // barrier inits + TMEM allocation visible in both CTAs before any cross-CTA signal
+    cluster_sync_all();  // barrier inits, TMEM allocation (and the stream-K tables) visible before any cross-CTA signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int n_ntiles = (p.N + BN - 1) / BN;
     int total_tiles;
-    if constexpr (WGRAD) total_tiles = p.E * ((p.M + kPairM - 1) / kPairM) * n_ntiles * p.ksplit;
+    if constexpr (WGRAD) total_tiles = p.E * ((p.M + kPairM - 1) / kPairM) * n_ntiles * (p.ksplit >= 2 ? p.ksplit : 1);
     else total_tiles = __ldg(p.num_mtiles) * n_ntiles;
-    const int first_tile = blockIdx.x >> 1;   // pair p takes tiles p, p + npairs, ...
-    const int tile_stride = gridDim.x >> 1;
+    [[maybe_unused]] const int first_tile = blockIdx.x >> 1;   // pair p takes tiles p, p + npairs, ... (or its stream-K span)
+    [[maybe_unused]] const int tile_stride = gridDim.x >> 1;
+    using Work = WorkIter<BN, WGRAD, kEpiKb>;
 
     if (warp == 0) {
         // ================================ TMA producer (one thread per CTA) =========================
@@ -373,8 +517,9 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int s = 0;
             uint32_t ph = 0;
             [[maybe_unused]] int ti = 0;
-            for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++ti) {
-                const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
+            [[maybe_unused]] const uint64_t pol_a = WGRAD ? l2_policy_evict_first() : 0, pol_b = WGRAD ? l2_policy_evict_last() : 0;
+            Work work(p, sk, n_ntiles, rank, total_tiles);
+            for (TileCoord c; work.next(c); ++ti) {
                 MOE_TL(0, ti, 0);
                 for (int kb = 0; kb < c.kb; ++kb) {
                     mbar_wait(empty_bar + s, ph ^ 1);
@@ -393,14 +538,29 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                                  c.e * p.N + c.n0 + b_block_col<BN>(rank, i));
                         }
                     } else {
+                        // Stream-K (only chosen when N is one tile wide and B fits L2, gemm_launch.cu): A (the dU / H columns of
+                        // this tile) is read once per launch: evict_first.  B (the expert's X / dY rows) is re-read by every M
+                        // tile of the expert, under stream-K at a different time by each of them: evict_last keeps it in L2
+                        // (38.7 MB at config 2; measured 240 -> 209 MB of DRAM reads, 71 -> 67 us).  Lock-step schedules
+                        // (whole tiles, equal split-K parts) share B in time and measured slower with the hints.
                         const int krow = c.row0 + (c.kb0 + kb) * kBK;
-                        tma_load_2d_pair(sa, &tmA, full_bar + s, c.m0, krow);
-                        tma_load_2d_pair(sa + 8192, &tmA, full_bar + s, c.m0 + 64, krow);
+                        if (p.streamk) {
+                            tma_load_2d_pair_hint(sa, &tmA, full_bar + s, c.m0, krow, pol_a);
+                            tma_load_2d_pair_hint(sa + 8192, &tmA, full_bar + s, c.m0 + 64, krow, pol_a);
 #pragma unroll
-                        for (int i = 0; i < (BN / 2) / Cfg::B_ATOM; ++i)
-                            tma_load_2d_pair(sb + i * (Cfg::B_ATOM * kBK * 2), &tmB, full_bar + s,
-                                             c.n0 + (Cfg::B_ATOM == 64 ? b_block_col<BN>(rank, i) : rank * (BN / 2) + i * Cfg::B_ATOM),
-                                             krow);
+                            for (int i = 0; i < (BN / 2) / Cfg::B_ATOM; ++i)
+                                tma_load_2d_pair_hint(sb + i * (Cfg::B_ATOM * kBK * 2), &tmB, full_bar + s,
+                                                      c.n0 + (Cfg::B_ATOM == 64 ? b_block_col<BN>(rank, i) : rank * (BN / 2) + i * Cfg::B_ATOM),
+                                                      krow, pol_b);
+                        } else {
+                            tma_load_2d_pair(sa, &tmA, full_bar + s, c.m0, krow);
+                            tma_load_2d_pair(sa + 8192, &tmA, full_bar + s, c.m0 + 64, krow);
+#pragma unroll
+                            for (int i = 0; i < (BN / 2) / Cfg::B_ATOM; ++i)
+                                tma_load_2d_pair(sb + i * (Cfg::B_ATOM * kBK * 2), &tmB, full_bar + s,
+                                                 c.n0 + (Cfg::B_ATOM == 64 ? b_block_col<BN>(rank, i) : rank * (BN / 2) + i * Cfg::B_ATOM),
+                                                 krow);
+                        }
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -416,8 +576,8 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
             [[maybe_unused]] int ti = 0;
-            for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++ti) {
-                const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
+            Work work(p, sk, n_ntiles, rank, total_tiles);
+            for (TileCoord c; work.next(c); ++ti) {
                 if (c.kb == 0) continue;
                 MOE_TL(1, ti, 0);
                 mbar_wait(tempty_bar + as, aph ^ 1);
@@ -473,15 +633,15 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             //   EPI_F32_T: slab = 16 rows (n) x 128 B, 128-byte swizzle (row j = accumulator column j, this lane = column)
             uint8_t* const slab0 = staging + ew * Cfg::SLAB_BYTES;
             uint32_t nhalf = 0;   // half-slabs filled so far (parity selects the slab)
-            for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++ti) {
-                const TileCoord c = decode_tile<BN, WGRAD>(p, tile, n_ntiles, rank);
+            Work work(p, sk, n_ntiles, rank, total_tiles);
+            for (TileCoord c; work.next(c); ++ti) {
                 const bool live = c.kb != 0;
                 if (tl_on) MOE_TL(tl_role, ti, 0);
-                // split-K: this warp's slabs of the tile are also written by the same warp of the pairs that run the other
+                // stream-K: this warp's slabs of the tile are also written by the same warp of the pairs that run the other
                 // parts.  Part 0 stores and sets the flag to 1; part s waits for the flag to read s, reduce-adds and passes
                 // s + 1 on (the last part leaves 0): one store, then the adds in one fixed order — bit-reproducible.
                 int* const my_flag = c.part >= 0 ? p.flags + (static_cast<size_t>(c.tile) * 2 + rank) * Cfg::EPI_WARPS + ew : nullptr;
-                const int pass_on = c.part + 1 == p.ksplit ? 0 : c.part + 1;
+                const int pass_on = c.last ? 0 : c.part + 1;
                 if (c.part > 0) {
                     if (lane == 0) {
                         uint32_t spins = 0;

@@ -136,15 +136,11 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
     p.seg_start = seg_start;
     p.bias = bias;
     p.aux = wgrad ? nullptr : static_cast<const __nv_bfloat16*>(aux);
-    // WGRAD: `aux` is the optional split-K flag workspace (moe_wgrad_flags_bytes(E, M, N) bytes, zero-filled once; the
-    // kernel leaves it zero).  With it every tile's K range runs as two work units on two CTA pairs — 96 tiles of
-    // 256 x 384 on 74 pairs would otherwise take two full rounds.
+    // WGRAD: `aux` is the optional stream-K flag workspace (moe_wgrad_flags_bytes(E, M, N) bytes, zero-filled once; the
+    // kernel leaves it zero)
     p.colsum = op == MOE_GEMM_DGELU ? static_cast<float*>(out1) : nullptr;   // DGELU: out1 = optional slab column sums
     p.flags = wgrad ? static_cast<int*>(const_cast<void*>(aux)) : nullptr;
-    p.ksplit = (wgrad && aux != nullptr) ? 2 : 1;
-#ifdef MOE_EXPERIMENT_HOOKS
-    if (getenv("MOE_WGRAD_NO_SPLIT") != nullptr) p.ksplit = 1;
-#endif
+    p.streamk = 0;
     p.E = E; p.M = M; p.N = N; p.K = K;
 
     CUtensorMap tA, tB, tO0, tO1, tAux;
@@ -177,20 +173,40 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
     }
     if (!ok) return 1;
     const int grid = (sm_count / 2) * 2;
-    if (wgrad && p.ksplit >= 2) {
-        // How many parts per tile: with three or more full rounds of tiles a split buys no balance, only epilogue work; with
-        // fewer tiles than CTA pairs (few local experts under expert parallelism: 12 tiles for 74 pairs at E_local = 2)
-        // every tile is cut into pairs / tiles parts, as long as a part keeps ~16 k-blocks to amortise its epilogue.
+    p.ksplit = 1;
+    if (wgrad && aux != nullptr) {
+        // How the K ranges of the output tiles are spread over the CTA pairs when whole tiles do not fill the grid evenly
+        // (measured, profiles/r02_wgrad_schedules.md):
+        //  * three or more rounds of tiles: whole tiles round-robin (balanced to a few percent, one epilogue per tile);
+        //  * stream-K (gemm.cuh) when a tile is cut in at most two or three pieces (tiles >= pairs / 2), the tile spans
+        //    all of N (the A columns of a tile are not shared with another tile) and B fits L2 with room to spare: pairs
+        //    work at unrelated K offsets, so every operand that is shared between tiles must come from L2, not from being
+        //    read at the same time.  Config 2: 96 tiles on 74 pairs, 76 -> 67 us;
+        //  * otherwise equal split-K: S = 2 parts per tile, or S = pairs / tiles when there are fewer tiles than half the
+        //    pairs (12 tiles at E_local = 2 under 8-way expert parallelism), as long as a part keeps ~16 k-blocks.  Parts
+        //    of sibling tiles run in lock-step, so shared operands are read once.
         const int pairs = grid / 2;
-        const int64_t ntile = static_cast<int64_t>(E) * ((M + 255) / 256) * ((N + bn - 1) / bn);
+        const int n_nt = (N + bn - 1) / bn;
+        const int64_t ntile = static_cast<int64_t>(E) * ((M + 255) / 256) * n_nt;
         const int64_t avg_kb = rows_cap / (64LL * (E > 0 ? E : 1));
-        int S = ntile >= 3LL * pairs ? 1 : 2;
-        if (ntile * 2 <= pairs) {
-            S = static_cast<int>(pairs / ntile);
-            if (S > 8) S = 8;
-            while (S > 2 && avg_kb / S < 16) --S;
+        const bool b_in_l2 = static_cast<int64_t>(rows_cap) * N * 2 <= (48LL << 20);
+        if (ntile >= 3LL * pairs) {
+            p.ksplit = 1;
+        } else if (n_nt == 1 && b_in_l2 && 2 * ntile >= pairs && E <= kSkMaxE && pairs <= kSkMaxPairs) {
+            p.streamk = 1;
+        } else {
+            int S = 2;
+            if (ntile * 2 <= pairs) {
+                S = static_cast<int>(pairs / ntile);
+                if (S > 8) S = 8;
+                while (S > 2 && avg_kb / S < 16) --S;
+            }
+            p.ksplit = S;
         }
-        p.ksplit = S;
+#ifdef MOE_EXPERIMENT_HOOKS
+        if (getenv("MOE_WGRAD_NO_SPLIT") != nullptr) { p.streamk = 0; p.ksplit = 1; }
+        if (getenv("MOE_WGRAD_STREAMK") != nullptr) { p.streamk = atoi(getenv("MOE_WGRAD_STREAMK")); if (p.streamk) p.ksplit = 1; }
+#endif
     }
 
 #define MOE_BN_ROWS_WIDE(EPI)                                                             \

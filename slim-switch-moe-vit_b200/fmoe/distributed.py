@@ -294,10 +294,7 @@ def ep_forward(layer, moe_inp: torch.Tensor) -> torch.Tensor:
     gate = layer.gate
     T = moe_inp.shape[0]
     spec = gate.route_spec(T)
-    if spec.capacity >= T * spec.top_k:
-        raise NotImplementedError(
-            f"{type(gate).__name__} has no per-expert capacity: expert parallelism exchanges rows into statically sized buffers and "
-            "needs a capacity-limited gate (SwitchGate / GShardGate)")
+    unlimited = spec.capacity >= T * spec.top_k
     if not getattr(layer, "_ep_group_checked", False):
         _check_group(layer)
         layer._ep_group_checked = True
@@ -306,13 +303,19 @@ def ep_forward(layer, moe_inp: torch.Tensor) -> torch.Tensor:
     transport = getattr(layer, "_ep_transport", None)
     if transport is None or TRANSPORT != "auto":
         transport = layer._ep_transport = _pick_transport(layer, moe_inp, spec)
+    if unlimited and transport != "peer":
+        # NCCL slabs are [E, ceil256(capacity), d] per rank: without a capacity that is E times the token buffer.  The peer
+        # transport packs live rows only and sizes its buffers for the worst case W * T * k rows per rank.
+        raise NotImplementedError(
+            f"{type(gate).__name__} has no per-expert capacity: under expert parallelism it runs on the NVLink peer-memory "
+            "transport only (one node, peer access); the NCCL slab exchange needs a capacity-limited gate (SwitchGate / GShardGate)")
     if transport == "peer":
         from .peer import EPPeerMoEFunction, peer_buffers
         try:
             pb = peer_buffers(layer, T, layer.d_model, layer.num_expert * layer.world_size, layer.num_expert, spec.top_k, spec.capacity,
                               moe_inp.device)
         except C.MoeB200Error as e:
-            if TRANSPORT != "auto":
+            if TRANSPORT != "auto" or unlimited:
                 raise
             # the heap set-up fails on every rank together (fmoe/peer.py): all of them fall back to the NCCL exchange
             import warnings

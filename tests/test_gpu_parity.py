@@ -568,7 +568,7 @@ def _gemm_setup(E, counts, dev="cuda"):
 
 
 # (op, counts, M, N, K): every tile shape the launcher can pick — 64 / 128 / 192 / 256-wide double-buffered tiles, the
-# 384-wide single-accumulator tiles of fc2 / dgrad / wgrad, 64-byte-swizzle B atoms (wgrad N = 192), split-K with and
+# 384-wide single-accumulator tiles of fc2 / dgrad / wgrad, 64-byte-swizzle B atoms (wgrad N = 192), stream-K with and
 # without empty / one-k-block experts, transposed weight-gradient stores
 GEMM_CASES = [
     ("fc2", [128, 128], 0, 64, 64), ("fc2", [300, 5, 0, 129], 0, 192, 384), ("fc2", [700, 300, 5, 129], 0, 384, 1536),
@@ -577,6 +577,10 @@ GEMM_CASES = [
     ("wgrad", [100, 100, 100, 100], 256, 64, 0), ("wgrad", [640, 64, 1], 1536, 384, 0), ("wgrad", [300, 5, 0, 129], 768, 192, 0),
     ("wgrad", [300, 5, 0, 129], 192, 768, 0), ("wgrad", [1024, 1024], 384, 1536, 0),
     ("wgrad_t", [100, 100, 100, 100], 256, 64, 0), ("wgrad_t", [700, 0, 129], 3072, 768, 0), ("wgrad_t", [640, 64, 1], 1536, 384, 0),
+    # few tiles with long K ranges (equal split-K, many parts per tile: the expert-parallel case); stream-K on ragged segments
+    # with an empty and two one-k-block experts (42 tiles) and on the config-2 shape (96 tiles on 74 pairs)
+    ("wgrad", [3000, 2800], 1536, 384, 0), ("wgrad_t", [1500, 40, 0, 2100, 900, 3100, 64], 1536, 384, 0),
+    ("wgrad", [3152] * 16, 1536, 384, 0), ("wgrad_t", [25000], 1024, 256, 0),
 ]
 
 
