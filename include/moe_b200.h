@@ -47,8 +47,10 @@ extern "C" {
 /* grouped GEMM ops (moe_grouped_gemm) */
 #define MOE_GEMM_FC1 0   /* U = A W^T + b: out0 = gelu_erf'(U), out1 = gelu_erf(U)   A[rows,K] B[E,N,K] */
 #define MOE_GEMM_FC2 1   /* out0 = A W^T + b                            A[rows,K] B[E,N,K]            */
-#define MOE_GEMM_DGELU 2 /* out0 = (A Wt^T) * aux  (aux = FC1's out0)       A[rows,K] B[E,N,K] aux[rows,N]; out1: optional slab column sums */
-#define MOE_GEMM_DGRAD 3 /* out0 = A Wt^T                               A[rows,K] B[E,N,K]            */
+#define MOE_GEMM_DGELU 2 /* out0 = (A W) * aux  (aux = FC1's out0)          A[rows,K] B[E,K,N] aux[rows,N]; out1: optional slab column sums */
+#define MOE_GEMM_DGRAD 3 /* out0 = A W                                  A[rows,K] B[E,K,N]            */
+/* (the backward contractions read the forward weights as they are — W2 [E,d,h] is [E,K,N] for DGELU, W1 [E,h,d] for
+ *  DGRAD — through MN-major UMMA descriptors: one bf16 copy per weight matrix, no transposes) */
 #define MOE_GEMM_WGRAD 4 /* out0[e] (fp32 [E,M,N]) = A_e^T B_e          A[rows,M] B[rows,N]           */
 #define MOE_GEMM_WGRAD_T 5 /* out0[e] (fp32 [E,N,M]) = (A_e^T B_e)^T = B_e^T A_e, same tiles as WGRAD, transposed store:
                               lets the wide dimension be M (256-row tiles) whatever the parameter's layout */
@@ -177,13 +179,13 @@ int moe_combine_bwd(const void *dy, int dy_dtype, const void *ybuf, const int32_
                     float *dscore, void *stream);
 
 /* ---- expert FFN backward: replaces fmoe_cuda.linear_backward x2 + GELU' + column_reduce.
- * W1tb[E,d,h] = W1^T and W2tb[E,h,d] = W2^T are the TRANSPOSED bf16 weight copies
- * (moe_cast_bf16_transposed), so that every row-mode contraction reads K-major operands.
+ * W1b[E,h,d] and W2b[E,d,h] are the SAME bf16 weight copies the forward reads (moe_cast_bf16): the two backward
+ * contractions read them MN-major.
  * dU[rows_cap,h] and dxbuf[rows_cap,d] are bf16 outputs (dU doubles as workspace);
  * dW1[E,h,d], db1[E,h], dW2[E,d,h], db2[E,d] are fp32 and are overwritten. */
 size_t moe_expert_ffn_bwd_workspace_bytes(int64_t rows_cap, int d, int h, int E);
-int moe_expert_ffn_bwd(const void *dybuf, const void *xbuf, const void *G, const void *H, const void *W1tb,
-                       const void *W2tb, const int32_t *tile_expert, const int32_t *num_mtiles,
+int moe_expert_ffn_bwd(const void *dybuf, const void *xbuf, const void *G, const void *H, const void *W1b,
+                       const void *W2b, const int32_t *tile_expert, const int32_t *num_mtiles,
                        const int32_t *seg_start, int64_t rows_cap, int d, int h, int E, void *dU, void *dxbuf,
                        float *dW1, float *db1, float *dW2, float *db2,
                        void *workspace /* moe_expert_ffn_bwd_workspace_bytes(rows_cap, d, h, E) bytes */, void *stream);
@@ -235,8 +237,6 @@ int moe_colsum(const void *buf, int dtype, int64_t rows, int cols, void *workspa
 
 /* ---- utilities */
 int moe_cast_bf16(const float *src, void *dst, int64_t n /* % 8 == 0 */, void *stream);
-/* src[E,R,C] fp32 -> dst[E,R,C] bf16 (nullable) and dst_t[E,C,R] bf16 (transposed per expert); R, C % 32 == 0 */
-int moe_cast_bf16_transposed(const float *src, void *dst, void *dst_t, int E, int R, int C, void *stream);
 /* out[E,cols] = per-segment column sums of the packed bf16 buffer buf[rows_cap,cols] (bias gradients;
  * replaces fmoe_cuda's column_reduce).  Two deterministic stages through `workspace`. */
 size_t moe_segment_colsum_workspace_bytes(int64_t rows_cap, int cols);

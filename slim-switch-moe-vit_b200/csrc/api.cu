@@ -282,11 +282,6 @@ int moe_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
     return check(launch_cast_bf16(src, dst, n, sm_count(), static_cast<cudaStream_t>(stream)), "moe_cast_bf16");
 }
 
-int moe_cast_bf16_transposed(const float* src, void* dst, void* dst_t, int E, int R, int C, void* stream) {
-    if (E <= 0 || R <= 0 || C <= 0 || R % 32 != 0 || C % 32 != 0 || dst_t == nullptr) { set_error("moe_cast_bf16_transposed: need E > 0, R, C positive multiples of 32 (E=%d R=%d C=%d)", E, R, C); return 1; }
-    return check(launch_cast_bf16_transposed(src, dst, dst_t, E, R, C, static_cast<cudaStream_t>(stream)), "moe_cast_bf16_transposed");
-}
-
 size_t moe_segment_colsum_workspace_bytes(int64_t rows_cap, int cols) { return segment_colsum_workspace_bytes(rows_cap, cols); }
 
 int moe_segment_colsum(const void* buf, const int32_t* seg_start, int64_t rows_cap, int E, int cols, void* workspace, float* out,
@@ -392,8 +387,8 @@ size_t moe_workspace_bytes(int64_t T, int d, int h, int E, int k, int64_t capaci
     return a > b ? a : b;
 }
 
-int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* G, const void* H, const void* W1tb,
-                       const void* W2tb, const int32_t* tile_expert, const int32_t* num_mtiles,
+int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* G, const void* H, const void* W1b,
+                       const void* W2b, const int32_t* tile_expert, const int32_t* num_mtiles,
                        const int32_t* seg_start, int64_t rows_cap, int d, int h, int E, void* dU, void* dxbuf,
                        float* dW1, float* db1, float* dW2, float* db2, void* workspace, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -404,9 +399,9 @@ int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* G, const
     float* slab_sums = reinterpret_cast<float*>(ws);
     void* colsum_ws = ws + align256(moe_slab_colsum_bytes(rows_cap, h));
     void* flags = static_cast<uint8_t*>(colsum_ws) + align256(segment_colsum_workspace_bytes(rows_cap, d));
-    // dU = (dY W2) * G, G = gelu'(U)                   [rows, h]   K = d, B = W2^T [E, h, d] K-major
+    // dU = (dY W2) * G, G = gelu'(U)                   [rows, h]   K = d, B = W2 [E, d, h] read MN-major
     // (the epilogue leaves the column sums of every 32-row slab of dU behind: db1 without a second pass over dU)
-    rc = launch_grouped_gemm(MOE_GEMM_DGELU, dybuf, W2tb, dU, slab_sums, nullptr, G, tile_expert, num_mtiles, nullptr,
+    rc = launch_grouped_gemm(MOE_GEMM_DGELU, dybuf, W2b, dU, slab_sums, nullptr, G, tile_expert, num_mtiles, nullptr,
                              rows_cap, E, 0, h, d, sms, st);
     if (rc) return rc;
     // split-K flags of the two weight gradients (cleared here; the kernels leave them clear)
@@ -419,8 +414,8 @@ int moe_expert_ffn_bwd(const void* dybuf, const void* xbuf, const void* G, const
     rc = launch_grouped_gemm(MOE_GEMM_WGRAD, dU, xbuf, dW1, nullptr, nullptr, flags, nullptr, nullptr, seg_start,
                              rows_cap, E, h, d, 0, sms, st);
     if (rc) return rc;
-    // dX = dU W1                                   [rows, d]   K = h, B = W1^T [E, d, h] K-major
-    rc = launch_grouped_gemm(MOE_GEMM_DGRAD, dU, W1tb, dxbuf, nullptr, nullptr, nullptr, tile_expert, num_mtiles, nullptr,
+    // dX = dU W1                                   [rows, d]   K = h, B = W1 [E, h, d] read MN-major
+    rc = launch_grouped_gemm(MOE_GEMM_DGRAD, dU, W1b, dxbuf, nullptr, nullptr, nullptr, tile_expert, num_mtiles, nullptr,
                              rows_cap, E, 0, d, h, sms, st);
     if (rc) return rc;
     if (check(launch_segment_colsum(dybuf, seg_start, rows_cap, E, d, colsum_ws, db2, st), "db2 colsum")) return 1;

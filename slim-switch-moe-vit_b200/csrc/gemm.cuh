@@ -4,11 +4,13 @@
 // expert FFN (replaces FastMoE's per-expert cuBLAS loop
 // `fmoe_cuda.linear_forward/backward`, reached from /root/reference/models/resMoE.py:27-29):
 //
-//   ROWS mode  (M = packed token rows, one weight matrix per 256-row pair tile; A and B K-major):
+//   ROWS mode  (M = packed token rows, one weight matrix per 256-row pair tile; A K-major, B K-major (forward) or MN-major (backward)):
 //     fc1   : U = X  W1^T + b1 -> G = gelu_erf'(U), H = gelu_erf(U)   B = W1   [E, h, d]   EPI_BIAS_GELU_DUAL
 //     fc2   : Y = H  W2^T + b2                      B = W2   [E, d, h]      EPI_BIAS
-//     dgelu : dU = (dY W2) * G                      B = W2^T [E, h, d]      EPI_DGELU
-//     dgrad : dX = dU W1                            B = W1^T [E, d, h]      EPI_PLAIN
+//     dgelu : dU = (dY W2) * G                      B = W2   [E, d, h] MN-major (N = h contiguous)   EPI_DGELU
+//     dgrad : dX = dU W1                            B = W1   [E, h, d] MN-major (N = d contiguous)   EPI_PLAIN
+//   (the two backward contractions read the SAME bf16 weight copies as the forward ones, through MN-major UMMA
+//    descriptors — no transposed copies: the per-step weight cast writes half as much)
 //   WGRAD mode (K = the rows of one expert's segment, fp32 output per expert; A and B MN-major):
 //     dW1[e] = dU_e^T X_e   [E, M = h, N = d]                               EPI_F32
 //     dW2[e] = (H_e^T dY_e)^T: computed as [M = h, N = d], stored transposed EPI_F32_T
@@ -116,6 +118,9 @@ struct GemmCfg {
     static constexpr int NCHUNK = BN / 32;
     static constexpr int MAXCH = (NCHUNK + NGRP - 1) / NGRP;   // chunks of one warp per tile
     static constexpr bool F32 = (EPI == EPI_F32 || EPI == EPI_F32_T);
+    // B is MN-major (N contiguous in global memory, read in [64 k] x [B_ATOM n] boxes) for the weight gradients and for
+    // the two backward row-mode contractions, which read the forward weights W2 [E, d, h] / W1 [E, h, d] as [K, N]
+    static constexpr bool B_MN = F32 || EPI == EPI_DGELU || EPI == EPI_PLAIN;
     // WGRAD reads B MN-major: whole 128-byte swizzle atoms (64 columns) when this CTA's half allows it, else
     // 64-byte swizzle atoms (32 columns): BN = 192 -> 96 columns per CTA = three 32-column atoms
     static constexpr int B_ATOM = ((BN / 2) % 64 == 0) ? 64 : 32;
@@ -529,7 +534,14 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (rank == 0) mbar_arrive_expect_tx(full_bar + s, 2 * Cfg::STAGE_BYTES);
                     if constexpr (!WGRAD) {
                         tma_load_2d_pair(sa, &tmA, full_bar + s, kb * kBK, c.m0);
-                        if constexpr (BN <= 256) {
+                        if constexpr (Cfg::B_MN) {
+                            const int krow = c.e * p.K + kb * kBK;   // B = [E * K, N]
+#pragma unroll
+                            for (int i = 0; i < (BN / 2) / Cfg::B_ATOM; ++i)
+                                tma_load_2d_pair(sb + i * (Cfg::B_ATOM * kBK * 2), &tmB, full_bar + s,
+                                                 c.n0 + (Cfg::B_ATOM == 64 ? b_block_col<BN>(rank, i) : rank * (BN / 2) + i * Cfg::B_ATOM),
+                                                 krow);
+                        } else if constexpr (BN <= 256) {
                             tma_load_2d_pair(sb, &tmB, full_bar + s, kb * kBK, c.e * p.N + c.n0 + rank * (BN / 2));
                         } else {
 #pragma unroll
@@ -571,8 +583,8 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else if (warp == 1) {
         // ================================ MMA issuer (one thread of the leader CTA) =================
         if (rank == 0 && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kPairM, BN <= 256 ? BN : 256, WGRAD, WGRAD);
-            [[maybe_unused]] constexpr uint32_t idesc1 = umma_idesc_bf16(kPairM, BN <= 256 ? 16 : BN - 256, WGRAD, WGRAD);
+            constexpr uint32_t idesc = umma_idesc_bf16(kPairM, BN <= 256 ? BN : 256, WGRAD, Cfg::B_MN);
+            [[maybe_unused]] constexpr uint32_t idesc1 = umma_idesc_bf16(kPairM, BN <= 256 ? 16 : BN - 256, WGRAD, Cfg::B_MN);
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
             [[maybe_unused]] int ti = 0;
@@ -594,7 +606,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int k4 = 0; k4 < kBK / 16; ++k4) {
                         const uint64_t ad = WGRAD ? umma_smem_desc(a_addr + k4 * 2048, 8192, 1024)
                                                   : umma_smem_desc(a_addr + k4 * 32, 16, 1024);
-                        const uint64_t bd = !WGRAD ? umma_smem_desc(b_addr + k4 * 32, 16, 1024)
+                        const uint64_t bd = !Cfg::B_MN ? umma_smem_desc(b_addr + k4 * 32, 16, 1024)
                                             : Cfg::B_ATOM == 64 ? umma_smem_desc(b_addr + k4 * 2048, 8192, 1024)
                                                                 : umma_smem_desc(b_addr + k4 * 1024, 4096, 512, 4);
                         umma_bf16(tmem_d, ad, bd, idesc, (kb | k4) != 0);

@@ -148,9 +148,14 @@ int launch_grouped_gemm(int op, const void* A, const void* B, void* out0, void* 
     const uint64_t R = static_cast<uint64_t>(rows_cap);
     bool ok = true;
     if (!wgrad) {
-        // A [rows, K] and B [E*N, K] K-major; each CTA of a pair loads 128 A rows and bn/2 B rows per k-block
+        // A [rows, K] K-major: each CTA of a pair loads its 128 A rows per k-block.  B: the forward ops read the weights
+        // [E*N, K] K-major (bn/2 rows per CTA and k-block); dgelu / dgrad read the SAME weights as [E*K, N] MN-major, in
+        // 64 x 64 boxes (32-column boxes with 64-byte swizzle when the CTA's half of the tile is not whole 64-column atoms)
         ok = ok && encode_2d(&tA, BF, 2, A, K, R, 64, 128);
-        ok = ok && encode_2d(&tB, BF, 2, B, K, static_cast<uint64_t>(E) * N, 64, bn <= 256 ? bn / 2 : 64);
+        const bool b_mn = op == MOE_GEMM_DGELU || op == MOE_GEMM_DGRAD;
+        if (!b_mn) ok = ok && encode_2d(&tB, BF, 2, B, K, static_cast<uint64_t>(E) * N, 64, bn <= 256 ? bn / 2 : 64);
+        else if ((bn / 2) % 64 == 0) ok = ok && encode_2d(&tB, BF, 2, B, N, static_cast<uint64_t>(E) * K, 64, 64);
+        else ok = ok && encode_2d(&tB, BF, 2, B, N, static_cast<uint64_t>(E) * K, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B);
         // each epilogue warp stores (and, for dgelu, loads its rows of the pre-activation as) 32-row x 32-column slabs
         const auto S64 = CU_TENSOR_MAP_SWIZZLE_64B;
         // fc1 without out0 (G = gelu'): forward-only pass, the single output H goes through the first descriptor

@@ -1219,29 +1219,6 @@ cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
     }
 }
 
-// src[E,R,C] fp32 -> dst[E,R,C] bf16 (optional) + dst_t[E,C,R] bf16; 32x32 tiles through shared memory
-__global__ void __launch_bounds__(256)
-cast_bf16_transposed_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                            __nv_bfloat16* __restrict__ dst_t, int R, int C) {
-    __shared__ float tile[32][33];
-    const int e = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const size_t base = static_cast<size_t>(e) * R * C;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = r0 + ty + i * 8;
-        const float v = src[base + static_cast<size_t>(r) * C + c0 + tx];
-        tile[ty + i * 8][tx] = v;
-        if (dst != nullptr) dst[base + static_cast<size_t>(r) * C + c0 + tx] = __float2bfloat16_rn(v);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = c0 + ty + i * 8;
-        dst_t[base + static_cast<size_t>(c) * R + r0 + tx] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
-    }
-}
-
 // Per-segment column sums (bias gradients) in two deterministic stages.
 // Stage 1: CTA = 128 rows x 256 columns; warp w reads rows w*16..w*16+15 with all 16 16-byte loads in
 // flight, the 8 warps are combined in shared memory in warp order -> part[rb][c].  128-row blocks never
@@ -1627,13 +1604,6 @@ cudaError_t launch_gate_wgrad(const float* dlogits, const void* x, int x_dtype, 
 cudaError_t launch_cast_bf16(const float* src, void* dst, int64_t n, int sm_count, cudaStream_t st) {
     const int64_t n8 = n / 8;
     cast_bf16_kernel<<<grid_for(n8, sm_count), 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), n8);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_cast_bf16_transposed(const float* src, void* dst, void* dst_t, int E, int R, int C, cudaStream_t st) {
-    dim3 grid(C / 32, R / 32, E);
-    cast_bf16_transposed_kernel<<<grid, 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst),
-                                                      static_cast<__nv_bfloat16*>(dst_t), R, C);
     return cudaGetLastError();
 }
 

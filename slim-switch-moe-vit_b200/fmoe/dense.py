@@ -60,7 +60,7 @@ class _DenseFFN(torch.autograd.Function):
                 raise C.MoeB200Error("DenseFFN parameters must be fp32 (master weights)")
         xb = _rows(x2, rows_cap)
         te, nm, sg = _tables(rows_cap, dev)
-        W1b, W2b, W1tb, W2tb = cache.get(W1.detach().view(1, h, d), W2.detach().view(1, d, h), fresh=True)
+        W1b, W2b = cache.get(W1.detach().view(1, h, d), W2.detach().view(1, d, h), fresh=True)
         G = torch.empty((rows_cap, h), dtype=bf, device=dev)
         H = torch.empty((rows_cap, h), dtype=bf, device=dev)
         Y = torch.empty((rows_cap, d), dtype=bf, device=dev)
@@ -68,7 +68,7 @@ class _DenseFFN(torch.autograd.Function):
                C.ptr(te), C.ptr(nm), None, rows_cap, 1, 0, h, d, st, tag="dense_fc1")
         C.call("moe_grouped_gemm", C.GEMM_FC2, C.ptr(H), C.ptr(W2b), C.ptr(Y), None, C.ptr(b2.detach().contiguous()), None,
                C.ptr(te), C.ptr(nm), None, rows_cap, 1, 0, d, h, st, tag="dense_fc2")
-        ctx.save_for_backward(xb, G, H, W1tb, W2tb)
+        ctx.save_for_backward(xb, G, H, W1b, W2b)
         ctx.meta = (shape, x.dtype, T, rows_cap, d, h)
         y = Y[:T].view(*shape[:-1], d)
         return y if x.dtype == bf else y.to(x.dtype)
@@ -76,7 +76,7 @@ class _DenseFFN(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
-        xb, G, H, W1tb, W2tb = ctx.saved_tensors
+        xb, G, H, W1b, W2b = ctx.saved_tensors
         shape, x_dtype, T, rows_cap, d, h = ctx.meta
         dev, st, bf = xb.device, C.stream_ptr(), torch.bfloat16
         te, nm, sg = _tables(rows_cap, dev)
@@ -87,14 +87,14 @@ class _DenseFFN(torch.autograd.Function):
         dW2, db2 = torch.empty((1, d, h), device=dev), torch.empty((1, d), device=dev)
         pte, pnm, psg = C.ptr(te), C.ptr(nm), C.ptr(sg)
         slab_sums = torch.empty(C.lib.moe_slab_colsum_bytes(rows_cap, h) // 4, dtype=torch.float32, device=dev)
-        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dyb), C.ptr(W2tb), C.ptr(dU), C.ptr(slab_sums), None, C.ptr(G),
+        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dyb), C.ptr(W2b), C.ptr(dU), C.ptr(slab_sums), None, C.ptr(G),
                pte, pnm, None, rows_cap, 1, 0, h, d, st, tag="dense_dgelu")
         wfl = C.ptr(C.wgrad_flags(1, h, d, dev))
         C.call("moe_grouped_gemm", C.GEMM_WGRAD_T, C.ptr(H), C.ptr(dyb), C.ptr(dW2), None, None, wfl,
                None, None, psg, rows_cap, 1, h, d, 0, st, tag="dense_wgrad2")
         C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dU), C.ptr(xb), C.ptr(dW1), None, None, wfl,
                None, None, psg, rows_cap, 1, h, d, 0, st, tag="dense_wgrad1")
-        C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1tb), C.ptr(dxb), None, None, None,
+        C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1b), C.ptr(dxb), None, None, None,
                pte, pnm, None, rows_cap, 1, 0, d, h, st, tag="dense_dgrad")
         cws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, d), dtype=torch.uint8, device=dev)
         C.call("moe_segment_colsum", C.ptr(dyb), psg, rows_cap, 1, d, C.ptr(cws), C.ptr(db2), st, tag="dense_db2")

@@ -162,7 +162,7 @@ class EPMoEFunction(torch.autograd.Function):
         recv_x = torch.empty((W, El * slab * d), dtype=torch.bfloat16, device=dev)
         w1 = dist.all_to_all_single(kept_recv, r["kept"].view(W, El), group=group, async_op=True)     # [W(src), El]
         w2 = dist.all_to_all_single(recv_x, r["xbuf"].view(W, El * slab * d), group=group, async_op=True)  # [W(src), El, slab, d]
-        W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c, fresh)
+        W1b, W2b = cache.get(W1_c, W2_c, fresh)
         w1.wait()
         w2.wait()
 
@@ -198,7 +198,7 @@ class EPMoEFunction(torch.autograd.Function):
         coef = r["aux_coef"] if spec.want_psum else torch.empty(0, dtype=torch.float32, device=dev)
         ctx.save_for_backward(x, Wg_c, r["logits"], r["idx"], r["score"], r["pos"], r["seg_start"], r["kept"], kept_recv,
                               tb["slab_dst"], tb["seg_start"], tb["kept"], tb["tile_expert"], tb["num_mtiles"], xbuf, G, H,
-                              ybuf, W1tb, W2tb, coef)
+                              ybuf, W1b, W2b, coef)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(r["count"], r["kept"])
         if spec.want_psum:
@@ -212,10 +212,10 @@ class EPMoEFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy, daux, _dcount, _dkept):
         (x, Wg, logits, idx, score, pos, seg_send, kept_send, kept_recv, slab_dst, seg_loc, kept_loc, tile_expert,
-         num_mtiles, xbuf, G, H, ybuf, W1tb, W2tb, coef) = ctx.saved_tensors
+         num_mtiles, xbuf, G, H, ybuf, W1b, W2b, coef) = ctx.saved_tensors
         spec, W, slab, rows_cap, group = ctx.spec, ctx.world, ctx.slab, ctx.rows_cap, ctx.group
         T, d = x.shape
-        El, h = W1tb.shape[0], W1tb.shape[2]
+        El, h = W1b.shape[0], W1b.shape[1]
         E, k = El * W, spec.top_k
         dev, st, bf = x.device, C.stream_ptr(), torch.bfloat16
         if dy is None:
@@ -238,9 +238,9 @@ class EPMoEFunction(torch.autograd.Function):
         dW2, db2 = _f32((El, d, h), dev), _f32((El, d), dev)
         te, nm, sg = C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_loc)
         slab_sums = torch.empty(C.lib.moe_slab_colsum_bytes(rows_cap, h) // 4, dtype=torch.float32, device=dev)
-        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), C.ptr(slab_sums), None, C.ptr(G),
+        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2b), C.ptr(dU), C.ptr(slab_sums), None, C.ptr(G),
                te, nm, None, rows_cap, El, 0, h, d, st, tag="gemm_dgelu")
-        C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1tb), C.ptr(dxbuf), None, None, None,
+        C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1b), C.ptr(dxbuf), None, None, None,
                te, nm, None, rows_cap, El, 0, d, h, st, tag="gemm_dgrad")
         # dX goes back to the token owners while the weight / bias gradients (which nobody waits for) are computed:
         # the all-to-all runs on NCCL's stream, the four kernels below on ours

@@ -28,8 +28,8 @@ class RouteSpec:
 
 
 class Bf16WeightCache:
-    """bf16 operand copies of the fp32 expert weights — W1b [E,h,d], W2b [E,d,h] and their per-expert
-    transposes W1tb [E,d,h], W2tb [E,h,d] (so that dgrad / dgelu read K-major operands too).
+    """bf16 operand copies of the fp32 expert weights — W1b [E,h,d], W2b [E,d,h].  One copy per matrix: the forward
+    contractions read them K-major, dgelu / dgrad read the same buffers MN-major (csrc/gemm.cuh), so no transposes.
 
     A training forward (`fresh=True`: autograd is recording and the weights require grad) ALWAYS re-casts: the
     weights move once per optimizer step anyway, and neither `p.data.add_` (many timm / apex optimizers) nor a CUDA-graph
@@ -53,13 +53,12 @@ class Bf16WeightCache:
             bf = torch.bfloat16
             E, h, d = W1.shape
             W1b, W2b = torch.empty((E, h, d), dtype=bf, device=W1.device), torch.empty((E, d, h), dtype=bf, device=W1.device)
-            W1tb, W2tb = torch.empty((E, d, h), dtype=bf, device=W1.device), torch.empty((E, h, d), dtype=bf, device=W1.device)
             st = C.stream_ptr()
-            C.call("moe_cast_bf16_transposed", C.ptr(W1.detach()), C.ptr(W1b), C.ptr(W1tb), E, h, d, st)
-            C.call("moe_cast_bf16_transposed", C.ptr(W2.detach()), C.ptr(W2b), C.ptr(W2tb), E, d, h, st)
+            C.call("moe_cast_bf16", C.ptr(W1.detach()), C.ptr(W1b), W1.numel(), st)
+            C.call("moe_cast_bf16", C.ptr(W2.detach()), C.ptr(W2b), W2.numel(), st)
             if capturing:
-                return W1b, W2b, W1tb, W2tb      # copies live in the graph's pool and are refreshed by every replay: not cached
-            self._key, self._val = key, (W1b, W2b, W1tb, W2tb)
+                return W1b, W2b      # copies live in the graph's pool and are refreshed by every replay: not cached
+            self._key, self._val = key, (W1b, W2b)
         return self._val
 
     def __deepcopy__(self, memo):  # ModelEma deep-copies the model (reference main.py:602-607)
@@ -160,7 +159,7 @@ class MoEFunction(torch.autograd.Function):
         bg_c = None if bg is None else bg.detach().contiguous()
         r = route(x, Wg_c, bg_c, spec, noise, token_mask=token_mask)
         rows_cap = r["rows_cap"]
-        W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c, fresh)
+        W1b, W2b = cache.get(W1_c, W2_c, fresh)
         G = None if infer else torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
         H = torch.empty((rows_cap, h), dtype=torch.bfloat16, device=dev)
         Y = torch.empty((rows_cap, d), dtype=torch.bfloat16, device=dev)
@@ -184,7 +183,7 @@ class MoEFunction(torch.autograd.Function):
             ctx.mark_non_differentiable(y, aux, r["count"], r["kept"])
             return y, aux, r["count"], r["kept"]
         ctx.save_for_backward(x, Wg_c, r["logits"], r["idx"], r["score"], r["pos"], r["seg_start"], r["kept"],
-                              r["tile_expert"], r["num_mtiles"], r["xbuf"], G, H, Y, W1tb, W2tb, coef)
+                              r["tile_expert"], r["num_mtiles"], r["xbuf"], G, H, Y, W1b, W2b, coef)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(r["count"], r["kept"])
         if spec.want_psum:
@@ -197,11 +196,11 @@ class MoEFunction(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy, daux, _dcount, _dkept):
-        (x, Wg, logits, idx, score, pos, seg_start, kept, tile_expert, num_mtiles, xbuf, G, H, Y, W1tb,
-         W2tb, coef) = ctx.saved_tensors
+        (x, Wg, logits, idx, score, pos, seg_start, kept, tile_expert, num_mtiles, xbuf, G, H, Y, W1b,
+         W2b, coef) = ctx.saved_tensors
         spec: RouteSpec = ctx.spec
         T, d = x.shape
-        E, h = W1tb.shape[0], W1tb.shape[2]
+        E, h = W1b.shape[0], W1b.shape[1]
         k = spec.top_k
         dev = x.device
         st = C.stream_ptr()
@@ -225,7 +224,7 @@ class MoEFunction(torch.autograd.Function):
         te, nm, sg = C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_start)
         # db1 = column sums of dU per expert: the dgelu epilogue leaves the sums of every 32-row slab behind
         slab_sums = torch.empty(C.lib.moe_slab_colsum_bytes(rows_cap, h) // 4, dtype=torch.float32, device=dev)
-        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2tb), C.ptr(dU), C.ptr(slab_sums), None, C.ptr(G),
+        C.call("moe_grouped_gemm", C.GEMM_DGELU, C.ptr(dybuf), C.ptr(W2b), C.ptr(dU), C.ptr(slab_sums), None, C.ptr(G),
                te, nm, None, rows_cap, E, 0, h, d, st, tag="gemm_dgelu")
         # dW2 = (H^T dY)^T: the wide dimension h is M (256-row tiles), the store is transposed
         wfl = C.ptr(C.wgrad_flags(E, h, d, dev))   # split-K flags: each tile's K range runs as two halves
@@ -233,7 +232,7 @@ class MoEFunction(torch.autograd.Function):
                None, None, sg, rows_cap, E, h, d, 0, st, tag="gemm_wgrad2")
         C.call("moe_grouped_gemm", C.GEMM_WGRAD, C.ptr(dU), C.ptr(xbuf), C.ptr(dW1), None, None, wfl,
                None, None, sg, rows_cap, E, h, d, 0, st, tag="gemm_wgrad1")
-        C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1tb), C.ptr(dxbuf), None, None, None,
+        C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1b), C.ptr(dxbuf), None, None, None,
                te, nm, None, rows_cap, E, 0, d, h, st, tag="gemm_dgrad")
         cws = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, d), dtype=torch.uint8, device=dev)
         C.call("moe_segment_colsum", C.ptr(dybuf), sg, rows_cap, E, d, C.ptr(cws), C.ptr(db2), st, tag="colsum_db2")

@@ -198,7 +198,7 @@ class EPPeerMoEFunction(torch.autograd.Function):
         pos = _i32((T, k), dev)
         C.call("moe_dispatch_fwd_peer", C.ptr(x), C.dtype_code(x), C.ptr(idx), C.ptr(tile_base), C.ptr(dst_row), T, d, E, k,
                spec.capacity, pb.ptrs["xbuf"], pb.rank, W, rpr, C.ptr(seg_loc), C.ptr(kept_loc), C.ptr(pos), st)
-        W1b, W2b, W1tb, W2tb = cache.get(W1_c, W2_c, fresh)      # the weight casts overlap the peers' pushes
+        W1b, W2b = cache.get(W1_c, W2_c, fresh)      # the weight casts overlap the peers' pushes
         pb.barrier(st)                                           # every source's rows have landed in my xbuf
 
         G = None if infer else torch.empty((rpr, h), dtype=bf, device=dev)   # forward-only pass: fc1 writes no gelu'
@@ -220,7 +220,7 @@ class EPPeerMoEFunction(torch.autograd.Function):
             aux = aux_loss.reshape(()) if spec.want_psum else torch.empty(0, dtype=torch.float32, device=dev)
             ctx.mark_non_differentiable(y, aux, count, kept)
             return y, aux, count, kept
-        ctx.save_for_backward(x, Wg_c, logits, idx, score, pos, seg_loc, kept_loc, tile_expert, num_mtiles, G, H, W1tb, W2tb, coef)
+        ctx.save_for_backward(x, Wg_c, logits, idx, score, pos, seg_loc, kept_loc, tile_expert, num_mtiles, G, H, W1b, W2b, coef)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(count, kept)
         if spec.want_psum:
@@ -233,10 +233,10 @@ class EPPeerMoEFunction(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy, daux, _dcount, _dkept):
-        (x, Wg, logits, idx, score, pos, seg_loc, kept_loc, tile_expert, num_mtiles, G, H, W1tb, W2tb, coef) = ctx.saved_tensors
+        (x, Wg, logits, idx, score, pos, seg_loc, kept_loc, tile_expert, num_mtiles, G, H, W1b, W2b, coef) = ctx.saved_tensors
         spec, pb = ctx.spec, ctx.pb
         T, d = x.shape
-        El, h = W1tb.shape[0], W1tb.shape[2]
+        El, h = W1b.shape[0], W1b.shape[1]
         W, rpr = pb.W, pb.rows_per_rank
         E, k = El * W, spec.top_k
         dev, st, bf = x.device, C.stream_ptr(), torch.bfloat16
@@ -256,9 +256,9 @@ class EPPeerMoEFunction(torch.autograd.Function):
         te, nm, sg = C.ptr(tile_expert), C.ptr(num_mtiles), C.ptr(seg_loc)
         dyb, xb, dxb = pb.local["dybuf"], pb.local["xbuf"], pb.local["dxbuf"]
         slab_sums = torch.empty(C.lib.moe_slab_colsum_bytes(rpr, h) // 4, dtype=torch.float32, device=dev)
-        C.call("moe_grouped_gemm", C.GEMM_DGELU, dyb, C.ptr(W2tb), C.ptr(dU), C.ptr(slab_sums), None, C.ptr(G),
+        C.call("moe_grouped_gemm", C.GEMM_DGELU, dyb, C.ptr(W2b), C.ptr(dU), C.ptr(slab_sums), None, C.ptr(G),
                te, nm, None, rpr, El, 0, h, d, st, tag="gemm_dgelu")
-        C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1tb), dxb, None, None, None,
+        C.call("moe_grouped_gemm", C.GEMM_DGRAD, C.ptr(dU), C.ptr(W1b), dxb, None, None, None,
                te, nm, None, rpr, El, 0, d, h, st, tag="gemm_dgrad")
         pb.barrier(st)                                           # every owner's dX is complete
         # token side first: the gather of remote dX rows runs while nothing else needs the links

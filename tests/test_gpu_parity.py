@@ -157,7 +157,7 @@ def test_ffn_intermediates_vs_model():
     x, Wg, bg, W1, b1, W2, b2 = make_problem(T, d, h, E, seed=5)
     spec = Fn.RouteSpec(k, mode, T * k, C.AUX_NONE)
     r = Fn.route(x.cuda(), Wg.cuda(), bg.cuda(), spec)
-    W1b, W2b, W1tb, W2tb = Fn.Bf16WeightCache().get(W1.cuda(), W2.cuda())
+    W1b, W2b = Fn.Bf16WeightCache().get(W1.cuda(), W2.cuda())
     rows_cap = r["rows_cap"]
     U = torch.zeros(rows_cap, h, dtype=torch.bfloat16, device="cuda")
     H, Y = torch.zeros_like(U), torch.zeros(rows_cap, d, dtype=torch.bfloat16, device="cuda")
@@ -169,7 +169,6 @@ def test_ffn_intermediates_vs_model():
     _, sv = O.forward_model(x, Wg, bg, W1, b1, W2, b2, k, mode, T * k)
     rows = sv.r.rows
     assert torch.equal(W1b.cpu().float(), sv.W1b) and torch.equal(W2b.cpu().float(), sv.W2b)
-    assert torch.equal(W1tb.cpu().float(), sv.W1b.transpose(1, 2)) and torch.equal(W2tb.cpu().float(), sv.W2b.transpose(1, 2))
     for name, got, want in (("G", U, sv.Gb), ("H", H, sv.Hb), ("Y", Y, sv.Yb)):
         assert rel_err(got[:rows], want) <= MODEL_REL, name
         assert max_abs(got[:rows], want) <= float(want.abs().max()) / 64, name
@@ -598,7 +597,8 @@ def test_grouped_gemm_ops_vs_torch(case):
     rnd = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf)
     if name in ("fc1", "fc2", "dgrad", "dgelu"):
         op = {"fc1": C.GEMM_FC1, "fc2": C.GEMM_FC2, "dgrad": C.GEMM_DGRAD, "dgelu": C.GEMM_DGELU}[name]
-        A, B, aux = rnd(rows_cap, K), rnd(E, N, K), rnd(rows_cap, N)
+        b_mn = name in ("dgrad", "dgelu")   # the backward ops read the weights as [E, K, N] (MN-major), the forward ones as [E, N, K]
+        A, B, aux = rnd(rows_cap, K), (rnd(E, K, N) if b_mn else rnd(E, N, K)), rnd(rows_cap, N)
         bias = torch.randn(E, N, device=dev) if name in ("fc1", "fc2") else None
         o0 = torch.zeros(rows_cap, N, dtype=bf, device=dev)
         o1 = torch.zeros_like(o0)
@@ -607,7 +607,7 @@ def test_grouped_gemm_ops_vs_torch(case):
         torch.cuda.synchronize()
         ref = torch.zeros(rows_cap, N, device=dev)
         for e in range(E):
-            ref[seg[e]:seg[e + 1]] = A[seg[e]:seg[e + 1]].float() @ B[e].float().t() + (bias[e] if bias is not None else 0.0)
+            ref[seg[e]:seg[e + 1]] = A[seg[e]:seg[e + 1]].float() @ (B[e].float() if b_mn else B[e].float().t()) + (bias[e] if bias is not None else 0.0)
         if name == "dgelu":
             ref = ref * aux.float()
         want0 = ref
@@ -651,7 +651,7 @@ def test_bundled_ffn_entry_points_equal_the_op_sequence(counts, d):
     X, dY = rnd(rows_cap, d), rnd(rows_cap, d)
     X[~live] = 0
     dY[~live] = 0
-    W1, W2, W1t, W2t = rnd(E, h, d), rnd(E, d, h), rnd(E, d, h), rnd(E, h, d)
+    W1, W2 = rnd(E, h, d), rnd(E, d, h)
     b1, b2 = torch.randn(E, h, device=dev), torch.randn(E, d, device=dev)
     P = C.ptr
 
@@ -663,17 +663,17 @@ def test_bundled_ffn_entry_points_equal_the_op_sequence(counts, d):
     a, b = buffers(), buffers()
     ws = torch.empty(C.lib.moe_expert_ffn_bwd_workspace_bytes(rows_cap, d, h, E), dtype=torch.uint8, device=dev)
     C.call("moe_expert_ffn_fwd", P(X), P(W1), P(b1), P(W2), P(b2), P(tile_e), P(nm), rows_cap, d, h, E, P(a["G"]), P(a["H"]), P(a["Y"]), st)
-    C.call("moe_expert_ffn_bwd", P(dY), P(X), P(a["G"]), P(a["H"]), P(W1t), P(W2t), P(tile_e), P(nm), P(seg_t), rows_cap, d, h, E,
+    C.call("moe_expert_ffn_bwd", P(dY), P(X), P(a["G"]), P(a["H"]), P(W1), P(W2), P(tile_e), P(nm), P(seg_t), rows_cap, d, h, E,
            P(a["dU"]), P(a["dX"]), P(a["dW1"]), P(a["db1"]), P(a["dW2"]), P(a["db2"]), P(ws), st)
     g = lambda op, *args: C.call("moe_grouped_gemm", op, *args)
     g(C.GEMM_FC1, P(X), P(W1), P(b["G"]), P(b["H"]), P(b1), None, P(tile_e), P(nm), None, rows_cap, E, 0, h, d, st)
     g(C.GEMM_FC2, P(b["H"]), P(W2), P(b["Y"]), None, P(b2), None, P(tile_e), P(nm), None, rows_cap, E, 0, d, h, st)
     slab = torch.empty(C.lib.moe_slab_colsum_bytes(rows_cap, h) // 4, dtype=torch.float32, device=dev)
-    g(C.GEMM_DGELU, P(dY), P(W2t), P(b["dU"]), P(slab), None, P(b["G"]), P(tile_e), P(nm), None, rows_cap, E, 0, h, d, st)
+    g(C.GEMM_DGELU, P(dY), P(W2), P(b["dU"]), P(slab), None, P(b["G"]), P(tile_e), P(nm), None, rows_cap, E, 0, h, d, st)
     fl = C.wgrad_flags(E, h, d, dev)
     g(C.GEMM_WGRAD_T, P(b["H"]), P(dY), P(b["dW2"]), None, None, P(fl), None, None, P(seg_t), rows_cap, E, h, d, 0, st)
     g(C.GEMM_WGRAD, P(b["dU"]), P(X), P(b["dW1"]), None, None, P(fl), None, None, P(seg_t), rows_cap, E, h, d, 0, st)
-    g(C.GEMM_DGRAD, P(b["dU"]), P(W1t), P(b["dX"]), None, None, None, P(tile_e), P(nm), None, rows_cap, E, 0, d, h, st)
+    g(C.GEMM_DGRAD, P(b["dU"]), P(W1), P(b["dX"]), None, None, None, P(tile_e), P(nm), None, rows_cap, E, 0, d, h, st)
     ws2 = torch.empty(C.lib.moe_segment_colsum_workspace_bytes(rows_cap, max(d, h)), dtype=torch.uint8, device=dev)
     C.call("moe_segment_colsum", P(dY), P(seg_t), rows_cap, E, d, P(ws2), P(b["db2"]), st)
     C.call("moe_slab_colsum_final", P(slab), P(seg_t), E, h, P(b["db1"]), st)
@@ -695,7 +695,7 @@ def test_dgelu_slab_column_sums(counts, N, K):
     torch.manual_seed(2)
     bf, dev, st = torch.bfloat16, "cuda", C.stream_ptr()
     rnd = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf)
-    A, B, aux = rnd(rows_cap, K), rnd(E, N, K), rnd(rows_cap, N)
+    A, B, aux = rnd(rows_cap, K), rnd(E, K, N), rnd(rows_cap, N)   # dgelu reads the weights as [E, K, N]
     A[~live] = 0
     o_plain = torch.zeros(rows_cap, N, dtype=bf, device=dev)
     o_sum = torch.zeros_like(o_plain)

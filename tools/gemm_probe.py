@@ -71,15 +71,15 @@ def main():
         print(f"      rows beyond live range untouched: {tail == 0.0}")
         ok = ok and tail == 0.0
     elif op in (C.GEMM_DGELU, C.GEMM_DGRAD):
-        A = rnd(rows_cap, K); B = rnd(E, N, K); aux = rnd(rows_cap, N)   # B = W^T, K-major like fc1/fc2
+        A = rnd(rows_cap, K); B = rnd(E, K, N); aux = rnd(rows_cap, N)   # B = the forward weight [E, K, N], read MN-major
         o0 = torch.zeros(rows_cap, N, dtype=bf, device=dev)
         C.call("moe_grouped_gemm", op, C.ptr(A), C.ptr(B), C.ptr(o0), None, None,
                C.ptr(aux) if op == C.GEMM_DGELU else None, C.ptr(tile_e), C.ptr(nm), None, rows_cap, E, 0, N, K, st)
         torch.cuda.synchronize()
         ref = torch.zeros(rows_cap, N, device=dev)
         for e in range(E):
-            ref[seg[e]:seg[e + 1]] = A[seg[e]:seg[e + 1]].float() @ B[e].float().t()
-        if op == C.GEMM_DGELU:   # out0 = (A B^T) * aux
+            ref[seg[e]:seg[e + 1]] = A[seg[e]:seg[e + 1]].float() @ B[e].float()
+        if op == C.GEMM_DGELU:   # out0 = (A B) * aux
             ref = ref * aux.float()
         err0 = (o0[:rows].float() - ref[:rows]).abs().max().item()
         print(f"op={op} out0 max_abs_err={err0:.4g} ref_max={ref[:rows].abs().max().item():.4g}")

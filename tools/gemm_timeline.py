@@ -29,7 +29,7 @@ tile_e[: seg_len * E // 256] = torch.arange(E, device=dev, dtype=torch.int32).re
 nm = torch.tensor([seg_len * E // 256], dtype=torch.int32, device=dev)
 rnd = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf)
 X, Hh, U, dY, dU = rnd(rows_cap, d), rnd(rows_cap, h), rnd(rows_cap, h), rnd(rows_cap, d), rnd(rows_cap, h)
-W1, W2, W1t, W2t = rnd(E, h, d), rnd(E, d, h), rnd(E, d, h), rnd(E, h, d)
+W1, W2 = rnd(E, h, d), rnd(E, d, h)
 b1, b2 = torch.randn(E, h, device=dev), torch.randn(E, d, device=dev)
 oU, oH, oY, odU, odX = (torch.empty(rows_cap, n, dtype=bf, device=dev) for n in (h, h, d, h, d))
 dW1, dW2 = torch.empty(E, h, d, device=dev), torch.empty(E, d, h, device=dev)
@@ -37,8 +37,8 @@ st, P = C.stream_ptr(), C.ptr
 ops = {
     "fc1": lambda: C.call("moe_grouped_gemm", C.GEMM_FC1, P(X), P(W1), P(oU), P(oH), P(b1), None, P(tile_e), P(nm), None, rows_cap, E, 0, h, d, st),
     "fc2": lambda: C.call("moe_grouped_gemm", C.GEMM_FC2, P(Hh), P(W2), P(oY), None, P(b2), None, P(tile_e), P(nm), None, rows_cap, E, 0, d, h, st),
-    "dgelu": lambda: C.call("moe_grouped_gemm", C.GEMM_DGELU, P(dY), P(W2t), P(odU), None, None, P(U), P(tile_e), P(nm), None, rows_cap, E, 0, h, d, st),
-    "dgrad": lambda: C.call("moe_grouped_gemm", C.GEMM_DGRAD, P(dU), P(W1t), P(odX), None, None, None, P(tile_e), P(nm), None, rows_cap, E, 0, d, h, st),
+    "dgelu": lambda: C.call("moe_grouped_gemm", C.GEMM_DGELU, P(dY), P(W2), P(odU), None, None, P(U), P(tile_e), P(nm), None, rows_cap, E, 0, h, d, st),
+    "dgrad": lambda: C.call("moe_grouped_gemm", C.GEMM_DGRAD, P(dU), P(W1), P(odX), None, None, None, P(tile_e), P(nm), None, rows_cap, E, 0, d, h, st),
     "wgrad1": lambda: C.call("moe_grouped_gemm", C.GEMM_WGRAD, P(dU), P(X), P(dW1), None, None, P(C.wgrad_flags(E, h, d, dev)), None, None, P(seg), rows_cap, E, h, d, 0, st),
     "wgrad2": lambda: C.call("moe_grouped_gemm", C.GEMM_WGRAD_T, P(Hh), P(dY), P(dW2), None, None, P(C.wgrad_flags(E, h, d, dev)), None, None, P(seg), rows_cap, E, h, d, 0, st),
 }
