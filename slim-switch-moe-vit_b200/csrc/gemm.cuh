@@ -151,9 +151,18 @@ struct GemmCfg {
 constexpr float kGeluAMax = 6.5f;
 constexpr float kNegHalfLog2e = -0.72134752044448170f;
 constexpr float kNegInvSqrt2Pi = -0.39894228040143268f;
+#ifndef MOE_GELU_DEG
+#define MOE_GELU_DEG 7
+#endif
+constexpr int kGeluDeg = MOE_GELU_DEG;
+#if MOE_GELU_DEG == 7
 __device__ constexpr float kGeluW[8] = {  // W(a) = 0.5 erfcx(a / sqrt 2) on [0, 6.5]
     4.999879883e-01f, -3.984107670e-01f, 2.460856669e-01f, -1.217100563e-01f, 4.573317066e-02f, -1.176512435e-02f,
     1.782060358e-03f, -1.172508184e-04f};
+#elif MOE_GELU_DEG == 5   // kernel experiments: 7.9e-5 (gelu) / 1.7e-4 (gelu') max abs error
+__device__ constexpr float kGeluW[6] = {4.998291619e-01f, -3.940517119e-01f, 2.266079638e-01f, -8.922066891e-02f, 2.040228419e-02f,
+                                        -1.967727139e-03f};
+#endif
 
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float2 v) {
@@ -203,9 +212,9 @@ __device__ __forceinline__ void epilogue_block16(const uint32_t* acc, uint32_t b
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = make_float2(ex2_approx(g[i].x), ex2_approx(g[i].y));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = __ffma2_rn(splat2(kGeluW[7]), a[i], splat2(kGeluW[6]));
+        for (int i = 0; i < 8; ++i) w[i] = __ffma2_rn(splat2(kGeluW[kGeluDeg]), a[i], splat2(kGeluW[kGeluDeg - 1]));
 #pragma unroll
-        for (int k = 5; k >= 0; --k) {
+        for (int k = kGeluDeg - 2; k >= 0; --k) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) w[i] = __ffma2_rn(w[i], a[i], splat2(kGeluW[k]));
         }
@@ -226,9 +235,9 @@ __device__ __forceinline__ void epilogue_block16(const uint32_t* acc, uint32_t b
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = make_float2(ex2_approx(g[i].x), ex2_approx(g[i].y));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = __ffma2_rn(splat2(kGeluW[7]), a[i], splat2(kGeluW[6]));
+        for (int i = 0; i < 8; ++i) w[i] = __ffma2_rn(splat2(kGeluW[kGeluDeg]), a[i], splat2(kGeluW[kGeluDeg - 1]));
 #pragma unroll
-        for (int k = 5; k >= 0; --k) {
+        for (int k = kGeluDeg - 2; k >= 0; --k) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) w[i] = __ffma2_rn(w[i], a[i], splat2(kGeluW[k]));
         }
