@@ -237,6 +237,8 @@ int moe_colsum(const void *buf, int dtype, int64_t rows, int cols, void *workspa
 
 /* ---- utilities */
 int moe_cast_bf16(const float *src, void *dst, int64_t n /* % 8 == 0 */, void *stream);
+/* two ranges in one launch: the per-step cast of a layer's two expert weight matrices (fp32 master -> bf16 operand copies) */
+int moe_cast_bf16_pair(const float *src0, void *dst0, int64_t n0, const float *src1, void *dst1, int64_t n1, void *stream);
 /* out[E,cols] = per-segment column sums of the packed bf16 buffer buf[rows_cap,cols] (bias gradients;
  * replaces fmoe_cuda's column_reduce).  Two deterministic stages through `workspace`. */
 size_t moe_segment_colsum_workspace_bytes(int64_t rows_cap, int cols);

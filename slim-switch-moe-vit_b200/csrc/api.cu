@@ -282,6 +282,14 @@ int moe_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
     return check(launch_cast_bf16(src, dst, n, sm_count(), static_cast<cudaStream_t>(stream)), "moe_cast_bf16");
 }
 
+int moe_cast_bf16_pair(const float* src0, void* dst0, int64_t n0, const float* src1, void* dst1, int64_t n1, void* stream) {
+    if (n0 <= 0 || n0 % 8 != 0 || n1 <= 0 || n1 % 8 != 0 || src0 == nullptr || dst0 == nullptr || src1 == nullptr || dst1 == nullptr) {
+        set_error("moe_cast_bf16_pair: two non-null ranges of positive multiples of 8 elements required (n0=%lld n1=%lld)", (long long)n0, (long long)n1);
+        return 1;
+    }
+    return check(launch_cast_bf16_pair(src0, dst0, n0, src1, dst1, n1, sm_count(), static_cast<cudaStream_t>(stream)), "moe_cast_bf16_pair");
+}
+
 size_t moe_segment_colsum_workspace_bytes(int64_t rows_cap, int cols) { return segment_colsum_workspace_bytes(rows_cap, cols); }
 
 int moe_segment_colsum(const void* buf, const int32_t* seg_start, int64_t rows_cap, int E, int cols, void* workspace, float* out,

@@ -68,6 +68,8 @@ size_t gate_wgrad_workspace_bytes(int64_t T, int d, int E);
 cudaError_t launch_gate_wgrad(const float* dlogits, const void* x, int x_dtype, int64_t T, int d, int E, void* workspace,
                               float* dWg, float* dbg, cudaStream_t st);
 cudaError_t launch_cast_bf16(const float* src, void* dst, int64_t n, int sm_count, cudaStream_t st);
+cudaError_t launch_cast_bf16_pair(const float* src0, void* dst0, int64_t n0, const float* src1, void* dst1, int64_t n1,
+                                  int sm_count, cudaStream_t st);
 size_t segment_colsum_workspace_bytes(int64_t rows_cap, int cols);
 cudaError_t launch_slab_colsum_final(const float* part, const int* seg_start, int E, int cols, float* out, cudaStream_t st);
 cudaError_t launch_segment_colsum(const void* buf, const int* seg_start, int64_t rows_cap, int E, int cols, void* workspace,

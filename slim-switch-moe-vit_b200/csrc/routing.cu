@@ -1186,21 +1186,35 @@ gate_wgrad_partial_mma_kernel(const float* __restrict__ dlogits, const __nv_bflo
     }
 }
 
-// out[i] = sum_b part[b][i]: one warp per output, lanes stride the per-block partials (independent loads), then the
-// xor butterfly — a fixed order, so the result is reproducible bit for bit
-__global__ void __launch_bounds__(256)
+// out[o] = sum_b part[b][o].  CTA = 64 outputs x 16 slices of the partials (slice s takes b = s, s + 16, ...; four
+// independent chains per thread), consecutive threads read consecutive outputs of one partial (coalesced: a warp per
+// output with lanes striding the partials read 4 bytes per 32-byte sector and took 12.4 us for the 296 partials of config
+// 2), slices combined in a fixed order: reproducible bit for bit.
+constexpr int kWgRedSlices = 16;
+__global__ void __launch_bounds__(64 * kWgRedSlices)
 gate_wgrad_reduce_kernel(const float* __restrict__ part_w, const float* __restrict__ part_b, int nparts, int d, int E,
                          float* __restrict__ dWg, float* __restrict__ dbg) {
+    __shared__ float red[kWgRedSlices][64];
     const int n = E * d, tot = n + (dbg != nullptr ? E : 0);
-    const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (o >= tot) return;
-    const float* src = o < n ? part_w + o : part_b + (o - n);
-    const size_t stride = o < n ? static_cast<size_t>(n) : static_cast<size_t>(E);
-    float v = 0.0f;
-#pragma unroll 4
-    for (int b = lane; b < nparts; b += 32) v += src[static_cast<size_t>(b) * stride];
-    v = warp_sum_xor(v);
-    if (lane == 0) {
+    const int cl = threadIdx.x & 63, slice = threadIdx.x >> 6;
+    const int o = blockIdx.x * 64 + cl;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (o < tot) {
+        const float* src = o < n ? part_w + o : part_b + (o - n);
+        const size_t stride = o < n ? static_cast<size_t>(n) : static_cast<size_t>(E);
+        int b = slice;
+        for (; b + 3 * kWgRedSlices < nparts; b += 4 * kWgRedSlices) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] += src[static_cast<size_t>(b + i * kWgRedSlices) * stride];
+        }
+        for (int i = 0; b < nparts; b += kWgRedSlices, ++i) acc[i] += src[static_cast<size_t>(b) * stride];
+    }
+    red[slice][cl] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    __syncthreads();
+    if (slice == 0 && o < tot) {
+        float v = 0.0f;
+#pragma unroll
+        for (int sl = 0; sl < kWgRedSlices; sl += 4) v += (red[sl][cl] + red[sl + 1][cl]) + (red[sl + 2][cl] + red[sl + 3][cl]);
         if (o < n) dWg[o] = v;
         else dbg[o - n] = v;
     }
@@ -1216,6 +1230,27 @@ cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
         float v[8];
         load8(src + i * 8, v);
         store8(dst + i * 8, v);
+    }
+}
+
+// Both expert weight matrices in ONE launch (items [0, n8_0) belong to the first, the rest to the second), four independent
+// 32-byte loads in flight per thread: the per-step weight cast of a layer.
+__global__ void __launch_bounds__(256)
+cast_bf16_pair_kernel(const float* __restrict__ src0, __nv_bfloat16* __restrict__ dst0, int64_t n8_0,
+                      const float* __restrict__ src1, __nv_bfloat16* __restrict__ dst1, int64_t n8_1) {
+    const int64_t total = n8_0 + n8_1, stride = static_cast<int64_t>(gridDim.x) * 256;
+    for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i0 < total; i0 += 4 * stride) {
+        float v[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = i0 + j * stride;
+            if (i < total) load8(i < n8_0 ? src0 + i * 8 : src1 + (i - n8_0) * 8, v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = i0 + j * stride;
+            if (i < total) store8(i < n8_0 ? dst0 + i * 8 : dst1 + (i - n8_0) * 8, v[j]);
+        }
     }
 }
 
@@ -1260,13 +1295,14 @@ segment_colsum_partial_kernel(const __nv_bfloat16* __restrict__ buf, const int* 
 }
 
 // part holds one row of column sums per `rows_per_part` packed rows (128: segment_colsum_partial_kernel; 32: the
-// slab sums the dgelu epilogue of the grouped GEMM leaves behind).  CTA = 64 columns x 4 slices of the expert's parts
-// (slice s takes parts b0 + s, b0 + s + 4, ...), four independent chains per thread, slices combined in a fixed order:
-// one dependent chain per column took 25 us for the 104 slabs per expert of config 2.
-__global__ void __launch_bounds__(256)
+// slab sums the dgelu epilogue of the grouped GEMM leaves behind).  CTA = 64 columns x 16 slices of the expert's parts
+// (slice s takes parts b0 + s, b0 + s + 16, ...), four independent chains per thread, slices combined in a fixed order:
+// one dependent chain per column took 25 us for the 104 slabs per expert of config 2, four slices 9.8 us.
+constexpr int kSegFinSlices = 16;
+__global__ void __launch_bounds__(64 * kSegFinSlices)
 segment_colsum_final_kernel(const float* __restrict__ part, const int* __restrict__ seg_start, int cols,
                             float* __restrict__ out, int rows_per_part) {
-    __shared__ float red[4][64];
+    __shared__ float red[kSegFinSlices][64];
     const int e = blockIdx.y;
     const int cl = threadIdx.x & 63, slice = threadIdx.x >> 6;
     const int c = blockIdx.x * 64 + cl;
@@ -1274,15 +1310,20 @@ segment_colsum_final_kernel(const float* __restrict__ part, const int* __restric
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (c < cols) {
         int b = b0 + slice;
-        for (; b + 12 < b1; b += 16) {
+        for (; b + 3 * kSegFinSlices < b1; b += 4 * kSegFinSlices) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] += part[static_cast<size_t>(b + 4 * i) * cols + c];
+            for (int i = 0; i < 4; ++i) acc[i] += part[static_cast<size_t>(b + kSegFinSlices * i) * cols + c];
         }
-        for (int i = 0; b < b1; b += 4, ++i) acc[i] += part[static_cast<size_t>(b) * cols + c];
+        for (int i = 0; b < b1; b += kSegFinSlices, ++i) acc[i] += part[static_cast<size_t>(b) * cols + c];
     }
     red[slice][cl] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     __syncthreads();
-    if (slice == 0 && c < cols) out[static_cast<size_t>(e) * cols + c] = (red[0][cl] + red[1][cl]) + (red[2][cl] + red[3][cl]);
+    if (slice == 0 && c < cols) {
+        float v = 0.0f;
+#pragma unroll
+        for (int sl = 0; sl < kSegFinSlices; sl += 4) v += (red[sl][cl] + red[sl + 1][cl]) + (red[sl + 2][cl] + red[sl + 3][cl]);
+        out[static_cast<size_t>(e) * cols + c] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1579,7 +1620,7 @@ cudaError_t launch_gate_wgrad(const float* dlogits, const void* x, int x_dtype, 
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
         const int n = E * d + E;
-        gate_wgrad_reduce_kernel<<<(n + 7) / 8, 256, 0, st>>>(part_w, part_b, nb, d, E, dWg, dbg);
+        gate_wgrad_reduce_kernel<<<(n + 63) / 64, 64 * kWgRedSlices, 0, st>>>(part_w, part_b, nb, d, E, dWg, dbg);
         return cudaGetLastError();
     }
     // bf16 activations: tensor cores, every expert in one pass over x.  MT 16-expert m-tiles x (d / 64 / slices) n-tiles per
@@ -1597,13 +1638,21 @@ cudaError_t launch_gate_wgrad(const float* dlogits, const void* x, int x_dtype, 
                   : launch_gate_wgrad_mma<4>(dlogits, xb, T, d, E, ntiles, nb, slices, part_w, part_b, st);
     if (err != cudaSuccess) return err;
     const int n = E * d + E;
-    gate_wgrad_reduce_kernel<<<(n + 7) / 8, 256, 0, st>>>(part_w, part_b, nb, d, E, dWg, dbg);
+    gate_wgrad_reduce_kernel<<<(n + 63) / 64, 64 * kWgRedSlices, 0, st>>>(part_w, part_b, nb, d, E, dWg, dbg);
     return cudaGetLastError();
 }
 
 cudaError_t launch_cast_bf16(const float* src, void* dst, int64_t n, int sm_count, cudaStream_t st) {
     const int64_t n8 = n / 8;
     cast_bf16_kernel<<<grid_for(n8, sm_count), 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), n8);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cast_bf16_pair(const float* src0, void* dst0, int64_t n0, const float* src1, void* dst1, int64_t n1,
+                                  int sm_count, cudaStream_t st) {
+    const int64_t n8_0 = n0 / 8, n8_1 = n1 / 8;
+    cast_bf16_pair_kernel<<<grid_for((n8_0 + n8_1 + 3) / 4, sm_count), 256, 0, st>>>(src0, static_cast<__nv_bfloat16*>(dst0), n8_0, src1,
+                                                                                 static_cast<__nv_bfloat16*>(dst1), n8_1);
     return cudaGetLastError();
 }
 
@@ -1619,13 +1668,13 @@ cudaError_t launch_segment_colsum(const void* buf, const int* seg_start, int64_t
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     dim3 g2((cols + 63) / 64, E);
-    segment_colsum_final_kernel<<<g2, 256, 0, st>>>(part, seg_start, cols, out, 128);
+    segment_colsum_final_kernel<<<g2, 64 * kSegFinSlices, 0, st>>>(part, seg_start, cols, out, 128);
     return cudaGetLastError();
 }
 
 cudaError_t launch_slab_colsum_final(const float* part, const int* seg_start, int E, int cols, float* out, cudaStream_t st) {
     dim3 g2((cols + 63) / 64, E);
-    segment_colsum_final_kernel<<<g2, 256, 0, st>>>(part, seg_start, cols, out, 32);
+    segment_colsum_final_kernel<<<g2, 64 * kSegFinSlices, 0, st>>>(part, seg_start, cols, out, 32);
     return cudaGetLastError();
 }
 

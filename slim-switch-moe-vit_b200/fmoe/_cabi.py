@@ -53,6 +53,7 @@ SIGNATURES = {
     "moe_gate_wgrad_workspace_bytes": (_sz, [_i64, _i, _i]),
     "moe_gate_wgrad": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p, _p]),
     "moe_cast_bf16": (_i, [_p, _p, _i64, _p]),
+    "moe_cast_bf16_pair": (_i, [_p, _p, _i64, _p, _p, _i64, _p]),
     "moe_segment_colsum_workspace_bytes": (_sz, [_i64, _i]),
     "moe_segment_colsum": (_i, [_p, _p, _i64, _i, _i, _p, _p, _p]),
     "moe_gate_dispatch_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _i, _p]),
@@ -94,7 +95,7 @@ KERNELS_PER_CALL = {
     "moe_gate_dispatch_bwd_peer": 1,
     "moe_gate_fwd": 2, "moe_route_scan": 2, "moe_ep_tables": 1, "moe_ep_repack": 1, "moe_dispatch_fwd": 1, "moe_expert_ffn_fwd": 2, "moe_combine_fwd": 1,
     "moe_combine_bwd": 1, "moe_expert_ffn_bwd": 8, "moe_gate_bwd": 1, "moe_dispatch_bwd": 1, "moe_gate_dispatch_bwd": 1,
-    "moe_gate_wgrad": 2, "moe_addln_fwd": 1, "moe_addln_bwd": 2, "moe_colsum": 2, "moe_cast_bf16": 1, "moe_segment_colsum": 2, "moe_grouped_gemm": 1, "moe_slab_colsum_final": 1,
+    "moe_gate_wgrad": 2, "moe_addln_fwd": 1, "moe_addln_bwd": 2, "moe_colsum": 2, "moe_cast_bf16": 1, "moe_cast_bf16_pair": 1, "moe_segment_colsum": 2, "moe_grouped_gemm": 1, "moe_slab_colsum_final": 1,
 }
 
 

@@ -54,8 +54,7 @@ class Bf16WeightCache:
             E, h, d = W1.shape
             W1b, W2b = torch.empty((E, h, d), dtype=bf, device=W1.device), torch.empty((E, d, h), dtype=bf, device=W1.device)
             st = C.stream_ptr()
-            C.call("moe_cast_bf16", C.ptr(W1.detach()), C.ptr(W1b), W1.numel(), st)
-            C.call("moe_cast_bf16", C.ptr(W2.detach()), C.ptr(W2b), W2.numel(), st)
+            C.call("moe_cast_bf16_pair", C.ptr(W1.detach()), C.ptr(W1b), W1.numel(), C.ptr(W2.detach()), C.ptr(W2b), W2.numel(), st)
             if capturing:
                 return W1b, W2b      # copies live in the graph's pool and are refreshed by every replay: not cached
             self._key, self._val = key, (W1b, W2b)

@@ -90,18 +90,22 @@ class PeerHeap:
         self.bases, self.local = [], 0
 
 
+def peer_rows_per_rank(W: int, El: int, T: int, k: int, capacity: int) -> int:
+    """Rows of a rank's packed buffers: every received row could be live — W sources x El local experts x capacity rows, but
+    never more than every pair of every source (W * T * k), which is the bound of a gate without a capacity (NaiveGate, the
+    reference's gate: /root/reference/models/resMoE.py:27-29; worst case = every token of every rank picks this rank's
+    experts).  Each segment is padded to a GEMM tile."""
+    total = min(W * El * capacity, W * T * k)
+    return C.rows_cap(total, 1, El, total)
+
+
 class PeerBuffers:
     """The per-layer regions of a heap for one problem shape (T_local, d, E, k, capacity)."""
 
     def __init__(self, T: int, d: int, E: int, El: int, k: int, capacity: int, group, device):
         W = dist.get_world_size(group)
         self.W, self.rank, self.El, self.E, self.d = W, dist.get_rank(group), El, E, d
-        # every received row could be live: W sources x El local experts x capacity rows — but never more than every pair of
-        # every source (W * T * k), which is the bound of a gate without a capacity (NaiveGate, the reference's gate:
-        # /root/reference/models/resMoE.py:27-29; worst case = every token of every rank picks this rank's experts).
-        # Each segment is padded to a GEMM tile.
-        total = min(W * El * capacity, W * T * k)
-        self.rows_per_rank = C.rows_cap(total, 1, El, total)
+        self.rows_per_rank = peer_rows_per_rank(W, El, T, k, capacity)
         row_bytes = _round_up(self.rows_per_rank * d * 2)
         off, self.off = 0, {}
         for name, nbytes in (("flags", _round_up(W * 4)), ("kept_all", _round_up(W * E * 4)), ("xbuf", row_bytes), ("ybuf", row_bytes),

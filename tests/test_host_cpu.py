@@ -115,6 +115,17 @@ def test_expert_parallel_transport_selection():
         D.TRANSPORT = "auto"
 
 
+def test_peer_buffer_row_bound():
+    """Static size of a rank's packed buffers under peer-memory expert parallelism: W * E_local * capacity rows for a
+    capacity-limited gate, W * T * k (every pair of every rank) for NaiveGate, + one 256-row tile of padding per local expert."""
+    from fmoe.peer import peer_rows_per_rank
+    W, El, T, k = 8, 2, 50432, 1
+    cap = 3940                                                    # ceil(1.25 * T / 16)
+    assert peer_rows_per_rank(W, El, T, k, cap) == (W * El * cap + 255) // 256 * 256 + 256 * El
+    assert peer_rows_per_rank(W, El, T, k, T * k) == (W * T * k + 255) // 256 * 256 + 256 * El      # no capacity: bounded by the pairs
+    assert peer_rows_per_rank(2, 4, 900, 2, 900 * 2) == (2 * 900 * 2 + 255) // 256 * 256 + 256 * 4
+
+
 def _layer(**kw):
     import fmoe
     act = torch.nn.Sequential(torch.nn.GELU(), torch.nn.Dropout(p=0.0))
