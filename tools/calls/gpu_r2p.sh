@@ -2,7 +2,7 @@
 # round 2, call p: the round's evidence set in one call — full GPU suite, default bench line (c2, N = 1) and the CPU
 # reference arm, launch list of one training step, per-kernel device times of four layer shapes, ncu --set full of the
 # gate kernels and of the six grouped-GEMM launches at the config-2 layer shape.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader > gpurun_out/r2p_gpu.txt
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2p_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2p_pytest.log

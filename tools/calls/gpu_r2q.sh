@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, call q: stream-K weight gradients — GEMM parity / determinism tests, then A/B against the two-way split-K
 # library of the previous commit (tools/variants/libmoe_r2o_splitk.so) inside one call
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "grouped_gemm or bundled or deterministic or ragged or full_size or dense_ffn" > gpurun_out/r2q_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r2q_pytest.log; tail -5 gpurun_out/r2q_pytest.log

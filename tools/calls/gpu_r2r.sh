@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, call r: stream-K weight gradients with L2 eviction hints (A evict_first, B evict_last): parity, A/B timing of
 # split-K (previous commit) / stream-K without hints / stream-K with hints, DRAM bytes of each (ncu), per-unit timeline
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "grouped_gemm or bundled or deterministic" > gpurun_out/r2r_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r2r_pytest.log; tail -3 gpurun_out/r2r_pytest.log

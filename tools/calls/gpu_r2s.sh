@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, call s: programmatic dependent launch on every layer kernel (A/B against the same tree built with -DMOE_NO_PDL),
 # weight-gradient schedule policy (stream-K / equal split-K / whole tiles) against the split-K library of the round's start
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2s_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2s_pytest.log
 tail -4 gpurun_out/r2s_pytest.log

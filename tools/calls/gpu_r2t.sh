@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, call t (2 GPUs): expert-parallel parity on both transports (with the NaiveGate case on peer memory), then the
 # config-2 bench at N = 2 over peer memory (stream-K weight gradients at E_local = 8)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_ep.py -m gpu -x -q > gpurun_out/r2t_ep_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2t_ep_pytest.log
 tail -4 gpurun_out/r2t_ep_pytest.log; cat gpurun_out/ep_worker_peer_w2.log | grep -E "case|EP_OK"

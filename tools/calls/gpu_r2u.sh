@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, call u: dgelu / dgrad read the forward bf16 weights MN-major (no transposed copies, plain weight cast):
 # full GPU suite, A/B of the row-mode GEMMs against the K-major library of the previous commit, bench c2, layer times c2 / c3
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2u_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2u_pytest.log
 tail -4 gpurun_out/r2u_pytest.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call v: fc1 / dgelu epilogue experiments — 16 epilogue warps (fc1), 12 / 16 (dgelu), degree-5 GELU polynomial
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for v in base fc1w16 dg12 dg16 both16 deg5 deg5w16 base; do
   if [ $v = base ]; then unset MOE_B200_LIB; else export MOE_B200_LIB=tools/variants/libmoe_r2v_$v.so; fi
