@@ -10,8 +10,8 @@
 // whatever E is:
 //   * one CTA per 64-token tile; its dlogits rows are computed by 4 threads per token into shared memory (A operand);
 //   * the packed dXbuf rows of a sub-tile (16-64 tokens) are requested with 16-byte cp.async up front (possibly from a
-//     peer GPU under expert parallelism: PeerRows), rows padded by 16 bytes so that fragment-shaped accesses are
-//     conflict-free;
+//     peer GPU under expert parallelism: PeerRows — then through L1, so that the requests cross NVLink as whole 128-byte
+//     lines), rows padded by 16 bytes so that fragment-shaped accesses are conflict-free;
 //   * warp w owns d / 8 output columns: Wg fragments (B operand, tf32) are loaded once per 32-column chunk and reused
 //     by every 16-token m-tile; the accumulator fragment is added to the staged rows IN PLACE (bf16 output) and the
 //     finished rows leave with coalesced 16-byte stores — or straight from the fragments for fp32 output (a quad
@@ -87,6 +87,7 @@ gate_dispatch_bwd_mma_kernel(PeerRows dxrows, const int* __restrict__ pos, const
     const int n_tok = static_cast<int>(min(static_cast<int64_t>(kTile), T - t_base));
     const bool dense = (score_mode == 1) || (dpsum != nullptr);
     const bool have_rows = dxrows.base[0] != nullptr;
+    const bool remote = dxrows.n > 1;
     const uint32_t rows_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(rows_s));
     const int c16 = d >> 3;   // 16-byte chunks per row
 
@@ -100,7 +101,13 @@ gate_dispatch_bwd_mma_kernel(PeerRows dxrows, const int* __restrict__ pos, const
             if (row >= 0) {
                 const __nv_bfloat16* src = peer_row<__nv_bfloat16>(dxrows, row, d);
                 for (int c = lane; c < c16; c += 32)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * 16), "l"(src + c * 8) : "memory");
+                    // Rows on a peer GPU go through L1 (.ca): the LSU then sends a warp's 32 x 16 bytes over NVLink as whole
+                    // 128-byte requests.  L2-only copies (.cg) measured 84 us against 57 us for this kernel with half the rows
+                    // remote (profiles/r02_cpasync_peer_ab.log); local rows keep .cg (nothing is re-read, no L1 allocation).
+                    if (remote)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + c * 16), "l"(src + c * 8) : "memory");
+                    else
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * 16), "l"(src + c * 8) : "memory");
             } else {
                 for (int c = lane; c < c16; c += 32)
                     *reinterpret_cast<uint4*>(rows_s + pr * RS + c * 16) = make_uint4(0u, 0u, 0u, 0u);   // dropped / skipped / past T
