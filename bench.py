@@ -13,7 +13,9 @@ data parallel: weak scaling.
 
   value   images/s, inputs resident in HBM (CUDA events, max over ranks)
   e2e     images/s through the public module API with HOST inputs: per step a pinned-host -> device
-          copy of the batch and a device -> host read of the loss are inside the timed region
+          copy of the batch and a device -> host read of the loss are inside the timed region (the loss is read
+          one step behind through a pinned buffer; `e2e.sync_readback_value` = the same loop with loss.item()
+          after every step)
   roofline   the grouped tcgen05 expert GEMM (the dominant kernel of the hot path): algorithmic flops
              12*R*d*h per layer fwd+bwd over the CUDA-event time of its launches inside the timed region
   moe_layer  the isolated layer at the same shape: tokens/s fwd+bwd and per-kernel times / HBM fractions
@@ -537,28 +539,52 @@ def main():
             lab_stage.copy_(lab_h, non_blocking=True)
             staged.record(copy_stream)
 
-    barrier()
-    t0 = time.perf_counter()
-    prefetch()
-    for i in range(args.steps):
-        torch.cuda.current_stream().wait_event(staged)
-        img_d.copy_(img_stage, non_blocking=True)
-        lab_d.copy_(lab_stage, non_blocking=True)
-        copy_stream.wait_stream(torch.cuda.current_stream())   # staging buffers are free again
-        if i + 1 < args.steps:
-            prefetch()
-        loss = run_step()
-        loss_host = loss.item()      # device -> host read of the step's result
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    def e2e_loop(pipelined: bool) -> tuple[float, float]:
+        """K steps from host buffers; returns (seconds, last loss).  Every step's loss is read on the host inside the timed
+        region.  pipelined: the loss of step i lands in a pinned buffer through an asynchronous copy and is read after step
+        i + 1 has been enqueued (a loop that logs one step behind), so the device never waits for the host round trip;
+        otherwise `loss.item()` right after every step, the way /root/reference/engine.py:56-60 reads it."""
+        loss_pin = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ev = [torch.cuda.Event() for _ in range(2)]
+        loss_host = float("nan")
+        barrier()
+        t0 = time.perf_counter()
+        prefetch()
+        for i in range(args.steps):
+            torch.cuda.current_stream().wait_event(staged)
+            img_d.copy_(img_stage, non_blocking=True)
+            lab_d.copy_(lab_stage, non_blocking=True)
+            copy_stream.wait_stream(torch.cuda.current_stream())   # staging buffers are free again
+            if i + 1 < args.steps:
+                prefetch()
+            loss = run_step()
+            if pipelined:
+                loss_pin[i & 1].copy_(loss.detach().float(), non_blocking=True)   # device -> host read of the step's result
+                loss_ev[i & 1].record()
+                if i > 0:
+                    loss_ev[(i - 1) & 1].synchronize()
+                    loss_host = float(loss_pin[(i - 1) & 1])
+                    if not (loss_host == loss_host):
+                        raise SystemExit("non-finite loss in the timed region")
+            else:
+                loss_host = loss.item()
+        torch.cuda.synchronize()
+        if pipelined:
+            loss_host = float(loss_pin[(args.steps - 1) & 1])
+        return time.perf_counter() - t0, loss_host
+
+    e2e_sync_s, loss_host = e2e_loop(pipelined=False)
+    e2e_s, loss_host2 = e2e_loop(pipelined=True)
+    if loss_host2 != loss_host2:
+        loss_host = loss_host2
     clocks = sampler.stop() if sampler is not None else None
     if not (loss_host == loss_host):
         raise SystemExit("non-finite loss in the timed region")
 
-    t = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    t = torch.tensor([ms_total, e2e_s * 1e3, e2e_sync_s * 1e3], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_total, e2e_ms, e2e_sync_ms = float(t[0]), float(t[1]), float(t[2])
     global_batch = B * world
     value = global_batch * args.steps / (ms_total * 1e-3)
     e2e_value = global_batch * args.steps / (e2e_ms * 1e-3)
@@ -624,7 +650,14 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": (img_h.numel() * img_h.element_size() + lab_h.numel() * lab_h.element_size()) * world,
-                    "d2h_bytes_per_step": 4 * world},
+                    "d2h_bytes_per_step": 4 * world,
+                    "readback": "every step's loss is copied to pinned host memory and read (and checked finite) on the host one step "
+                                "behind, inside the timed region; the first batch's host -> device copy is exposed, the others are "
+                                "prefetched on a copy stream",
+                    "sync_readback_value": global_batch * args.steps / (e2e_sync_ms * 1e-3),
+                    "sync_readback_ms_per_step": e2e_sync_ms / args.steps,
+                    "sync_readback": "loss.item() after every step (the device drains before the next step is enqueued), "
+                                     "as /root/reference/engine.py:56-60 does"},
             "gpu_launches": launches,
             "roofline": roofline,
             "model_roofline": {"train_flops_per_image": flops_img, "achieved_tflops": round(flops_img * value / 1e12, 1),

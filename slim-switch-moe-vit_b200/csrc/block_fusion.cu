@@ -10,11 +10,16 @@
 // Backward is persistent: every lane owns fixed columns, so the dgamma / dbeta partial sums live in
 // registers across all rows of the CTA, are combined over the CTA's 8 warps in shared memory in warp order
 // and written as one partial per CTA; a second kernel adds the partials in CTA order (deterministic).
+// Its operands come through a per-warp ring of row slots in shared memory filled by cp.async.bulk
+// (addln_bwd_bulk_kernel: 5.9 TB/s at d = 384 against 4.2 TB/s for the register-staged version, which
+// remains for d % 8 != 0).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace moe {
 
@@ -195,6 +200,154 @@ addln_bwd_kernel(const NT* __restrict__ dn, const float* __restrict__ dx_out, co
     }
 }
 
+// Same arithmetic, operands staged by the copy engine (d % 8 == 0).  The register version above holds at most two rows per
+// warp in flight (its 128 registers are the per-lane dgamma / dbeta accumulators plus two rows of operands): ~80 KB of loads
+// per SM, short of what 6.5 TB/s needs under load.  Here every warp owns a ring of `stages` row slots in shared memory
+// (x | dx_out | dn of one row, 10 d bytes with a bf16 dn); lane 0 refills a slot with three `cp.async.bulk` copies that
+// complete on the slot's mbarrier as soon as the warp has read it, so stages - 1 rows per warp are always in flight without
+// costing a register: one CTA of 8 warps per SM, 6 stages at d = 384 = 150 KB of loads in flight per SM.  Row statistics
+// are fetched 32 rows at a time, one batch ahead (lane l holds the row of iteration 32 b + l).  Wide rows (NV > 3) read
+// their slot twice instead of keeping the row in registers.
+template <typename NT, typename DT, int NV>
+__global__ void __launch_bounds__(256, 1)
+addln_bwd_bulk_kernel(const NT* __restrict__ dn, const float* __restrict__ dx_out, const float* __restrict__ x, const float* __restrict__ mean,
+                      const float* __restrict__ rstd, const float* __restrict__ gamma, int64_t T, int d, int stages, float* __restrict__ dx_in,
+                      DT* __restrict__ d_delta, float* __restrict__ part /* [grid][2][d] */) {
+    extern __shared__ __align__(128) uint8_t ln_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nv = d / 4;
+    const uint32_t xb = static_cast<uint32_t>(d) * 4u, gb = static_cast<uint32_t>(d) * static_cast<uint32_t>(sizeof(NT));
+    const uint32_t slot_bytes = 2 * xb + gb;   // x | dx_out | dn
+    uint8_t* const ring = ln_smem + static_cast<size_t>(warp) * stages * slot_bytes;
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(ln_smem + static_cast<size_t>(8) * stages * slot_bytes) + warp * stages;
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(bars + s, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * 8;
+    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+    const int nrows = row0 < T ? static_cast<int>((T - 1 - row0) / stride) + 1 : 0;
+    const uint32_t tx = xb + gb + (dx_out != nullptr ? xb : 0u);
+    auto issue = [&](int it, int s) {   // lane 0 only
+        const int64_t row = row0 + it * stride;
+        const uint32_t dst = smem_u32(ring + static_cast<size_t>(s) * slot_bytes);
+        mbar_arrive_expect_tx(bars + s, tx);
+        bulk_load_1d(dst, x + row * d, xb, bars + s);
+        if (dx_out != nullptr) bulk_load_1d(dst + xb, dx_out + row * d, xb, bars + s);
+        bulk_load_1d(dst + 2 * xb, dn + row * d, gb, bars + s);
+    };
+    if (lane == 0)
+        for (int it = 0; it < stages && it < nrows; ++it) issue(it, it);
+
+    float4 gam[NV], dg[NV], db[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gam[i] = (i * 32 + lane < nv) ? __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float inv_d = 1.0f / static_cast<float>(d);
+    auto ld_stats = [&](int it0, float& mu, float& rs) {
+        const int it = it0 + lane;
+        mu = 0.0f; rs = 0.0f;
+        if (it < nrows) {
+            const int64_t r = row0 + it * stride;
+            mu = __ldg(mean + r);
+            rs = __ldg(rstd + r);
+        }
+    };
+    float mu_c = 0.0f, rs_c = 0.0f, mu_n, rs_n;
+    ld_stats(0, mu_n, rs_n);
+    constexpr bool kKeep = NV <= 3;   // the row stays in registers between the two passes
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nrows; ++it) {
+        if ((it & 31) == 0) {
+            mu_c = mu_n; rs_c = rs_n;
+            ld_stats(it + 32, mu_n, rs_n);
+        }
+        const float mu = __shfl_sync(0xffffffffu, mu_c, it & 31), rs = __shfl_sync(0xffffffffu, rs_c, it & 31);
+        const int64_t row = row0 + it * stride;
+        mbar_wait(bars + s, ph);
+        const uint8_t* const slot = ring + static_cast<size_t>(s) * slot_bytes;
+        const float* const sx = reinterpret_cast<const float*>(slot);
+        const float* const sr = reinterpret_cast<const float*>(slot + xb);
+        const NT* const sg = reinterpret_cast<const NT*>(slot + 2 * xb);
+        float c1 = 0.0f, c2 = 0.0f;
+        [[maybe_unused]] float4 kxh[kKeep ? NV : 1], kg[kKeep ? NV : 1];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (i * 32 + lane < nv) {
+                const int c = (i * 32 + lane) * 4;
+                const float4 xv = ld_f4(sx + c), gv = ld_f4(sg + c);
+                const float4 xh = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                dg[i].x += gv.x * xh.x; dg[i].y += gv.y * xh.y; dg[i].z += gv.z * xh.z; dg[i].w += gv.w * xh.w;
+                db[i].x += gv.x; db[i].y += gv.y; db[i].z += gv.z; db[i].w += gv.w;
+                const float4 g = make_float4(gv.x * gam[i].x, gv.y * gam[i].y, gv.z * gam[i].z, gv.w * gam[i].w);
+                c1 += (g.x + g.y) + (g.z + g.w);
+                c2 += (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w);
+                if constexpr (kKeep) { kxh[i] = xh; kg[i] = g; }
+            }
+        }
+        c1 = warp_sum(c1) * inv_d;
+        c2 = warp_sum(c2) * inv_d;
+        float4 o[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (i * 32 + lane < nv) {
+                const int c = (i * 32 + lane) * 4;
+                float4 xh, g;
+                if constexpr (kKeep) {
+                    xh = kxh[i]; g = kg[i];
+                } else {
+                    const float4 xv = ld_f4(sx + c), gv = ld_f4(sg + c);
+                    xh = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                    g = make_float4(gv.x * gam[i].x, gv.y * gam[i].y, gv.z * gam[i].z, gv.w * gam[i].w);
+                }
+                const float4 r = dx_out != nullptr ? ld_f4(sr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                o[i].x = rs * (g.x - c1 - xh.x * c2); o[i].y = rs * (g.y - c1 - xh.y * c2);
+                o[i].z = rs * (g.z - c1 - xh.z * c2); o[i].w = rs * (g.w - c1 - xh.w * c2);
+                o[i].x += r.x; o[i].y += r.y; o[i].z += r.z; o[i].w += r.w;
+            }
+        }
+        // every lane has read the slot: refill it (generic-proxy reads ordered before the async-proxy write)
+        __syncwarp();
+        if (lane == 0 && it + stages < nrows) {
+            fence_proxy_async_smem();
+            issue(it + stages, s);
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (i * 32 + lane < nv) {
+                const int c = (i * 32 + lane) * 4;
+                st_f4(dx_in + row * d + c, o[i]);
+                if (d_delta != nullptr) st_f4(d_delta + row * d + c, o[i]);
+            }
+        }
+        if (++s == stages) { s = 0; ph ^= 1; }
+    }
+    // every copy a warp issued has been waited for: the ring is free, the warps are combined in warp order through it
+    __syncthreads();
+    float* const red = reinterpret_cast<float*>(ln_smem);   // [8][2*d]
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (i * 32 + lane < nv) {
+            st_f4(red + warp * 2 * d + c, dg[i]);
+            st_f4(red + warp * 2 * d + d + c, db[i]);
+        }
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 2 * d; o += 256) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += red[w * 2 * d + o];
+        part[static_cast<size_t>(blockIdx.x) * 2 * d + o] = sum;
+    }
+}
+
 // out[o] = sum_b part[b][o]: one warp per output, lanes stride the partials (independent loads), xor butterfly
 __global__ void __launch_bounds__(256)
 addln_bwd_reduce_kernel(const float* __restrict__ part, int nparts, int d, float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -278,11 +431,43 @@ cudaError_t launch_colsum(const void* buf, int dtype, int64_t rows, int cols, vo
     return cudaGetLastError();
 }
 
-static int addln_bwd_blocks(int64_t T, int d) {
+// The staged kernel (addln_bwd_bulk_kernel) runs one 8-warp CTA per SM with as many row slots per warp as fit
+// kLnRingBudget; rows it cannot take (d % 8 != 0, fewer than two stages) go to the register kernel.
+constexpr int kLnRingBudget = 200 * 1024;
+struct LnBwdPlan { int bulk, stages, grid; size_t smem; };
+static LnBwdPlan addln_bwd_plan(int64_t T, int d, int n_dtype) {
+    LnBwdPlan p{0, 0, 0, 0};
     const int64_t want = (T + 7) / 8;
-    const int per_sm = d <= 768 ? 2 : 1;   // matches the kernels' __launch_bounds__ residency
+    const size_t slot = static_cast<size_t>(d) * (8 + (n_dtype == MOE_DTYPE_BF16 ? 2 : 4));
+    // narrow rows are latency-bound with 8 warps per SM (two warp reductions per 2 KB row): two CTAs per SM, half the ring each
+    // (measured at T = 50 432, profiles/r02_addln_bwd_staged.md: d = 192 42.5 -> 31.5 us with two CTAs, d = 384 52.7 -> 56.9 us)
+    int ctas = d <= 256 ? 2 : 1, budget = kLnRingBudget, stages_max = 8, mode = 1;
+#ifdef MOE_EXPERIMENT_HOOKS   // tools/build_variant.sh only: the shipped library never reads the environment
+    if (getenv("MOE_LN_BWD_MODE")) mode = atoi(getenv("MOE_LN_BWD_MODE"));
+    if (getenv("MOE_LN_CTAS")) ctas = atoi(getenv("MOE_LN_CTAS"));
+    if (getenv("MOE_LN_BUDGET_KB")) budget = atoi(getenv("MOE_LN_BUDGET_KB")) * 1024;
+    if (getenv("MOE_LN_STAGES")) stages_max = atoi(getenv("MOE_LN_STAGES"));
+#endif
+    int stages = static_cast<int>(budget / ctas / (8 * slot));
+    if (stages > stages_max) stages = stages_max;
+    if (mode == 1 && d % 8 == 0 && stages >= 2) {
+        p.bulk = 1;
+        p.stages = stages;
+        const int64_t cap = static_cast<int64_t>(sm_count()) * ctas;
+        p.grid = static_cast<int>(want < cap ? want : cap);
+        p.smem = static_cast<size_t>(8) * stages * slot + static_cast<size_t>(8) * stages * 8;
+        return p;
+    }
+    const int per_sm = d <= 768 ? 2 : 1;   // matches the register kernel's __launch_bounds__ residency
     const int64_t cap = static_cast<int64_t>(sm_count()) * per_sm;
-    return static_cast<int>(want < cap ? want : cap);
+    p.grid = static_cast<int>(want < cap ? want : cap);
+    p.smem = static_cast<size_t>(8) * 2 * d * 4;
+    return p;
+}
+// partials per CTA: sized for the larger of the two grids so the workspace does not depend on the operand dtype
+static int addln_bwd_blocks(int64_t T, int d) {
+    const int a = addln_bwd_plan(T, d, MOE_DTYPE_BF16).grid, b = addln_bwd_plan(T, d, MOE_DTYPE_F32).grid;
+    return a > b ? a : b;
 }
 
 size_t addln_bwd_workspace_bytes(int64_t T, int d) { return static_cast<size_t>(addln_bwd_blocks(T, d)) * 2 * d * 4; }
@@ -313,12 +498,25 @@ cudaError_t launch_addln_fwd(const float* x_in, const void* delta, int delta_dty
 cudaError_t launch_addln_bwd(const void* dn, int n_dtype, const float* dx_out, const float* x, const float* mean, const float* rstd,
                              const float* gamma, int64_t T, int d, float* dx_in, void* d_delta, int delta_dtype, void* workspace,
                              float* dgamma, float* dbeta, cudaStream_t st) {
-    const int grid = addln_bwd_blocks(T, d);
+    const bool nbf = n_dtype == MOE_DTYPE_BF16, dbf = d_delta != nullptr && delta_dtype == MOE_DTYPE_BF16;
+    LnBwdPlan plan = addln_bwd_plan(T, d, n_dtype);
+    const auto misaligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) != 0; };
+    if (plan.bulk && (misaligned(dn) || misaligned(x) || misaligned(dx_out))) {   // cp.async.bulk needs 16-byte aligned rows
+        plan.bulk = 0;
+        plan.smem = static_cast<size_t>(8) * 2 * d * 4;
+    }
+    const int grid = plan.grid;
     float* part = static_cast<float*>(workspace);
-    const size_t smem = static_cast<size_t>(8) * 2 * d * 4;
+    const size_t smem = plan.smem;
     cudaError_t err = cudaSuccess;
 #define MOE_LN_BWD_NV(NT, DT, NVV)                                                                                          \
-    {                                                                                                                       \
+    if (plan.bulk) {                                                                                                        \
+        auto kfn = addln_bwd_bulk_kernel<NT, DT, NVV>;                                                                      \
+        err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                            \
+        if (err != cudaSuccess) return err;                                                                                 \
+        kfn<<<grid, 256, smem, st>>>(static_cast<const NT*>(dn), dx_out, x, mean, rstd, gamma, T, d, plan.stages, dx_in,   \
+                                     static_cast<DT*>(d_delta), part);                                                      \
+    } else {                                                                                                                \
         auto kfn = addln_bwd_kernel<NT, DT, NVV>;                                                                           \
         err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                            \
         if (err != cudaSuccess) return err;                                                                                 \
@@ -332,7 +530,6 @@ cudaError_t launch_addln_bwd(const void* dn, int n_dtype, const float* dx_out, c
         else if (d <= 768) MOE_LN_BWD_NV(NT, DT, 6)                                                                         \
         else MOE_LN_BWD_NV(NT, DT, 8)                                                                                       \
     }
-    const bool nbf = n_dtype == MOE_DTYPE_BF16, dbf = d_delta != nullptr && delta_dtype == MOE_DTYPE_BF16;
     if (nbf && dbf) MOE_LN_BWD(__nv_bfloat16, __nv_bfloat16)
     else if (nbf) MOE_LN_BWD(__nv_bfloat16, float)
     else if (dbf) MOE_LN_BWD(float, __nv_bfloat16)

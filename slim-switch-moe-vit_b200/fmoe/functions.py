@@ -35,7 +35,9 @@ class Bf16WeightCache:
     weights move once per optimizer step anyway, and neither `p.data.add_` (many timm / apex optimizers) nor a CUDA-graph
     replay of the optimizer bumps `p._version`, so no host-side key can be trusted there.  Inference forwards
     (`torch.no_grad()`, frozen weights) reuse the copies keyed on (data_ptr, _version); `invalidate()` drops them
-    (call it after writing weights through `.data` outside of training)."""
+    (call it after writing weights through `.data` outside of training).  A training forward leaves NO key behind: the
+    optimizer step that follows it may be one of those invisible writes, so the first inference forward after training
+    (the reference's `evaluate` after `train_one_epoch`, main.py:930-940) casts once more and only then starts reusing."""
 
     def __init__(self):
         self._key = None
@@ -57,7 +59,7 @@ class Bf16WeightCache:
             C.call("moe_cast_bf16_pair", C.ptr(W1.detach()), C.ptr(W1b), W1.numel(), C.ptr(W2.detach()), C.ptr(W2b), W2.numel(), st)
             if capturing:
                 return W1b, W2b      # copies live in the graph's pool and are refreshed by every replay: not cached
-            self._key, self._val = key, (W1b, W2b)
+            self._key, self._val = (None if fresh else key), (W1b, W2b)
         return self._val
 
     def __deepcopy__(self, memo):  # ModelEma deep-copies the model (reference main.py:602-607)

@@ -255,38 +255,68 @@ def test_rejects_cpu_and_bad_config():
         layer(torch.randn(3, 64))
 
 
-@pytest.mark.parametrize("d,dt", [(384, torch.bfloat16), (192, torch.float32), (768, torch.bfloat16), (1024, torch.bfloat16), (64, torch.float32)])
-def test_add_layer_norm_vs_torch(d, dt):
-    """Fused residual-add + LayerNorm (fmoe.AddLayerNorm) against plain PyTorch fp32 (a floating-point kernel:
-    the torch fp32 reference is its oracle).  fp32 outputs: rel 1e-5; bf16 outputs: 4e-3 (bf16 rounding)."""
+def _check_add_layer_norm(rows_shape, d, dt, with_delta=True):
     fmoe, C, Fn = _fm()
     torch.manual_seed(3)
-    B, N = 5, 197
     ln = fmoe.AddLayerNorm(d, eps=1e-6).cuda()
     with torch.no_grad():
         ln.weight.uniform_(0.5, 1.5); ln.bias.uniform_(-0.5, 0.5)
-    x = torch.randn(B, N, d, device="cuda", requires_grad=True)
-    delta = (torch.randn(B, N, d, device="cuda") * 0.5).to(dt).requires_grad_()
-    gx, gn = torch.randn(B, N, d, device="cuda"), torch.randn(B, N, d, device="cuda").to(dt)
-    x_out, n = fmoe.add_layer_norm(x, delta, ln.weight, ln.bias, ln.eps, out_dtype=dt)
-    assert x_out.dtype == torch.float32 and n.dtype == dt
-    torch.autograd.backward([x_out, n], [gx, gn])
-    got = [x_out.detach(), n.detach(), x.grad, delta.grad, ln.weight.grad, ln.bias.grad]
-    xr = x.detach().clone().requires_grad_(); dr = delta.detach().float().requires_grad_()
+    x = torch.randn(*rows_shape, d, device="cuda", requires_grad=True)
+    gx, gn = torch.randn(*rows_shape, d, device="cuda"), torch.randn(*rows_shape, d, device="cuda").to(dt)
+    xr = x.detach().clone().requires_grad_()
     wr, br = ln.weight.detach().clone().requires_grad_(), ln.bias.detach().clone().requires_grad_()
-    xo = xr + dr
-    nr = torch.nn.functional.layer_norm(xo, (d,), wr, br, 1e-6)
-    torch.autograd.backward([xo, nr], [gx, gn.float()])
-    want = [xo.detach(), nr.detach(), xr.grad, dr.grad, wr.grad, br.grad]
+    if with_delta:
+        delta = (torch.randn(*rows_shape, d, device="cuda") * 0.5).to(dt).requires_grad_()
+        x_out, n = fmoe.add_layer_norm(x, delta, ln.weight, ln.bias, ln.eps, out_dtype=dt)
+        assert x_out.dtype == torch.float32 and n.dtype == dt
+        torch.autograd.backward([x_out, n], [gx, gn])
+        got = [x_out.detach(), n.detach(), x.grad, delta.grad, ln.weight.grad, ln.bias.grad]
+        dr = delta.detach().float().requires_grad_()
+        xo = xr + dr
+        nr = torch.nn.functional.layer_norm(xo, (d,), wr, br, 1e-6)
+        torch.autograd.backward([xo, nr], [gx, gn.float()])
+        want = [xo.detach(), nr.detach(), xr.grad, dr.grad, wr.grad, br.grad]
+        names = ["x_out", "n", "dx", "ddelta", "dgamma", "dbeta"]
+    else:   # nothing to add: plain LayerNorm, no incoming residual gradient in the backward
+        n = fmoe.add_layer_norm(x, None, ln.weight, ln.bias, ln.eps, out_dtype=dt)
+        n.backward(gn)
+        got = [n.detach(), x.grad, ln.weight.grad, ln.bias.grad]
+        nr = torch.nn.functional.layer_norm(xr, (d,), wr, br, 1e-6)
+        nr.backward(gn.float())
+        want = [nr.detach(), xr.grad, wr.grad, br.grad]
+        names = ["n", "dx", "dgamma", "dbeta"]
     tol = 1e-5 if dt == torch.float32 else 4e-3
-    for name, a, b in zip(["x_out", "n", "dx", "ddelta", "dgamma", "dbeta"], got, want):
+    for name, a, b in zip(names, got, want):
         lim = 1e-5 if name in ("x_out", "dx") and dt == torch.float32 else tol
         if name in ("dgamma", "dbeta", "dx"):
             lim = max(lim, 2e-5)
         assert rel_err(a, b) <= lim, f"{name}: {rel_err(a, b)}"
+    return ln, x
+
+
+@pytest.mark.parametrize("d,dt", [(384, torch.bfloat16), (192, torch.float32), (768, torch.bfloat16), (1024, torch.bfloat16), (64, torch.float32)])
+def test_add_layer_norm_vs_torch(d, dt):
+    """Fused residual-add + LayerNorm (fmoe.AddLayerNorm) against plain PyTorch fp32 (a floating-point kernel:
+    the torch fp32 reference is its oracle).  fp32 outputs: rel 1e-5; bf16 outputs: 4e-3 (bf16 rounding)."""
+    ln, x = _check_add_layer_norm((5, 197), d, dt)
     # no pending delta: plain LayerNorm
     n2 = ln(x.detach())
     assert rel_err(n2, torch.nn.functional.layer_norm(x.detach(), (d,), ln.weight, ln.bias, 1e-6)) <= 1e-5
+
+
+@pytest.mark.parametrize("T,d,dt,with_delta", [
+    (50432, 384, torch.bfloat16, True),     # config 2: 42-43 rows per warp through a 6-slot ring
+    (40003, 384, torch.bfloat16, False),    # no incoming residual gradient: two copies per slot
+    (20011, 768, torch.bfloat16, True),     # config 3 width: 3 slots, the row is read twice from its slot
+    (9001, 1024, torch.bfloat16, True),     # config 4 width: 2 slots
+    (30001, 192, torch.float32, True),      # fp32 dn / delta, 8 slots
+    (2369, 384, torch.bfloat16, True),      # one more row than warps in the grid: ring barely used, most warps one row
+    (3000, 100, torch.float32, True),       # d % 8 != 0: the register kernel
+], ids=lambda v: str(v).replace("torch.", ""))
+def test_add_layer_norm_backward_row_pipeline(T, d, dt, with_delta):
+    """The staged backward (cp.async.bulk ring per warp, csrc/block_fusion.cu addln_bwd_bulk_kernel) with many rows per
+    warp — slots refilled and barrier phases wrapped several times — and ragged row counts, against PyTorch fp32."""
+    _check_add_layer_norm((T,), d, dt, with_delta)
 
 
 def test_fused_block_model_matches_stock_blocks():

@@ -233,3 +233,40 @@ def test_train_loop_body_on_the_cuda_layer():
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):   # evaluate(), engine.py:88-121, on the EMA copy
         out = ema(samples)
     assert torch.isfinite(out).all()
+
+
+def test_expert_weight_copies_follow_invisible_weight_updates():
+    """The bf16 operand copies of the expert weights must follow updates that do not bump the tensor version: many
+    optimizers reachable through the reference's `--opt` write through `p.data`.  (a) train forward,
+    `.data` update, evaluation forward: the first no_grad forward after training re-casts; (b) two training forwards
+    around a `.data` update; (c) between two evaluation forwards `.data` writes need `invalidate_weight_cache()`."""
+    import fmoe
+    torch.manual_seed(0)
+    d, h, E = 128, 256, 4
+    layer = fmoe.FMoETransformerMLP(E, d, h, torch.nn.Sequential(torch.nn.GELU(), torch.nn.Dropout(0.0)), top_k=2).cuda()
+    x = torch.randn(600, d, device="cuda")
+
+    def fresh_eval():   # what a layer without any cached state returns for the current weights
+        twin = copy.deepcopy(layer)
+        with torch.no_grad():
+            return twin(x)
+
+    y0 = layer(x)                                   # training forward (autograd records, weights require grad)
+    y0.square().mean().backward()
+    with torch.no_grad():
+        assert rel_err(layer(x), y0.detach()) <= 1e-6
+    layer.experts.htoh4.weight.data.mul_(1.5)       # invisible to `_version`
+    layer.experts.h4toh.weight.data.add_(0.01)
+    # (b) the next training forward sees the new weights
+    y1 = layer(x)
+    want = fresh_eval()
+    assert rel_err(y1.detach(), want) <= 1e-6 and rel_err(y1.detach(), y0.detach()) > 1e-2
+    # (a) train forward, invisible update, evaluation forward
+    layer.experts.htoh4.weight.data.mul_(0.5)
+    with torch.no_grad():
+        y2 = layer(x)
+        assert rel_err(y2, fresh_eval()) <= 1e-6 and rel_err(y2, y1.detach()) > 1e-2
+        # (c) evaluation forwards reuse their copies until told otherwise
+        layer.experts.h4toh.weight.data.mul_(2.0)
+        layer.invalidate_weight_cache()
+        assert rel_err(layer(x), fresh_eval()) <= 1e-6
