@@ -573,6 +573,16 @@ def main():
             loss_host = float(loss_pin[(args.steps - 1) & 1])
         return time.perf_counter() - t0, loss_host
 
+    # one batch's host -> device copy alone (device idle): what the first step of each loop below exposes
+    h2d_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    with torch.cuda.stream(copy_stream):
+        h2d_ev[0].record(copy_stream)
+        img_stage.copy_(img_h, non_blocking=True)
+        lab_stage.copy_(lab_h, non_blocking=True)
+        h2d_ev[1].record(copy_stream)
+    copy_stream.synchronize()
+    h2d_ms = h2d_ev[0].elapsed_time(h2d_ev[1])
+
     e2e_sync_s, loss_host = e2e_loop(pipelined=False)
     e2e_s, loss_host2 = e2e_loop(pipelined=True)
     if loss_host2 != loss_host2:
@@ -651,6 +661,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": (img_h.numel() * img_h.element_size() + lab_h.numel() * lab_h.element_size()) * world,
                     "d2h_bytes_per_step": 4 * world,
+                    "h2d_ms_per_batch_alone": round(h2d_ms, 3),
                     "readback": "every step's loss is copied to pinned host memory and read (and checked finite) on the host one step "
                                 "behind, inside the timed region; the first batch's host -> device copy is exposed, the others are "
                                 "prefetched on a copy stream",
