@@ -85,6 +85,22 @@ def test_gate_kernels_are_tensor_core_code():
     assert any("STSM" in f for f in gdb)
 
 
+def test_layer_norm_backward_is_bulk_copy_staged():
+    """The fused add+LayerNorm backward that ships stages its rows with non-tensor bulk copies on mbarriers
+    (cp.async.bulk -> UBLKCP, mbarrier try_wait -> SYNCS) and spills nothing; its workspace is one partial per CTA of
+    the larger of the two grids (one 8-warp CTA per SM for d > 256, two below)."""
+    from fmoe import _cabi as C
+    sass = subprocess.run(["cuobjdump", "-sass", C.LIB_PATH], capture_output=True, text=True)
+    if sass.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    funcs = [f for f in sass.stdout.split("Function : ") if f.startswith("_ZN3moe21addln_bwd_bulk_kernel")]
+    assert len(funcs) == 16                                    # {f32, bf16} dn x {f32, bf16} d_delta x four row widths
+    assert all("UBLKCP" in f and "SYNCS.PHASECHK" in f and "LDS.128" in f for f in funcs)
+    assert not any("STL" in f or "LDL" in f for f in funcs)    # no local-memory spills
+    ws = C.lib.moe_addln_bwd_workspace_bytes(50432, 384)
+    assert ws % (2 * 384 * 4) == 0 and ws // (2 * 384 * 4) >= 1
+
+
 def test_peer_entry_points_validate_their_arguments_without_gpu():
     """Expert parallelism over peer memory: group size, rank and pointer-table checks happen before anything touches a GPU."""
     import ctypes
