@@ -198,3 +198,43 @@ def test_model_ideal_and_bruteforce_agree():
         yb = O.bruteforce_forward(*prob, k, mode, cap)
         assert rel_err(yi, yb) <= 1e-5          # two independent fp64 restatements
         assert rel_err(ym, yi) <= 1e-2          # bf16 arithmetic model vs ideal
+
+
+@pytest.mark.parametrize("T,E,cf,seed", [(1576, 8, 1.25, 0), (5000, 16, 1.25, 1), (777, 32, 1.0, 2), (4096, 64, 2.0, 3)])
+def test_gate_losses_against_upstream_fastmoe_formulas(T, E, cf, seed):
+    """What exactly differs from upstream FastMoE's capacity-limited gates (un-vendored; formulas restated from its
+    published `fmoe/gates/switch_gate.py` and `fmoe/gates/gshard_gate.py`, v1.1.0), pinned as identities on the same routing:
+
+    * SwitchGate, upstream: `fraction_expert = kept_e / sum(kept)`, `prob_expert = sum_t p[t, e] / sum(kept)`,
+      `loss = E * sum(fraction_expert * prob_expert)`; here P_e divides by T:  upstream == ours * T / sum(kept).
+    * SwitchGate capacity, upstream `ceil(cf * T)` PER EXPERT: with cf >= 1 it can never bind on one worker; ours is
+      `ceil(cf * T / E)`.
+    * GShardGate, upstream: `c_e` = histogram of the FIRST pick / T, `m_e = mean_t softmax(logits)[t, e]`,
+      `loss = mean(c_e * m_e) * num_expert^2` = E * sum(c_e m_e) on one worker; ours counts both picks / (2 T):
+      ours evaluated on the first-pick histogram == upstream.
+    * GShardGate capacity, upstream `ceil(cf * T) * k // (W * E)`; ours `ceil(cf * T * k / E)`: equal up to rounding (<= k)."""
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(T, E, generator=g) + torch.linspace(0.0, 1.5, E)   # skewed: real drops at cf 1.0 / 1.25
+    p = torch.softmax(logits.double(), dim=-1)
+    # ---- Switch (top-1, full-softmax score)
+    cap = O.capacity_from_factor(cf, T, 1, E)
+    r = O.route(logits, 1, 1, cap)
+    ours = O.switch_aux_loss(r, r.psum, T)
+    assert abs(float((O.aux_coef(r, T, O.AUX_SWITCH) * r.psum).sum()) - float(ours)) <= 1e-12
+    kept = r.kept.double()
+    valid = kept.sum()
+    upstream = E * ((kept / valid) * (p.sum(0) / valid)).sum()
+    assert abs(float(upstream) - float(ours) * T / float(valid)) <= 1e-6 * float(upstream)   # psum of the C oracle: fp32 exp
+    assert int(np.ceil(cf * T)) >= int(r.count.max())            # upstream's per-expert capacity never binds (cf >= 1)
+    assert cap == int(np.ceil(cf * T / E))
+    # ---- GShard (top-2, scores = softmax over the two picks), before capacity
+    cap2 = O.capacity_from_factor(cf, T, 2, E)
+    r2 = O.route(logits, 2, 0, cap2)
+    ours2 = float((O.aux_coef(r2, T, O.AUX_GSHARD) * r2.psum).sum())
+    assert abs(ours2 - float(E * ((r2.count.double() / (2 * T)) * (r2.psum / T)).sum())) <= 1e-12
+    top1 = torch.bincount(r2.idx[:, 0].long(), minlength=E).double()
+    c_e, m_e = top1 / T, p.mean(0)
+    upstream2 = float((c_e * m_e).mean() * E ** 2)
+    ours_on_first_picks = float(E * ((top1 / T) * (r2.psum / T)).sum())
+    assert abs(upstream2 - ours_on_first_picks) <= 1e-6 * upstream2
+    assert abs(int(np.ceil(cf * T)) * 2 // E - cap2) <= 2
