@@ -96,7 +96,8 @@ class SwitchGate(NaiveGate):
     Deliberate differences from upstream FastMoE's SwitchGate (SURVEY.md §8a defines the north-star semantics; tuned
     aux-loss coefficients do not carry over unchanged): capacity is ceil(cf * T * k / E) per expert (upstream: ceil(cf * T),
     which never binds on one worker); P_e averages the softmax probability over ALL T tokens (upstream: over the kept
-    tokens only); dropped tokens are the LAST ones of an expert in token order (upstream: whichever lose an atomics race)."""
+    tokens only: upstream's loss == this one * T / sum(kept)); dropped tokens are the LAST ones of an expert in token order
+    (upstream: whichever lose an atomics race)."""
 
     def __init__(self, d_model, num_expert, world_size, topk=1, switch_eps=0.1, capacity=(1.2, 2.4), gate_bias=True):
         assert topk == 1, "topk should be 1 in switch"
@@ -132,8 +133,9 @@ class GShardGate(NaiveGate):
     Upstream's `random_routing` of the second expert is not implemented (raises if requested).
 
     Deliberate differences from upstream FastMoE's GShardGate: c_e counts all k picks of a token divided by T * k (upstream:
-    the top-1 pick only, divided by T) and the scale is (global expert count)^2 (upstream: the local `num_expert`^2), so
-    the loss magnitude differs by a constant factor on one worker; capacity as in SwitchGate above."""
+    the top-1 pick only, divided by T) and the scale is (global expert count)^2 (upstream: the local `num_expert`^2): on one
+    worker both losses are E * sum_e c_e m_e and differ only in which picks c_e counts; capacity ceil(cf * T * k / E) equals
+    upstream's ceil(cf * T) * k // (W * E) up to rounding (tests/test_oracle_cpu.py pins these relations as identities)."""
 
     def __init__(self, d_model, num_expert, world_size, topk=2, capacity=(1.2, 2.4), random_routing=False,
                  gate_bias=True):
