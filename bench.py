@@ -389,6 +389,9 @@ def main():
     ap.add_argument("--no-layer", action="store_true", help="skip the isolated-layer breakdown (profiling runs)")
     ap.add_argument("--ep-transport", choices=["auto", "peer", "nccl"], default="auto",
                     help="expert-parallel row exchange: NVLink peer memory (fmoe/peer.py) or NCCL all-to-all on slabs (fmoe/distributed.py)")
+    ap.add_argument("--e2e-breakdown", action="store_true",
+                    help="diagnostic: after the timed regions, time the same K steps again device-only, with the staging copy only and "
+                         "with the host->device prefetch only (e2e.breakdown_ms_per_step)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of replaying the captured training step")
     ap.add_argument("--profile-window", action="store_true",
                     help="cudaProfilerStart/Stop around the device-resident timed region (ncu --profile-from-start off)")
@@ -591,6 +594,31 @@ def main():
     if not (loss_host == loss_host):
         raise SystemExit("non-finite loss in the timed region")
 
+    breakdown = None
+    if args.e2e_breakdown:   # where the difference between `e2e` and `value` comes from: one ingredient of the e2e loop at a time
+        def timed(body):
+            barrier()
+            t0_ = time.perf_counter()
+            for i in range(args.steps):
+                body(i)
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0_) * 1e3 / args.steps
+
+        def only_staging_copy(i):
+            img_d.copy_(img_stage, non_blocking=True)
+            lab_d.copy_(lab_stage, non_blocking=True)
+            run_step()
+
+        def only_prefetch(i):
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            prefetch()
+            run_step()
+
+        breakdown = {"device_only_again": round(timed(lambda i: run_step()), 3),
+                     "plus_staging_copy": round(timed(only_staging_copy), 3),
+                     "plus_h2d_prefetch_overlapped": round(timed(only_prefetch), 3),
+                     "device_only_last": round(timed(lambda i: run_step()), 3)}
+
     t = torch.tensor([ms_total, e2e_s * 1e3, e2e_sync_s * 1e3], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -662,6 +690,7 @@ def main():
                     "h2d_bytes_per_step": (img_h.numel() * img_h.element_size() + lab_h.numel() * lab_h.element_size()) * world,
                     "d2h_bytes_per_step": 4 * world,
                     "h2d_ms_per_batch_alone": round(h2d_ms, 3),
+                    **({"breakdown_ms_per_step": breakdown} if breakdown is not None else {}),
                     "readback": "every step's loss is copied to pinned host memory and read (and checked finite) on the host one step "
                                 "behind, inside the timed region; the first batch's host -> device copy is exposed, the others are "
                                 "prefetched on a copy stream",
