@@ -614,9 +614,35 @@ def main():
             prefetch()
             run_step()
 
+        done_ev, rec_ev = torch.cuda.Event(), torch.cuda.Event()
+        done_ev.record()
+        done_ev.synchronize()
+        pin1 = torch.empty((), dtype=torch.float32).pin_memory()
+
+        def only_event_record(i):
+            rec_ev.record()
+            run_step()
+
+        def only_event_wait(i):
+            torch.cuda.current_stream().wait_event(done_ev)   # completed long ago
+            run_step()
+
+        def only_free_running_h2d(i):   # the copy engine busy beside the step, no dependency on the main stream at all
+            with torch.cuda.stream(copy_stream):
+                img_stage.copy_(img_h, non_blocking=True)
+            run_step()
+
+        def only_loss_d2h(i):
+            pin1.copy_(run_step().detach().float(), non_blocking=True)
+
         breakdown = {"device_only_again": round(timed(lambda i: run_step()), 3),
                      "plus_staging_copy": round(timed(only_staging_copy), 3),
                      "plus_h2d_prefetch_overlapped": round(timed(only_prefetch), 3),
+                     "device_only_2": round(timed(lambda i: run_step()), 3),
+                     "plus_event_record": round(timed(only_event_record), 3),
+                     "plus_event_wait": round(timed(only_event_wait), 3),
+                     "plus_free_running_h2d": round(timed(only_free_running_h2d), 3),
+                     "plus_loss_d2h": round(timed(only_loss_d2h), 3),
                      "device_only_last": round(timed(lambda i: run_step()), 3)}
 
     t = torch.tensor([ms_total, e2e_s * 1e3, e2e_sync_s * 1e3], device="cuda", dtype=torch.float64)
