@@ -217,6 +217,28 @@ print('OK')
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not mounted (GPU box)")
+def test_reference_flop_hook_reads_the_drop_in_layer():
+    """The reference's own flop counter for the MoE layer (/root/reference/models/resmoe_flop_hook.py:4-10) walks
+    `mlp.gate.gate.in_features / .out_features`: run the unmodified function on the drop-in layer of each reference model."""
+    code = r"""
+import sys
+sys.path[:0] = [%r, %r, '/root/reference']
+import torch, fmoe, models
+from models.resmoe_flop_hook import moe_flops
+from timm.models import create_model
+kw = dict(num_classes=10, drop_rate=0., drop_path_rate=0., drop_block_rate=None, img_size=224)
+for name, extra in (('moe_tiny_patch16_224_expert8', {}), ('resmoe_tiny_patch16_224_expert8', dict(starting_threshold=1., target_threshold=.9))):
+    m = create_model(name, **kw, **extra)
+    mlp = [b for b in m.modules() if type(b).__name__ == 'Block'][0].mlp
+    shape = (8, 197, 192)
+    assert int(moe_flops(mlp, shape)) == 8 * 197 * 192 * 8 + 8 * 197 * (3 * 192 - 1)
+print('OK')
+""" % (os.path.join(ROOT, "oracle", "stubs"), os.path.join(ROOT, "slim-switch-moe-vit_b200"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "slim-switch-moe-vit_b200")
     for dirpath, _, files in os.walk(pkg):
